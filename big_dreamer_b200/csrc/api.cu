@@ -1,0 +1,126 @@
+// extern "C" surface of libbd_b200.so (include/bd_b200.h): argument checks that are common to
+// all arithmetic modes and dispatch on bd_precision.  No CPU fallback anywhere: a precision
+// that this build does not implement returns BD_ERR_UNSUPPORTED.
+#include "api_internal.h"
+
+namespace bd {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace bd
+
+using namespace bd;
+
+#define BD_NEED(p, what)                                           \
+  do {                                                             \
+    if (!(p)) BD_FAIL(BD_ERR_BAD_ARG, "%s: null %s", __func__, what); \
+  } while (0)
+
+#define BD_ONLY_FP32(precision)                                                             \
+  do {                                                                                      \
+    if ((precision) != BD_PREC_FP32)                                                        \
+      BD_FAIL(BD_ERR_UNSUPPORTED, "%s: precision %d is not implemented for this entry point", \
+              __func__, (int)(precision));                                                  \
+  } while (0)
+
+extern "C" {
+
+int bd_version(void) { return BD_ABI_VERSION; }
+const char* bd_last_error(void) { return bd::g_err; }
+int bd_precision_supported(int precision) { return precision == BD_PREC_FP32 ? 1 : 0; }
+
+size_t bd_mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {
+  return m ? f32::mlp_workspace_bytes(m, rows, backward) : 0;
+}
+int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
+                   float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
+  BD_NEED(m, "mlp"); BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
+  BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward: bad k1/k2/x2");
+  BD_ONLY_FP32(precision);
+  return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
+}
+int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
+                    int precision, bd_stream_t stream) {
+  BD_NEED(m, "mlp"); BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_NEED(a->x1, "x1"); BD_NEED(a->dy, "dy");
+  BD_CHECK_ARG(a->k1 > 0 && a->k2 >= 0 && (a->k2 == 0 || a->x2), "bd_mlp_backward: bad k1/k2/x2");
+  BD_ONLY_FP32(precision);
+  return f32::mlp_backward(m, a, ws, ws_bytes, stream);
+}
+
+int bd_lambda_return_forward(const float* reward, const float* value, const float* bootstrap, int T,
+                             int64_t N, double discount, double lambda_, float* returns,
+                             bd_stream_t stream) {
+  BD_NEED(reward, "reward"); BD_NEED(value, "value"); BD_NEED(bootstrap, "bootstrap");
+  BD_NEED(returns, "returns");
+  return f32::lambda_return_forward(reward, value, bootstrap, T, N, discount, lambda_, returns, stream);
+}
+int bd_lambda_return_backward(const float* d_returns, int T, int64_t N, double discount,
+                              double lambda_, float* d_reward, float* d_value, float* d_bootstrap,
+                              bd_stream_t stream) {
+  BD_NEED(d_returns, "d_returns");
+  return f32::lambda_return_backward(d_returns, T, N, discount, lambda_, d_reward, d_value,
+                                     d_bootstrap, stream);
+}
+
+size_t bd_transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
+  return r ? f32::transition_workspace_bytes(r, L, B, observe, backward) : 0;
+}
+int bd_transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, int precision,
+                          bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::transition_forward(a, ws, ws_bytes, stream);
+}
+int bd_transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, int precision,
+                           bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::transition_backward(a, ws, ws_bytes, stream);
+}
+
+size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N,
+                                  int backward) {
+  return (r && actor) ? f32::imagine_workspace_bytes(r, actor, T, N, backward) : 0;
+}
+int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
+                       bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::imagine_forward(a, ws, ws_bytes, stream);
+}
+int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, int precision,
+                        bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::imagine_backward(a, ws, ws_bytes, stream);
+}
+
+size_t bd_cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H) {
+  return (r && reward) ? f32::cem_workspace_bytes(r, reward, B, C_local, H) : 0;
+}
+int bd_cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision,
+                    bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::cem_evaluate(a, ws, ws_bytes, stream);
+}
+int bd_cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,
+                 int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream) {
+  return f32::cem_refit(returns, actions, B, C, K, H, A, topk_idx, action_mean, action_std, stream);
+}
+size_t bd_cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C, int K, int H) {
+  return (r && reward) ? f32::cem_plan_workspace_bytes(r, reward, B, C, K, H) : 0;
+}
+int bd_cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, int precision,
+                bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  return f32::cem_plan(a, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Internal C++ entry points behind the C ABI, one namespace per arithmetic mode.
+#pragma once
+#include "common.cuh"
+
+namespace bd {
+
+constexpr int64_t kMaxChunkRows = 65536;   // rows processed per pass of the check-mode path
+constexpr size_t kSlackBytes = 65536;      // alignment slack for workspace carving
+
+namespace f32 {
+size_t mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward);
+int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
+                float* y, void* ws, size_t ws_bytes, bd_stream_t stream);
+int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
+                 bd_stream_t stream);
+int lambda_return_forward(const float* reward, const float* value, const float* bootstrap, int T,
+                          int64_t N, double discount, double lambda_, float* returns,
+                          bd_stream_t stream);
+int lambda_return_backward(const float* d_returns, int T, int64_t N, double discount,
+                           double lambda_, float* d_reward, float* d_value, float* d_bootstrap,
+                           bd_stream_t stream);
+size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward);
+int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes,
+                        bd_stream_t stream);
+size_t imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N, int backward);
+int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H);
+int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,
+              int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream);
+size_t cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C, int K, int H);
+int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+}  // namespace f32
+
+}  // namespace bd

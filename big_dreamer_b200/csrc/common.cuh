@@ -1,0 +1,83 @@
+// Shared helpers for libbd_b200: error reporting, activation math, workspace carving.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bd_b200.h"
+
+namespace bd {
+
+void set_error(const char* fmt, ...);
+
+#define BD_FAIL(code, ...)        \
+  do {                            \
+    bd::set_error(__VA_ARGS__);   \
+    return (code);                \
+  } while (0)
+
+#define BD_CHECK_ARG(cond, ...)                     \
+  do {                                              \
+    if (!(cond)) BD_FAIL(BD_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define BD_CUDA_LAUNCH_CHECK()                                                        \
+  do {                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess)                                                           \
+      BD_FAIL(BD_ERR_CUDA, "%s:%d CUDA launch failed: %s", __FILE__, __LINE__,        \
+              cudaGetErrorString(e__));                                               \
+  } while (0)
+
+#define BD_TRY(expr)               \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != BD_OK) return rc__; \
+  } while (0)
+
+// ---------------------------------------------------------------- activations
+// torch semantics: ELU(alpha=1) uses expm1; softplus(beta=1, threshold=20).
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case BD_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case BD_ACT_RELU: return x > 0.f ? x : 0.f;
+    case BD_ACT_TANH: return tanhf(x);
+    case BD_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    default: return x;
+  }
+}
+// derivative expressed through the activation OUTPUT y (what backward has at hand)
+__device__ __forceinline__ float act_bwd_from_out(int act, float y) {
+  switch (act) {
+    case BD_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case BD_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case BD_ACT_TANH: return 1.f - y * y;
+    case BD_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// d softplus / dx with the same threshold rule as torch's softplus_backward
+__device__ __forceinline__ float softplus_gradf_(float x) { return x > 20.f ? 1.f : sigmoidf_(x); }
+
+// ---------------------------------------------------------------- workspace
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), cap(bytes), off(0) {}
+  float* f32(size_t n) {
+    size_t bytes = (n * sizeof(float) + 255) & ~size_t(255);
+    if (off + bytes > cap) { off = cap + 1; return nullptr; }
+    float* r = reinterpret_cast<float*>(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+inline size_t pad256(size_t n_floats) { return (n_floats * sizeof(float) + 255) & ~size_t(255); }
+
+inline bool valid_act(int a) { return a >= BD_ACT_IDENTITY && a <= BD_ACT_SIGMOID; }
+
+}  // namespace bd

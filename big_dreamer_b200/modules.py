@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's operator interface for the RSSM hot path.
+
+Same constructor signatures, ``forward`` signatures, tensor layouts and
+``state_dict`` keys as the reference classes they replace, so ``planet.py`` /
+``dreamer.py`` / ``planner.py`` can use them as drop-ins:
+
+    TransitionModel   <- src/models.py:120-299
+    DenseModel        <- src/models.py:365-408
+    MPCPlanner        <- src/planner.py:5-90
+    imagine_ahead     <- Dreamer.imagine_ahead, src/dreamer.py:178-237
+    lambda_return     <- src/dreamer.py:447-471
+
+All arithmetic runs in libbd_b200.so on the current CUDA device.  CPU tensors,
+Categorical latents and unknown activations raise -- there is no fallback.
+Every function takes an optional ``noise=`` argument carrying the Gaussian draws
+the reference makes internally, for bit-for-bit comparable parity runs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn, Tensor
+
+from . import _lib
+from . import functions as F_
+from ._lib import BdError
+
+ENTROPY_SAMPLES = 100  # SampleDist(samples=100), src/models.py:684
+
+
+def build_mlp(input_size: int, hidden_size: int, output_size: int, n_layers: int,
+              activation="ELU", output_activation="Identity") -> nn.Sequential:
+    """Same layer structure (and therefore the same parameter names
+    ``{0,2,4,...}.{weight,bias}``) as the reference's build_mlp, src/utils.py:368-404."""
+    act = getattr(nn, activation) if isinstance(activation, str) else activation
+    out_act = getattr(nn, output_activation) if isinstance(output_activation, str) \
+        else output_activation
+    layers, in_size = [], input_size
+    for _ in range(n_layers):
+        layers += [nn.Linear(in_size, hidden_size), act()]
+        in_size = hidden_size
+    layers += [nn.Linear(in_size, output_size), out_act()]
+    return nn.Sequential(*layers)
+
+
+def _act_name(activation) -> str:
+    if isinstance(activation, str):
+        return activation
+    return getattr(activation, "__name__", type(activation).__name__)
+
+
+def _linears(seq: nn.Sequential):
+    return [m for m in seq if isinstance(m, nn.Linear)]
+
+
+# =============================================================================
+# DenseModel
+# =============================================================================
+class DenseModel(nn.Module):
+    """General fused MLP: ``forward(belief, state)`` (concatenated on the last dim) or
+    ``forward(x)``; any leading dims.  Reference: src/models.py:365-408."""
+
+    def __init__(self, input_size: int, hidden_size: int, output_size: int = 1,
+                 activation: str = "ELU", n_layers: int = 4, distribution: str = "normal") -> None:
+        super().__init__()
+        self.model = build_mlp(input_size, hidden_size, output_size, n_layers, activation)
+        self.distribution = distribution
+        self._act_id = _lib.activation_id(_act_name(activation))
+
+    def forward(self, *args: Tensor) -> Tensor:
+        if len(args) == 2:
+            x1, x2 = args
+        else:
+            (x1,), x2 = args, None
+        lin = _linears(self.model)
+        return F_.mlp_apply(self._act_id, x1, x2, [l.weight for l in lin], [l.bias for l in lin])
+
+
+# =============================================================================
+# TransitionModel
+# =============================================================================
+class GaussianBeliefModel(nn.Module):
+    """Parameter container with the reference's layout (src/models.py:44-73).  ``forward`` keeps
+    the reference behaviour for code that drives the RSSM step by step from Python."""
+
+    def __init__(self, input_size, hidden_size, state_size, activation, min_std_dev) -> None:
+        super().__init__()
+        self.min_std_dev = min_std_dev
+        self.model = build_mlp(input_size, hidden_size, 2 * state_size, 1, activation)
+
+    def forward(self, belief: Tensor):
+        mean, raw = torch.chunk(self.model(belief), 2, dim=1)
+        std = torch.nn.functional.softplus(raw) + self.min_std_dev
+        return mean + std * torch.randn_like(mean), (mean, std)
+
+
+def rssm_params(tm, with_posterior: bool):
+    """The 14 tensors of functions.RSSM_PARAM_NAMES read off a TransitionModel-shaped module
+    (ours or the reference's own: same attribute names, src/models.py:149-167)."""
+    emb = _linears(tm.fc_embed_state_action)[0]
+    p1, p2 = _linears(tm.belief_prior.model)
+    out = [emb.weight, emb.bias, tm.rnn.weight_ih, tm.rnn.weight_hh, tm.rnn.bias_ih,
+           tm.rnn.bias_hh, p1.weight, p1.bias, p2.weight, p2.bias]
+    if with_posterior:
+        q1, q2 = _linears(tm.belief_posterior.model)
+        out += [q1.weight, q1.bias, q2.weight, q2.bias]
+    else:
+        out += [None] * 4
+    return out
+
+
+def rssm_dims(tm) -> Dict:
+    emb = _linears(tm.fc_embed_state_action)[0]
+    p1, p2 = _linears(tm.belief_prior.model)
+    q1 = _linears(tm.belief_posterior.model)[0]
+    Be, S = emb.out_features, p2.out_features // 2
+    act = None
+    for m in tm.fc_embed_state_action:
+        if not isinstance(m, nn.Linear):
+            act = type(m).__name__
+            break
+    return dict(Be=Be, S=S, A=emb.in_features - S, Hi=p1.out_features, E=q1.in_features - Be,
+                act_id=_lib.activation_id(act or "Identity"), min_std=float(tm.min_std_dev))
+
+
+class TransitionModel(nn.Module):
+    """RSSM transition model; reference: src/models.py:120-299."""
+
+    def __init__(self, belief_size: int, state_size: int, action_size: int, hidden_size: int,
+                 embedding_size: int, activation: Optional[str] = "ELU", min_std_dev: float = 0.1,
+                 latent_distribution: Optional[str] = "Gaussian",
+                 discrete_latent_dimensions: Optional[int] = 32,
+                 discrete_latent_classes: Optional[int] = 32) -> None:
+        super().__init__()
+        assert latent_distribution in ["Gaussian", "Categorical"], f"{latent_distribution}"
+        if latent_distribution != "Gaussian":
+            raise NotImplementedError(
+                "big_dreamer_b200.TransitionModel implements the Gaussian latent path only "
+                "(latent_distribution='Categorical' stays on the reference module)")
+        act = _act_name(activation)
+        self._act_id = _lib.activation_id(act)
+        self.min_std_dev = min_std_dev
+        self.latent_distribution = latent_distribution
+        self.rnn = nn.GRUCell(belief_size, belief_size)
+        self.fc_embed_state_action = build_mlp(state_size + action_size, -1, belief_size, 0,
+                                               output_activation=act)
+        self.belief_prior = GaussianBeliefModel(belief_size, hidden_size, state_size, act,
+                                                min_std_dev)
+        self.belief_posterior = GaussianBeliefModel(belief_size + embedding_size, hidden_size,
+                                                    state_size, act, min_std_dev)
+        # the reference overwrites nn.Module.modules with this list (src/models.py:184-188);
+        # FreezeParameters(self.transition_model.modules + ...) depends on it.
+        self.modules = [self.fc_embed_state_action, self.belief_prior, self.belief_posterior]
+
+    def forward(self, init_state: Tensor, actions: Tensor, init_belief: Tensor,
+                embeddings: Optional[Tensor] = None, nonterminals: Optional[Tensor] = None,
+                noise: Optional[Dict[str, Tensor]] = None):
+        """init_state (B,S), actions (L,B,A), init_belief (B,Be), embeddings (L,B,E)|None,
+        nonterminals (L,B,1)|None -> beliefs (L,B,Be), prior_states (L,B,S),
+        (prior_means, prior_std_devs), posterior_states|None, (post_means, post_std_devs)|None.
+        noise: {'eps_prior': (L,B,S), 'eps_post': (L,B,S)} (drawn with torch.randn if absent;
+        the reference draws prior then posterior per step, src/models.py:256,267)."""
+        observe = embeddings is not None
+        L, B = actions.shape[0], actions.shape[1]
+        dims = rssm_dims(self)
+        S = dims["S"]
+        if noise is None:
+            eps = torch.randn(2 if observe else 1, L, B, S, device=actions.device,
+                              dtype=torch.float32)
+            eps_prior, eps_post = eps[0], (eps[1] if observe else None)
+        else:
+            eps_prior, eps_post = noise["eps_prior"], noise.get("eps_post")
+            if observe and eps_post is None:
+                raise BdError("TransitionModel: observe mode needs noise['eps_post']")
+        params = rssm_params(self, with_posterior=observe)
+        outs = F_.TransitionFunction.apply(dims, init_state, actions, init_belief, embeddings,
+                                           nonterminals, eps_prior, eps_post, *params)
+        if observe:
+            return outs[0], outs[1], (outs[2], outs[3]), outs[4], (outs[5], outs[6])
+        return outs[0], outs[1], (outs[2], outs[3]), None, None
+
+
+# =============================================================================
+# Dreamer.imagine_ahead / lambda_return
+# =============================================================================
+def actor_config(actor) -> Dict:
+    """Squashing constants read from the reference's ActorModel (src/models.py:499-503)."""
+    raw = actor.raw_init_std
+    raw = float(raw.item()) if isinstance(raw, torch.Tensor) else float(raw)
+    return dict(mean_scale=float(actor._mean_scale), raw_init_std=raw,
+                min_std=float(actor._min_std), entropy_samples=ENTROPY_SAMPLES)
+
+
+def draw_imagine_noise(T: int, N: int, S: int, A: int, device, generator=None):
+    """ε_a (T,N,A), ε_e (T,100,N,A), ε_s (T,N,S).  (The reference draws them per step in
+    the order action, entropy, prior state: src/dreamer.py:443-444, src/models.py:72.)"""
+    kw = dict(device=device, dtype=torch.float32, generator=generator)
+    return dict(eps_a=torch.randn(T, N, A, **kw), eps_e=torch.randn(T, ENTROPY_SAMPLES, N, A, **kw),
+                eps_s=torch.randn(T, N, S, **kw))
+
+
+def imagine_ahead(self, prev_state: Tensor, prev_belief: Tensor,
+                  noise: Optional[Dict[str, Tensor]] = None, return_actions: bool = False):
+    """Drop-in for ``Dreamer.imagine_ahead`` (bind as a method; ``self`` needs
+    ``transition_model``, ``actor``, ``planning_horizon``, ``latent_distribution``).
+
+    prev_state (L,B,S), prev_belief (L,B,Be) -> beliefs (T,N,Be), prior_states (T,N,S),
+    (prior_means, prior_std_devs), action_entropy (T,N); T = planning_horizon-1, N = L*B."""
+    if getattr(self, "latent_distribution", "Gaussian") != "Gaussian":
+        raise NotImplementedError("imagine_ahead: only Gaussian latents run on the B200 path")
+    tm, actor = self.transition_model, self.actor
+    if getattr(actor, "action_distribution", "Gaussian") != "Gaussian":
+        raise NotImplementedError("imagine_ahead: only the Gaussian actor runs on the B200 path")
+    T = self.planning_horizon - 1
+    b0 = prev_belief.reshape(-1, prev_belief.shape[-1])
+    s0 = prev_state.reshape(-1, prev_state.shape[-1])
+    dims = rssm_dims(tm)
+    N = s0.shape[0]
+    rp = rssm_params(tm, with_posterior=False)[:10]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in rp):
+        raise NotImplementedError(
+            "imagine_ahead: transition-model parameters require grad; the B200 path computes "
+            "actor gradients only -- call it under FreezeParameters(model_modules) as "
+            "Dreamer.train_step does (src/dreamer.py:313)")
+    if noise is None:
+        noise = draw_imagine_noise(T, N, dims["S"], dims["A"], s0.device)
+    lin = _linears(actor.model)
+    ap = []
+    for l in lin:
+        ap += [l.weight, l.bias]
+    beliefs, states, means, stds, entropy, actions = F_.ImagineFunction.apply(
+        dims, actor_config(actor), T, s0, b0, noise["eps_a"], noise["eps_e"], noise["eps_s"],
+        len(lin), *ap, *rp)
+    if return_actions:
+        return beliefs, states, (means, stds), entropy, actions
+    return beliefs, states, (means, stds), entropy
+
+
+def lambda_return(imged_reward: Tensor, value_pred: Tensor, bootstrap: Tensor,
+                  discount: float = 0.99, lambda_: float = 0.95) -> Tensor:
+    """Drop-in for src/dreamer.py:447-471.  (T,N,1),(T,N,1),(N,1) -> (T,N,1)."""
+    return F_.LambdaReturnFunction.apply(imged_reward, value_pred, bootstrap, discount, lambda_)
+
+
+def imagine_and_returns(self, prev_state: Tensor, prev_belief: Tensor, reward_model, value_model,
+                        discount: float, lambda_: float,
+                        noise: Optional[Dict[str, Tensor]] = None):
+    """Added fused entry (level L2): imagine_ahead + reward/value heads +
+    lambda_return in one call.  Returns beliefs, states, (means, stds), entropy, reward, value,
+    returns with the reference's shapes."""
+    beliefs, states, (means, stds), entropy = imagine_ahead(self, prev_state, prev_belief, noise)
+    reward = reward_model(beliefs, states)
+    value = value_model(beliefs, states)
+    returns = lambda_return(reward, value, value[-1], discount, lambda_)
+    return beliefs, states, (means, stds), entropy, reward, value, returns
+
+
+# =============================================================================
+# MPCPlanner (CEM)
+# =============================================================================
+class MPCPlanner(nn.Module):
+    """Cross-entropy-method planner; reference: src/planner.py:5-90."""
+
+    def __init__(self, action_size, planning_horizon, optimisation_iters, candidates,
+                 top_candidates, transition_model, reward_model):
+        super().__init__()
+        self.transition_model = transition_model
+        self.reward_model = reward_model
+        self.action_size = action_size
+        self.planning_horizon = planning_horizon
+        self.optimisation_iters = optimisation_iters
+        self.candidates, self.top_candidates = candidates, top_candidates
+        self.last_trace = None
+
+    def _models(self):
+        tm, rm = self.transition_model, self.reward_model
+        dims = rssm_dims(tm)
+        rp = [F_._f32c(p.detach()) for p in rssm_params(tm, with_posterior=False)[:10]] + [None] * 4
+        lin = _linears(rm.model)
+        act = None
+        for m in rm.model:
+            if not isinstance(m, nn.Linear):
+                act = type(m).__name__
+                break
+        ws_ = [F_._f32c(l.weight.detach()) for l in lin]
+        bs_ = [F_._f32c(l.bias.detach()) for l in lin]
+        return dims, rp, ws_, bs_, _lib.activation_id(act or "Identity")
+
+    def draw_noise(self, B: int, device, generator=None):
+        """ε_act (iters,H,B,C,A) and ε_s (iters,H,B*C,S); the reference draws, per iteration,
+        randn(H,B,C,A) then H x randn_like((B*C,S)) (src/planner.py:53, src/models.py:72)."""
+        dims = rssm_dims(self.transition_model)
+        kw = dict(device=device, dtype=torch.float32, generator=generator)
+        I, H, Cn = self.optimisation_iters, self.planning_horizon, self.candidates
+        return dict(eps_act=torch.randn(I, H, B, Cn, self.action_size, **kw),
+                    eps_s=torch.randn(I, H, B * Cn, dims["S"], **kw))
+
+    @torch.no_grad()
+    def forward(self, belief: Tensor, state: Tensor, noise: Optional[Dict[str, Tensor]] = None,
+                trace: bool = False) -> Tensor:
+        """belief (B,Be), state (B,S) -> first action mean (B,A)."""
+        lib = _lib.load()
+        belief, state = F_._f32c(belief), F_._f32c(state)
+        B = belief.shape[0]
+        dims, rp, ws_, bs_, ract = self._models()
+        if dims["A"] != self.action_size:
+            raise BdError("MPCPlanner: action_size differs from the transition model's")
+        if noise is None:
+            noise = self.draw_noise(B, belief.device)
+        ea, es = F_._f32c(noise["eps_act"]), F_._f32c(noise["eps_s"])
+        I, H, Cn, K, A = (self.optimisation_iters, self.planning_horizon, self.candidates,
+                          self.top_candidates, self.action_size)
+        if ea.shape != (I, H, B, Cn, A) or es.shape != (I, H, B * Cn, dims["S"]):
+            raise BdError(f"MPCPlanner: noise shapes {tuple(ea.shape)}, {tuple(es.shape)} mismatch")
+        a = _lib.CemPlanArgs()
+        a.rssm = F_.make_rssm(rp, dims)
+        a.reward = _lib.make_mlp(ws_, bs_, ract)
+        a.B, a.C, a.K, a.H, a.iters = B, Cn, K, H, I
+        a.belief, a.state, a.eps_act, a.eps_s = (_lib.ptr(t) for t in (belief, state, ea, es))
+        out = torch.empty(B, A, device=belief.device, dtype=torch.float32)
+        a.action_out = _lib.ptr(out)
+        if trace:
+            rt = torch.empty(I, B, Cn, device=belief.device, dtype=torch.float32)
+            tk = torch.empty(I, B, K, device=belief.device, dtype=torch.int64)
+            a.returns_trace, a.topk_trace = _lib.ptr(rt), _lib.ptr(tk)
+            self.last_trace = dict(returns=rt, topk=tk)
+        nbytes = lib.bd_cem_plan_workspace_bytes(C.byref(a.rssm), C.byref(a.reward), B, Cn, K, H)
+        ws = _lib.workspace(nbytes, belief.device)
+        _lib.check(lib.bd_cem_plan(C.byref(a), ws.data_ptr(), ws.numel(), F_._prec(),
+                                   _lib.stream_ptr()), "bd_cem_plan")
+        return out
