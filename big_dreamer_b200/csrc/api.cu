@@ -38,15 +38,18 @@ size_t bd_mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {
 }
 int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
                    float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
-  BD_NEED(m, "mlp"); BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
+  BD_NEED(m, "mlp");
+  if (rows == 0) return BD_OK;
+  BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
   BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
   return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
 }
 int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
                     int precision, bd_stream_t stream) {
-  BD_NEED(m, "mlp"); BD_NEED(a, "args"); BD_NEED(ws, "workspace");
-  BD_NEED(a->x1, "x1"); BD_NEED(a->dy, "dy");
+  BD_NEED(m, "mlp"); BD_NEED(a, "args");
+  if (a->rows == 0) return BD_OK;
+  BD_NEED(ws, "workspace"); BD_NEED(a->x1, "x1"); BD_NEED(a->dy, "dy");
   BD_CHECK_ARG(a->k1 > 0 && a->k2 >= 0 && (a->k2 == 0 || a->x2), "bd_mlp_backward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
   return f32::mlp_backward(m, a, ws, ws_bytes, stream);
