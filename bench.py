@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the RSSM hot path (BASELINE.json metric): imagined latent steps/s, forward +
+BPTT backward of Dreamer's actor loss, on synthetic latents of the named shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16|tf32] [--rows R] [--no-cpu-baseline]
+
+One "step" = one pass of the hot path over one batch of start states:
+imagine_ahead (actor + 100-sample entropy + embed + GRU + prior + sample, T = 14 transitions)
+-> reward and value heads -> lambda_return -> actor loss -> backward to the actor gradients
+(+ one NCCL all-reduce of those gradients when N > 1).  The optimizer step is not part of the
+metric.  Workload at every N: BASELINE.json configs[1] per GPU (weak scaling).
+
+Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# BASELINE.json configs[1]: Dreamer default RSSM
+CFG = dict(Be=200, Hi=200, S=30, A=1, E=8, H=15, act="ELU")
+ROWS_DEFAULT = 2500                # batch 50 x chunk 50 start states
+DISCOUNT, LAMBDA, ENT_W = 0.995, 0.95, 1e-5
+L2_FLUSH_BYTES = 256 << 20         # > 126 MB L2
+
+
+def algorithmic_flops_per_row_step(d):
+    """FLOP = 2*MAC; fwd + bwd of one imagined row-step (no recompute, no padding)."""
+    Be, Hi, S, A = d["Be"], d["Hi"], d["S"], d["A"]
+    embed = (S + A) * Be
+    gru = 6 * Be * Be
+    prior = Be * Hi + 2 * S * Hi
+    head = (Be + S) * Hi + 3 * Hi * Hi + Hi
+    actor = (Be + S) * Hi + 3 * Hi * Hi + 2 * A * Hi
+    fwd = embed + gru + prior + actor + 2 * head
+    bwd = (embed + gru + prior) + 2 * head + actor + (3 * Hi * Hi + 2 * A * Hi)
+    return 2 * (fwd + bwd)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        j = json.load(open(p))
+        return dict(bf16_burst=j["bf16_tflops"], bf16_sustained=j["bf16_tflops_sustained"],
+                    hbm=j["hbm_gbs"], source="measured")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, smax = [], set(), None
+        for r in rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); smax = float(r[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------
+def cpu_actor_step(models, s0, b0, noise, d):
+    from oracle import rssm_oracle as orc
+    trans, actor, reward, value = models
+    for v in actor.values():
+        v.grad = None
+    loss, _ = orc.actor_loss(trans, actor, reward, value, d["act"], 0.1, d["H"], s0[None], b0[None],
+                             *noise, DISCOUNT, LAMBDA, ENT_W)
+    loss.backward()
+    return float(loss)
+
+
+def cpu_setup(d, rows, seed=0):
+    from oracle import rssm_oracle as orc
+    trans, actor, reward, value = orc.make_models(seed, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    actor = {k: v.requires_grad_(True) for k, v in actor.items()}
+    s0, b0 = orc.make_latents(seed, rows, d["Be"], d["S"])
+    noise = orc.make_imagine_noise(seed, d["H"] - 1, rows, d["S"], d["A"])
+    return (trans, actor, reward, value), s0, b0, noise
+
+
+def time_cpu(d, rows, steps, warmup):
+    models, s0, b0, noise = cpu_setup(d, rows)
+    for _ in range(warmup):
+        cpu_actor_step(models, s0, b0, noise, d)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_actor_step(models, s0, b0, noise, d)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, rows, T = CFG, args.rows, CFG["H"] - 1
+    steps = min(args.steps, 20)
+    ts = time_cpu(d, rows, steps, max(1, min(args.warmup, 2)))
+    mean = sum(ts) / len(ts)
+    val = rows * T / mean
+    cores = torch.get_num_threads()
+    sample = (f"oracle port of Dreamer.imagine_ahead + heads + lambda_return + actor backward "
+              f"(torch CPU, {cores} threads), full {rows} start states x {T} transitions per step, "
+              f"{steps} timed steps")
+    print(json.dumps({
+        "impl": "reference", "metric": "imagined_latent_steps_per_sec_fwd_bwd", "value": val,
+        "unit": "steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(rows, "fp32"),
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(rows, precision):
+    return {"workload": "BASELINE configs[1]: Dreamer default RSSM imagine_ahead + reward/value heads"
+                        " + lambda_return, fwd + BPTT actor loss",
+            "belief_size": CFG["Be"], "hidden_size": CFG["Hi"], "state_size": CFG["S"],
+            "action_size": CFG["A"], "start_states_per_gpu": rows, "planning_horizon": CFG["H"],
+            "transitions": CFG["H"] - 1, "entropy_samples": 100, "precision": precision,
+            "l2": "flushed between timed iterations (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import big_dreamer_b200 as bd
+    from big_dreamer_b200 import dist as D_
+    from big_dreamer_b200 import _lib
+    from oracle import rssm_oracle as orc           # weights/latents recipe only (synthetic data)
+    from tests import parity_utils as pu
+    import torch.distributed as tdist
+
+    rank, world, local = D_.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = bd.load_library()
+    bd.set_precision(args.precision)
+    d, rows, T = CFG, args.rows, CFG["H"] - 1
+
+    trans, actor, reward, value = orc.make_models(0, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    mods = pu.build_gpu_models(d, trans, actor, reward, value, device=dev)
+    pu.freeze(mods.transition, mods.reward, mods.critic)
+    agent = pu.agent_ns(mods, d["H"])
+    actor_params = list(mods.actor.parameters())
+    # each rank owns its own start states (weak scaling): different seed per rank
+    s0_h, b0_h = orc.make_latents(rank, rows, d["Be"], d["S"])
+    s0_h, b0_h = s0_h.pin_memory(), b0_h.pin_memory()
+    s0, b0 = s0_h.to(dev), b0_h.to(dev)
+    noise = bd.draw_imagine_noise(T, rows, d["S"], d["A"], dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(s0_, b0_, noise_):
+        for p in actor_params:
+            p.grad = None
+        beliefs, states, _, entropy = bd.imagine_ahead(agent, s0_[None], b0_[None], noise_)
+        rew = mods.reward(beliefs, states)
+        val = mods.critic(beliefs, states)
+        ret = bd.lambda_return(rew, val, val[-1], DISCOUNT, LAMBDA)
+        loss = -(ret + ENT_W * entropy.unsqueeze(-1)).mean()
+        loss.backward()
+        D_.allreduce_grads(actor_params)
+        return loss, entropy
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        n0 = lib.bd_launch_count()
+        for a, b in ev:
+            flush.fill_(1)                    # evict L2 (untimed)
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        launches = lib.bd_launch_count() - n0
+        ms = [a.elapsed_time(b) for a, b in ev]
+        return ms, launches
+
+    warmup = max(3, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    # (1) device-resident inputs: the kernel-side number
+    ms_dev, launches = timed(lambda: step(s0, b0, noise), args.steps, warmup)
+
+    # (2) end to end through the public API: host latents in pinned memory, H2D inside the timed
+    # region, noise drawn by the API itself (as the reference does), D2H of the logged scalars
+    def e2e_step():
+        s = s0_h.to(dev, non_blocking=True)
+        b = b0_h.to(dev, non_blocking=True)
+        loss, ent = step(s, b, None)
+        return float(loss.item()), float(ent.mean().item())
+    ms_e2e, _ = timed(e2e_step, args.steps, warmup)
+    clocks = sampler.stop() if sampler else None
+
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_ms = reduce_max(sum(ms_dev))
+    total_e2e_ms = reduce_max(sum(ms_e2e))
+    if rank != 0:
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * rows * T / (ms_per_step * 1e-3)
+    e2e_value = world * rows * T / (total_e2e_ms / args.steps * 1e-3)
+    pk = peaks()
+    flops = algorithmic_flops_per_row_step(d) * rows * T           # per GPU per step
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    peak = pk["bf16_sustained"]
+    out = {
+        "metric": "imagined_latent_steps_per_sec_fwd_bwd", "value": value, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16": "bf16", "tf32": "tf32"}[args.precision],
+        "data": "synthetic", "config": workload_config(rows, args.precision),
+        "e2e": {"value": e2e_value, "unit": "steps/s",
+                "h2d_bytes_per_step": int(s0_h.numel() * 4 + b0_h.numel() * 4),
+                "d2h_bytes_per_step": 8, "ms_per_step": total_e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "note": f"algorithmic FLOPs of the whole step ({flops / 1e9:.1f} GFLOP) / "
+                             f"CUDA-event step time; peak = bf16 sustained of {pk['source']} peaks"},
+        "clocks": clocks,
+        "ms_min": min(ms_dev), "ms_median": statistics.median(ms_dev),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ts = time_cpu(d, rows, 5, 1)
+        cores = torch.get_num_threads()
+        out["cpu_baseline"] = {
+            "value": rows * T / (sum(ts) / len(ts)), "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch CPU, {cores} threads) on the full workload "
+                      f"({rows} start states x {T}), 1 warm-up + 5 timed steps"}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BD_PRECISION", "fp32"))
+    ap.add_argument("--rows", type=int, default=ROWS_DEFAULT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    import torch.distributed as tdist
+    if tdist.is_initialized():
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

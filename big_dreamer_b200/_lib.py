@@ -110,6 +110,7 @@ class CemPlanArgs(C.Structure):
 SIGNATURES = {
     "bd_version": (C.c_int, []),
     "bd_last_error": (C.c_char_p, []),
+    "bd_launch_count": (C.c_ulonglong, []),
     "bd_precision_supported": (C.c_int, [C.c_int]),
     "bd_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int64, C.c_int]),
     "bd_mlp_forward": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,

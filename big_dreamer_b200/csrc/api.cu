@@ -5,6 +5,7 @@
 
 namespace bd {
 static thread_local char g_err[1024] = "";
+unsigned long long g_launch_count = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -31,6 +32,7 @@ extern "C" {
 
 int bd_version(void) { return BD_ABI_VERSION; }
 const char* bd_last_error(void) { return bd::g_err; }
+unsigned long long bd_launch_count(void) { return bd::g_launch_count; }
 int bd_precision_supported(int precision) { return precision == BD_PREC_FP32 ? 1 : 0; }
 
 size_t bd_mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {

@@ -646,7 +646,9 @@ int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream
   for (int l = 0; l < BD_MAX_LAYERS; ++l) hid[l] = (l & 1) ? hb : ha;
 
   cem_expand_kernel<<<grid1d(rows * Be), 256, 0, s>>>(a->belief, B, Cl, Be, bel[0]);
+  BD_CUDA_LAUNCH_CHECK();
   cem_expand_kernel<<<grid1d(rows * Sz), 256, 0, s>>>(a->state, B, Cl, Sz, sta[0]);
+  BD_CUDA_LAUNCH_CHECK();
   cem_sample_kernel<<<grid1d((long long)H * rows * A), 256, 0, s>>>(
       a->action_mean, a->action_std, a->eps_act, H, B, C, a->c_begin, Cl, A, a->actions);
   BD_CUDA_LAUNCH_CHECK();
@@ -717,6 +719,7 @@ int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t s
   size_t sub_bytes = ar.cap - ar.off;
   const long long nm = (long long)H * B * A;
   fill_kernel<<<grid1d(nm), 256, 0, s>>>(mean, 0.f, nm);    // src/planner.py:42-47
+  BD_CUDA_LAUNCH_CHECK();
   fill_kernel<<<grid1d(nm), 256, 0, s>>>(stdv, 1.f, nm);
   BD_CUDA_LAUNCH_CHECK();
   for (int it = 0; it < a->iters; ++it) {

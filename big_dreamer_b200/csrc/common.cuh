@@ -10,6 +10,7 @@
 namespace bd {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launch_count;   // kernels launched by this library (bd_launch_count)
 
 #define BD_FAIL(code, ...)        \
   do {                            \
@@ -24,6 +25,7 @@ void set_error(const char* fmt, ...);
 
 #define BD_CUDA_LAUNCH_CHECK()                                                        \
   do {                                                                                \
+    ++bd::g_launch_count;                                                             \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess)                                                           \
       BD_FAIL(BD_ERR_CUDA, "%s:%d CUDA launch failed: %s", __FILE__, __LINE__,        \

@@ -274,6 +274,7 @@ class MPCPlanner(nn.Module):
         self.optimisation_iters = optimisation_iters
         self.candidates, self.top_candidates = candidates, top_candidates
         self.last_trace = None
+        self.shard_candidates = True   # split candidates over ranks when torch.distributed is up
 
     def _models(self):
         tm, rm = self.transition_model, self.reward_model
@@ -315,6 +316,9 @@ class MPCPlanner(nn.Module):
                           self.top_candidates, self.action_size)
         if ea.shape != (I, H, B, Cn, A) or es.shape != (I, H, B * Cn, dims["S"]):
             raise BdError(f"MPCPlanner: noise shapes {tuple(ea.shape)}, {tuple(es.shape)} mismatch")
+        from . import dist as D_
+        if self.shard_candidates and D_.world_size() > 1:
+            return self._forward_sharded(belief, state, ea, es, dims, rp, ws_, bs_, ract, trace)
         a = _lib.CemPlanArgs()
         a.rssm = F_.make_rssm(rp, dims)
         a.reward = _lib.make_mlp(ws_, bs_, ract)
@@ -332,3 +336,49 @@ class MPCPlanner(nn.Module):
         _lib.check(lib.bd_cem_plan(C.byref(a), ws.data_ptr(), ws.numel(), F_._prec(),
                                    _lib.stream_ptr()), "bd_cem_plan")
         return out
+
+    def _forward_sharded(self, belief, state, ea, es, dims, rp, ws_, bs_, ract, trace):
+        """Candidates split over ranks (weights replicated).  Per iteration: local rollout of
+        C/G candidates -> all-gather of (returns, actions) -> identical global top-K + refit on
+        every rank.  The noise tensors are the GLOBAL ones, sliced along the candidate axis, so
+        the result does not depend on the number of ranks."""
+        import torch.distributed as tdist
+        from . import dist as D_
+        lib = _lib.load()
+        world, rank = D_.world_size(), tdist.get_rank()
+        I, H, Cn, K, A = (self.optimisation_iters, self.planning_horizon, self.candidates,
+                          self.top_candidates, self.action_size)
+        B, dev = belief.shape[0], belief.device
+        ranges = [D_.shard_range(Cn, r, world) for r in range(world)]
+        sizes = [e - b for b, e in ranges]
+        c0, c1 = ranges[rank]
+        Cl = c1 - c0
+        e = _lib.CemEvalArgs()
+        e.rssm = F_.make_rssm(rp, dims)
+        e.reward = _lib.make_mlp(ws_, bs_, ract)
+        e.B, e.C, e.H, e.c_begin, e.c_end = B, Cn, H, c0, c1
+        e.belief, e.state = _lib.ptr(belief), _lib.ptr(state)
+        mean = torch.zeros(H, B, A, device=dev)
+        std = torch.ones(H, B, A, device=dev)
+        actions = torch.empty(H, B, Cl, A, device=dev)
+        returns = torch.empty(B, Cl, device=dev)
+        e.action_mean, e.action_std = _lib.ptr(mean), _lib.ptr(std)
+        e.actions, e.returns = _lib.ptr(actions), _lib.ptr(returns)
+        nbytes = lib.bd_cem_workspace_bytes(C.byref(e.rssm), C.byref(e.reward), B, Cl, H)
+        ws = _lib.workspace(nbytes, dev)
+        idx = torch.empty(B, K, device=dev, dtype=torch.int64)
+        tr_r, tr_k = [], []
+        for it in range(I):
+            e.eps_act, e.eps_s = _lib.ptr(ea[it]), _lib.ptr(es[it])
+            _lib.check(lib.bd_cem_evaluate(C.byref(e), ws.data_ptr(), ws.numel(), F_._prec(),
+                                           _lib.stream_ptr()), "bd_cem_evaluate")
+            g_ret, g_act = D_.gather_candidates(returns, actions, sizes)
+            _lib.check(lib.bd_cem_refit(_lib.ptr(g_ret), _lib.ptr(g_act), B, Cn, K, H, A,
+                                        _lib.ptr(idx), _lib.ptr(mean), _lib.ptr(std),
+                                        _lib.stream_ptr()), "bd_cem_refit")
+            if trace:
+                tr_r.append(g_ret.clone())
+                tr_k.append(idx.clone())
+        if trace:
+            self.last_trace = dict(returns=torch.stack(tr_r), topk=torch.stack(tr_k))
+        return mean[0].clone()

@@ -112,6 +112,8 @@ typedef struct {
 
 int bd_version(void);
 const char* bd_last_error(void);
+/* number of CUDA kernels this library has launched in this process (monotonic) */
+unsigned long long bd_launch_count(void);
 /* 1 if the named precision is implemented by this build for these sizes */
 int bd_precision_supported(int precision);
 
