@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libbd_b200.so")
 
 BD_MAX_LAYERS = 8
 ACTIVATIONS = {"Identity": 0, "ELU": 1, "ReLU": 2, "Tanh": 3, "Sigmoid": 4}
-PRECISIONS = {"fp32": 0, "bf16": 1, "tf32": 2}
+PRECISIONS = {"fp32": 0, "bf16": 1, "tf32": 2, "fp16": 3}
 
 f32p = C.POINTER(C.c_float)
 i64p = C.POINTER(C.c_int64)
@@ -144,6 +144,8 @@ SIGNATURES = {
                                                  C.c_int, C.c_int]),
     "bd_cem_plan": (C.c_int, [C.POINTER(CemPlanArgs), C.c_void_p, C.c_size_t, C.c_int,
                               C.c_void_p]),
+    "bd_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -21,9 +21,12 @@ using namespace bd;
     if (!(p)) BD_FAIL(BD_ERR_BAD_ARG, "%s: null %s", __func__, what); \
   } while (0)
 
+// Entry points that have no tensor-core implementation (yet) run their fp32 CUDA kernels when a
+// 16-bit mode is requested: higher precision, same device path, never a CPU fallback.
 #define BD_ONLY_FP32(precision)                                                             \
   do {                                                                                      \
-    if ((precision) != BD_PREC_FP32)                                                        \
+    if ((precision) != BD_PREC_FP32 && (precision) != BD_PREC_FP16 &&                        \
+        (precision) != BD_PREC_BF16)                                                        \
       BD_FAIL(BD_ERR_UNSUPPORTED, "%s: precision %d is not implemented for this entry point", \
               __func__, (int)(precision));                                                  \
   } while (0)
@@ -33,7 +36,9 @@ extern "C" {
 int bd_version(void) { return BD_ABI_VERSION; }
 const char* bd_last_error(void) { return bd::g_err; }
 unsigned long long bd_launch_count(void) { return bd::g_launch_count; }
-int bd_precision_supported(int precision) { return precision == BD_PREC_FP32 ? 1 : 0; }
+int bd_precision_supported(int precision) {
+  return (precision == BD_PREC_FP32 || precision == BD_PREC_FP16 || precision == BD_PREC_BF16) ? 1 : 0;
+}
 
 size_t bd_mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {
   return m ? f32::mlp_workspace_bytes(m, rows, backward) : 0;
@@ -90,11 +95,16 @@ int bd_transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_
 
 size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N,
                                   int backward) {
-  return (r && actor) ? f32::imagine_workspace_bytes(r, actor, T, N, backward) : 0;
+  if (!(r && actor)) return 0;
+  size_t f = f32::imagine_workspace_bytes(r, actor, T, N, backward);
+  size_t t = tc::imagine_pack_bytes(*r, *actor);
+  return f > t ? f : t;
 }
 int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                        bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  if (precision == BD_PREC_FP16 || precision == BD_PREC_BF16)
+    return tc::imagine_forward(a, ws, ws_bytes, precision, stream);
   BD_ONLY_FP32(precision);
   return f32::imagine_forward(a, ws, ws_bytes, stream);
 }

@@ -34,4 +34,11 @@ size_t cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, i
 int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
 }  // namespace f32
 
+namespace tc {   // tensor-core (tcgen05) path: 16-bit operands, fp32 accumulation and state
+bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision);
+size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor);
+int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
+                    bd_stream_t stream);
+}  // namespace tc
+
 }  // namespace bd

@@ -1,0 +1,217 @@
+// Host side of the tensor-core rollout: builds the per-step PROGRAM (GEMM / phase tables), the
+// weight-packing jobs and the shared-memory plan from the model dimensions, then launches the
+// pack kernel and the persistent rollout kernel (tc_engine.cuh).
+#include "api_internal.h"
+#include "tc_engine.cuh"
+#include <stdlib.h>
+
+namespace bd {
+namespace tc {
+
+static inline int r16(int x) { return (x + 15) / 16 * 16; }
+
+struct Builder {
+  PackTable pack{};
+  Program prog{};
+  long long w_elems = 0;
+  int cur_phase_g0 = 0;
+  uint32_t max_stage = 0;
+  bool ok = true;
+
+  // packs rows [row0,row0+n) of w (ld cols) into an image (Np x Kp); returns element offset
+  uint32_t add_pack(const float* w, int ld, int row0, int n, int Np, int Kp, int src_c0, int len,
+                    const float* bias, int bias_k) {
+    if (pack.njobs >= kMaxPackJobs) { ok = false; return 0; }
+    PackJob& j = pack.job[pack.njobs++];
+    j = PackJob{};
+    j.w = w; j.bias = bias; j.dst_off = w_elems; j.ld = ld; j.row0 = row0; j.N = n; j.Np = Np;
+    j.Kp = Kp; j.bias_k = bias ? bias_k : -1; j.nseg = 1; j.seg[0] = {0, src_c0, len}; j.transpose = 0;
+    uint32_t off = (uint32_t)w_elems;
+    w_elems += (long long)Np * Kp;
+    return off;
+  }
+  void add_gemm(uint32_t w_off, int Np, int Kp, int a_tile, int a_k0, int d_col, int accumulate) {
+    if (prog.n_gemms >= kMaxGemms) { ok = false; return; }
+    Gemm& g = prog.g[prog.n_gemms++];
+    g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
+    g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
+    max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
+  }
+  void end_phase(int epi, int dep_back, int n_valid, int Np, int Kp_out, int d_col, int aux0,
+                 int out_tile) {
+    if (prog.n_phases >= kMaxPhases) { ok = false; return; }
+    Phase& p = prog.p[prog.n_phases++];
+    p.g0 = (uint8_t)cur_phase_g0; p.ng = (uint8_t)(prog.n_gemms - cur_phase_g0); p.epi = (uint8_t)epi;
+    p.dep_back = (uint8_t)dep_back; p.n_valid = (uint16_t)n_valid; p.Np = (uint16_t)Np;
+    p.Kp_out = (uint16_t)Kp_out; p.d_col = (uint16_t)d_col; p.aux0 = (uint16_t)aux0;
+    p.out_tile = (uint8_t)out_tile; p.pad = 0;
+    cur_phase_g0 = prog.n_gemms;
+  }
+  int dcol() const { return (prog.n_phases & 1) * 256; }
+};
+
+bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
+  if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
+  if (!(r.activation == BD_ACT_ELU || r.activation == BD_ACT_RELU || r.activation == BD_ACT_TANH ||
+        r.activation == BD_ACT_IDENTITY)) return false;
+  if (actor.activation != r.activation) return false;
+  if (r.belief_size + 1 > 256 || r.hidden_size + 1 > 256 || r.state_size > 128 || r.action_size > 16)
+    return false;
+  if (actor.n_layers < 2) return false;
+  for (int l = 0; l + 1 < actor.n_layers; ++l)
+    if (actor.layer[l].out_features != r.hidden_size) return false;
+  return true;
+}
+
+size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor) {
+  // generous upper bound: every weight padded to multiples of 16 in both dims (+ bias column)
+  size_t e = 0;
+  auto img = [&](int n, int k) { e += (size_t)r16(n) * r16(k + 1); };
+  for (int l = 0; l < actor.n_layers; ++l) img(actor.layer[l].out_features + 16, actor.layer[l].in_features + 16);
+  img(r.belief_size, r.state_size + r.action_size);
+  e += (size_t)8 * 6 * 64 * r16(r.belief_size + 1);       // GRU slices (<= 8 slices of 64)
+  img(r.hidden_size, r.belief_size);
+  img(2 * r.state_size + 32, r.hidden_size);
+  return e * 2 + 4096;
+}
+
+static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& sm) {
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 1023) & ~1023u; return o; };
+  sm.off_tile[0] = take(kTileRows * Kp_b * 2);
+  sm.off_tile[1] = take(kTileRows * Kp_b * 2);
+  sm.off_tile[2] = take(kTileRows * Kp_sa * 2);
+  sm.off_tile[3] = take(kTileRows * Kp_h * 2);
+  sm.off_tile[4] = sm.off_tile[3];
+  sm.stage_bytes = (stage + 1023) & ~1023u;
+  sm.off_ring = off;
+  const uint32_t budget = 227 * 1024 - 2048;   // static barriers + alignment slack
+  if (off + 2 * sm.stage_bytes > budget) return false;
+  sm.nstage = min(8u, (budget - off) / sm.stage_bytes);
+  sm.total = off + sm.nstage * sm.stage_bytes + 1024;
+  return true;
+}
+
+int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
+                    bd_stream_t stream) {
+  const bd_rssm& r = a->rssm;
+  const bd_mlp& ac = a->actor;
+  if (!imagine_supported(r, ac, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: sizes/activation not supported "
+                                "(Be,Hi <= 255, S <= 128, A <= 16, ELU/ReLU/Tanh/Identity)");
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1);
+  const int Kp_h = max(Kp_hid, Kp_x), Ks = r16(S);
+  const int Nh = r16(Hi), Nb = r16(Be), Ap = 16, Sp = r16(S);
+  Builder b;
+  // ---- actor (src/models.py:506-517): L0 on [b ; s], hidden layers, output (mean | std)
+  {
+    const bd_linear& L0 = ac.layer[0];
+    uint32_t w0b = b.add_pack(L0.w, Be + S, 0, Hi, Nh, Kp_b, 0, Be, L0.b, Be);
+    uint32_t w0s = b.add_pack(L0.w, Be + S, 0, Hi, Nh, Ks, Be, S, nullptr, -1);
+    int d = b.dcol();
+    b.add_gemm(w0b, Nh, Kp_b, TILE_BCUR, 0, d, 0);
+    b.add_gemm(w0s, Nh, Ks, TILE_SA, 0, d, 1);
+    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+    for (int l = 1; l + 1 < ac.n_layers; ++l) {
+      const bd_linear& L = ac.layer[l];
+      uint32_t w = b.add_pack(L.w, Hi, 0, Hi, Nh, Kp_hid, 0, Hi, L.b, Hi);
+      d = b.dcol();
+      b.add_gemm(w, Nh, Kp_hid, TILE_H, 0, d, 0);
+      b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+    }
+    const bd_linear& Lo = ac.layer[ac.n_layers - 1];
+    uint32_t wm = b.add_pack(Lo.w, Hi, 0, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
+    uint32_t wsd = b.add_pack(Lo.w, Hi, A, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
+    d = b.dcol();
+    b.add_gemm(wm, Ap, Kp_hid, TILE_H, 0, d, 0);
+    b.add_gemm(wsd, Ap, Kp_hid, TILE_H, 0, d + Ap, 0);
+    b.end_phase(EPI_ACTOR_OUT, 1, 2 * A, Ap, 0, d, 0, TILE_SA);
+  }
+  // ---- embed: x = act(W_sa [s ; a] + b)
+  {
+    uint32_t w = b.add_pack(r.embed.w, S + A, 0, Be, Nb, Kp_sa, 0, S + A, r.embed.b, S + A);
+    int d = b.dcol();
+    b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
+    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, 0, TILE_H);
+  }
+  // ---- GRUCell in N-slices of <= 64 belief columns: accumulators R | Z | IN | HN per slice
+  {
+    int slice = 0;
+    for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
+      const int nv = min(64, Be - n0), Ns = r16(nv);
+      int d = b.dcol();
+      uint32_t w[6];
+      for (int g = 0; g < 3; ++g) {
+        w[2 * g] = b.add_pack(r.w_ih, Be, g * Be + n0, nv, Ns, Kp_x, 0, Be, r.b_ih, Be);
+        w[2 * g + 1] = b.add_pack(r.w_hh, Be, g * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
+      }
+      b.add_gemm(w[0], Ns, Kp_x, TILE_H, 0, d, 0);             // R  = x W_ir^T + b_ir
+      b.add_gemm(w[1], Ns, Kp_b, TILE_BCUR, 0, d, 1);          //    + h W_hr^T + b_hr
+      b.add_gemm(w[2], Ns, Kp_x, TILE_H, 0, d + Ns, 0);        // Z
+      b.add_gemm(w[3], Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
+      b.add_gemm(w[4], Ns, Kp_x, TILE_H, 0, d + 2 * Ns, 0);    // IN = x W_in^T + b_in
+      b.add_gemm(w[5], Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0); // HN = h W_hn^T + b_hn
+      b.end_phase(EPI_GRU, (slice == 0 || getenv("BD_TC_SERIAL")) ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
+    }
+  }
+  // ---- prior: h = act(W_p1 b' + b), (mean | raw std) = W_p2 h + b
+  {
+    uint32_t w1 = b.add_pack(r.prior1.w, Be, 0, Hi, Nh, Kp_b, 0, Be, r.prior1.b, Be);
+    int d = b.dcol();
+    b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
+    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+    uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+    uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+    d = b.dcol();
+    b.add_gemm(wm, Sp, Kp_hid, TILE_H, 0, d, 0);
+    b.add_gemm(wsd, Sp, Kp_hid, TILE_H, 0, d + Sp, 0);
+    b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: program too large");
+  const size_t pack_bytes = (size_t)b.w_elems * 2;
+  if (pack_bytes > ws_bytes)
+    BD_FAIL(BD_ERR_WORKSPACE, "tensor-core imagine_forward: workspace %zu < %zu", ws_bytes, pack_bytes);
+
+  RolloutArgs ra{};
+  ra.prog = b.prog;
+  if (!plan_smem(Kp_b, Kp_sa, Kp_h, b.max_stage, ra.sm))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: tiles do not fit shared memory");
+  ra.wpack = static_cast<const uint16_t*>(ws);
+  ra.N = a->N; ra.T = a->T; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = a->actor_cfg.entropy_samples;
+  ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
+  ra.cfg = a->actor_cfg;
+  ra.prev_state = a->prev_state; ra.prev_belief = a->prev_belief;
+  ra.eps_a = a->eps_a; ra.eps_e = a->eps_e; ra.eps_s = a->eps_s;
+  ra.beliefs = a->beliefs; ra.states = a->states; ra.means = a->means; ra.stds = a->stds;
+  ra.entropy = a->entropy; ra.actions = a->actions; ra.actor_raw = a->actor_raw; ra.dent = a->dent;
+
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long max_img = 0;
+  for (int i = 0; i < b.pack.njobs; ++i)
+    max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+  long long pgx = (max_img + 255) / 256;
+  if (pgx > 64) pgx = 64;
+  dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+  const long long ntiles = (a->N + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  if (precision == BD_PREC_FP16) {
+    pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+    BD_CUDA_LAUNCH_CHECK();
+    cudaFuncSetAttribute(rollout_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
+    rollout_fwd_kernel<0, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
+  } else {
+    pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+    BD_CUDA_LAUNCH_CHECK();
+    cudaFuncSetAttribute(rollout_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
+    rollout_fwd_kernel<1, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
+  }
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+}  // namespace tc
+}  // namespace bd

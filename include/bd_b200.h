@@ -63,7 +63,8 @@ enum bd_activation {
 enum bd_precision {
   BD_PREC_FP32 = 0, /* check mode: FFMA, fp32 everywhere              */
   BD_PREC_BF16 = 1, /* tcgen05 kind::f16 (bf16 operands, fp32 accum)  */
-  BD_PREC_TF32 = 2  /* tcgen05 kind::tf32                             */
+  BD_PREC_TF32 = 2, /* tcgen05 kind::tf32 (reserved)                  */
+  BD_PREC_FP16 = 3  /* tcgen05 kind::f16 (fp16 operands: 10-bit mantissa, fp32 accum) */
 };
 
 typedef struct {
@@ -269,6 +270,13 @@ size_t bd_cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B
 /* whole MPCPlanner.forward on one GPU */
 int bd_cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, int precision,
                 bd_stream_t stream);
+
+/* ---------------------------------------------------------------- self-test ---- */
+/* One 128-row tile of y (128,N) = x (128,K) w(N,K)^T + b through the tcgen05 building block
+ * (16-bit operands: fmt 0 = fp16, 1 = bf16; fp32 accumulation).  ws: >= 2*roundup16(N)*roundup16(K+1)
+ * bytes.  Used by the GPU tests to validate the UMMA descriptors / TMEM layout in isolation. */
+int bd_tc_selftest(const float* x, const float* w, const float* b, int K, int N, int fmt,
+                   int swap_lbo_sbo, void* ws, size_t ws_bytes, float* y, bd_stream_t stream);
 
 #ifdef __cplusplus
 }
