@@ -275,7 +275,7 @@ def run_ours(args):
         "metric": "imagined_latent_steps_per_sec_fwd_bwd", "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16": "bf16", "tf32": "tf32"}[args.precision],
+        "dtype": {"fp32": "f32", "bf16": "bf16", "tf32": "tf32", "fp16": "f16"}[args.precision],
         "data": "synthetic", "config": workload_config(rows, args.precision),
         "e2e": {"value": e2e_value, "unit": "steps/s",
                 "h2d_bytes_per_step": int(s0_h.numel() * 4 + b0_h.numel() * 4),

@@ -13,7 +13,7 @@
 // The work of one time step is a host-built PROGRAM: a list of GEMMs grouped into PHASES, each
 // phase ending in one epilogue.  All three roles walk the same program, which makes the
 // producer / issuer / epilogue hand-offs structurally consistent:
-//     w_full[s] / w_empty[s]   producer <-> issuer, one ring stage = one K-block of 32
+//     w_full[s] / w_empty[s]   producer <-> issuer, one ring stage = one K-block of the weight image
 //     acc_full[Gm & 3]         issuer -> epilogue, tcgen05.commit after the last GEMM of phase Gm
 //     epi_done[Ge & 3]         epilogue -> issuer, 256 arrivals when epilogue Ge is done
 // A phase names how far back its dependency is (dep_back = 1: previous phase; 2: the one before,
@@ -49,6 +49,8 @@ struct Gemm {
   uint16_t d_col;     // TMEM column of the accumulator
   uint8_t a_tile;     // TileId
   uint8_t accumulate; // 1: continue a running sum in D
+  uint16_t kc;        // K columns per weight-ring stage (mult of 16): Np*kc*2 <= stage bytes
+  uint16_t pad;
 };
 struct Phase {
   uint8_t g0, ng;     // GEMM range
@@ -89,6 +91,7 @@ struct RolloutArgs {
   float *beliefs, *states, *means, *stds, *entropy, *actions, *actor_raw, *dent;
   float *head_out[2];     // optional fused heads: (T,N) reward / value
   const float* ext_actions;   // CEM / TransitionModel.forward: actions given, no actor
+  long long* prof;            // optional (debug): per-phase cycle counters of CTA 0, see tc_imagine.cu
 };
 
 // fast-math activations for the 16-bit path (the result is rounded to 10 / 7 mantissa bits anyway)
@@ -122,7 +125,24 @@ __device__ __forceinline__ void store1(uint8_t* tile, int row, int col, float v)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int FMT, bool WITH_ACTOR>
+template <int ACT>
+__device__ __forceinline__ float tc_act_t(float x) {
+  if (ACT == BD_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (ACT == BD_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == BD_ACT_TANH) return fast_tanh(x);
+  return x;
+}
+// sigmoid through the single-MUFU tanh: s(x) = 0.5 tanh(x/2) + 0.5
+__device__ __forceinline__ float sigmoid_via_tanh(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+
+template <int FMT>
+__device__ __forceinline__ void store8(uint8_t* p, const float* v) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(Half16<FMT>::pack2(v[0], v[1]), Half16<FMT>::pack2(v[2], v[3]),
+                 Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
+}
+
+template <int FMT, int ACT, bool WITH_ACTOR, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_constant__ RolloutArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RolloutArgs& a = A_;
@@ -131,9 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   __shared__ uint32_t tmem_holder;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nstage = a.sm.nstage;
+  const uint32_t nstage = a.sm.nstage;
   if (tid == 0) {
-    for (int i = 0; i < nstage; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], kEpiThreads); }
     fence_barrier_init();
   }
@@ -142,6 +162,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_holder;
+  long long prof_c0 = 0, prof_g0 = 0;
+  if (PROF && tid == 0) {
+    prof_c0 = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(prof_g0));
+  }
 
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = a.prog;
@@ -149,64 +174,89 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
 
   if (warp == 0) {
     // =========================================================== weight producer
-    if (lane == 0) {
-      uint32_t cnt = 0;
+    // (the whole warp walks the program so every address stays in uniform registers; one
+    //  elected lane issues the copies)
+    {
+      uint32_t st = 0, ph = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
         for (int t = 0; t < a.T; ++t)
           for (int gi = 0; gi < P.n_gemms; ++gi) {
             const Gemm g = P.g[gi];
-            for (int k0 = 0; k0 < g.Kp; k0 += 32) {
-              const int kc = min(32, g.Kp - k0);
+            const uint16_t* src = a.wpack + g.w_off;
+            for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+              const int kc = min((int)g.kc, g.Kp - k0);
               const uint32_t bytes = (uint32_t)g.Np * kc * 2;
-              const uint32_t st = cnt % nstage, ph = (cnt / nstage) & 1;
               mbar_wait(&w_empty[st], ph ^ 1);
-              mbar_expect_tx(&w_full[st], bytes);
-              tma_bulk_g2s(ring + st * a.sm.stage_bytes, a.wpack + g.w_off + (size_t)k0 * g.Np, bytes,
-                           &w_full[st]);
-              ++cnt;
+              if (elect_one()) {
+                mbar_expect_tx(&w_full[st], bytes);
+                tma_bulk_g2s(ring + st * a.sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, &w_full[st]);
+              }
+              __syncwarp();
+              if (++st == nstage) { st = 0; ph ^= 1; }
             }
           }
     }
   } else if (warp == 1) {
     // =========================================================== MMA issuer
-    if (lane == 0) {
+    {
       // Ge counts epilogue completions (incl. the per-tile init pseudo-phase, which has no MMAs);
       // Gm counts phases with MMAs.  Each indexes its own barrier ring so generations stay in step.
-      uint32_t cnt = 0, Ge = 0, Gm = 0;
+      uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
+      const uint32_t ring_addr = smem_u32(ring);
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
         for (int t = 0; t < a.T; ++t) {
           const int par = t & 1;
           for (int pi = 0; pi < P.n_phases; ++pi) {
             const Phase ph = P.p[pi];
+            long long c0 = 0, c1 = 0, wsum = 0;
+            if (PROF) c0 = clock64();
             {
               const uint32_t D = Ge - ph.dep_back;
               mbar_wait(&epi_done[D & 3], (D >> 2) & 1);
               tc_fence_after_sync();
             }
+            if (PROF) c1 = clock64();
             for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
               const Gemm g = P.g[gi];
               uint32_t tile_id = g.a_tile;
               if (tile_id < 2) tile_id ^= par;
-              const uint32_t a_base = smem_u32(smem + a.sm.off_tile[tile_id]) + (g.a_k0 >> 3) * kLboA;
+              const uint64_t a_desc0 =
+                  make_smem_desc(smem_u32(smem + a.sm.off_tile[tile_id]) + (g.a_k0 >> 3) * kLboA, kLboA, 128);
               const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
               const uint32_t lbo_b = (uint32_t)g.Np * 16;
-              for (int k0 = 0; k0 < g.Kp; k0 += 32) {
-                const int kc = min(32, g.Kp - k0);
-                const uint32_t st = cnt % nstage, wph = (cnt / nstage) & 1;
+              const uint64_t b_desc0 = make_smem_desc(0, lbo_b, 128);
+              const uint32_t d_tmem = tmem_base + g.d_col;
+              uint32_t acc = g.accumulate;
+              for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+                const int kc = min((int)g.kc, g.Kp - k0);
+                long long w0 = 0;
+                if (PROF) w0 = clock64();
                 mbar_wait(&w_full[st], wph);
                 tc_fence_after_sync();
-                const uint32_t b_base = smem_u32(ring + st * a.sm.stage_bytes);
-                for (int ks = 0; ks < kc; ks += 16) {
-                  const uint64_t ad = make_smem_desc(a_base + ((k0 + ks) >> 3) * kLboA, kLboA, 128);
-                  const uint64_t bd_ = make_smem_desc(b_base + (ks >> 3) * lbo_b, lbo_b, 128);
-                  umma_f16(tmem_base + g.d_col, ad, bd_, idesc, (g.accumulate | (k0 + ks)) ? 1u : 0u);
+                if (PROF) wsum += clock64() - w0;
+                const uint64_t bd0 = b_desc0 | (uint64_t)(((ring_addr + st * a.sm.stage_bytes) >> 4) & 0x3FFF);
+                if (elect_one()) {
+                  for (int ks = 0; ks < kc; ks += 16) {
+                    // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
+                    const uint64_t ad = a_desc0 + (uint64_t)(((k0 + ks) >> 3) * (kLboA >> 4));
+                    const uint64_t bd_ = bd0 + (uint64_t)((ks >> 3) * (lbo_b >> 4));
+                    umma_f16(d_tmem, ad, bd_, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
+                  }
+                  umma_commit(&w_empty[st]);
                 }
-                umma_commit(&w_empty[st]);
-                ++cnt;
+                __syncwarp();
+                acc = 1;
+                if (++st == nstage) { st = 0; wph ^= 1; }
               }
             }
-            umma_commit(&acc_full[Gm & 3]);
+            if (elect_one()) umma_commit(&acc_full[Gm & 3]);
+            __syncwarp();
+            if (PROF && blockIdx.x == 0 && lane == 0) {
+              a.prof[pi * 8 + 0] += c1 - c0;               // issuer: wait for the dependency epilogue
+              a.prof[pi * 8 + 1] += wsum;                  // issuer: wait for weight stages
+              a.prof[pi * 8 + 2] += clock64() - c1 - wsum; // issuer: issue time
+            }
             ++Gm;
             ++Ge;
           }
@@ -220,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int etid = tid - 64;
     const int Be = a.Be, S = a.S, Ad = a.A;
+    const bool be4 = (Be & 3) == 0;
     uint32_t Ge = 0, Gm = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long grow = tile * kTileRows + row;
@@ -230,22 +281,42 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         uint8_t* B1 = smem + a.sm.off_tile[1];
         uint8_t* SA = smem + a.sm.off_tile[2];
         uint8_t* H = smem + a.sm.off_tile[3];
-        for (int i = etid; i < kTileRows * a.Kp_b; i += kEpiThreads) {
-          const int r = i / a.Kp_b, k = i - r * a.Kp_b;
+        // one 8-column group (16 B of the operand tile) per item; consecutive threads take
+        // consecutive rows of the same group -> conflict-free 16 B shared stores
+        const int gb = a.Kp_b >> 3;
+        for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
+          const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
-          float v = (k < Be) ? ((gr < a.N) ? a.prev_belief[gr * Be + k] : 0.f) : (k == Be ? 1.f : 0.f);
-          store1<FMT>(B0, r, k, v);
-          store1<FMT>(B1, r, k, k == Be ? 1.f : 0.f);
+          float v[8], z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            v[j] = (k < Be) ? ((gr < a.N) ? a.prev_belief[gr * Be + k] : 0.f) : (k == Be ? 1.f : 0.f);
+            z[j] = (k == Be) ? 1.f : 0.f;
+          }
+          store8<FMT>(B0 + kg * kLboA + r * 16, v);
+          store8<FMT>(B1 + kg * kLboA + r * 16, z);
         }
-        for (int i = etid; i < kTileRows * a.Kp_sa; i += kEpiThreads) {
-          const int r = i / a.Kp_sa, k = i - r * a.Kp_sa;
+        const int gs = a.Kp_sa >> 3;
+        for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
+          const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
-          float v = (k < S) ? ((gr < a.N) ? a.prev_state[gr * S + k] : 0.f) : (k == S + Ad ? 1.f : 0.f);
-          store1<FMT>(SA, r, k, v);
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            float x = 0.f;
+            if (k < S) x = (gr < a.N) ? a.prev_state[gr * S + k] : 0.f;
+            else if (k == S + Ad) x = 1.f;
+            else if (!WITH_ACTOR && k < S + Ad && gr < a.N) x = a.ext_actions[gr * Ad + (k - S)];
+            v[j] = x;
+          }
+          store8<FMT>(SA + kg * kLboA + r * 16, v);
         }
-        for (int i = etid; i < kTileRows * a.Kp_h; i += kEpiThreads) {
-          const int r = i / a.Kp_h, k = i - r * a.Kp_h;
-          store1<FMT>(H, r, k, 0.f);
+        const int gh = a.Kp_h >> 3;
+        for (int i = etid; i < kTileRows * gh; i += kEpiThreads) {
+          const int kg = i / kTileRows, r = i - kg * kTileRows;
+          *reinterpret_cast<uint4*>(H + kg * kLboA + r * 16) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();
         mbar_arrive(&epi_done[Ge & 3]);
@@ -258,27 +329,42 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         const long long orow = (long long)t * a.N + grow;        // row in (T,N,.) outputs
         for (int pi = 0; pi < P.n_phases; ++pi) {
           const Phase ph = P.p[pi];
-          mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
-          tc_fence_after_sync();
+          long long e0 = 0, e1 = 0;
+          if (PROF) e0 = clock64();
           const uint32_t tacc = trow + ph.d_col;
           switch (ph.epi) {
             case EPI_ACT_H: {
-              uint8_t* out = smem + a.sm.off_tile[ph.out_tile];
-              for (int c = half * 16; c < ph.Kp_out; c += 32) {
-                float v[16];
-                if (c < ph.Np) {
-                  tmem_ld16(tacc + c, v);
-                  tmem_ld_wait();
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
+              uint8_t* out = smem + a.sm.off_tile[ph.out_tile] + (row >> 3) * 128 + (row & 7) * 16;
+              const int nv = ph.n_valid;
+              for (int c = half * 32; c < ph.Kp_out; c += 64) {
+                float v[32];
+                const bool two = (c + 16) < ph.Kp_out;
+                if (c + 32 <= ph.Np) {
+                  tmem_ld32(tacc + c, v);
                 } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                  if (c < ph.Np) tmem_ld16(tacc + c, v);
+                  if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
                 }
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int col = c + j;
-                  v[j] = col < ph.n_valid ? tc_act(a.act, v[j]) : (col == ph.n_valid ? 1.f : 0.f);
+                for (int j = 0; j < 32; ++j) v[j] = tc_act_t<ACT>(v[j]);
+                if (c + 32 > nv) {   // the chunk holding the constant-1 (bias) column and zero padding
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const int col = c + j;
+                    if (col >= nv) v[j] = (col == nv) ? 1.f : 0.f;
+                  }
                 }
-                store16<FMT>(out, row, c, v);
+                uint8_t* p = out + (c >> 3) * kLboA;
+                store8<FMT>(p, v);
+                store8<FMT>(p + kLboA, v + 8);
+                if (two) {
+                  store8<FMT>(p + 2 * kLboA, v + 16);
+                  store8<FMT>(p + 3 * kLboA, v + 24);
+                }
               }
             } break;
             case EPI_GRU: {
@@ -286,67 +372,120 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               const float* bold = (t == 0) ? a.prev_belief + grow * Be
                                            : a.beliefs + ((long long)(t - 1) * a.N + grow) * Be;
               float* bnew = a.beliefs + orow * Be;
-              for (int c = half * 16; c < Ns; c += 32) {
-                float r_[16], z_[16], in_[16], hn_[16], o[16];
-                tmem_ld16(tacc + c, r_);
-                tmem_ld16(tacc + Ns + c, z_);
-                tmem_ld16(tacc + 2 * Ns + c, in_);
-                tmem_ld16(tacc + 3 * Ns + c, hn_);
-                tmem_ld_wait();
+              // previous belief (fp32 master copy) for this thread's columns: issued before the wait
+              float hb[2][16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int col = n0 + c + j;
-                  float val = (col == Be) ? 1.f : 0.f;
-                  if (col < Be) {
-                    const float h = rvalid ? bold[col] : 0.f;
-                    const float r = fast_sigmoid(r_[j]);
-                    const float z = fast_sigmoid(z_[j]);
-                    const float n = fast_tanh(in_[j] + r * hn_[j]);
-                    val = (1.f - z) * n + z * h;
-                    if (rvalid) bnew[col] = val;
+              for (int it = 0; it < 2; ++it) {
+                const int c = half * 16 + it * 32;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const int col = n0 + c + j4 * 4;
+                  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (rvalid && c < Ns) {
+                    if (be4 && col + 3 < Be) x = *reinterpret_cast<const float4*>(bold + col);
+                    else {
+                      if (col < Be) x.x = bold[col];
+                      if (col + 1 < Be) x.y = bold[col + 1];
+                      if (col + 2 < Be) x.z = bold[col + 2];
+                      if (col + 3 < Be) x.w = bold[col + 3];
+                    }
                   }
-                  o[j] = val;
+                  hb[it][j4 * 4] = x.x; hb[it][j4 * 4 + 1] = x.y; hb[it][j4 * 4 + 2] = x.z; hb[it][j4 * 4 + 3] = x.w;
                 }
-                if (n0 + c < a.Kp_b) store16<FMT>(Bnxt, row, n0 + c, o);
               }
-            } break;
-            case EPI_PRIOR_OUT: {
-              if (half == 0) {
-                const int Sp = ph.Np;    // mean at [0,Sp), raw std at [Sp, 2Sp)
-                for (int c = 0; c < Sp; c += 16) {
-                  float m_[16], s_[16];
-                  tmem_ld16(tacc + c, m_);
-                  tmem_ld16(tacc + Sp + c, s_);
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                const int c = half * 16 + it * 32;
+                if (c < Ns) {
+                  float r_[16], z_[16], in_[16], hn_[16], o[16];
+                  tmem_ld16(tacc + c, r_);
+                  tmem_ld16(tacc + Ns + c, z_);
+                  tmem_ld16(tacc + 2 * Ns + c, in_);
+                  tmem_ld16(tacc + 3 * Ns + c, hn_);
                   tmem_ld_wait();
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
-                    const int col = c + j;
-                    if (col < S) {
-                      const float sd = softplusf_(s_[j]) + a.min_std;
-                      const float e = rvalid ? a.eps_s[orow * S + col] : 0.f;
-                      const float st = m_[j] + sd * e;
-                      if (rvalid) {
-                        a.means[orow * S + col] = m_[j];
-                        a.stds[orow * S + col] = sd;
-                        a.states[orow * S + col] = st;
+                    const float r = sigmoid_via_tanh(r_[j]);
+                    const float z = sigmoid_via_tanh(z_[j]);
+                    const float n = fast_tanh(fmaf(r, hn_[j], in_[j]));
+                    o[j] = fmaf(z, hb[it][j] - n, n);          // (1-z) n + z h
+                  }
+                  const int col0 = n0 + c;
+                  if (rvalid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                      const int col = col0 + j4 * 4;
+                      if (be4 && col + 3 < Be)
+                        *reinterpret_cast<float4*>(bnew + col) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+                      else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < Be) bnew[col + j] = o[j4 * 4 + j];
                       }
-                      store1<FMT>(SAt, row, col, st);
                     }
+                  }
+                  if (col0 + 16 > Be) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (col0 + j >= Be) o[j] = (col0 + j == Be) ? 1.f : 0.f;
+                  }
+                  if (col0 < a.Kp_b) {
+                    uint8_t* p = Bnxt + (col0 >> 3) * kLboA + (row >> 3) * 128 + (row & 7) * 16;
+                    store8<FMT>(p, o);
+                    store8<FMT>(p + kLboA, o + 8);
                   }
                 }
               }
             } break;
+            case EPI_PRIOR_OUT: {
+              const int Sp = ph.Np;    // mean at [0,Sp), raw std at [Sp, 2Sp)
+              const int c = half * 16;
+              float eps[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) eps[j] = (rvalid && c + j < S) ? a.eps_s[orow * S + c + j] : 0.f;
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
+              for (int cc = c, it = 0; cc < Sp; cc += 32, ++it) {
+                if (it > 0) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[orow * S + cc + j] : 0.f;
+                }
+                float m_[16], s_[16];
+                tmem_ld16(tacc + cc, m_);
+                tmem_ld16(tacc + Sp + cc, s_);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int col = cc + j;
+                  if (col < S) {
+                    const float sd = softplusf_(s_[j]) + a.min_std;
+                    const float st = fmaf(sd, eps[j], m_[j]);
+                    if (rvalid) {
+                      a.means[orow * S + col] = m_[j];
+                      a.stds[orow * S + col] = sd;
+                      a.states[orow * S + col] = st;
+                    }
+                    store1<FMT>(SAt, row, col, st);
+                  }
+                }
+              }
+              if (!WITH_ACTOR && half == 0 && t + 1 < a.T) {   // next step's given action -> [s ; a] tile
+                for (int j = 0; j < Ad; ++j)
+                  store1<FMT>(SAt, row, S + j, rvalid ? a.ext_actions[((long long)(t + 1) * a.N + grow) * Ad + j] : 0.f);
+              }
+            } break;
             case EPI_ACTOR_OUT: {
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
               if (WITH_ACTOR && half == 0) {
                 const int Ap = ph.Np;
                 float m_[16], s_[16];
                 tmem_ld16(tacc, m_);
                 tmem_ld16(tacc + Ap, s_);
                 tmem_ld_wait();
-                const float kClamp = 0.99999997f, kLogSqrt2Pi = 0.9189385332046727f,
-                            kLog2 = 0.6931471805599453f;
-                const int J = a.J;
-                float ent_acc = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   if (j < Ad) {
@@ -355,36 +494,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                     const float ea = rvalid ? a.eps_a[orow * Ad + j] : 0.f;
                     const float act = tanhf(mean + ea * sd);
                     store1<FMT>(SAt, row, S + j, act);
-                    float lp_sum = 0.f, dm_sum = 0.f, ds_sum = 0.f;
                     if (rvalid) {
                       a.actions[orow * Ad + j] = act;
                       a.actor_raw[orow * 2 * Ad + j] = m_[j];
                       a.actor_raw[orow * 2 * Ad + Ad + j] = s_[j];
-                      const float var2 = 2.f * sd * sd, log_sd = logf(sd), inv_var = 1.f / (sd * sd);
-                      const float* ee = a.eps_e + ((long long)t * J * a.N + grow) * Ad + j;
-                      for (int s = 0; s < J; ++s) {
-                        const float e = ee[(long long)s * a.N * Ad];
-                        const float y = tanhf(mean + e * sd);
-                        const float yc = fminf(fmaxf(y, -kClamp), kClamp);
-                        const float gate = (yc == y) ? 1.f : 0.f;
-                        const float xh = 0.5f * logf((1.f + yc) / (1.f - yc));
-                        const float d = xh - mean;
-                        lp_sum += -(d * d) / var2 - log_sd - kLogSqrt2Pi -
-                                  2.f * (kLog2 - xh - softplusf_(-2.f * xh));
-                        const float dlp = -d * inv_var + 2.f * tanhf(xh);
-                        dm_sum += d * inv_var + gate * dlp;
-                        ds_sum += d * d * inv_var / sd - 1.f / sd + gate * e * dlp;
-                      }
-                      a.dent[orow * 2 * Ad + j] = -dm_sum / (float)J;
-                      a.dent[orow * 2 * Ad + Ad + j] = -ds_sum / (float)J;
                     }
-                    ent_acc += lp_sum;
                   }
                 }
-                if (rvalid) a.entropy[orow] = -ent_acc / (float)J;
               }
             } break;
             case EPI_HEAD_OUT: {
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
               if (half == 0) {
                 float v[16];
                 tmem_ld16(tacc, v);
@@ -392,11 +514,19 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 if (rvalid && a.head_out[ph.aux0]) a.head_out[ph.aux0][orow] = v[0];
               }
             } break;
-            default: break;
+            default: {
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+            } break;
           }
           tc_fence_before_sync();
           fence_proxy_async_smem();
           mbar_arrive(&epi_done[Ge & 3]);
+          if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
+            const int o = pi * 8 + (warp == 2 ? 3 : 5);
+            a.prof[o] += e1 - e0;                          // epilogue: wait for the accumulator
+            a.prof[o + 1] += clock64() - e1;               // epilogue: work
+          }
           ++Ge;
           ++Gm;
         }
@@ -405,7 +535,62 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (PROF && tid == 0) {
+    long long g1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+    if (blockIdx.x == 0) {
+      a.prof[39 * 8 + 0] += clock64() - prof_c0;   // whole-kernel SM cycles of CTA 0
+      a.prof[39 * 8 + 1] += g1 - prof_g0;          // same interval in ns
+    }
+    if (blockIdx.x < 160) {                        // per-CTA start / end timestamps
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      a.prof[40 * 8 + blockIdx.x * 3 + 0] = prof_g0;
+      a.prof[40 * 8 + blockIdx.x * 3 + 1] = g1;
+      a.prof[40 * 8 + blockIdx.x * 3 + 2] = smid;
+    }
+  }
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// J-sample Monte-Carlo entropy of the tanh-Normal policy and its gradient wrt (mean, std)
+// (src/models.py:725-733, 656-673), computed after the rollout from the saved raw actor outputs:
+// it does not feed the recurrence, so it runs as a plain fully-parallel kernel over (t, row).
+__global__ void actor_entropy_kernel(const float* __restrict__ raw, const float* __restrict__ eps_e,
+                                     bd_actor_cfg cfg, long long N, int A,
+                                     float* __restrict__ entropy, float* __restrict__ dent) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (n >= N) return;
+  const long long r = (long long)t * N + n;
+  const float kClamp = 0.99999997f, kLogSqrt2Pi = 0.9189385332046727f, kLog2 = 0.6931471805599453f;
+  const int J = cfg.entropy_samples;
+  float ent_acc = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float mean = cfg.mean_scale * tanhf(raw[r * 2 * A + a] / cfg.mean_scale);
+    const float sd = softplusf_(raw[r * 2 * A + A + a] + cfg.raw_init_std) + cfg.min_std;
+    const float var2 = 2.f * sd * sd, log_sd = logf(sd), inv_var = 1.f / (sd * sd), inv_sd = 1.f / sd;
+    const float* ee = eps_e + ((long long)t * J * N + n) * A + a;
+    float lp_sum = 0.f, dm_sum = 0.f, ds_sum = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < J; ++j) {
+      const float e = ee[(long long)j * N * A];
+      const float y = tanhf(mean + e * sd);
+      const float yc = fminf(fmaxf(y, -kClamp), kClamp);
+      const float gate = (yc == y) ? 1.f : 0.f;
+      const float xh = 0.5f * logf((1.f + yc) / (1.f - yc));
+      const float d = xh - mean;
+      lp_sum += -(d * d) / var2 - log_sd - kLogSqrt2Pi - 2.f * (kLog2 - xh - softplusf_(-2.f * xh));
+      const float dlp = -d * inv_var + 2.f * tanhf(xh);
+      dm_sum += d * inv_var + gate * dlp;
+      ds_sum += d * d * inv_var * inv_sd - inv_sd + gate * e * dlp;
+    }
+    ent_acc += lp_sum;
+    dent[r * 2 * A + a] = -dm_sum / (float)J;
+    dent[r * 2 * A + A + a] = -ds_sum / (float)J;
+  }
+  entropy[r] = -ent_acc / (float)J;
 }
 
 }  // namespace tc

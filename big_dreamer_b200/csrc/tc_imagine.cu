@@ -35,7 +35,18 @@ struct Builder {
     Gemm& g = prog.g[prog.n_gemms++];
     g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
     g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
+    g.kc = 32; g.pad = 0;
     max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
+  }
+  // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
+  void finalize_blocks(uint32_t stage_bytes) {
+    for (int i = 0; i < prog.n_gemms; ++i) {
+      Gemm& g = prog.g[i];
+      uint32_t kc = stage_bytes / (g.Np * 2u) / 16u * 16u;
+      if (kc > g.Kp) kc = g.Kp;
+      if (kc < 16) kc = 16;
+      g.kc = (uint16_t)kc;
+    }
   }
   void end_phase(int epi, int dep_back, int n_valid, int Np, int Kp_out, int d_col, int aux0,
                  int out_tile) {
@@ -90,6 +101,38 @@ static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& s
   sm.nstage = min(8u, (budget - off) / sm.stage_bytes);
   sm.total = off + sm.nstage * sm.stage_bytes + 1024;
   return true;
+}
+
+template <int FMT, int ACT, bool WITH_ACTOR>
+static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s) {
+  if (prof && FMT == 0 && ACT == BD_ACT_ELU) {
+    cudaFuncSetAttribute(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
+    rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
+  } else {
+    cudaFuncSetAttribute(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
+    rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false><<<grid, kThreads, ra.sm.total, s>>>(ra);
+  }
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+template <int FMT, bool WITH_ACTOR>
+static int launch_rollout_a(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s) {
+  switch (act) {
+    case BD_ACT_ELU: return launch_rollout_t<FMT, BD_ACT_ELU, WITH_ACTOR>(prof, grid, ra, s);
+    case BD_ACT_RELU: return launch_rollout_t<FMT, BD_ACT_RELU, WITH_ACTOR>(prof, grid, ra, s);
+    case BD_ACT_TANH: return launch_rollout_t<FMT, BD_ACT_TANH, WITH_ACTOR>(prof, grid, ra, s);
+    default: return launch_rollout_t<FMT, BD_ACT_IDENTITY, WITH_ACTOR>(prof, grid, ra, s);
+  }
+}
+static int launch_rollout(int fmt, int act, bool with_actor, bool prof, unsigned grid,
+                          const RolloutArgs& ra, cudaStream_t s) {
+  if (fmt == 0)
+    return with_actor ? launch_rollout_a<0, true>(act, prof, grid, ra, s)
+                      : launch_rollout_a<0, false>(act, prof, grid, ra, s);
+  return with_actor ? launch_rollout_a<1, true>(act, prof, grid, ra, s)
+                    : launch_rollout_a<1, false>(act, prof, grid, ra, s);
 }
 
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
@@ -177,6 +220,8 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   ra.prog = b.prog;
   if (!plan_smem(Kp_b, Kp_sa, Kp_h, b.max_stage, ra.sm))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: tiles do not fit shared memory");
+  b.finalize_blocks(ra.sm.stage_bytes);
+  ra.prog = b.prog;
   ra.wpack = static_cast<const uint16_t*>(ws);
   ra.N = a->N; ra.T = a->T; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = a->actor_cfg.entropy_samples;
   ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
@@ -187,6 +232,12 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   ra.entropy = a->entropy; ra.actions = a->actions; ra.actor_raw = a->actor_raw; ra.dent = a->dent;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // debug: BD_TC_PROF=1 appends cycle counters after the packed weights (scripts/prof_fwd.py)
+  const bool prof = getenv("BD_TC_PROF") && pack_bytes + 8192 + kMaxPhases * 64 + 160 * 24 <= ws_bytes;
+  if (prof) {
+    ra.prof = reinterpret_cast<long long*>(static_cast<char*>(ws) + ((pack_bytes + 4095) & ~size_t(4095)));
+    cudaMemsetAsync(ra.prof, 0, kMaxPhases * 64 + 160 * 24, s);
+  }
   long long max_img = 0;
   for (int i = 0; i < b.pack.njobs; ++i)
     max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
@@ -198,17 +249,15 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  if (precision == BD_PREC_FP16) {
-    pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
-    BD_CUDA_LAUNCH_CHECK();
-    cudaFuncSetAttribute(rollout_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
-    rollout_fwd_kernel<0, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
-  } else {
-    pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
-    BD_CUDA_LAUNCH_CHECK();
-    cudaFuncSetAttribute(rollout_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
-    rollout_fwd_kernel<1, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
-  }
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  BD_CUDA_LAUNCH_CHECK();
+  BD_TRY(launch_rollout(fmt, r.activation, true, prof, grid, ra, s));
+  // entropy + its gradient wrt (mean, std): independent of the recurrence -> separate parallel pass
+  dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
+  actor_entropy_kernel<<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy,
+                                             a->dent);
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
 }
