@@ -41,7 +41,14 @@ int bd_precision_supported(int precision) {
 }
 
 size_t bd_mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {
-  return m ? f32::mlp_workspace_bytes(m, rows, backward) : 0;
+  if (!m) return 0;
+  size_t f = f32::mlp_workspace_bytes(m, rows, backward), t = tc::mlp_pack_bytes(*m);
+  if (backward && m->n_layers >= 1) {
+    const int kin = m->layer[0].in_features;
+    size_t tb = tc::mlp_backward_workspace_bytes(*m, kin, 0, rows);
+    if (tb > t) t = tb;
+  }
+  return f > t ? f : t;
 }
 int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
                    float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
@@ -50,6 +57,8 @@ int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, in
   BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
   BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
+  if (tc::mlp_supported(*m, k1, k2, precision))
+    return tc::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, precision, stream);
   return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
 }
 int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
@@ -59,6 +68,8 @@ int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t 
   BD_NEED(ws, "workspace"); BD_NEED(a->x1, "x1"); BD_NEED(a->dy, "dy");
   BD_CHECK_ARG(a->k1 > 0 && a->k2 >= 0 && (a->k2 == 0 || a->x2), "bd_mlp_backward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
+  if (tc::mlp_backward_supported(*m, a->k1, a->k2, precision))
+    return tc::mlp_backward(m, a, ws, ws_bytes, precision, stream);
   return f32::mlp_backward(m, a, ws, ws_bytes, stream);
 }
 

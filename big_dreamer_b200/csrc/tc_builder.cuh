@@ -1,0 +1,64 @@
+// Host-side builder of engine programs and weight-packing tables (shared by all tensor-core
+// entry points).
+#pragma once
+#include "tc_engine.cuh"
+
+namespace bd {
+namespace tc {
+
+inline int r16(int x) { return (x + 15) / 16 * 16; }
+
+struct Builder {
+  PackTable pack{};
+  Program prog{};
+  long long w_elems = 0;
+  int cur_phase_g0 = 0;
+  uint32_t max_stage = 0;
+  bool ok = true;
+
+  // packs rows [row0,row0+n) of w (ld cols) into an image (Np x Kp); returns element offset
+  uint32_t add_pack(const float* w, int ld, int row0, int n, int Np, int Kp, int src_c0, int len,
+                    const float* bias, int bias_k) {
+    if (pack.njobs >= kMaxPackJobs) { ok = false; return 0; }
+    PackJob& j = pack.job[pack.njobs++];
+    j = PackJob{};
+    j.w = w; j.bias = bias; j.dst_off = w_elems; j.ld = ld; j.row0 = row0; j.N = n; j.Np = Np;
+    j.Kp = Kp; j.bias_k = bias ? bias_k : -1; j.nseg = 1; j.seg[0] = {0, src_c0, len}; j.transpose = 0;
+    uint32_t off = (uint32_t)w_elems;
+    w_elems += (long long)Np * Kp;
+    return off;
+  }
+  void add_gemm(uint32_t w_off, int Np, int Kp, int a_tile, int a_k0, int d_col, int accumulate) {
+    if (prog.n_gemms >= kMaxGemms) { ok = false; return; }
+    Gemm& g = prog.g[prog.n_gemms++];
+    g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
+    g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
+    g.kc = 32; g.pad = 0;
+    max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
+  }
+  // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
+  void finalize_blocks(uint32_t stage_bytes) {
+    for (int i = 0; i < prog.n_gemms; ++i) {
+      Gemm& g = prog.g[i];
+      uint32_t kc = stage_bytes / (g.Np * 2u) / 16u * 16u;
+      if (kc > g.Kp) kc = g.Kp;
+      if (kc < 16) kc = 16;
+      g.kc = (uint16_t)kc;
+    }
+  }
+  void end_phase(int epi, int dep_back, int n_valid, int Np, int Kp_out, int d_col, int aux0,
+                 int out_tile) {
+    if (prog.n_phases >= kMaxPhases) { ok = false; return; }
+    Phase& p = prog.p[prog.n_phases++];
+    p.g0 = (uint8_t)cur_phase_g0; p.ng = (uint8_t)(prog.n_gemms - cur_phase_g0); p.epi = (uint8_t)epi;
+    p.dep_back = (uint8_t)dep_back; p.n_valid = (uint16_t)n_valid; p.Np = (uint16_t)Np;
+    p.Kp_out = (uint16_t)Kp_out; p.d_col = (uint16_t)d_col; p.aux0 = (uint16_t)aux0;
+    p.out_tile = (uint8_t)out_tile; p.pad = 0;
+    cur_phase_g0 = prog.n_gemms;
+  }
+  int dcol() const { return (prog.n_phases & 1) * 256; }
+};
+
+
+}  // namespace tc
+}  // namespace bd

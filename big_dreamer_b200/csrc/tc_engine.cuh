@@ -39,7 +39,8 @@ enum EpiKind : uint8_t {
   EPI_ACTOR_OUT = 2,  // action sample + entropy
   EPI_GRU = 3,        // GRU gates for one N-slice -> b'
   EPI_PRIOR_OUT = 4,  // mean / std / sampled state
-  EPI_HEAD_OUT = 5    // scalar head output (reward / value)
+  EPI_HEAD_OUT = 5,   // scalar head output (reward / value) of the fused rollout
+  EPI_STORE_OUT = 6   // plain fp32 store of n_valid output columns (MLP forward)
 };
 
 struct Gemm {
@@ -92,6 +93,8 @@ struct RolloutArgs {
   float *head_out[2];     // optional fused heads: (T,N) reward / value
   const float* ext_actions;   // CEM / TransitionModel.forward: actions given, no actor
   long long* prof;            // optional (debug): per-phase cycle counters of CTA 0, see tc_imagine.cu
+  float* mlp_out;             // EPI_STORE_OUT target (rows, n_valid)
+  int has_b1;                 // 0: single belief tile (MLP forward), 1: ping-pong
 };
 
 // fast-math activations for the 16-bit path (the result is rounded to 10 / 7 mantissa bits anyway)
@@ -125,6 +128,126 @@ __device__ __forceinline__ void store1(uint8_t* tile, int row, int col, float v)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared skeleton of every kernel on this path: barrier setup, the weight-producer warp and the
+// MMA-issuer warp.  Kernels differ only in their tile initialisation and epilogues.
+struct EngineShared {
+  uint64_t w_full[8], w_empty[8], acc_full[4], epi_done[4];
+  uint32_t tmem_holder;
+};
+
+__device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.epi_done[i], kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&sh.tmem_holder);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  return sh.tmem_holder;
+}
+
+// The whole warp walks the program so every address stays in uniform registers; one elected
+// lane issues the copies.
+__device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
+                                              const uint16_t* wpack, long long ntiles, int T,
+                                              uint8_t* smem, EngineShared& sh) {
+  uint8_t* ring = smem + sm.off_ring;
+  const uint32_t nstage = sm.nstage;
+  uint32_t st = 0, ph = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    for (int t = 0; t < T; ++t)
+      for (int gi = 0; gi < P.n_gemms; ++gi) {
+        const Gemm g = P.g[gi];
+        const uint16_t* src = wpack + g.w_off;
+        for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+          const int kc = min((int)g.kc, g.Kp - k0);
+          const uint32_t bytes = (uint32_t)g.Np * kc * 2;
+          mbar_wait(&sh.w_empty[st], ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&sh.w_full[st], bytes);
+            tma_bulk_g2s(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, &sh.w_full[st]);
+          }
+          __syncwarp();
+          if (++st == nstage) { st = 0; ph ^= 1; }
+        }
+      }
+}
+
+// Ge counts epilogue completions (incl. the per-tile init pseudo-phase, which has no MMAs); Gm
+// counts phases with MMAs.  Each indexes its own barrier ring so generations stay in step.
+template <int FMT, bool PROF>
+__device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
+                                            int T, uint8_t* smem, EngineShared& sh,
+                                            uint32_t tmem_base, long long* prof) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nstage = sm.nstage;
+  uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
+  const uint32_t ring_addr = smem_u32(smem + sm.off_ring);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
+    for (int t = 0; t < T; ++t) {
+      const int par = t & 1;
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        const Phase ph = P.p[pi];
+        long long c0 = 0, c1 = 0, wsum = 0;
+        if (PROF) c0 = clock64();
+        {
+          const uint32_t D = Ge - ph.dep_back;
+          mbar_wait(&sh.epi_done[D & 3], (D >> 2) & 1);
+          tc_fence_after_sync();
+        }
+        if (PROF) c1 = clock64();
+        for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
+          const Gemm g = P.g[gi];
+          uint32_t tile_id = g.a_tile;
+          if (tile_id < 2) tile_id ^= par;
+          const uint64_t a_desc0 =
+              make_smem_desc(smem_u32(smem + sm.off_tile[tile_id]) + (g.a_k0 >> 3) * kLboA, kLboA, 128);
+          const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
+          const uint32_t lbo_b = (uint32_t)g.Np * 16;
+          const uint64_t b_desc0 = make_smem_desc(0, lbo_b, 128);
+          const uint32_t d_tmem = tmem_base + g.d_col;
+          uint32_t acc = g.accumulate;
+          for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+            const int kc = min((int)g.kc, g.Kp - k0);
+            long long w0 = 0;
+            if (PROF) w0 = clock64();
+            mbar_wait(&sh.w_full[st], wph);
+            tc_fence_after_sync();
+            if (PROF) wsum += clock64() - w0;
+            const uint64_t bd0 = b_desc0 | (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFF);
+            if (elect_one()) {
+              for (int ks = 0; ks < kc; ks += 16) {
+                // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
+                const uint64_t ad = a_desc0 + (uint64_t)(((k0 + ks) >> 3) * (kLboA >> 4));
+                const uint64_t bd_ = bd0 + (uint64_t)((ks >> 3) * (lbo_b >> 4));
+                umma_f16(d_tmem, ad, bd_, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
+              }
+              umma_commit(&sh.w_empty[st]);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++st == nstage) { st = 0; wph ^= 1; }
+          }
+        }
+        if (elect_one()) umma_commit(&sh.acc_full[Gm & 3]);
+        __syncwarp();
+        if (PROF && blockIdx.x == 0 && lane == 0) {
+          prof[pi * 8 + 0] += c1 - c0;               // issuer: wait for the dependency epilogue
+          prof[pi * 8 + 1] += wsum;                  // issuer: wait for weight stages
+          prof[pi * 8 + 2] += clock64() - c1 - wsum; // issuer: issue time
+        }
+        ++Gm;
+        ++Ge;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ float tc_act_t(float x) {
   if (ACT == BD_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
@@ -147,21 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RolloutArgs& a = A_;
   uint8_t* smem = smem_raw;
-  __shared__ uint64_t w_full[8], w_empty[8], acc_full[4], epi_done[4];
-  __shared__ uint32_t tmem_holder;
-
+  __shared__ EngineShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t nstage = a.sm.nstage;
-  if (tid == 0) {
-    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&epi_done[i], kEpiThreads); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(&tmem_holder);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_holder;
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
+  uint64_t* const acc_full = sh.acc_full;
+  uint64_t* const epi_done = sh.epi_done;
   long long prof_c0 = 0, prof_g0 = 0;
   if (PROF && tid == 0) {
     prof_c0 = clock64();
@@ -170,99 +283,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
 
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = a.prog;
-  uint8_t* ring = smem + a.sm.off_ring;
 
   if (warp == 0) {
-    // =========================================================== weight producer
-    // (the whole warp walks the program so every address stays in uniform registers; one
-    //  elected lane issues the copies)
-    {
-      uint32_t st = 0, ph = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-        for (int t = 0; t < a.T; ++t)
-          for (int gi = 0; gi < P.n_gemms; ++gi) {
-            const Gemm g = P.g[gi];
-            const uint16_t* src = a.wpack + g.w_off;
-            for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
-              const int kc = min((int)g.kc, g.Kp - k0);
-              const uint32_t bytes = (uint32_t)g.Np * kc * 2;
-              mbar_wait(&w_empty[st], ph ^ 1);
-              if (elect_one()) {
-                mbar_expect_tx(&w_full[st], bytes);
-                tma_bulk_g2s(ring + st * a.sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, &w_full[st]);
-              }
-              __syncwarp();
-              if (++st == nstage) { st = 0; ph ^= 1; }
-            }
-          }
-    }
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh);
   } else if (warp == 1) {
-    // =========================================================== MMA issuer
-    {
-      // Ge counts epilogue completions (incl. the per-tile init pseudo-phase, which has no MMAs);
-      // Gm counts phases with MMAs.  Each indexes its own barrier ring so generations stay in step.
-      uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
-      const uint32_t ring_addr = smem_u32(ring);
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
-        for (int t = 0; t < a.T; ++t) {
-          const int par = t & 1;
-          for (int pi = 0; pi < P.n_phases; ++pi) {
-            const Phase ph = P.p[pi];
-            long long c0 = 0, c1 = 0, wsum = 0;
-            if (PROF) c0 = clock64();
-            {
-              const uint32_t D = Ge - ph.dep_back;
-              mbar_wait(&epi_done[D & 3], (D >> 2) & 1);
-              tc_fence_after_sync();
-            }
-            if (PROF) c1 = clock64();
-            for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
-              const Gemm g = P.g[gi];
-              uint32_t tile_id = g.a_tile;
-              if (tile_id < 2) tile_id ^= par;
-              const uint64_t a_desc0 =
-                  make_smem_desc(smem_u32(smem + a.sm.off_tile[tile_id]) + (g.a_k0 >> 3) * kLboA, kLboA, 128);
-              const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
-              const uint32_t lbo_b = (uint32_t)g.Np * 16;
-              const uint64_t b_desc0 = make_smem_desc(0, lbo_b, 128);
-              const uint32_t d_tmem = tmem_base + g.d_col;
-              uint32_t acc = g.accumulate;
-              for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
-                const int kc = min((int)g.kc, g.Kp - k0);
-                long long w0 = 0;
-                if (PROF) w0 = clock64();
-                mbar_wait(&w_full[st], wph);
-                tc_fence_after_sync();
-                if (PROF) wsum += clock64() - w0;
-                const uint64_t bd0 = b_desc0 | (uint64_t)(((ring_addr + st * a.sm.stage_bytes) >> 4) & 0x3FFF);
-                if (elect_one()) {
-                  for (int ks = 0; ks < kc; ks += 16) {
-                    // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
-                    const uint64_t ad = a_desc0 + (uint64_t)(((k0 + ks) >> 3) * (kLboA >> 4));
-                    const uint64_t bd_ = bd0 + (uint64_t)((ks >> 3) * (lbo_b >> 4));
-                    umma_f16(d_tmem, ad, bd_, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
-                  }
-                  umma_commit(&w_empty[st]);
-                }
-                __syncwarp();
-                acc = 1;
-                if (++st == nstage) { st = 0; wph ^= 1; }
-              }
-            }
-            if (elect_one()) umma_commit(&acc_full[Gm & 3]);
-            __syncwarp();
-            if (PROF && blockIdx.x == 0 && lane == 0) {
-              a.prof[pi * 8 + 0] += c1 - c0;               // issuer: wait for the dependency epilogue
-              a.prof[pi * 8 + 1] += wsum;                  // issuer: wait for weight stages
-              a.prof[pi * 8 + 2] += clock64() - c1 - wsum; // issuer: issue time
-            }
-            ++Gm;
-            ++Ge;
-          }
-        }
-      }
-    }
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof);
   } else {
     // =========================================================== epilogue warps
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
             z[j] = (k == Be) ? 1.f : 0.f;
           }
           store8<FMT>(B0 + kg * kLboA + r * 16, v);
-          store8<FMT>(B1 + kg * kLboA + r * 16, z);
+          if (a.has_b1) store8<FMT>(B1 + kg * kLboA + r * 16, z);
         }
         const int gs = a.Kp_sa >> 3;
         for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
@@ -306,9 +331,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
             float x = 0.f;
-            if (k < S) x = (gr < a.N) ? a.prev_state[gr * S + k] : 0.f;
+            if (k < S) x = (gr < a.N && a.prev_state) ? a.prev_state[gr * S + k] : 0.f;
             else if (k == S + Ad) x = 1.f;
-            else if (!WITH_ACTOR && k < S + Ad && gr < a.N) x = a.ext_actions[gr * Ad + (k - S)];
+            else if (!WITH_ACTOR && k < S + Ad && gr < a.N && a.ext_actions) x = a.ext_actions[gr * Ad + (k - S)];
             v[j] = x;
           }
           store8<FMT>(SA + kg * kLboA + r * 16, v);
@@ -471,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   }
                 }
               }
-              if (!WITH_ACTOR && half == 0 && t + 1 < a.T) {   // next step's given action -> [s ; a] tile
+              if (!WITH_ACTOR && half == 0 && t + 1 < a.T && a.ext_actions) {   // next step's given action -> [s ; a] tile
                 for (int j = 0; j < Ad; ++j)
                   store1<FMT>(SAt, row, S + j, rvalid ? a.ext_actions[((long long)(t + 1) * a.N + grow) * Ad + j] : 0.f);
               }
@@ -512,6 +537,22 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 tmem_ld16(tacc, v);
                 tmem_ld_wait();
                 if (rvalid && a.head_out[ph.aux0]) a.head_out[ph.aux0][orow] = v[0];
+              }
+            } break;
+            case EPI_STORE_OUT: {
+              mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
+              tc_fence_after_sync();
+              if (PROF) e1 = clock64();
+              const int nv = ph.n_valid;
+              for (int c = half * 16; c < ph.Np; c += 32) {
+                float v[16];
+                tmem_ld16(tacc + c, v);
+                tmem_ld_wait();
+                if (rvalid) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c + j < nv) a.mlp_out[orow * nv + c + j] = v[j];
+                }
               }
             } break;
             default: {
@@ -557,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
 // J-sample Monte-Carlo entropy of the tanh-Normal policy and its gradient wrt (mean, std)
 // (src/models.py:725-733, 656-673), computed after the rollout from the saved raw actor outputs:
 // it does not feed the recurrence, so it runs as a plain fully-parallel kernel over (t, row).
-__global__ void actor_entropy_kernel(const float* __restrict__ raw, const float* __restrict__ eps_e,
+static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const float* __restrict__ eps_e,
                                      bd_actor_cfg cfg, long long N, int A,
                                      float* __restrict__ entropy, float* __restrict__ dent) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -3,63 +3,11 @@
 // pack kernel and the persistent rollout kernel (tc_engine.cuh).
 #include "api_internal.h"
 #include "tc_engine.cuh"
+#include "tc_builder.cuh"
 #include <stdlib.h>
 
 namespace bd {
 namespace tc {
-
-static inline int r16(int x) { return (x + 15) / 16 * 16; }
-
-struct Builder {
-  PackTable pack{};
-  Program prog{};
-  long long w_elems = 0;
-  int cur_phase_g0 = 0;
-  uint32_t max_stage = 0;
-  bool ok = true;
-
-  // packs rows [row0,row0+n) of w (ld cols) into an image (Np x Kp); returns element offset
-  uint32_t add_pack(const float* w, int ld, int row0, int n, int Np, int Kp, int src_c0, int len,
-                    const float* bias, int bias_k) {
-    if (pack.njobs >= kMaxPackJobs) { ok = false; return 0; }
-    PackJob& j = pack.job[pack.njobs++];
-    j = PackJob{};
-    j.w = w; j.bias = bias; j.dst_off = w_elems; j.ld = ld; j.row0 = row0; j.N = n; j.Np = Np;
-    j.Kp = Kp; j.bias_k = bias ? bias_k : -1; j.nseg = 1; j.seg[0] = {0, src_c0, len}; j.transpose = 0;
-    uint32_t off = (uint32_t)w_elems;
-    w_elems += (long long)Np * Kp;
-    return off;
-  }
-  void add_gemm(uint32_t w_off, int Np, int Kp, int a_tile, int a_k0, int d_col, int accumulate) {
-    if (prog.n_gemms >= kMaxGemms) { ok = false; return; }
-    Gemm& g = prog.g[prog.n_gemms++];
-    g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
-    g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
-    g.kc = 32; g.pad = 0;
-    max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
-  }
-  // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
-  void finalize_blocks(uint32_t stage_bytes) {
-    for (int i = 0; i < prog.n_gemms; ++i) {
-      Gemm& g = prog.g[i];
-      uint32_t kc = stage_bytes / (g.Np * 2u) / 16u * 16u;
-      if (kc > g.Kp) kc = g.Kp;
-      if (kc < 16) kc = 16;
-      g.kc = (uint16_t)kc;
-    }
-  }
-  void end_phase(int epi, int dep_back, int n_valid, int Np, int Kp_out, int d_col, int aux0,
-                 int out_tile) {
-    if (prog.n_phases >= kMaxPhases) { ok = false; return; }
-    Phase& p = prog.p[prog.n_phases++];
-    p.g0 = (uint8_t)cur_phase_g0; p.ng = (uint8_t)(prog.n_gemms - cur_phase_g0); p.epi = (uint8_t)epi;
-    p.dep_back = (uint8_t)dep_back; p.n_valid = (uint16_t)n_valid; p.Np = (uint16_t)Np;
-    p.Kp_out = (uint16_t)Kp_out; p.d_col = (uint16_t)d_col; p.aux0 = (uint16_t)aux0;
-    p.out_tile = (uint8_t)out_tile; p.pad = 0;
-    cur_phase_g0 = prog.n_gemms;
-  }
-  int dcol() const { return (prog.n_phases & 1) * 256; }
-};
 
 bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
   if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
@@ -86,11 +34,11 @@ size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor) {
   return e * 2 + 4096;
 }
 
-static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& sm) {
+static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& sm, bool has_b1 = true) {
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 1023) & ~1023u; return o; };
   sm.off_tile[0] = take(kTileRows * Kp_b * 2);
-  sm.off_tile[1] = take(kTileRows * Kp_b * 2);
+  sm.off_tile[1] = has_b1 ? take(kTileRows * Kp_b * 2) : sm.off_tile[0];
   sm.off_tile[2] = take(kTileRows * Kp_sa * 2);
   sm.off_tile[3] = take(kTileRows * Kp_h * 2);
   sm.off_tile[4] = sm.off_tile[3];
@@ -230,6 +178,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   ra.eps_a = a->eps_a; ra.eps_e = a->eps_e; ra.eps_s = a->eps_s;
   ra.beliefs = a->beliefs; ra.states = a->states; ra.means = a->means; ra.stds = a->stds;
   ra.entropy = a->entropy; ra.actions = a->actions; ra.actor_raw = a->actor_raw; ra.dent = a->dent;
+  ra.has_b1 = 1;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // debug: BD_TC_PROF=1 appends cycle counters after the packed weights (scripts/prof_fwd.py)
@@ -260,6 +209,87 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
                                              a->dent);
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DenseModel forward (src/models.py:393-408) on the tensor-core engine: T = 1, no recurrence.
+// ---------------------------------------------------------------------------------------------
+bool mlp_supported(const bd_mlp& m, int k1, int k2, int precision) {
+  if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
+  if (!(m.activation == BD_ACT_ELU || m.activation == BD_ACT_RELU || m.activation == BD_ACT_TANH ||
+        m.activation == BD_ACT_IDENTITY)) return false;
+  if (k1 + 1 > 256 || k2 > 240 || m.n_layers < 1) return false;
+  for (int l = 0; l < m.n_layers; ++l)
+    if (m.layer[l].out_features + 1 > 256) return false;
+  return true;
+}
+size_t mlp_pack_bytes(const bd_mlp& m) {
+  size_t e = 0;
+  for (int l = 0; l < m.n_layers; ++l)
+    e += (size_t)r16(m.layer[l].out_features) * (r16(m.layer[l].in_features + 1) + 16);
+  return e * 2 + 4096;
+}
+
+int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
+                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
+  if (!mlp_supported(*m, k1, k2, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: sizes/activation not supported");
+  Builder b;
+  const int Kp_b = r16(k1 + 1), Ks = k2 > 0 ? r16(k2) : 0;
+  int Kp_h = 16;
+  for (int l = 0; l < m->n_layers; ++l) {
+    const bd_linear& L = m->layer[l];
+    const bool last = (l == m->n_layers - 1);
+    const int n = L.out_features, Np = r16(n);
+    const int d = b.dcol();
+    if (l == 0) {
+      uint32_t wb = b.add_pack(L.w, k1 + k2, 0, n, Np, Kp_b, 0, k1, L.b, k1);
+      b.add_gemm(wb, Np, Kp_b, TILE_BCUR, 0, d, 0);
+      if (k2 > 0) {
+        uint32_t wsx = b.add_pack(L.w, k1 + k2, 0, n, Np, Ks, k1, k2, nullptr, -1);
+        b.add_gemm(wsx, Np, Ks, TILE_SA, 0, d, 1);
+      }
+    } else {
+      const int kin = L.in_features, Kp = r16(kin + 1);
+      uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
+      b.add_gemm(w, Np, Kp, TILE_H, 0, d, 0);
+    }
+    if (last) b.end_phase(EPI_STORE_OUT, 1, n, Np, 0, d, 0, TILE_H);
+    else {
+      b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H);
+      Kp_h = max(Kp_h, r16(n + 1));
+    }
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: program too large");
+  const size_t pack_bytes = (size_t)b.w_elems * 2;
+  if (pack_bytes > ws_bytes)
+    BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_forward: workspace %zu < %zu", ws_bytes, pack_bytes);
+  RolloutArgs ra{};
+  if (!plan_smem(Kp_b, max(Ks, 16), Kp_h, b.max_stage, ra.sm, false))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: tiles do not fit shared memory");
+  b.finalize_blocks(ra.sm.stage_bytes);
+  ra.prog = b.prog;
+  ra.wpack = static_cast<const uint16_t*>(ws);
+  ra.N = rows; ra.T = 1; ra.Be = k1; ra.S = k2; ra.A = 0; ra.Hi = 0; ra.J = 0;
+  ra.Kp_b = Kp_b; ra.Kp_sa = max(Ks, 16); ra.Kp_h = Kp_h; ra.act = m->activation;
+  ra.prev_belief = x1; ra.prev_state = x2; ra.mlp_out = y; ra.has_b1 = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long max_img = 0;
+  for (int i = 0; i < b.pack.njobs; ++i)
+    max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+  long long pgx = (max_img + 255) / 256;
+  if (pgx > 64) pgx = 64;
+  dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+  const long long ntiles = (rows + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  BD_CUDA_LAUNCH_CHECK();
+  return launch_rollout(fmt, m->activation, false, false, grid, ra, s);
 }
 
 }  // namespace tc

@@ -1,0 +1,293 @@
+// Host side of the tensor-core MLP backward (tc_mlp_bwd.cuh): program / pack tables, scratch
+// carving, row chunking, and the three launches (dgrad chain, streaming wgrad, unpack).
+#include "api_internal.h"
+#include "tc_mlp_bwd.cuh"
+#include "tc_builder.cuh"
+
+namespace bd {
+namespace tc {
+
+static inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct BwdPlan {
+  int L, k1, k2, Kp_b, Ks, Kp_h, Kp_g;
+  int n[BD_MAX_LAYERS], kp_xs[BD_MAX_LAYERS], kp_ds[BD_MAX_LAYERS];
+  size_t pack_elems;       // fwd images + transposed dgrad images
+  size_t per_tile_bytes;   // scratch images per 128-row tile
+  size_t dwp_bytes;        // fp32 gradient images
+  bool want_w;
+};
+
+static void make_plan(const bd_mlp& m, int k1, int k2, bool want_w, BwdPlan& p) {
+  p.L = m.n_layers; p.k1 = k1; p.k2 = k2; p.want_w = want_w;
+  p.Kp_b = r16(k1 + 1); p.Ks = k2 > 0 ? r16(k2) : 16;
+  p.Kp_h = 16; p.Kp_g = 16; p.pack_elems = 0; p.per_tile_bytes = 0; p.dwp_bytes = 0;
+  for (int l = 0; l < p.L; ++l) {
+    p.n[l] = m.layer[l].out_features;
+    p.kp_xs[l] = r16(p.n[l] + 1);
+    p.kp_ds[l] = r16(p.n[l]);
+    if (l + 1 < p.L) { p.Kp_h = max(p.Kp_h, p.kp_xs[l]); p.per_tile_bytes += 128 * p.kp_xs[l] * 2; }
+    p.Kp_g = max(p.Kp_g, p.kp_ds[l]);
+    const int kin = m.layer[l].in_features;
+    p.pack_elems += (size_t)r16(p.n[l]) * (l == 0 ? p.Kp_b + p.Ks : r16(kin + 1));   // forward images
+    p.pack_elems += (size_t)r16(kin) * r16(p.n[l]);                                   // W^T images
+    if (want_w) {
+      p.per_tile_bytes += 128 * p.kp_ds[l] * 2;
+      p.dwp_bytes += al256((size_t)256 * (l == 0 ? p.Kp_b : r16(kin + 1)) * 4);
+      if (l == 0 && k2 > 0) p.dwp_bytes += al256((size_t)256 * p.Ks * 4);
+    }
+  }
+  if (want_w) p.per_tile_bytes += 128 * (p.Kp_b + p.Ks) * 2;
+}
+
+bool mlp_backward_supported(const bd_mlp& m, int k1, int k2, int precision) {
+  if (!mlp_supported(m, k1, k2, precision)) return false;
+  if (k1 + k2 > 256) return false;                    // dX accumulator width
+  for (int l = 0; l < m.n_layers; ++l)
+    if (m.layer[l].out_features > 255) return false;
+  return m.n_layers >= 1;
+}
+
+static const int64_t kMaxBwdRows = 1 << 18;
+size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t rows) {
+  BwdPlan p;
+  make_plan(m, k1, k2, true, p);
+  int64_t r = rows < kMaxBwdRows ? rows : kMaxBwdRows;
+  size_t tiles = (size_t)((r + 127) / 128);
+  return al256(p.pack_elems * 2) + p.dwp_bytes + tiles * p.per_tile_bytes + 65536;
+}
+
+template <int FMT>
+static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStream_t s) {
+#define BD_LAUNCH_BWD(ACTV)                                                                          \
+  do {                                                                                               \
+    cudaFuncSetAttribute(mlp_bwd_kernel<FMT, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                         ba.sm.total);                                                               \
+    mlp_bwd_kernel<FMT, ACTV><<<grid, kThreads, ba.sm.total, s>>>(ba);                               \
+  } while (0)
+  switch (act) {
+    case BD_ACT_ELU: BD_LAUNCH_BWD(BD_ACT_ELU); break;
+    case BD_ACT_RELU: BD_LAUNCH_BWD(BD_ACT_RELU); break;
+    case BD_ACT_TANH: BD_LAUNCH_BWD(BD_ACT_TANH); break;
+    default: BD_LAUNCH_BWD(BD_ACT_IDENTITY); break;
+  }
+#undef BD_LAUNCH_BWD
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
+                 bd_stream_t stream) {
+  const int k1 = a->k1, k2 = a->k2, L = m->n_layers;
+  if (!mlp_backward_supported(*m, k1, k2, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: sizes/activation not supported");
+  bool want_w = false;
+  for (int l = 0; l < L; ++l) want_w |= (a->dw[l] != nullptr) || (a->db[l] != nullptr);
+  const bool want_dx = a->dx1 || a->dx2;
+  BwdPlan p;
+  make_plan(*m, k1, k2, want_w, p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+
+  // ---- program: forward recompute of the hidden layers, then the dgrad chain
+  Builder b;
+  for (int l = 0; l < L; ++l) {
+    const bd_linear& Lr = m->layer[l];
+    const int n = Lr.out_features, Np = r16(n);
+    if (l + 1 < L) {
+      const int d = b.dcol();
+      if (l == 0) {
+        uint32_t wb = b.add_pack(Lr.w, k1 + k2, 0, n, Np, p.Kp_b, 0, k1, Lr.b, k1);
+        b.add_gemm(wb, Np, p.Kp_b, TILE_BCUR, 0, d, 0);
+        if (k2 > 0) {
+          uint32_t wsx = b.add_pack(Lr.w, k1 + k2, 0, n, Np, p.Ks, k1, k2, nullptr, -1);
+          b.add_gemm(wsx, Np, p.Ks, TILE_SA, 0, d, 1);
+        }
+      } else {
+        const int kin = Lr.in_features, Kp = r16(kin + 1);
+        uint32_t w = b.add_pack(Lr.w, kin, 0, n, Np, Kp, 0, kin, Lr.b, kin);
+        b.add_gemm(w, Np, Kp, TILE_H, 0, d, 0);
+      }
+      b.end_phase(EPI_B_ACT_SAVE, 1, n, Np, p.kp_xs[l], d, l, TILE_H);
+    }
+  }
+  b.end_phase(EPI_B_LOAD_DY, 1, m->layer[L - 1].out_features, 0, 0, 0, L - 1, TILE_H2);
+  for (int l = L - 1; l >= 0; --l) {
+    const bd_linear& Lr = m->layer[l];
+    const int kin = Lr.in_features, n = Lr.out_features;
+    if (l == 0 && !want_dx) break;
+    const int Np = r16(kin), Kp = r16(n);
+    if (b.pack.njobs >= kMaxPackJobs) BD_FAIL(BD_ERR_UNSUPPORTED, "mlp_backward: too many layers");
+    // W^T image: packed(n_in, k_out) = W[k_out, n_in]
+    PackJob& j = b.pack.job[b.pack.njobs++];
+    j = PackJob{};
+    j.w = Lr.w; j.bias = nullptr; j.dst_off = b.w_elems; j.ld = kin; j.row0 = 0; j.N = kin; j.Np = Np;
+    j.Kp = Kp; j.bias_k = -1; j.nseg = 1; j.seg[0] = {0, 0, n}; j.transpose = 1;
+    const uint32_t woff = (uint32_t)b.w_elems;
+    b.w_elems += (long long)Np * Kp;
+    const int d = b.dcol();
+    b.add_gemm(woff, Np, Kp, TILE_H2, 0, d, 0);
+    if (l > 0) b.end_phase(EPI_B_DACT, 1, kin, Np, p.kp_ds[l - 1], d, l - 1, TILE_H2);
+    else b.end_phase(EPI_B_DX, 1, kin, Np, 0, d, 0, TILE_H2);
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: program too large");
+
+  // ---- workspace carve
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = base + off; off += al256(bytes); return r; };
+  uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
+  float* dwp[BD_MAX_LAYERS][2] = {};
+  int dwp_kp[BD_MAX_LAYERS][2] = {};
+  if (want_w) {
+    const size_t start = off;
+    for (int l = 0; l < L; ++l) {
+      dwp_kp[l][0] = (l == 0) ? p.Kp_b : r16(m->layer[l].in_features + 1);
+      dwp[l][0] = reinterpret_cast<float*>(take((size_t)256 * dwp_kp[l][0] * 4));
+      if (l == 0 && k2 > 0) {
+        dwp_kp[l][1] = p.Ks;
+        dwp[l][1] = reinterpret_cast<float*>(take((size_t)256 * p.Ks * 4));
+      }
+    }
+    cudaMemsetAsync(base + start, 0, off - start, s);
+  }
+  if (off + p.per_tile_bytes + 4096 > ws_bytes)
+    BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_backward: workspace %zu too small", ws_bytes);
+  long long chunk_tiles = (long long)((ws_bytes - off - 4096) / (p.per_tile_bytes ? p.per_tile_bytes : 1));
+  const long long total_tiles = (a->rows + 127) / 128;
+  if (chunk_tiles > total_tiles) chunk_tiles = total_tiles;
+  if (chunk_tiles < 1) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_backward: workspace too small");
+  char* scratch = base + off;
+
+  // ---- pack weights once
+  {
+    long long max_img = 0;
+    for (int i = 0; i < b.pack.njobs; ++i)
+      max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+    long long pgx = (max_img + 255) / 256;
+    if (pgx > 64) pgx = 64;
+    dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+    if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    BD_CUDA_LAUNCH_CHECK();
+  }
+
+  MlpBwdArgs ba{};
+  {
+    // tiles: B0 | SA | H | G
+    SmemPlan& sm = ba.sm;
+    uint32_t o = 0;
+    auto tk = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 1023) & ~1023u; return r; };
+    sm.off_tile[0] = tk(kTileRows * p.Kp_b * 2);
+    sm.off_tile[1] = sm.off_tile[0];
+    sm.off_tile[2] = tk(kTileRows * p.Ks * 2);
+    sm.off_tile[3] = tk(kTileRows * p.Kp_h * 2);
+    sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);
+    sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
+    sm.off_ring = o;
+    const uint32_t budget = 227 * 1024 - 2048;
+    if (o + 2 * sm.stage_bytes > budget)
+      BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: tiles do not fit shared memory");
+    sm.nstage = min(8u, (budget - o) / sm.stage_bytes);
+    sm.total = o + sm.nstage * sm.stage_bytes + 1024;
+  }
+  b.finalize_blocks(ba.sm.stage_bytes);
+  ba.prog = b.prog;
+  ba.wpack = wpack; ba.T = 1; ba.prof = nullptr;
+  ba.k1 = k1; ba.k2 = k2; ba.out = m->layer[L - 1].out_features; ba.n_layers = L; ba.act = m->activation;
+  ba.Kp_b = p.Kp_b; ba.Ks = p.Ks; ba.Kp_h = p.Kp_h; ba.Kp_g = p.Kp_g; ba.want_images = want_w ? 1 : 0;
+  for (int l = 0; l < L; ++l) { ba.kp_xs[l] = p.kp_xs[l]; ba.kp_ds[l] = p.kp_ds[l]; }
+
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int out = ba.out;
+
+  for (long long t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
+    const long long nt = chunk_tiles < total_tiles - t0 ? chunk_tiles : total_tiles - t0;
+    const long long r0 = t0 * 128;
+    long long nrows = a->rows - r0;
+    if (nrows > nt * 128) nrows = nt * 128;
+    // scratch images for this chunk
+    size_t so = 0;
+    auto st = [&](size_t bytes) { char* r = scratch + so; so += bytes; return reinterpret_cast<uint16_t*>(r); };
+    for (int l = 0; l + 1 < L; ++l) ba.xs[l] = st((size_t)nt * 128 * p.kp_xs[l] * 2);
+    for (int l = 0; l < L; ++l) ba.ds[l] = want_w ? st((size_t)nt * 128 * p.kp_ds[l] * 2) : nullptr;
+    if (!want_w) ba.ds[L - 1] = nullptr;
+    ba.x0b = want_w ? st((size_t)nt * 128 * p.Kp_b * 2) : nullptr;
+    ba.x0s = want_w ? st((size_t)nt * 128 * p.Ks * 2) : nullptr;
+    ba.N = nrows;
+    ba.x1 = a->x1 + r0 * k1;
+    ba.x2 = a->x2 ? a->x2 + r0 * k2 : nullptr;
+    ba.dy = a->dy + r0 * out;
+    ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
+    ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
+    const unsigned grid = (unsigned)(nt < sms ? nt : sms);
+    if (fmt == 0) BD_TRY(launch_bwd_act<0>(m->activation, grid, ba, s));
+    else BD_TRY(launch_bwd_act<1>(m->activation, grid, ba, s));
+
+    if (want_w) {
+      WgradArgs wa{};
+      int nj = 0;
+      uint32_t max_x = 0;
+      for (int l = 0; l < L; ++l) {
+        if (!a->dw[l] && !a->db[l]) continue;
+        for (int part = 0; part < 2; ++part) {
+          if (!dwp[l][part]) continue;
+          WgradJob& j = wa.job[nj++];
+          j.dyimg = ba.ds[l]; j.kp_dy = p.kp_ds[l]; j.m_valid = m->layer[l].out_features;
+          j.dwp = dwp[l][part]; j.kp_x = dwp_kp[l][part];
+          j.ximg = (l == 0) ? (part == 0 ? ba.x0b : ba.x0s) : ba.xs[l - 1];
+          max_x = max(max_x, (uint32_t)j.kp_x);
+        }
+      }
+      if (nj > 0) {
+        wa.ntiles = nt;
+        wa.stage_bytes = 128 * 256 * 2 + ((128 * max_x * 2 + 1023) & ~1023u);
+        wa.nstage = (2 * wa.stage_bytes <= 220 * 1024) ? 2 : 1;
+        const size_t smem = (size_t)wa.nstage * wa.stage_bytes;
+        long long per = (sms + nj - 1) / nj;
+        if (per > nt) per = nt;
+        if (per < 1) per = 1;
+        dim3 wgrid((unsigned)per, (unsigned)nj);
+        if (fmt == 0) {
+          cudaFuncSetAttribute(wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          wgrad_kernel<0><<<wgrid, 128, smem, s>>>(wa);
+        } else {
+          cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          wgrad_kernel<1><<<wgrid, 128, smem, s>>>(wa);
+        }
+        BD_CUDA_LAUNCH_CHECK();
+      }
+    }
+  }
+
+  if (want_w) {
+    UnpackTable ut{};
+    for (int l = 0; l < L; ++l) {
+      if (!a->dw[l] && !a->db[l]) continue;
+      for (int part = 0; part < 2; ++part) {
+        if (!dwp[l][part]) continue;
+        UnpackJob& u = ut.job[ut.njobs++];
+        const bd_linear& Lr = m->layer[l];
+        u.dwp = dwp[l][part]; u.dw = a->dw[l]; u.db = part == 0 ? a->db[l] : nullptr;
+        u.kp = dwp_kp[l][part]; u.n = Lr.out_features; u.ld = Lr.in_features; u.nseg = 1;
+        if (l == 0) {
+          u.seg[0] = part == 0 ? PackSeg{0, 0, k1} : PackSeg{0, k1, k2};
+          u.bias_k = part == 0 ? k1 : -1;
+        } else {
+          u.seg[0] = PackSeg{0, 0, Lr.in_features};
+          u.bias_k = Lr.in_features;
+        }
+      }
+    }
+    if (ut.njobs > 0) {
+      unpack_dw_kernel<<<dim3(32, ut.njobs), 256, 0, s>>>(ut);
+      BD_CUDA_LAUNCH_CHECK();
+    }
+  }
+  return BD_OK;
+}
+
+}  // namespace tc
+}  // namespace bd

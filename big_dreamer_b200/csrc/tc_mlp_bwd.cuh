@@ -1,0 +1,391 @@
+// Tensor-core backward of a build_mlp chain (DenseModel; the reward / value heads and the actor
+// inside Dreamer's behaviour-learning block): per 128-row tile, recompute the hidden activations,
+// run the dgrad chain dY_{l-1} = (dY_l W_l) . act'(h_{l-1}) on tcgen05, and -- when parameter
+// gradients are wanted -- leave 16-bit KM8 images of every layer input X_l and every dY_l in a
+// scratch area.  A second, streaming kernel (wgrad_kernel) then contracts those images over the
+// row dimension with MN-major UMMA descriptors (the same tile viewed transposed), accumulating
+// dW for one layer per CTA in TMEM across all of its tiles and flushing once.  The constant-1
+// column of X_l makes the bias gradient fall out of the same contraction.
+#pragma once
+#include "tc_engine.cuh"
+
+namespace bd {
+namespace tc {
+
+enum MlpBwdEpi : uint8_t {
+  EPI_B_ACT_SAVE = 1,  // forward recompute: h_l = act(D) -> H tile + scratch image
+  EPI_B_LOAD_DY = 2,   // (no MMA) dy -> G tile
+  EPI_B_DACT = 3,      // dY_{l-1} = D . act'(h_{l-1}) -> G tile
+  EPI_B_DX = 4         // d[x1 | x2] = D -> global
+};
+
+struct MlpBwdArgs {
+  Program prog;
+  SmemPlan sm;
+  const uint16_t* wpack;
+  long long N;
+  int T;  // = 1
+  long long* prof;
+  int k1, k2, out, n_layers, act;
+  int Kp_b, Ks, Kp_h, Kp_g;
+  int want_images;              // 1: also dump X / dY images for wgrad
+  const float *x1, *x2, *dy;
+  float *dx1, *dx2;
+  uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
+  uint16_t* ds[BD_MAX_LAYERS];  // ds[l]: images of dY_l (cols kp_ds[l]), l = 0..L-1
+  uint16_t *x0b, *x0s;          // images of [x1 | 1] and x2
+  int kp_xs[BD_MAX_LAYERS], kp_ds[BD_MAX_LAYERS];
+};
+
+template <int ACT>
+__device__ __forceinline__ float tc_dact_from_out(float y) {
+  if (ACT == BD_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+  if (ACT == BD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (ACT == BD_ACT_TANH) return 1.f - y * y;
+  return 1.f;
+}
+template <int FMT>
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (FMT == 0) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+      const float2 f = __half22float2(h);
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    } else {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      const float2 f = __bfloat1622float2(h);
+      v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+  }
+}
+template <int FMT>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(Half16<FMT>::pack2(v[0], v[1]), Half16<FMT>::pack2(v[2], v[3]),
+                    Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
+}
+
+template <int FMT, int ACT>
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ MlpBwdArgs A_) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const MlpBwdArgs& a = A_;
+  uint8_t* smem = smem_raw;
+  __shared__ EngineShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
+  const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
+  const Program& P = a.prog;
+
+  if (warp == 0) {
+    producer_role(P, a.sm, a.wpack, ntiles, 1, smem, sh);
+  } else if (warp == 1) {
+    issuer_role<FMT, false>(P, a.sm, ntiles, 1, smem, sh, tmem_base, nullptr);
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int etid = tid - 64;
+    const uint32_t rowoff = (row >> 3) * 128 + (row & 7) * 16;   // byte offset of this row in a KM8 group
+    uint8_t* B0 = smem + a.sm.off_tile[0];
+    uint8_t* SA = smem + a.sm.off_tile[2];
+    uint8_t* H = smem + a.sm.off_tile[3];
+    uint8_t* Gt = smem + a.sm.off_tile[4];
+    uint32_t Ge = 0, Gm = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long grow = tile * kTileRows + row;
+      const bool rvalid = grow < a.N;
+      // ---------------- init: B0 <- [x1 | 1], SA <- x2 (and their images for wgrad)
+      {
+        const int gb = a.Kp_b >> 3;
+        for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
+          const int kg = i / kTileRows, r = i - kg * kTileRows;
+          const long long gr = tile * kTileRows + r;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            v[j] = (k < a.k1) ? ((gr < a.N) ? a.x1[gr * a.k1 + k] : 0.f) : ((k == a.k1 && gr < a.N) ? 1.f : 0.f);
+          }
+          const uint4 u = pack8<FMT>(v);
+          *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
+          if (a.want_images)
+            *reinterpret_cast<uint4*>(a.x0b + (size_t)tile * kTileRows * a.Kp_b + (size_t)kg * kTileRows * 8 + r * 8) = u;
+        }
+        const int gs = a.Ks >> 3;
+        for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
+          const int kg = i / kTileRows, r = i - kg * kTileRows;
+          const long long gr = tile * kTileRows + r;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = kg * 8 + j;
+            v[j] = (k < a.k2 && gr < a.N) ? a.x2[gr * a.k2 + k] : 0.f;
+          }
+          const uint4 u = pack8<FMT>(v);
+          *reinterpret_cast<uint4*>(SA + kg * kLboA + r * 16) = u;
+          if (a.want_images)
+            *reinterpret_cast<uint4*>(a.x0s + (size_t)tile * kTileRows * a.Ks + (size_t)kg * kTileRows * 8 + r * 8) = u;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&sh.epi_done[Ge & 3]);
+        ++Ge;
+      }
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        const Phase ph = P.p[pi];
+        const uint32_t tacc = trow + ph.d_col;
+        mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);
+        tc_fence_after_sync();
+        switch (ph.epi) {
+          case EPI_B_ACT_SAVE: {
+            const int l = ph.aux0, nv = ph.n_valid;
+            uint16_t* img = a.xs[l] + (size_t)tile * kTileRows * ph.Kp_out;
+            for (int c = half * 32; c < ph.Kp_out; c += 64) {
+              float v[32];
+              const bool two = (c + 16) < ph.Kp_out;
+              if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
+              else {
+                if (c < ph.Np) tmem_ld16(tacc + c, v);
+                if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tc_act_t<ACT>(v[j]);
+              if (c + 32 > nv) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int col = c + j;
+                  if (col >= nv) v[j] = (col == nv && rvalid) ? 1.f : 0.f;
+                }
+              }
+              if (!rvalid) {   // padded rows carry exact zeros so they add nothing to dW / db
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
+              uint8_t* p = H + (c >> 3) * kLboA + rowoff;
+              uint16_t* gi = img + (size_t)(c >> 3) * kTileRows * 8 + row * 8;
+              const int ngroups = two ? 4 : 2;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                if (g8 < ngroups) {
+                  const uint4 u = pack8<FMT>(v + 8 * g8);
+                  *reinterpret_cast<uint4*>(p + g8 * kLboA) = u;
+                  *reinterpret_cast<uint4*>(gi + (size_t)g8 * kTileRows * 8) = u;
+                }
+              }
+            }
+          } break;
+          case EPI_B_LOAD_DY: {
+            const int l = a.n_layers - 1, kp = a.kp_ds[l];
+            uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
+            for (int c = half * 8; c < kp; c += 16) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[j] = (rvalid && c + j < a.out) ? a.dy[grow * a.out + c + j] : 0.f;
+              const uint4 u = pack8<FMT>(v);
+              *reinterpret_cast<uint4*>(Gt + (c >> 3) * kLboA + rowoff) = u;
+              if (a.want_images) *reinterpret_cast<uint4*>(img + (size_t)(c >> 3) * kTileRows * 8 + row * 8) = u;
+            }
+          } break;
+          case EPI_B_DACT: {
+            const int l = ph.aux0;          // produces dY_l from D and h_l
+            const int nv = ph.n_valid, kp = a.kp_ds[l];
+            const uint16_t* himg = a.xs[l] + (size_t)tile * kTileRows * a.kp_xs[l];
+            uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
+            for (int c = half * 32; c < kp; c += 64) {
+              float v[32];
+              const bool two = (c + 16) < kp;
+              const int ngroups = two ? 4 : 2;
+              uint4 hu[4];
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8)
+                if (g8 < ngroups)
+                  hu[g8] = *reinterpret_cast<const uint4*>(himg + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8);
+              if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
+              else {
+                if (c < ph.Np) tmem_ld16(tacc + c, v);
+                if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                if (g8 < ngroups) {
+                  float h[8];
+                  unpack8<FMT>(hu[g8], h);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const int col = c + g8 * 8 + j;
+                    v[g8 * 8 + j] = (col < nv && rvalid) ? v[g8 * 8 + j] * tc_dact_from_out<ACT>(h[j]) : 0.f;
+                  }
+                  const uint4 u = pack8<FMT>(v + 8 * g8);
+                  *reinterpret_cast<uint4*>(Gt + ((c >> 3) + g8) * kLboA + rowoff) = u;
+                  if (a.want_images)
+                    *reinterpret_cast<uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8) = u;
+                }
+              }
+            }
+          } break;
+          case EPI_B_DX: {
+            const int nin = a.k1 + a.k2;
+            for (int c = half * 16; c < ph.Np; c += 32) {
+              float v[16];
+              tmem_ld16(tacc + c, v);
+              tmem_ld_wait();
+              if (rvalid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int col = c + j;
+                  if (col < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + col] = v[j]; }
+                  else if (col < nin) { if (a.dx2) a.dx2[grow * a.k2 + (col - a.k1)] = v[j]; }
+                }
+              }
+            }
+          } break;
+          default: break;
+        }
+        tc_fence_before_sync();
+        fence_proxy_async_smem();
+        mbar_arrive(&sh.epi_done[Ge & 3]);
+        ++Ge;
+        ++Gm;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming wgrad:  dWp[m, k] += sum_rows dY[row, m] * X[row, k]   per (job = layer part).
+// A = dY image and B = X image are the [128 rows x cols] KM8 tiles viewed as MN-major operands
+// (M/N = feature index, K = row): 8 features x 16 B is again a canonical core matrix, with
+// SBO = 2048 B between feature groups and LBO = 128 B between 8-row groups.
+// ---------------------------------------------------------------------------------------------
+struct WgradJob {
+  const uint16_t* dyimg;   // per tile: 128 * kp_dy elements
+  const uint16_t* ximg;    // per tile: 128 * kp_x elements
+  float* dwp;              // (256, kp_x) fp32, zero-initialised, accumulated with atomics
+  int kp_dy, kp_x, m_valid;
+};
+struct WgradArgs {
+  WgradJob job[BD_MAX_LAYERS + 1];
+  long long ntiles;
+  uint32_t stage_bytes, nstage;
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int ab_format, int M, int N) {
+  return make_idesc_f16(ab_format, M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ WgradArgs A_) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const WgradArgs& a = A_;
+  const WgradJob j = a.job[blockIdx.y];
+  __shared__ uint64_t full[2], empty[2], done;
+  __shared__ uint32_t tmem_holder;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_holder);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_holder;
+  const int nmt = j.m_valid > 128 ? 2 : 1;
+  const uint32_t bytes_dy = 128u * j.kp_dy * 2, bytes_x = 128u * j.kp_x * 2;
+  const long long first = blockIdx.x;
+  const bool any = first < a.ntiles;
+
+  if (warp == 0) {
+    uint32_t st = 0, ph = 0;
+    for (long long tile = first; tile < a.ntiles; tile += gridDim.x) {
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* dst = smem + st * a.stage_bytes;
+        mbar_expect_tx(&full[st], bytes_dy + bytes_x);
+        tma_bulk_g2s(dst, j.dyimg + (size_t)tile * 128 * j.kp_dy, bytes_dy, &full[st]);
+        tma_bulk_g2s(dst + 128 * 256 * 2, j.ximg + (size_t)tile * 128 * j.kp_x, bytes_x, &full[st]);
+      }
+      __syncwarp();
+      if (++st == a.nstage) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    uint32_t st = 0, ph = 0;
+    const uint32_t idesc = make_idesc_f16_mn(FMT, 128, j.kp_x);
+    uint32_t acc = 0;
+    for (long long tile = first; tile < a.ntiles; tile += gridDim.x) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after_sync();
+      const uint32_t base = smem_u32(smem + st * a.stage_bytes);
+      if (elect_one()) {
+        for (int mt = 0; mt < nmt; ++mt) {
+          // dY image has kp_dy columns; the second M tile may run past them into the (finite-or-not)
+          // tail of the stage: those accumulator rows (>= m_valid) are never read back.
+          const uint64_t ad0 = make_smem_desc(base + mt * 16 * kLboA, 128, kLboA);
+          const uint64_t bd0 = make_smem_desc(base + 128 * 256 * 2, 128, kLboA);
+          for (int ks = 0; ks < 8; ++ks)   // K = 128 rows, 16 per MMA = two 8-row groups of 128 B
+            umma_f16(tmem_base + mt * 256, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), idesc,
+                     (acc | (uint32_t)ks) ? 1u : 0u);
+        }
+        umma_commit(&empty[st]);
+      }
+      __syncwarp();
+      acc = 1;
+      if (++st == a.nstage) { st = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(&done);
+    __syncwarp();
+  }
+  // flush: every warp reads its 32 accumulator lanes (= output features)
+  mbar_wait(&done, 0);
+  tc_fence_after_sync();
+  if (any) {
+    for (int mt = 0; mt < nmt; ++mt) {
+      const int m = mt * 128 + tid;
+      for (int c = 0; c < j.kp_x; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * 256 + c, v);
+        tmem_ld_wait();
+        if (m < j.m_valid) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) atomicAdd(j.dwp + (size_t)m * j.kp_x + c + jj, v[jj]);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dw / db (+=) from the packed fp32 gradient image, using the forward pack job as the map
+struct UnpackJob {
+  const float* dwp;
+  float *dw, *db;
+  int kp, n, ld, nseg, bias_k;
+  PackSeg seg[3];
+};
+struct UnpackTable { int njobs; UnpackJob job[BD_MAX_LAYERS + 1]; };
+
+static __global__ void unpack_dw_kernel(const __grid_constant__ UnpackTable tab) {
+  const UnpackJob& j = tab.job[blockIdx.y];
+  for (int s = 0; s < j.nseg; ++s) {
+    const int total = j.n * j.seg[s].len;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int n = i / j.seg[s].len, c = i - n * j.seg[s].len;
+      if (j.dw) j.dw[(size_t)n * j.ld + j.seg[s].src_c0 + c] += j.dwp[(size_t)n * j.kp + j.seg[s].dst_k0 + c];
+    }
+  }
+  if (j.db && j.bias_k >= 0)
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < j.n; n += gridDim.x * blockDim.x)
+      j.db[n] += j.dwp[(size_t)n * j.kp + j.bias_k];
+}
+
+}  // namespace tc
+}  // namespace bd

@@ -30,6 +30,65 @@ def test_imagine_actor_loss_tc(d, prec):
     res = pu.run_imagine_case(d, seed=3, precision=prec, oracle_dtype=torch.float64)
     errs = res["errors"]
     print(prec, d, {k: f"{v:.2e}" for k, v in errs.items()})
-    tol = TOL if prec == "fp16" else 3e-2
+    tol = TOL if prec == "fp16" else 5e-2   # bf16: documented looser bound (7-bit mantissa)
     for k, e in errs.items():
         assert e < tol, errs
+
+
+@pytest.mark.parametrize("shape", [((14, 300), 200, 30, 200, 1, "ELU"), ((130,), 48, 10, 40, 3, "Tanh"),
+                                   ((3, 4), 17, 0, 24, 5, "ReLU"), ((1,), 32, 30, 32, 1, "ELU")])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_dense_model_tc(shape, prec):
+    from oracle import rssm_oracle as orc
+    lead, k1, k2, hid, out, act = shape
+    g = torch.Generator().manual_seed(1)
+    sd = orc.make_mlp_sd(g, [k1 + k2] + [hid] * 4 + [out])
+    x1 = torch.randn(*lead, k1, generator=g)
+    x2 = torch.randn(*lead, k2, generator=g) if k2 else None
+    ref = orc.dense({k: v.double() for k, v in sd.items()}, act,
+                    *([x1.double(), x2.double()] if k2 else [x1.double()]))
+    dm = bd.DenseModel(k1 + k2, hid, out, act).cuda()
+    dm.load_state_dict(sd)
+    bd.set_precision(prec)
+    with torch.no_grad():
+        y = dm(*([x1.cuda(), x2.cuda()] if k2 else [x1.cuda()]))
+    err = pu.relerr(y, ref.float())
+    assert y.shape == ref.shape
+    assert err < (3e-3 if prec == "fp16" else 3e-2), err
+
+
+@pytest.mark.parametrize("shape", [((14, 300), 200, 30, 200, 1, "ELU"), ((130,), 48, 10, 40, 3, "Tanh"),
+                                   ((3, 4), 17, 0, 24, 5, "ReLU"), ((1,), 32, 30, 32, 1, "ELU"),
+                                   ((700,), 200, 30, 200, 2, "ELU")])
+@pytest.mark.parametrize("freeze", [False, True])
+def test_dense_model_tc_backward(shape, freeze):
+    """dgrad chain + streaming wgrad on tcgen05 vs fp64 autograd of the oracle."""
+    from oracle import rssm_oracle as orc
+    lead, k1, k2, hid, out, act = shape
+    g = torch.Generator().manual_seed(2)
+    sd = orc.make_mlp_sd(g, [k1 + k2] + [hid] * 4 + [out])
+    x1 = torch.randn(*lead, k1, generator=g)
+    x2 = torch.randn(*lead, k2, generator=g) if k2 else None
+    cot = torch.randn(*lead, out, generator=g)
+    sdc = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    x1c = x1.double().requires_grad_(True)
+    x2c = x2.double().requires_grad_(True) if k2 else None
+    ref = orc.dense(sdc, act, *([x1c, x2c] if k2 else [x1c]))
+    (ref * cot.double()).sum().backward()
+    dm = bd.DenseModel(k1 + k2, hid, out, act).cuda()
+    dm.load_state_dict(sd)
+    if freeze:
+        pu.freeze(dm)
+    bd.set_precision("fp16")
+    x1g = x1.cuda().requires_grad_(True)
+    x2g = x2.cuda().requires_grad_(True) if k2 else None
+    y = dm(*([x1g, x2g] if k2 else [x1g]))
+    (y * cot.cuda()).sum().backward()
+    assert pu.relerr(x1g.grad, x1c.grad.float()) < 5e-3
+    if k2:
+        assert pu.relerr(x2g.grad, x2c.grad.float()) < 5e-3
+    for k, p in dm.state_dict(keep_vars=True).items():
+        if freeze:
+            assert p.grad is None
+        else:
+            assert pu.relerr(p.grad, sdc[k].grad.float()) < 5e-3, k
