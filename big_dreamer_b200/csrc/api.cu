@@ -109,6 +109,11 @@ size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, 
   if (!(r && actor)) return 0;
   size_t f = f32::imagine_workspace_bytes(r, actor, T, N, backward);
   size_t t = tc::imagine_pack_bytes(*r, *actor);
+  if (backward) {   // tensor-core modes: d_raw (T,N,2A) + the larger of the BPTT / actor-MLP workspaces
+    size_t mb = tc::mlp_backward_workspace_bytes(*actor, r->belief_size, r->state_size, (int64_t)T * N);
+    size_t draw = ((size_t)T * N * 2 * r->action_size * sizeof(float) + 255) & ~size_t(255);
+    t = draw + (mb > f ? mb : f);
+  }
   return f > t ? f : t;
 }
 int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
@@ -123,6 +128,32 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
                         bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
+  const bd_imagine_args& f = a->fwd;
+  bool want_actor = false;
+  for (int l = 0; l < f.actor.n_layers; ++l) want_actor |= (a->actor_dw[l] || a->actor_db[l]);
+  if (precision != BD_PREC_FP32 && want_actor && f.T >= 1 && f.N > 0 &&
+      tc::mlp_backward_supported(f.actor, f.rssm.belief_size, f.rssm.state_size, precision)) {
+    // BPTT dgrad chain (fp32 kernels) -> d_raw for every step; then the actor's recompute + dgrad +
+    // wgrad as two batched tensor-core MLP backwards (step 0 reads prev_*, steps 1.. read the outputs)
+    const int A = f.rssm.action_size, Be = f.rssm.belief_size, S = f.rssm.state_size;
+    const size_t draw_bytes = ((size_t)f.T * f.N * 2 * A * sizeof(float) + 255) & ~size_t(255);
+    BD_CHECK_ARG(ws_bytes > draw_bytes + 65536, "bd_imagine_backward: workspace too small");
+    float* d_raw = static_cast<float*>(ws);
+    void* rest = static_cast<char*>(ws) + draw_bytes;
+    const size_t rest_bytes = ws_bytes - draw_bytes;
+    BD_TRY(f32::imagine_backward_ex(a, rest, rest_bytes, stream, d_raw));
+    bd_mlp_bwd_args m{};
+    m.k1 = Be; m.k2 = S;
+    for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }
+    m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = f.N; m.dy = d_raw;
+    BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream));
+    if (f.T > 1) {
+      m.x1 = f.beliefs; m.x2 = f.states; m.rows = (int64_t)(f.T - 1) * f.N;
+      m.dy = d_raw + (size_t)f.N * 2 * A;
+      BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream));
+    }
+    return BD_OK;
+  }
   return f32::imagine_backward(a, ws, ws_bytes, stream);
 }
 

@@ -539,6 +539,13 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, bd_stre
 }
 
 int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream) {
+  return imagine_backward_ex(a, ws, ws_bytes, stream, nullptr);
+}
+
+// d_raw_all != nullptr: write the gradient wrt the raw actor outputs of every step to
+// d_raw_all (T,N,2A) and leave the actor's own backward to the caller (tensor-core path).
+int imagine_backward_ex(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+                        float* d_raw_all) {
   const bd_imagine_args& f = a->fwd;
   BD_TRY(check_imagine(f));
   if (f.N == 0) return BD_OK;
@@ -551,6 +558,7 @@ int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd
   const int aw = mlp_max_width(actor);
   bool want_actor = false;
   for (int l = 0; l < actor.n_layers; ++l) want_actor |= (a->actor_dw[l] || a->actor_db[l]);
+  if (d_raw_all) want_actor = true;
   for (long long r0 = 0; r0 < N; r0 += chunk) {
     int nr = (int)((N - r0) < chunk ? (N - r0) : chunk);
     Arena ar(ws, ws_bytes);
@@ -584,8 +592,9 @@ int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd
         actor_head_bwd_kernel<<<grid1d((long long)nr * A), 256, 0, s>>>(
             f.actor_raw + o * 2 * A, f.eps_a + o * A, f.actions + o * A, f.dent + o * 2 * A,
             w.dsa + Sz, Sz + A, a->g_entropy ? a->g_entropy + o : nullptr, f.actor_cfg, nr, (int)A,
-            d_raw);
+            d_raw_all ? d_raw_all + o * 2 * A : d_raw);
         BD_CUDA_LAUNCH_CHECK();
+        if (d_raw_all) continue;
         // actor inputs are detached (src/dreamer.py:215): recompute hiddens, wgrad only
         BD_TRY(mlp_forward_rows(actor, b_prev, (int)Be, Be, s_prev, (int)Sz, Sz, nr, hid, d0, 2 * A, s));
         BD_TRY(mlp_backward_rows(actor, b_prev, (int)Be, Be, s_prev, (int)Sz, Sz, nr, hid, d_raw,

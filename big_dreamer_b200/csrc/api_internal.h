@@ -26,6 +26,8 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
 size_t imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N, int backward);
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
 int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int imagine_backward_ex(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+                        float* d_raw_all);
 size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H);
 int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
 int cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,

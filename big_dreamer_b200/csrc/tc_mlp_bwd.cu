@@ -54,7 +54,7 @@ size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t row
   make_plan(m, k1, k2, true, p);
   int64_t r = rows < kMaxBwdRows ? rows : kMaxBwdRows;
   size_t tiles = (size_t)((r + 127) / 128);
-  return al256(p.pack_elems * 2) + p.dwp_bytes + tiles * p.per_tile_bytes + 65536;
+  return al256(p.pack_elems * 2) + 256 + p.dwp_bytes + tiles * p.per_tile_bytes + 65536;
 }
 
 template <int FMT>
@@ -137,6 +137,15 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   size_t off = 0;
   auto take = [&](size_t bytes) { char* r = base + off; off += al256(bytes); return r; };
   uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
+  unsigned int* amax = reinterpret_cast<unsigned int*>(take(256));
+  cudaMemsetAsync(amax, 0, 256, s);
+  {
+    const long long n = a->rows * m->layer[L - 1].out_features;
+    long long g = (n + 255) / 256;
+    if (g > 1184) g = 1184;
+    absmax_kernel<<<(unsigned)(g < 1 ? 1 : g), 256, 0, s>>>(a->dy, n, amax);
+    BD_CUDA_LAUNCH_CHECK();
+  }
   float* dwp[BD_MAX_LAYERS][2] = {};
   int dwp_kp[BD_MAX_LAYERS][2] = {};
   if (want_w) {
@@ -193,7 +202,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   }
   b.finalize_blocks(ba.sm.stage_bytes);
   ba.prog = b.prog;
-  ba.wpack = wpack; ba.T = 1; ba.prof = nullptr;
+  ba.wpack = wpack; ba.T = 1; ba.prof = nullptr; ba.amax_bits = amax;
   ba.k1 = k1; ba.k2 = k2; ba.out = m->layer[L - 1].out_features; ba.n_layers = L; ba.act = m->activation;
   ba.Kp_b = p.Kp_b; ba.Ks = p.Ks; ba.Kp_h = p.Kp_h; ba.Kp_g = p.Kp_g; ba.want_images = want_w ? 1 : 0;
   for (int l = 0; l < L; ++l) { ba.kp_xs[l] = p.kp_xs[l]; ba.kp_ds[l] = p.kp_ds[l]; }
@@ -243,6 +252,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
       }
       if (nj > 0) {
         wa.ntiles = nt;
+        wa.amax_bits = amax;
         wa.stage_bytes = 128 * 256 * 2 + ((128 * max_x * 2 + 1023) & ~1023u);
         wa.nstage = (2 * wa.stage_bytes <= 220 * 1024) ? 2 : 1;
         const size_t smem = (size_t)wa.nstage * wa.stage_bytes;

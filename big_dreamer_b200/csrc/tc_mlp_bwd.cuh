@@ -35,7 +35,37 @@ struct MlpBwdArgs {
   uint16_t* ds[BD_MAX_LAYERS];  // ds[l]: images of dY_l (cols kp_ds[l]), l = 0..L-1
   uint16_t *x0b, *x0s;          // images of [x1 | 1] and x2
   int kp_xs[BD_MAX_LAYERS], kp_ds[BD_MAX_LAYERS];
+  const unsigned int* amax_bits;  // device: bit pattern of max|dy| (see grad_scale)
 };
+
+// Gradients reach this kernel scaled by 1/(T*N) and can sit far below fp16's normal range, so the
+// 16-bit operands carry dy * 2^k with k chosen (on the device, from max|dy|) so that the largest
+// magnitude lands in [128, 256); results are multiplied by 2^-k on the way out.  Powers of two
+// make the scaling exact.
+__device__ __forceinline__ float grad_scale(const unsigned int* amax_bits, float* inv) {
+  const float amax = __uint_as_float(*amax_bits);
+  int e = 0;
+  float sc = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) {
+    frexpf(amax, &e);
+    int k = 8 - e;
+    k = max(-100, min(100, k));
+    sc = ldexpf(1.f, k);
+  }
+  *inv = 1.f / sc;
+  return sc;
+}
+static __global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned int* out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    if (v < 3.0e38f) m = fmaxf(m, v);      // ignore inf / nan
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
 
 template <int ACT>
 __device__ __forceinline__ float tc_dact_from_out(float y) {
@@ -92,6 +122,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
     uint8_t* H = smem + a.sm.off_tile[3];
     uint8_t* Gt = smem + a.sm.off_tile[4];
     uint32_t Ge = 0, Gm = 0;
+    float inv_scale;
+    const float scale = grad_scale(a.amax_bits, &inv_scale);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
@@ -182,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                v[j] = (rvalid && c + j < a.out) ? a.dy[grow * a.out + c + j] : 0.f;
+                v[j] = (rvalid && c + j < a.out) ? a.dy[grow * a.out + c + j] * scale : 0.f;
               const uint4 u = pack8<FMT>(v);
               *reinterpret_cast<uint4*>(Gt + (c >> 3) * kLboA + rowoff) = u;
               if (a.want_images) *reinterpret_cast<uint4*>(img + (size_t)(c >> 3) * kTileRows * 8 + row * 8) = u;
@@ -236,8 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int col = c + j;
-                  if (col < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + col] = v[j]; }
-                  else if (col < nin) { if (a.dx2) a.dx2[grow * a.k2 + (col - a.k1)] = v[j]; }
+                  if (col < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + col] = v[j] * inv_scale; }
+                  else if (col < nin) { if (a.dx2) a.dx2[grow * a.k2 + (col - a.k1)] = v[j] * inv_scale; }
                 }
               }
             }
@@ -273,6 +305,7 @@ struct WgradArgs {
   WgradJob job[BD_MAX_LAYERS + 1];
   long long ntiles;
   uint32_t stage_bytes, nstage;
+  const unsigned int* amax_bits;
 };
 
 __host__ __device__ constexpr uint32_t make_idesc_f16_mn(int ab_format, int M, int N) {
@@ -346,6 +379,8 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ W
   mbar_wait(&done, 0);
   tc_fence_after_sync();
   if (any) {
+    float inv_scale;
+    grad_scale(a.amax_bits, &inv_scale);
     for (int mt = 0; mt < nmt; ++mt) {
       const int m = mt * 128 + tid;
       for (int c = 0; c < j.kp_x; c += 16) {
@@ -354,7 +389,7 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ W
         tmem_ld_wait();
         if (m < j.m_valid) {
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) atomicAdd(j.dwp + (size_t)m * j.kp_x + c + jj, v[jj]);
+          for (int jj = 0; jj < 16; ++jj) atomicAdd(j.dwp + (size_t)m * j.kp_x + c + jj, v[jj] * inv_scale);
         }
       }
     }
