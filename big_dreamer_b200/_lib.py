@@ -79,7 +79,7 @@ class ImagineArgs(C.Structure):
                 ("N", C.c_int64)] + \
                [(n, C.c_void_p) for n in
                 ("prev_state", "prev_belief", "eps_a", "eps_e", "eps_s", "beliefs", "states",
-                 "means", "stds", "entropy", "actions", "actor_raw", "dent")]
+                 "means", "stds", "entropy", "actions", "actor_raw", "dent", "tc_saved")]
 
 
 class ImagineBwdArgs(C.Structure):
@@ -130,6 +130,7 @@ SIGNATURES = {
                                          C.c_int, C.c_void_p]),
     "bd_imagine_workspace_bytes": (C.c_size_t, [C.POINTER(Rssm), C.POINTER(Mlp), C.c_int,
                                                 C.c_int64, C.c_int]),
+    "bd_imagine_saved_bytes": (C.c_size_t, [C.POINTER(Rssm), C.c_int, C.c_int64, C.c_int]),
     "bd_imagine_forward": (C.c_int, [C.POINTER(ImagineArgs), C.c_void_p, C.c_size_t, C.c_int,
                                      C.c_void_p]),
     "bd_imagine_backward": (C.c_int, [C.POINTER(ImagineBwdArgs), C.c_void_p, C.c_size_t, C.c_int,

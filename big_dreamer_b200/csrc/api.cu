@@ -112,9 +112,15 @@ size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, 
   if (backward) {   // tensor-core modes: d_raw (T,N,2A) + the larger of the BPTT / actor-MLP workspaces
     size_t mb = tc::mlp_backward_workspace_bytes(*actor, r->belief_size, r->state_size, (int64_t)T * N);
     size_t draw = ((size_t)T * N * 2 * r->action_size * sizeof(float) + 255) & ~size_t(255);
+    size_t bp = tc::bptt_workspace_bytes(*r);
+    if (bp > mb) mb = bp;
     t = draw + (mb > f ? mb : f);
   }
   return f > t ? f : t;
+}
+size_t bd_imagine_saved_bytes(const bd_rssm* r, int T, int64_t N, int precision) {
+  if (!r || (precision != BD_PREC_FP16 && precision != BD_PREC_BF16)) return 0;
+  return tc::imagine_saved_bytes(*r, T, N);
 }
 int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                        bd_stream_t stream) {
@@ -141,7 +147,10 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
     float* d_raw = static_cast<float*>(ws);
     void* rest = static_cast<char*>(ws) + draw_bytes;
     const size_t rest_bytes = ws_bytes - draw_bytes;
-    BD_TRY(f32::imagine_backward_ex(a, rest, rest_bytes, stream, d_raw));
+    if (f.tc_saved && tc::imagine_supported(f.rssm, f.actor, precision))
+      BD_TRY(tc::imagine_bptt(a, d_raw, rest, rest_bytes, precision, stream));
+    else
+      BD_TRY(f32::imagine_backward_ex(a, rest, rest_bytes, stream, d_raw));
     bd_mlp_bwd_args m{};
     m.k1 = Be; m.k2 = S;
     for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }

@@ -41,6 +41,10 @@ bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision);
 size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor);
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                     bd_stream_t stream);
+size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
+size_t bptt_workspace_bytes(const bd_rssm& r);
+int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
+                 bd_stream_t stream);
 bool mlp_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_pack_bytes(const bd_mlp& m);
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,

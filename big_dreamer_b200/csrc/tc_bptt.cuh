@@ -1,0 +1,299 @@
+// Tensor-core BPTT of the imagination rollout (the dgrad chain of Dreamer's actor loss through
+// prior -> GRU -> embed, src/dreamer.py:363 over the graph built at :213-227).  Transition weights
+// are frozen there (FreezeParameters, src/dreamer.py:313), so this kernel computes data gradients
+// only: dL/d(action_t) -> dL/d(raw actor outputs) for every step (the actor's own backward is a
+// batched MLP backward, tc_mlp_bwd.cuh) and optionally dL/d(prev_state), dL/d(prev_belief).
+//
+// Same engine as the forward (one CTA = 128 rows for all T steps, reverse time).  The forward pass
+// saved, per step and 128-row tile, 16-bit images of
+//     gate coefficients  c_r, c_z, c_n, c_nr, z   (5 planes x Be)   [d pre-gates per unit dL/db']
+//     act'(x) of the embed output and act'(h) of the prior hidden layer
+// so nothing is recomputed here.  Per step (t = T-1 .. 0), with G = dL/d b_{t+1} (total):
+//     p0  d_pre2 = [d mu ; d raw_sigma] from (carry d s_{t+1}, upstream g_*)          -> D2 tile
+//     p1  DH  = d_pre2 W_p2 ;            d_h = DH . act'(h)                            -> H tile
+//     p2  ACC_B (+)= d_h W_p1            (ACC_B already holds  d_gh(t+1) W_hh )
+//         gate stage A, slice 0:  G = ACC_B + g_beliefs[t] + z(t+1) G(t+1)  -> scratch; slab <- d_gi
+//     p3..  DX (+)= slab W_ih[slice]  |  next gate stage A / B (B re-reads G, slab <- d_gh)
+//     ..    ACC_B' (+)= slab W_hh[slice]
+//     p10 d_pre_x = DX . act'(x)                                                       -> H tile
+//     p11 DSA = d_pre_x W_sa  -> d s_t (stays in TMEM for the next step's p0), d a_t -> d raw_t
+// TMEM: ACC_B at column 0, DH / DX / DSA share the region at column 256.
+#pragma once
+#include "tc_engine.cuh"
+#include "tc_mlp_bwd.cuh"
+
+namespace bd {
+namespace tc {
+
+enum BpttEpi : uint8_t {
+  EPI_P_DPRE2 = 1,
+  EPI_P_MULSAVED = 2,   // D . saved act' image -> H tile   (aux0: 2 = prior hidden, 1 = embed x)
+  EPI_P_GATE = 3,       // gate stage (aux1 = 0: pass A, 1: pass B); aux0 = first column of the slice
+  EPI_P_DSA = 4
+};
+
+struct BpttArgs {
+  Program prog;
+  SmemPlan sm;
+  const uint16_t* wpack;
+  long long N;
+  int T;
+  long long* prof;
+  int Be, S, A, Hi, Kb, Kh, Sp, Ksa;
+  float min_std;
+  bd_actor_cfg cfg;
+  const uint16_t *sv_gate, *sv_xa, *sv_ha;
+  const float *stds, *eps_s, *eps_a, *actions, *actor_raw, *dent;
+  const float *g_beliefs, *g_states, *g_means, *g_stds, *g_entropy;
+  float* d_raw;
+  float *d_prev_state, *d_prev_belief;
+  float *scr_carry, *scr_gtot;   // per-CTA scratch, [gridDim.x][128][Kb] fp32
+  const unsigned int* amax_bits;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const BpttArgs& a = A_;
+  uint8_t* smem = smem_raw;
+  __shared__ EngineShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
+  const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
+  const Program& P = a.prog;
+
+  if (warp == 0) {
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh);
+  } else if (warp == 1) {
+    issuer_role<FMT, false>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, nullptr);
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t rowoff = (row >> 3) * 128 + (row & 7) * 16;
+    const int Be = a.Be, S = a.S, Ad = a.A, Kb = a.Kb;
+    uint8_t* Ht = smem + a.sm.off_tile[TILE_H];
+    uint8_t* D2 = smem + a.sm.off_tile[TILE_D2];
+    float* carry = a.scr_carry + ((size_t)blockIdx.x * kTileRows + row) * Kb;
+    float* gtot = a.scr_gtot + ((size_t)blockIdx.x * kTileRows + row) * Kb;
+    float inv_scale;
+    const float scale = grad_scale(a.amax_bits, &inv_scale);
+    uint32_t Ge = 0, Gm = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long grow = tile * kTileRows + row;
+      const bool rvalid = grow < a.N;
+      mbar_arrive(&sh.epi_done[Ge & 3]);   // nothing to initialise per tile
+      ++Ge;
+      for (int i = 0; i < a.T; ++i) {
+        const int t = a.T - 1 - i;
+        const long long orow = (long long)t * a.N + grow;
+        const size_t tl = (size_t)t * ntiles + tile;          // (t, tile) index of the saved images
+        for (int pi = 0; pi < P.n_phases; ++pi) {
+          const Phase ph = P.p[pi];
+          mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);
+          tc_fence_after_sync();
+          switch (ph.epi) {
+            case EPI_P_DPRE2: {
+              const int Sp = a.Sp;
+              for (int c = half * 16; c < Sp; c += 32) {
+                float cs[16], m_[16], s_[16];
+                if (i > 0) {
+                  tmem_ld16(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA
+                  tmem_ld_wait();
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) cs[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int col = c + j;
+                  float dmu = 0.f, draw = 0.f;
+                  if (col < S && rvalid) {
+                    const long long o = orow * S + col;
+                    const float gs = cs[j] + (a.g_states ? a.g_states[o] * scale : 0.f);
+                    dmu = gs + (a.g_means ? a.g_means[o] * scale : 0.f);
+                    const float sd = a.stds[o];
+                    const float dsd = gs * a.eps_s[o] + (a.g_stds ? a.g_stds[o] * scale : 0.f);
+                    draw = dsd * (1.f - __expf(-(sd - a.min_std)));   // softplus' = 1 - exp(-softplus)
+                  }
+                  m_[j] = dmu; s_[j] = draw;
+                }
+                uint8_t* p = D2 + (c >> 3) * kLboA + rowoff;
+                store8<FMT>(p, m_);
+                store8<FMT>(p + kLboA, m_ + 8);
+                uint8_t* p2 = D2 + ((Sp + c) >> 3) * kLboA + rowoff;
+                store8<FMT>(p2, s_);
+                store8<FMT>(p2 + kLboA, s_ + 8);
+              }
+            } break;
+            case EPI_P_MULSAVED: {
+              const int kp = ph.aux0 == 1 ? Kb : a.Kh;
+              const uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) + tl * kTileRows * kp + row * 8;
+              const uint32_t tacc = trow + ph.d_col;
+              for (int c = half * 32; c < kp; c += 64) {
+                float v[32];
+                const bool two = (c + 16) < kp;
+                const int ngroups = two ? 4 : 2;
+                uint4 hu[4];
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8)
+                  if (g8 < ngroups) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
+                if (two) tmem_ld32(tacc + c, v);
+                else tmem_ld16(tacc + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  if (g8 < ngroups) {
+                    float h[8];
+                    unpack8<FMT>(hu[g8], h);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= h[j];
+                    store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, v + g8 * 8);
+                  }
+                }
+              }
+            } break;
+            case EPI_P_GATE: {
+              const int n0 = ph.aux0, Ns = ph.Np;
+              const bool passB = ph.pad != 0;
+              uint8_t* slab = smem + a.sm.off_tile[ph.out_tile];
+              const uint16_t* gimg = a.sv_gate + tl * 5 * kTileRows * Kb + row * 8;
+              const size_t plane = (size_t)kTileRows * Kb;
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                const int c = half * 16 + it * 32;
+                if (c < Ns) {
+                  const int col0 = n0 + c;
+                  float G[16];
+                  if (!passB) {
+                    tmem_ld16(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                      float4 cin = make_float4(0.f, 0.f, 0.f, 0.f);
+                      if (i > 0) cin = *reinterpret_cast<const float4*>(carry + col0 + j4 * 4);
+                      float gb[4] = {0.f, 0.f, 0.f, 0.f};
+                      if (a.g_beliefs && rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                          if (col0 + j4 * 4 + j < Be) gb[j] = a.g_beliefs[orow * Be + col0 + j4 * 4 + j] * scale;
+                      }
+                      G[j4 * 4] += cin.x + gb[0]; G[j4 * 4 + 1] += cin.y + gb[1];
+                      G[j4 * 4 + 2] += cin.z + gb[2]; G[j4 * 4 + 3] += cin.w + gb[3];
+                      *reinterpret_cast<float4*>(gtot + col0 + j4 * 4) =
+                          make_float4(G[j4 * 4], G[j4 * 4 + 1], G[j4 * 4 + 2], G[j4 * 4 + 3]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                      const float4 g4 = *reinterpret_cast<const float4*>(gtot + col0 + j4 * 4);
+                      G[j4 * 4] = g4.x; G[j4 * 4 + 1] = g4.y; G[j4 * 4 + 2] = g4.z; G[j4 * 4 + 3] = g4.w;
+                    }
+                  }
+                  const uint16_t* gp = gimg + (size_t)(col0 >> 3) * kTileRows * 8;
+                  // planes: 0 c_r, 1 c_z, 2 c_n, 3 c_nr, 4 z
+                  const int pl3 = passB ? 3 : 2;
+#pragma unroll
+                  for (int part = 0; part < 3; ++part) {
+                    const int pl = part == 0 ? 0 : (part == 1 ? 1 : pl3);
+                    float o[16];
+#pragma unroll
+                    for (int g8 = 0; g8 < 2; ++g8) {
+                      float cf[8];
+                      unpack8<FMT>(*reinterpret_cast<const uint4*>(gp + pl * plane + (size_t)g8 * kTileRows * 8), cf);
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) o[g8 * 8 + j] = G[g8 * 8 + j] * cf[j];
+                    }
+                    uint8_t* p = slab + ((part * Ns + c) >> 3) * kLboA + rowoff;
+                    store8<FMT>(p, o);
+                    store8<FMT>(p + kLboA, o + 8);
+                  }
+                  if (!passB) {   // carry for the next (earlier) step: z . G
+#pragma unroll
+                    for (int g8 = 0; g8 < 2; ++g8) {
+                      float zf[8];
+                      unpack8<FMT>(*reinterpret_cast<const uint4*>(gp + 4 * plane + (size_t)g8 * kTileRows * 8), zf);
+                      *reinterpret_cast<float4*>(carry + col0 + g8 * 8) =
+                          make_float4(G[g8 * 8] * zf[0], G[g8 * 8 + 1] * zf[1], G[g8 * 8 + 2] * zf[2], G[g8 * 8 + 3] * zf[3]);
+                      *reinterpret_cast<float4*>(carry + col0 + g8 * 8 + 4) =
+                          make_float4(G[g8 * 8 + 4] * zf[4], G[g8 * 8 + 5] * zf[5], G[g8 * 8 + 6] * zf[6], G[g8 * 8 + 7] * zf[7]);
+                    }
+                  }
+                }
+              }
+            } break;
+            case EPI_P_DSA: {
+              const uint32_t tacc = trow + 256;
+              if (half == 0) {
+                const int c0 = (S >> 4) << 4;
+                float vv[32];
+                tmem_ld16(tacc + c0, vv);
+                if (c0 + 16 < a.Ksa) tmem_ld16(tacc + c0 + 16, vv + 16);
+                else {
+#pragma unroll
+                  for (int j = 16; j < 32; ++j) vv[j] = 0.f;
+                }
+                tmem_ld_wait();
+                if (rvalid) {
+                  const float ge = a.g_entropy ? a.g_entropy[orow] * scale : 0.f;
+                  for (int j = 0; j < Ad; ++j) {
+                    const int idx = S - c0 + j;
+                    float da = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) if (k == idx) da = vv[k];
+                    const long long oa = orow * Ad + j;
+                    const float m_raw = a.actor_raw[orow * 2 * Ad + j], s_raw = a.actor_raw[orow * 2 * Ad + Ad + j];
+                    const float act = a.actions[oa];
+                    const float dy = da * (1.f - act * act);
+                    const float dmean = dy + ge * a.dent[orow * 2 * Ad + j];
+                    const float dsd = dy * a.eps_a[oa] + ge * a.dent[orow * 2 * Ad + Ad + j];
+                    const float th = tanhf(m_raw / a.cfg.mean_scale);
+                    a.d_raw[orow * 2 * Ad + j] = dmean * (1.f - th * th) * inv_scale;
+                    a.d_raw[orow * 2 * Ad + Ad + j] = dsd * softplus_gradf_(s_raw + a.cfg.raw_init_std) * inv_scale;
+                  }
+                }
+              }
+              if (t == 0) {   // gradients wrt the start latents
+                if (a.d_prev_state) {
+                  for (int c = half * 16; c < a.Sp; c += 32) {
+                    float v[16];
+                    tmem_ld16(tacc + c, v);            // warp-collective: never under a per-lane branch
+                    tmem_ld_wait();
+                    if (rvalid) {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j) if (c + j < S) a.d_prev_state[grow * S + c + j] = v[j] * inv_scale;
+                    }
+                  }
+                }
+                if (a.d_prev_belief) {
+                  for (int c = half * 16; c < Kb; c += 32) {
+                    float v[16];
+                    tmem_ld16(trow + c, v);            // ACC_B = d_gh(0) W_hh
+                    tmem_ld_wait();
+                    if (rvalid) {
+#pragma unroll
+                      for (int j = 0; j < 16; ++j)
+                        if (c + j < Be) a.d_prev_belief[grow * Be + c + j] = (v[j] + carry[c + j]) * inv_scale;
+                    }
+                  }
+                }
+              }
+            } break;
+            default: break;
+          }
+          tc_fence_before_sync();
+          fence_proxy_async_smem();
+          mbar_arrive(&sh.epi_done[Ge & 3]);
+          ++Ge;
+          ++Gm;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace tc
+}  // namespace bd

@@ -33,7 +33,8 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxGemms = 64, kMaxPhases = 40;
 constexpr uint32_t kLboA = kTileRows * 16;   // bytes between 8-column groups of an activation tile
 
-enum TileId : uint8_t { TILE_BCUR = 0, TILE_BNXT = 1, TILE_SA = 2, TILE_H = 3, TILE_H2 = 4 };
+enum TileId : uint8_t { TILE_BCUR = 0, TILE_BNXT = 1, TILE_SA = 2, TILE_H = 3, TILE_H2 = 4,
+                       TILE_SLAB0 = 5, TILE_SLAB1 = 6, TILE_D2 = 7 };
 enum EpiKind : uint8_t {
   EPI_ACT_H = 1,      // act(D) -> H tile
   EPI_ACTOR_OUT = 2,  // action sample + entropy
@@ -49,7 +50,7 @@ struct Gemm {
   uint16_t a_k0;      // first K column inside the A tile (mult of 8)
   uint16_t d_col;     // TMEM column of the accumulator
   uint8_t a_tile;     // TileId
-  uint8_t accumulate; // 1: continue a running sum in D
+  uint8_t accumulate; // 1: continue a running sum in D; 2: only from the second time step on
   uint16_t kc;        // K columns per weight-ring stage (mult of 16): Np*kc*2 <= stage bytes
   uint16_t pad;
 };
@@ -72,7 +73,7 @@ struct Program {
 };
 
 struct SmemPlan {
-  uint32_t off_tile[5];   // B0, B1, SA, H, H2 (byte offsets from the 1024-aligned base)
+  uint32_t off_tile[8];   // indexed by TileId (byte offsets from the 1024-aligned base)
   uint32_t off_ring, stage_bytes, nstage;
   uint32_t total;
 };
@@ -94,6 +95,9 @@ struct RolloutArgs {
   const float* ext_actions;   // CEM / TransitionModel.forward: actions given, no actor
   long long* prof;            // optional (debug): per-phase cycle counters of CTA 0, see tc_imagine.cu
   float* mlp_out;             // EPI_STORE_OUT target (rows, n_valid)
+  // saved for the tensor-core BPTT (16-bit tile images, see tc_bptt.cuh); null = do not save
+  uint16_t *sv_gate, *sv_xa, *sv_ha;
+  int kb_sv, kh_sv;
   int has_b1;                 // 0: single belief tile (MLP forward), 1: ping-pong
 };
 
@@ -210,7 +214,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           const uint32_t lbo_b = (uint32_t)g.Np * 16;
           const uint64_t b_desc0 = make_smem_desc(0, lbo_b, 128);
           const uint32_t d_tmem = tmem_base + g.d_col;
-          uint32_t acc = g.accumulate;
+          uint32_t acc = g.accumulate == 2 ? (t > 0 ? 1u : 0u) : g.accumulate;
           for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
             const int kc = min((int)g.kc, g.Kp - k0);
             long long w0 = 0;
@@ -254,6 +258,13 @@ __device__ __forceinline__ float tc_act_t(float x) {
   if (ACT == BD_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == BD_ACT_TANH) return fast_tanh(x);
   return x;
+}
+template <int ACT>
+__device__ __forceinline__ float tc_dact_from_out(float y) {
+  if (ACT == BD_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+  if (ACT == BD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (ACT == BD_ACT_TANH) return 1.f - y * y;
+  return 1.f;
 }
 // sigmoid through the single-MUFU tanh: s(x) = 0.5 tanh(x/2) + 0.5
 __device__ __forceinline__ float sigmoid_via_tanh(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
@@ -390,6 +401,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   store8<FMT>(p + 2 * kLboA, v + 16);
                   store8<FMT>(p + 3 * kLboA, v + 24);
                 }
+                if (ph.aux0 && a.sv_xa) {   // act'(output) for the backward pass (1: embed x, 2: prior h)
+                  const int kp = ph.aux0 == 1 ? a.kb_sv : a.kh_sv;
+                  uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) +
+                                  ((size_t)t * ntiles + tile) * kTileRows * kp + row * 8;
+#pragma unroll
+                  for (int g8 = 0; g8 < 4; ++g8) {
+                    const int cg = c + g8 * 8;
+                    if (cg < kp) {
+                      float dv[8];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j)
+                        dv[j] = (cg + j < nv && rvalid) ? tc_dact_from_out<ACT>(v[g8 * 8 + j]) : 0.f;
+                      *reinterpret_cast<uint4*>(img + (size_t)(cg >> 3) * kTileRows * 8) =
+                          make_uint4(Half16<FMT>::pack2(dv[0], dv[1]), Half16<FMT>::pack2(dv[2], dv[3]),
+                                     Half16<FMT>::pack2(dv[4], dv[5]), Half16<FMT>::pack2(dv[6], dv[7]));
+                    }
+                  }
+                }
               }
             } break;
             case EPI_GRU: {
@@ -431,14 +460,42 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   tmem_ld16(tacc + 2 * Ns + c, in_);
                   tmem_ld16(tacc + 3 * Ns + c, hn_);
                   tmem_ld_wait();
+                  const int col0 = n0 + c;
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const float r = sigmoid_via_tanh(r_[j]);
                     const float z = sigmoid_via_tanh(z_[j]);
                     const float n = fast_tanh(fmaf(r, hn_[j], in_[j]));
                     o[j] = fmaf(z, hb[it][j] - n, n);          // (1-z) n + z h
+                    if (a.sv_gate) {
+                      // backward coefficients of this gate column: d(pre_r), d(pre_z), d(pre_n),
+                      // d(pre_n)*r per unit of dL/db', and z for the carry (SURVEY A.1 / tc_bptt.cuh)
+                      const bool ok = rvalid && (col0 + j < Be);
+                      const float cn = ok ? (1.f - z) * (1.f - n * n) : 0.f;
+                      r_[j] = cn * hn_[j] * r * (1.f - r);           // c_r
+                      in_[j] = cn;                                   // c_n
+                      hn_[j] = cn * r;                               // c_nr
+                      const float cz = ok ? (hb[it][j] - n) * z * (1.f - z) : 0.f;
+                      z_[j] = ok ? z : 0.f;                          // z (plane 4)
+                      hb[it][j] = cz;                                // c_z (plane 1); hb no longer needed
+                    }
                   }
-                  const int col0 = n0 + c;
+                  if (a.sv_gate && col0 < a.kb_sv) {
+                    uint16_t* img = a.sv_gate + ((size_t)t * ntiles + tile) * 5 * kTileRows * a.kb_sv +
+                                    (size_t)(col0 >> 3) * kTileRows * 8 + row * 8;
+                    const size_t plane = (size_t)kTileRows * a.kb_sv;
+                    const float* src[5] = {r_, hb[it], in_, hn_, z_};
+#pragma unroll
+                    for (int pl = 0; pl < 5; ++pl) {
+#pragma unroll
+                      for (int g8 = 0; g8 < 2; ++g8) {
+                        const float* q8 = src[pl] + g8 * 8;
+                        *reinterpret_cast<uint4*>(img + pl * plane + (size_t)g8 * kTileRows * 8) =
+                            make_uint4(Half16<FMT>::pack2(q8[0], q8[1]), Half16<FMT>::pack2(q8[2], q8[3]),
+                                       Half16<FMT>::pack2(q8[4], q8[5]), Half16<FMT>::pack2(q8[6], q8[7]));
+                      }
+                    }
+                  }
                   if (rvalid) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {

@@ -4,10 +4,24 @@
 #include "api_internal.h"
 #include "tc_engine.cuh"
 #include "tc_builder.cuh"
+#include "tc_bptt.cuh"
 #include <stdlib.h>
 
 namespace bd {
 namespace tc {
+
+struct SavedLayout { size_t off_gate, off_xa, off_ha, total; int Kb, Kh; };
+static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
+  SavedLayout s;
+  s.Kb = r16(r.belief_size); s.Kh = r16(r.hidden_size);
+  const size_t tiles = (size_t)((N + kTileRows - 1) / kTileRows) * T;
+  s.off_gate = 0;
+  s.off_xa = s.off_gate + tiles * 5 * kTileRows * s.Kb * 2;
+  s.off_ha = s.off_xa + tiles * kTileRows * s.Kb * 2;
+  s.total = s.off_ha + tiles * kTileRows * s.Kh * 2;
+  return s;
+}
+size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N) { return saved_layout(r, T, N).total + 256; }
 
 bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
   if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
@@ -124,7 +138,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     uint32_t w = b.add_pack(r.embed.w, S + A, 0, Be, Nb, Kp_sa, 0, S + A, r.embed.b, S + A);
     int d = b.dcol();
     b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, 0, TILE_H);
+    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, 1, TILE_H);      // aux0 = 1: save act'(x)
   }
   // ---- GRUCell in N-slices of <= 64 belief columns: accumulators R | Z | IN | HN per slice
   {
@@ -151,7 +165,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     uint32_t w1 = b.add_pack(r.prior1.w, Be, 0, Hi, Nh, Kp_b, 0, Be, r.prior1.b, Be);
     int d = b.dcol();
     b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 2, TILE_H);    // aux0 = 2: save act'(h)
     uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     d = b.dcol();
@@ -179,6 +193,14 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   ra.beliefs = a->beliefs; ra.states = a->states; ra.means = a->means; ra.stds = a->stds;
   ra.entropy = a->entropy; ra.actions = a->actions; ra.actor_raw = a->actor_raw; ra.dent = a->dent;
   ra.has_b1 = 1;
+  if (a->tc_saved) {
+    SavedLayout sl = saved_layout(r, a->T, a->N);
+    char* sb = static_cast<char*>(a->tc_saved);
+    ra.sv_gate = reinterpret_cast<uint16_t*>(sb + sl.off_gate);
+    ra.sv_xa = reinterpret_cast<uint16_t*>(sb + sl.off_xa);
+    ra.sv_ha = reinterpret_cast<uint16_t*>(sb + sl.off_ha);
+    ra.kb_sv = sl.Kb; ra.kh_sv = sl.Kh;
+  }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // debug: BD_TC_PROF=1 appends cycle counters after the packed weights (scripts/prof_fwd.py)
@@ -207,6 +229,170 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
   actor_entropy_kernel<<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy,
                                              a->dent);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BPTT of the imagination rollout on the tensor-core engine (tc_bptt.cuh)
+// ---------------------------------------------------------------------------------------------
+static uint32_t add_pack_T(Builder& b, const float* w, int ld, int n_valid, int Np, int Kp, int nseg,
+                           const PackSeg* segs) {
+  // packed(n, k) = w[src_row(k), n]: the dgrad (transposed) image of an nn.Linear weight
+  if (b.pack.njobs >= kMaxPackJobs) { b.ok = false; return 0; }
+  PackJob& j = b.pack.job[b.pack.njobs++];
+  j = PackJob{};
+  j.w = w; j.bias = nullptr; j.dst_off = b.w_elems; j.ld = ld; j.row0 = 0; j.N = n_valid; j.Np = Np;
+  j.Kp = Kp; j.bias_k = -1; j.nseg = nseg; j.transpose = 1;
+  for (int i = 0; i < nseg; ++i) j.seg[i] = segs[i];
+  const uint32_t off = (uint32_t)b.w_elems;
+  b.w_elems += (long long)Np * Kp;
+  return off;
+}
+
+size_t bptt_workspace_bytes(const bd_rssm& r) {
+  const int Kb = r16(r.belief_size);
+  size_t pack = (size_t)r16(r.hidden_size) * 2 * r16(r.state_size) + (size_t)Kb * r16(r.hidden_size) +
+                (size_t)2 * Kb * 3 * (r.belief_size + 64) + (size_t)r16(r.state_size + r.action_size) * Kb;
+  return pack * 2 + 4096 + (size_t)2 * 160 * kTileRows * Kb * 4 + 65536;
+}
+
+int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
+                 bd_stream_t stream) {
+  const bd_imagine_args& f = a->fwd;
+  const bd_rssm& r = f.rssm;
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Kb = r16(Be), Kh = r16(Hi), Sp = r16(S), Ksa = r16(S + A);
+  if (!f.tc_saved) BD_FAIL(BD_ERR_BAD_ARG, "imagine_bptt: forward did not save tensor-core state");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Builder b;
+  // p0: d_pre2 (no MMA)
+  b.end_phase(EPI_P_DPRE2, 1, 2 * S, 0, 0, 0, 0, TILE_D2);
+  // p1: DH = d_pre2 * W_p2  (K = [mean rows | std rows], N = Hi)
+  {
+    PackSeg sg[2] = {{0, 0, S}, {Sp, S, S}};
+    uint32_t w = add_pack_T(b, r.prior2.w, Hi, Hi, Kh, 2 * Sp, 2, sg);
+    b.add_gemm(w, Kh, 2 * Sp, TILE_D2, 0, 256, 0);
+    b.end_phase(EPI_P_MULSAVED, 1, Hi, Kh, 0, 256, 2, TILE_H);
+  }
+  // p2: ACC_B (+)= d_h * W_p1 ; then gate stage A slice 0
+  int slab = 0;
+  {
+    PackSeg sg[1] = {{0, 0, Hi}};
+    uint32_t w = add_pack_T(b, r.prior1.w, Be, Be, Kb, Kh, 1, sg);
+    b.add_gemm(w, Kb, Kh, TILE_H, 0, 0, 2);
+  }
+  int nsl = 0, n0s[8], nss[8], nvs[8];
+  for (int n0 = 0; n0 < Be; n0 += 64) { n0s[nsl] = n0; nvs[nsl] = min(64, Be - n0); nss[nsl] = r16(nvs[nsl]); ++nsl; }
+  auto gate_phase = [&](int sl, bool passB) {
+    b.end_phase(EPI_P_GATE, 1, nvs[sl], nss[sl], 0, 0, n0s[sl], slab ? TILE_SLAB1 : TILE_SLAB0);
+    b.prog.p[b.prog.n_phases - 1].pad = passB ? 1 : 0;
+  };
+  gate_phase(0, false);
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* wsrc = pass == 0 ? r.w_ih : r.w_hh;
+    const int dcol = pass == 0 ? 256 : 0;
+    for (int sl = 0; sl < nsl; ++sl) {
+      const int Ns = nss[sl], nv = nvs[sl], n0 = n0s[sl];
+      PackSeg sg[3] = {{0, n0, nv}, {Ns, Be + n0, nv}, {2 * Ns, 2 * Be + n0, nv}};
+      uint32_t w = add_pack_T(b, wsrc, Be, Be, Kb, 3 * Ns, 3, sg);
+      b.add_gemm(w, Kb, 3 * Ns, slab ? TILE_SLAB1 : TILE_SLAB0, 0, dcol, sl > 0 ? 1 : 0);
+      slab ^= 1;
+      if (pass == 0 && sl + 1 < nsl) gate_phase(sl + 1, false);
+      else if (pass == 0) gate_phase(0, true);
+      else if (sl + 1 < nsl) gate_phase(sl + 1, true);
+      else b.end_phase(EPI_P_MULSAVED, 1, Be, Kb, 0, 256, 1, TILE_H);
+    }
+  }
+  {
+    PackSeg sg[1] = {{0, 0, Be}};
+    uint32_t w = add_pack_T(b, r.embed.w, S + A, S + A, Ksa, Kb, 1, sg);
+    b.add_gemm(w, Ksa, Kb, TILE_H, 0, 256, 0);
+    b.end_phase(EPI_P_DSA, 1, S + A, Ksa, 0, 256, 0, TILE_H);
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core BPTT: program too large");
+
+  BpttArgs ba{};
+  {
+    SmemPlan& sm = ba.sm;
+    uint32_t o = 0;
+    auto tk = [&](uint32_t bytes) { uint32_t r_ = o; o += (bytes + 1023) & ~1023u; return r_; };
+    for (int i = 0; i < 8; ++i) sm.off_tile[i] = 0;
+    sm.off_tile[TILE_D2] = tk(kTileRows * 2 * Sp * 2);
+    sm.off_tile[TILE_H] = tk(kTileRows * max(Kb, Kh) * 2);
+    sm.off_tile[TILE_SLAB0] = tk(kTileRows * 192 * 2);
+    sm.off_tile[TILE_SLAB1] = tk(kTileRows * 192 * 2);
+    sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
+    sm.off_ring = o;
+    const uint32_t budget = 227 * 1024 - 2048;
+    if (o + 2 * sm.stage_bytes > budget) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core BPTT: tiles do not fit shared memory");
+    sm.nstage = min(8u, (budget - o) / sm.stage_bytes);
+    sm.total = o + sm.nstage * sm.stage_bytes + 1024;
+  }
+  b.finalize_blocks(ba.sm.stage_bytes);
+  ba.prog = b.prog;
+
+  const long long ntiles = (f.N + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+
+  // workspace: packed weights | amax | per-CTA scratch
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p_ = base + off; off += (bytes + 255) & ~size_t(255); return p_; };
+  uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
+  unsigned int* amax = reinterpret_cast<unsigned int*>(take(256));
+  float* scr_carry = reinterpret_cast<float*>(take((size_t)grid * kTileRows * Kb * 4));
+  float* scr_gtot = reinterpret_cast<float*>(take((size_t)grid * kTileRows * Kb * 4));
+  if (off > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core BPTT: workspace %zu < %zu", ws_bytes, off);
+  cudaMemsetAsync(amax, 0, 256, s);
+  {
+    const float* gs[5] = {a->g_beliefs, a->g_states, a->g_means, a->g_stds, a->g_entropy};
+    const long long ns[5] = {(long long)f.T * f.N * Be, (long long)f.T * f.N * S, (long long)f.T * f.N * S,
+                             (long long)f.T * f.N * S, (long long)f.T * f.N};
+    for (int i = 0; i < 5; ++i) {
+      if (!gs[i]) continue;
+      long long g = (ns[i] + 255) / 256;
+      if (g > 1184) g = 1184;
+      absmax_kernel<<<(unsigned)(g < 1 ? 1 : g), 256, 0, s>>>(gs[i], ns[i], amax);
+      BD_CUDA_LAUNCH_CHECK();
+    }
+  }
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  {
+    long long max_img = 0;
+    for (int i = 0; i < b.pack.njobs; ++i)
+      max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+    long long pgx = (max_img + 255) / 256;
+    if (pgx > 64) pgx = 64;
+    dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+    if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    BD_CUDA_LAUNCH_CHECK();
+  }
+  SavedLayout sl = saved_layout(r, f.T, f.N);
+  const char* sb = static_cast<const char*>(f.tc_saved);
+  ba.wpack = wpack; ba.N = f.N; ba.T = f.T; ba.prof = nullptr;
+  ba.Be = Be; ba.S = S; ba.A = A; ba.Hi = Hi; ba.Kb = Kb; ba.Kh = Kh; ba.Sp = Sp; ba.Ksa = Ksa;
+  ba.min_std = r.min_std_dev; ba.cfg = f.actor_cfg;
+  ba.sv_gate = reinterpret_cast<const uint16_t*>(sb + sl.off_gate);
+  ba.sv_xa = reinterpret_cast<const uint16_t*>(sb + sl.off_xa);
+  ba.sv_ha = reinterpret_cast<const uint16_t*>(sb + sl.off_ha);
+  ba.stds = f.stds; ba.eps_s = f.eps_s; ba.eps_a = f.eps_a; ba.actions = f.actions;
+  ba.actor_raw = f.actor_raw; ba.dent = f.dent;
+  ba.g_beliefs = a->g_beliefs; ba.g_states = a->g_states; ba.g_means = a->g_means; ba.g_stds = a->g_stds;
+  ba.g_entropy = a->g_entropy;
+  ba.d_raw = d_raw; ba.d_prev_state = a->d_prev_state; ba.d_prev_belief = a->d_prev_belief;
+  ba.scr_carry = scr_carry; ba.scr_gtot = scr_gtot; ba.amax_bits = amax;
+  if (fmt == 0) {
+    cudaFuncSetAttribute(bptt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
+    bptt_kernel<0><<<grid, kThreads, ba.sm.total, s>>>(ba);
+  } else {
+    cudaFuncSetAttribute(bptt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
+    bptt_kernel<1><<<grid, kThreads, ba.sm.total, s>>>(ba);
+  }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
 }

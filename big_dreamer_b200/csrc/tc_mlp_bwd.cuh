@@ -67,13 +67,6 @@ static __global__ void absmax_kernel(const float* __restrict__ x, long long n, u
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
-template <int ACT>
-__device__ __forceinline__ float tc_dact_from_out(float y) {
-  if (ACT == BD_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
-  if (ACT == BD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (ACT == BD_ACT_TANH) return 1.f - y * y;
-  return 1.f;
-}
 template <int FMT>
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};

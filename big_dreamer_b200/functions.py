@@ -309,6 +309,14 @@ class ImagineFunction(torch.autograd.Function):
         a.beliefs, a.states, a.means, a.stds = (_lib.ptr(t) for t in (beliefs, states, means, stds))
         a.entropy, a.actions = _lib.ptr(entropy), _lib.ptr(actions)
         a.actor_raw, a.dent = _lib.ptr(actor_raw), _lib.ptr(dent)
+        saved = None
+        need_bwd = any(ctx.needs_input_grad)   # (grad mode is always off inside Function.forward)
+        nsaved = lib.bd_imagine_saved_bytes(C.byref(a.rssm), T, N, _prec()) if need_bwd else 0
+        if nsaved:
+            saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+            a.tc_saved = saved.data_ptr()
+        ctx.tc_saved = saved
+        ctx.prec = _prec()
         nbytes = lib.bd_imagine_workspace_bytes(C.byref(a.rssm), C.byref(a.actor), T, N, 0)
         ws = _lib.workspace(nbytes, dev)
         _lib.check(lib.bd_imagine_forward(C.byref(a), ws.data_ptr(), ws.numel(), _prec(),
@@ -344,6 +352,8 @@ class ImagineFunction(torch.autograd.Function):
         f.beliefs, f.states, f.means, f.stds = (_lib.ptr(t) for t in (beliefs, states, means, stds))
         f.entropy, f.actions = _lib.ptr(entropy), _lib.ptr(actions)
         f.actor_raw, f.dent = _lib.ptr(actor_raw), _lib.ptr(dent)
+        if ctx.tc_saved is not None:
+            f.tc_saved = ctx.tc_saved.data_ptr()
         gc = lambda t: _f32c(t) if t is not None else None
         g_b, g_s, g_m, g_sd, g_ent = gc(g_b), gc(g_s), gc(g_m), gc(g_sd), gc(g_ent)
         a.g_beliefs, a.g_states, a.g_means = _lib.ptr(g_b), _lib.ptr(g_s), _lib.ptr(g_m)
@@ -360,6 +370,6 @@ class ImagineFunction(torch.autograd.Function):
             dA += [dw, db]
         nbytes = lib.bd_imagine_workspace_bytes(C.byref(f.rssm), C.byref(f.actor), T, N, 1)
         ws = _lib.workspace(nbytes, s0.device)
-        _lib.check(lib.bd_imagine_backward(C.byref(a), ws.data_ptr(), ws.numel(), _prec(),
+        _lib.check(lib.bd_imagine_backward(C.byref(a), ws.data_ptr(), ws.numel(), ctx.prec,
                                            _lib.stream_ptr()), "bd_imagine_backward")
         return (None, None, None, d_s0, d_b0, None, None, None, None, *dA, *([None] * 10))

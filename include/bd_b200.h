@@ -204,7 +204,13 @@ typedef struct {
   float* actions;    /* (T,N,A)                                 */
   float* actor_raw;  /* (T,N,2A) raw actor outputs              */
   float* dent;       /* (T,N,2A) d entropy / d (mean, std)      */
+  /* tensor-core modes only: opaque buffer of bd_imagine_saved_bytes() bytes in which the forward
+   * leaves 16-bit images of the GRU gate coefficients and activation derivatives for the backward
+   * (NULL: not saved; the backward then runs the fp32 recompute kernels) */
+  void* tc_saved;
 } bd_imagine_args;
+
+size_t bd_imagine_saved_bytes(const bd_rssm* r, int T, int64_t N, int precision);
 
 size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N,
                                   int backward);

@@ -95,3 +95,36 @@ def test_dense_model_tc_backward(shape, freeze):
             assert p.grad is None
         else:
             assert pu.relerr(p.grad, sdc[k].grad.float()) < 5e-3, k
+
+
+@pytest.mark.parametrize("d", [dict(Be=200, Hi=200, S=30, A=1, E=8, N=200, H=6, act="ELU"),
+                               dict(Be=32, Hi=32, S=30, A=2, E=8, N=50, H=5, act="ELU")])
+def test_imagine_tc_input_grads_and_cotangents(d):
+    """TC BPTT: grad wrt prev_state / prev_belief and arbitrary cotangents on every output."""
+    from oracle import rssm_oracle as orc
+    trans, actor, _, _ = orc.make_models(5, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    actor["model.8.bias"][d["A"]:] -= 6.0
+    s0, b0 = orc.make_latents(5, d["N"], d["Be"], d["S"])
+    ea, ee, es = orc.make_imagine_noise(5, d["H"] - 1, d["N"], d["S"], d["A"])
+    g = torch.Generator().manual_seed(11)
+    T, N = d["H"] - 1, d["N"]
+    cots = [torch.randn(T, N, k, generator=g) for k in (d["Be"], d["S"], d["S"], d["S"])] + \
+           [torch.randn(T, N, generator=g)]
+    dd = torch.float64
+    s0c, b0c = s0.to(dd).requires_grad_(True), b0.to(dd).requires_grad_(True)
+    asd = {k: v.to(dd).requires_grad_(True) for k, v in actor.items()}
+    tsd = {k: v.to(dd) for k, v in trans.items()}
+    ob, os_, (om, osd), oe, _ = orc.imagine_ahead(tsd, asd, d["act"], 0.1, d["H"], s0c[None],
+                                                  b0c[None], ea.to(dd), ee.to(dd), es.to(dd))
+    sum((o * c.to(dd)).sum() for o, c in zip((ob, os_, om, osd, oe), cots)).backward()
+    mods = pu.build_gpu_models(d, trans, actor)
+    pu.freeze(mods.transition)
+    bd.set_precision("fp16")
+    s0g, b0g = s0.cuda().requires_grad_(True), b0.cuda().requires_grad_(True)
+    noise = dict(eps_a=ea.cuda(), eps_e=ee.cuda(), eps_s=es.cuda())
+    gb, gs, (gm, gsd), ge = bd.imagine_ahead(pu.agent_ns(mods, d["H"]), s0g[None], b0g[None], noise)
+    sum((o * c.cuda()).sum() for o, c in zip((gb, gs, gm, gsd, ge), cots)).backward()
+    assert pu.relerr(s0g.grad, s0c.grad.float()) < TOL
+    assert pu.relerr(b0g.grad, b0c.grad.float()) < TOL
+    for k, p in mods.actor.named_parameters():
+        assert pu.relerr(p.grad, asd[k].grad.float()) < TOL, k
