@@ -3,7 +3,7 @@
 BPTT backward of Dreamer's actor loss, on synthetic latents of the named shapes.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp32|bf16|tf32] [--rows R] [--no-cpu-baseline]
+                    [--precision fp16|bf16|fp32] [--rows R] [--no-cpu-baseline]
 
 One "step" = one pass of the hot path over one batch of start states:
 imagine_ahead (actor + 100-sample entropy + embed + GRU + prior + sample, T = 14 transitions)
@@ -48,6 +48,21 @@ def algorithmic_flops_per_row_step(d):
     fwd = embed + gru + prior + actor + 2 * head
     bwd = (embed + gru + prior) + 2 * head + actor + (3 * Hi * Hi + 2 * A * Hi)
     return 2 * (fwd + bwd)
+
+
+def kernel_macs_per_row_step(d):
+    """Algorithmic MACs per imagined row-step attributed to each of the library's kernels
+    (no recompute, no padding): the roofline numerators."""
+    Be, Hi, S, A = d["Be"], d["Hi"], d["S"], d["A"]
+    embed, gru, prior = (S + A) * Be, 6 * Be * Be, Be * Hi + 2 * S * Hi
+    head = (Be + S) * Hi + 3 * Hi * Hi + Hi
+    actor = (Be + S) * Hi + 3 * Hi * Hi + 2 * A * Hi
+    return {"rollout_fwd": embed + gru + prior + actor, "mlp_fwd": 2 * head,
+            "bptt": embed + gru + prior, "mlp_bwd": 2 * head + 3 * Hi * Hi + 2 * A * Hi,
+            "wgrad": actor, "entropy": 0}
+
+
+PROF_IDS = {"rollout_fwd": 0, "mlp_fwd": 1, "bptt": 2, "mlp_bwd": 3, "wgrad": 4, "entropy": 5}
 
 
 def peaks():
@@ -241,8 +256,21 @@ def run_ours(args):
 
     warmup = max(3, args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
-    # (1) device-resident inputs: the kernel-side number
-    ms_dev, launches = timed(lambda: step(s0, b0, noise), args.steps, warmup)
+    # (1) device-resident inputs: the kernel-side number (per-kernel CUDA events recorded by the
+    # library on its launch stream during the same timed loop)
+    import ctypes as C
+    lib.bd_prof_enable(0)
+    for _ in range(warmup):
+        step(s0, b0, noise)
+    lib.bd_prof_enable(1)
+    ms_dev, launches = timed(lambda: step(s0, b0, noise), args.steps, 0)
+    kernels = {}
+    for name, kid in PROF_IDS.items():
+        ms, n = C.c_float(0), C.c_int(0)
+        lib.bd_prof_read(kid, C.byref(ms), C.byref(n))
+        if n.value:
+            kernels[name] = {"ms_per_step": ms.value / args.steps, "launches_per_step": n.value / args.steps}
+    lib.bd_prof_enable(0)
 
     # (2) end to end through the public API: host latents in pinned memory, H2D inside the timed
     # region, noise drawn by the API itself (as the reference does), D2H of the logged scalars
@@ -269,8 +297,21 @@ def run_ours(args):
     e2e_value = world * rows * T / (total_e2e_ms / args.steps * 1e-3)
     pk = peaks()
     flops = algorithmic_flops_per_row_step(d) * rows * T           # per GPU per step
-    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    step_tflops = flops / (ms_per_step * 1e-3) / 1e12
     peak = pk["bf16_sustained"]
+    macs = kernel_macs_per_row_step(d)
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    if dom is not None and macs[dom] > 0:
+        kflops = 2 * macs[dom] * rows * T
+        achieved = kflops / (kernels[dom]["ms_per_step"] * 1e-3) / 1e12
+        note = (f"dominant kernel '{dom}': algorithmic {kflops / 1e9:.1f} GFLOP per step / its CUDA-event "
+                f"time {kernels[dom]['ms_per_step']:.3f} ms (sum of its launches in a step); whole step: "
+                f"{flops / 1e9:.1f} GFLOP -> {step_tflops:.1f} TFLOP/s = {step_tflops / peak:.4f} of peak; "
+                f"peak = bf16 sustained of {pk['source']} peaks")
+    else:
+        achieved = step_tflops
+        note = (f"algorithmic FLOPs of the whole step ({flops / 1e9:.1f} GFLOP) / CUDA-event step time; "
+                f"peak = bf16 sustained of {pk['source']} peaks")
     out = {
         "metric": "imagined_latent_steps_per_sec_fwd_bwd", "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
@@ -281,10 +322,10 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(s0_h.numel() * 4 + b0_h.numel() * 4),
                 "d2h_bytes_per_step": 8, "ms_per_step": total_e2e_ms / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None,
-                     "note": f"algorithmic FLOPs of the whole step ({flops / 1e9:.1f} GFLOP) / "
-                             f"CUDA-event step time; peak = bf16 sustained of {pk['source']} peaks"},
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "step_frac": step_tflops / peak, "note": note},
+        "kernels": kernels,
         "clocks": clocks,
         "ms_min": min(ms_dev), "ms_median": statistics.median(ms_dev),
     }
@@ -304,7 +345,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BD_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("BD_PRECISION", "fp16"),
+                    help="fp16 (default: tcgen05, fp16 operands / fp32 accumulate), bf16, or fp32 check mode")
     ap.add_argument("--rows", type=int, default=ROWS_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

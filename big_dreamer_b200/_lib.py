@@ -112,6 +112,8 @@ SIGNATURES = {
     "bd_last_error": (C.c_char_p, []),
     "bd_launch_count": (C.c_ulonglong, []),
     "bd_precision_supported": (C.c_int, [C.c_int]),
+    "bd_prof_enable": (None, [C.c_int]),
+    "bd_prof_read": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "bd_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int64, C.c_int]),
     "bd_mlp_forward": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,

@@ -14,6 +14,38 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace bd
 
+#include <vector>
+namespace bd {
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[BD_PROF_COUNT];
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t open_start[BD_PROF_COUNT] = {};
+} g_prof;
+cudaEvent_t prof_event() {
+  if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+bool prof_enabled() { return g_prof.on; }
+void prof_begin(int k, cudaStream_t s) {
+  if (!g_prof.on || k < 0 || k >= BD_PROF_COUNT) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, s);
+  g_prof.open_start[k] = e;
+}
+void prof_end(int k, cudaStream_t s) {
+  if (!g_prof.on || k < 0 || k >= BD_PROF_COUNT || !g_prof.open_start[k]) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, s);
+  g_prof.ev[k].push_back({g_prof.open_start[k], e});
+  g_prof.open_start[k] = nullptr;
+}
+}  // namespace bd
+
 using namespace bd;
 
 #define BD_NEED(p, what)                                           \
@@ -36,6 +68,23 @@ extern "C" {
 int bd_version(void) { return BD_ABI_VERSION; }
 const char* bd_last_error(void) { return bd::g_err; }
 unsigned long long bd_launch_count(void) { return bd::g_launch_count; }
+void bd_prof_enable(int on) { bd::g_prof.on = on != 0; }
+int bd_prof_read(int kernel, float* ms_total, int* launches) {
+  if (kernel < 0 || kernel >= BD_PROF_COUNT) BD_FAIL(BD_ERR_BAD_ARG, "bd_prof_read: bad kernel id");
+  float tot = 0.f;
+  int n = 0;
+  for (auto& pr : bd::g_prof.ev[kernel]) {
+    float ms = 0.f;
+    cudaEventSynchronize(pr.second);
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { tot += ms; ++n; }
+    bd::g_prof.pool.push_back(pr.first);
+    bd::g_prof.pool.push_back(pr.second);
+  }
+  bd::g_prof.ev[kernel].clear();
+  if (ms_total) *ms_total = tot;
+  if (launches) *launches = n;
+  return BD_OK;
+}
 int bd_precision_supported(int precision) {
   return (precision == BD_PREC_FP32 || precision == BD_PREC_FP16 || precision == BD_PREC_BF16) ? 1 : 0;
 }

@@ -38,6 +38,16 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
     if (rc__ != BD_OK) return rc__; \
   } while (0)
 
+// ---------------------------------------------------------------- optional per-kernel timing
+bool prof_enabled();
+void prof_begin(int kernel, cudaStream_t s);   // records a start event (no-op when disabled)
+void prof_end(int kernel, cudaStream_t s);     // records the matching stop event
+struct ProfScope {
+  int k; cudaStream_t s;
+  ProfScope(int kernel, cudaStream_t stream) : k(kernel), s(stream) { prof_begin(k, s); }
+  ~ProfScope() { prof_end(k, s); }
+};
+
 // ---------------------------------------------------------------- activations
 // torch semantics: ELU(alpha=1) uses expm1; softplus(beta=1, threshold=20).
 __device__ __forceinline__ float act_fwd(int act, float x) {

@@ -252,9 +252,14 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
 }
 
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_exp(float x) {   // single MUFU.EX2, flush-to-zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
 template <int ACT>
 __device__ __forceinline__ float tc_act_t(float x) {
-  if (ACT == BD_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (ACT == BD_ACT_ELU) return fmaxf(x, 0.f) + fminf(fast_exp(x) - 1.f, 0.f);
   if (ACT == BD_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == BD_ACT_TANH) return fast_tanh(x);
   return x;

@@ -224,7 +224,11 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
   else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
   BD_CUDA_LAUNCH_CHECK();
-  BD_TRY(launch_rollout(fmt, r.activation, true, prof, grid, ra, s));
+  {
+    ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
+    BD_TRY(launch_rollout(fmt, r.activation, true, prof, grid, ra, s));
+  }
+  ProfScope pe(BD_PROF_ENTROPY, s);
   // entropy + its gradient wrt (mean, std): independent of the recurrence -> separate parallel pass
   dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
   actor_entropy_kernel<<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy,
@@ -386,6 +390,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   ba.g_entropy = a->g_entropy;
   ba.d_raw = d_raw; ba.d_prev_state = a->d_prev_state; ba.d_prev_belief = a->d_prev_belief;
   ba.scr_carry = scr_carry; ba.scr_gtot = scr_gtot; ba.amax_bits = amax;
+  ProfScope ps(BD_PROF_BPTT, s);
   if (fmt == 0) {
     cudaFuncSetAttribute(bptt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
     bptt_kernel<0><<<grid, kThreads, ba.sm.total, s>>>(ba);
@@ -475,6 +480,7 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
   if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
   else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
   BD_CUDA_LAUNCH_CHECK();
+  ProfScope ps(BD_PROF_MLP_FWD, s);
   return launch_rollout(fmt, m->activation, false, false, grid, ra, s);
 }
 

@@ -232,8 +232,11 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
     const unsigned grid = (unsigned)(nt < sms ? nt : sms);
-    if (fmt == 0) BD_TRY(launch_bwd_act<0>(m->activation, grid, ba, s));
-    else BD_TRY(launch_bwd_act<1>(m->activation, grid, ba, s));
+    {
+      ProfScope ps(BD_PROF_MLP_BWD, s);
+      if (fmt == 0) BD_TRY(launch_bwd_act<0>(m->activation, grid, ba, s));
+      else BD_TRY(launch_bwd_act<1>(m->activation, grid, ba, s));
+    }
 
     if (want_w) {
       WgradArgs wa{};
@@ -260,6 +263,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
         if (per > nt) per = nt;
         if (per < 1) per = 1;
         dim3 wgrid((unsigned)per, (unsigned)nj);
+        ProfScope ps(BD_PROF_WGRAD, s);
         if (fmt == 0) {
           cudaFuncSetAttribute(wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           wgrad_kernel<0><<<wgrid, 128, smem, s>>>(wa);

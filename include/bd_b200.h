@@ -277,6 +277,23 @@ size_t bd_cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B
 int bd_cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, int precision,
                 bd_stream_t stream);
 
+/* ---------------------------------------------------------------- profiling ---- */
+/* Optional CUDA-event timing of the library's own main kernels, recorded on the stream each
+ * kernel is launched on.  bd_prof_enable(1) starts collecting; bd_prof_read synchronises the
+ * recorded events and returns the accumulated milliseconds and launch count of one kernel id,
+ * then clears it.  Used by bench.py for the roofline block; off by default (no overhead). */
+enum bd_prof_kernel {
+  BD_PROF_ROLLOUT_FWD = 0, /* persistent tcgen05 rollout (imagine / transition / CEM)   */
+  BD_PROF_MLP_FWD = 1,     /* tcgen05 MLP forward (DenseModel)                            */
+  BD_PROF_BPTT = 2,        /* tcgen05 reverse-time dgrad chain                            */
+  BD_PROF_MLP_BWD = 3,     /* tcgen05 MLP recompute + dgrad chain                         */
+  BD_PROF_WGRAD = 4,       /* streaming tcgen05 wgrad                                     */
+  BD_PROF_ENTROPY = 5,     /* Monte-Carlo policy entropy                                  */
+  BD_PROF_COUNT = 6
+};
+void bd_prof_enable(int on);
+int bd_prof_read(int kernel, float* ms_total, int* launches);
+
 /* ---------------------------------------------------------------- self-test ---- */
 /* One 128-row tile of y (128,N) = x (128,K) w(N,K)^T + b through the tcgen05 building block
  * (16-bit operands: fmt 0 = fp16, 1 = bf16; fp32 accumulation).  ws: >= 2*roundup16(N)*roundup16(K+1)
