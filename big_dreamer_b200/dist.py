@@ -82,8 +82,9 @@ def gather_candidates(local_returns: torch.Tensor, local_actions: torch.Tensor,
     pack = torch.zeros(cmax, B * (1 + H * A), device=local_returns.device, dtype=torch.float32)
     pack[:Cl, :B] = local_returns.t()
     pack[:Cl, B:] = local_actions.permute(2, 1, 0, 3).reshape(Cl, B * H * A)
-    out = torch.empty(world, cmax, B * (1 + H * A), device=pack.device, dtype=torch.float32)
-    dist.all_gather_into_tensor(out, pack)
+    out = torch.empty(world * cmax, B * (1 + H * A), device=pack.device, dtype=torch.float32)
+    dist.all_gather_into_tensor(out, pack)      # concatenated along dim 0 (works on nccl and gloo)
+    out = out.view(world, cmax, B * (1 + H * A))
     rets, acts = [], []
     for r in range(world):
         blk = out[r, :sizes[r]]
