@@ -160,6 +160,11 @@ def run_reference(args):
         return
     d, rows, T = CFG, args.rows, CFG["H"] - 1
     steps = min(args.steps, 20)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it is allowed
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     ts = time_cpu(d, rows, steps, max(1, min(args.warmup, 2)))
     mean = sum(ts) / len(ts)
     val = rows * T / mean
@@ -177,6 +182,49 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+CEM_CFG = dict(B=1, C=1000, K=100, H=12, iters=10)      # BASELINE configs[2]
+
+
+def cem_block(bd, orc, pu, dev, precision, with_cpu):
+    """Secondary metric: CEM candidate evaluations/s of MPCPlanner.forward (BASELINE configs[2])."""
+    d = dict(CFG, **CEM_CFG)
+    trans, _, reward, _ = orc.make_models(0, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    mods = pu.build_gpu_models(d, trans, reward_sd=reward, device=dev)
+    pl = bd.MPCPlanner(d["A"], d["H"], d["iters"], d["C"], d["K"], mods.transition, mods.reward)
+    belief = torch.zeros(d["B"], d["Be"], device=dev)      # episode start (src/main.py:93-94)
+    state = torch.zeros(d["B"], d["S"], device=dev)
+    for _ in range(3):
+        pl(belief, state)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        pl(belief, state)                                  # draws its own noise, as the reference does
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out = {"metric": "cem_candidate_evaluations_per_sec", "value": d["B"] * d["C"] * d["iters"] / (ms * 1e-3),
+           "unit": "candidate_evals/s", "ms_per_plan": ms, "candidate_steps_per_sec":
+           d["B"] * d["C"] * d["iters"] * d["H"] / (ms * 1e-3), "config": dict(CEM_CFG, belief_size=d["Be"],
+           state_size=d["S"], action_size=d["A"]), "precision": precision}
+    if with_cpu:
+        g = torch.Generator().manual_seed(0)
+        ea = torch.randn(d["iters"], d["H"], d["B"], d["C"], d["A"], generator=g)
+        es = torch.randn(d["iters"], d["H"], d["B"] * d["C"], d["S"], generator=g)
+        b0, s0 = torch.zeros(d["B"], d["Be"]), torch.zeros(d["B"], d["S"])
+        with torch.no_grad():
+            orc.cem_plan(trans, reward, d["act"], 0.1, d["A"], d["H"], d["iters"], d["C"], d["K"], b0, s0, ea, es)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                orc.cem_plan(trans, reward, d["act"], 0.1, d["A"], d["H"], d["iters"], d["C"], d["K"], b0, s0, ea, es)
+            cpu_s = (time.perf_counter() - t0) / 3
+        out["cpu_baseline"] = {"value": d["B"] * d["C"] * d["iters"] / cpu_s, "unit": "candidate_evals/s",
+                               "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "3 full plans of the oracle port"}
+    return out
 
 
 def workload_config(rows, precision):
@@ -329,6 +377,8 @@ def run_ours(args):
         "clocks": clocks,
         "ms_min": min(ms_dev), "ms_median": statistics.median(ms_dev),
     }
+    if world == 1:
+        out["cem"] = cem_block(bd, orc, pu, dev, args.precision, not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         ts = time_cpu(d, rows, 5, 1)
         cores = torch.get_num_threads()

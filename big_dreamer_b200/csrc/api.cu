@@ -222,7 +222,7 @@ int bd_cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int pr
                     bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
-  return f32::cem_evaluate(a, ws, ws_bytes, stream);
+  return f32::cem_evaluate(a, ws, ws_bytes, stream, precision);
 }
 int bd_cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,
                  int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream) {
@@ -235,7 +235,7 @@ int bd_cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, int precis
                 bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
-  return f32::cem_plan(a, ws, ws_bytes, stream);
+  return f32::cem_plan(a, ws, ws_bytes, stream, precision);
 }
 
 }  // extern "C"

@@ -621,10 +621,14 @@ static size_t cem_row_floats(const bd_rssm& r, const bd_mlp& reward, int H) {
          2 * (size_t)(r.belief_size + r.state_size) + (size_t)H + 3 * r.state_size;
 }
 size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H) {
-  return (size_t)B * C_local * cem_row_floats(*r, *reward, H) * sizeof(float) + kSlackBytes;
+  size_t f = (size_t)B * C_local * cem_row_floats(*r, *reward, H) * sizeof(float) + kSlackBytes;
+  size_t t = tc::cem_tc_workspace_bytes(*r, *reward, (long long)B * C_local, H) +
+             (size_t)B * C_local * H * sizeof(float) + kSlackBytes;
+  return f > t ? f : t;
 }
 
-int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream) {
+int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+                 int precision) {
   const bd_rssm& r = a->rssm;
   BD_TRY(check_rssm(r, false));
   BD_TRY(check_mlp(a->reward, r.belief_size + r.state_size));
@@ -638,6 +642,19 @@ int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream
   const int Cl = a->c_end - a->c_begin;
   const long long rows = (long long)B * Cl;
   BD_CHECK_ARG(rows <= kMaxChunkRows * 4LL, "cem: too many candidate rows for one call");
+  if (precision != BD_PREC_FP32 && tc::cem_supported(r, a->reward, precision)) {
+    // tensor-core path: sample the actions, then one persistent rollout with the reward head fused
+    Arena ar(ws, ws_bytes);
+    float* rew = ar.f32((size_t)rows * H);
+    if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "cem_evaluate: workspace too small");
+    cem_sample_kernel<<<grid1d((long long)H * rows * A), 256, 0, s>>>(
+        a->action_mean, a->action_std, a->eps_act, H, B, C, a->c_begin, Cl, A, a->actions);
+    BD_CUDA_LAUNCH_CHECK();
+    BD_TRY(tc::cem_rollout(a, ar.base + ar.off, ar.cap - ar.off, precision, rew, stream));
+    cem_sum_rewards_kernel<<<grid1d(rows), 256, 0, s>>>(rew, H, rows, a->returns);
+    BD_CUDA_LAUNCH_CHECK();
+    return BD_OK;
+  }
   Arena ar(ws, ws_bytes);
   StepBuf w;
   bool ok = carve_step(ar, r, rows, false, false, w);
@@ -712,7 +729,7 @@ size_t cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, i
          ((size_t)H * B * C * A + (size_t)B * C + 2 * (size_t)H * B * A) * sizeof(float) + kSlackBytes;
 }
 
-int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream) {
+int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream, int precision) {
   const bd_rssm& r = a->rssm;
   BD_CHECK_ARG(a->iters >= 1 && a->K >= 1 && a->K <= a->C, "cem_plan: bad iters/K");
   BD_CHECK_ARG(a->action_out && a->eps_act && a->eps_s, "cem_plan: null pointer");
@@ -738,7 +755,7 @@ int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t s
     e.eps_act = a->eps_act + (long long)it * H * B * C * A;
     e.eps_s = a->eps_s + (long long)it * H * B * C * r.state_size;
     e.actions = actions; e.returns = returns;
-    BD_TRY(cem_evaluate(&e, sub, sub_bytes, stream));
+    BD_TRY(cem_evaluate(&e, sub, sub_bytes, stream, precision));
     if (a->returns_trace)
       cudaMemcpyAsync(a->returns_trace + (long long)it * B * C, returns, (size_t)B * C * sizeof(float),
                       cudaMemcpyDeviceToDevice, s);

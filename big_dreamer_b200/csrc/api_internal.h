@@ -29,11 +29,13 @@ int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd
 int imagine_backward_ex(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
                         float* d_raw_all);
 size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H);
-int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+                 int precision = BD_PREC_FP32);
 int cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,
               int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream);
 size_t cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C, int K, int H);
-int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+             int precision = BD_PREC_FP32);
 }  // namespace f32
 
 namespace tc {   // tensor-core (tcgen05) path: 16-bit operands, fp32 accumulation and state
@@ -45,6 +47,10 @@ size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
 size_t bptt_workspace_bytes(const bd_rssm& r);
 int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
                  bd_stream_t stream);
+bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision);
+size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long rows, int H);
+int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,
+                bd_stream_t stream);
 bool mlp_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_pack_bytes(const bd_mlp& m);
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,

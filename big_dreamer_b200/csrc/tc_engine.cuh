@@ -99,6 +99,9 @@ struct RolloutArgs {
   uint16_t *sv_gate, *sv_xa, *sv_ha;
   int kb_sv, kh_sv;
   int has_b1;                 // 0: single belief tile (MLP forward), 1: ping-pong
+  // CEM: rows are (batch row, local candidate); start latents are per batch row and the state
+  // noise is indexed by the GLOBAL candidate (src/planner.py:37-39, 53-65)
+  int cem_cl, cem_c, cem_c0;  // local candidates per batch row (0 = off), global candidates, first
 };
 
 // fast-math activations for the 16-bit path (the result is rounded to 10 / 7 mantissa bits anyway)
@@ -328,11 +331,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
+          const long long sr = a.cem_cl ? gr / a.cem_cl : gr;     // CEM: latents are per batch row
           float v[8], z[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = (k < Be) ? ((gr < a.N) ? a.prev_belief[gr * Be + k] : 0.f) : (k == Be ? 1.f : 0.f);
+            v[j] = (k < Be) ? ((gr < a.N) ? a.prev_belief[sr * Be + k] : 0.f) : (k == Be ? 1.f : 0.f);
             z[j] = (k == Be) ? 1.f : 0.f;
           }
           store8<FMT>(B0 + kg * kLboA + r * 16, v);
@@ -342,12 +346,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
+          const long long sr = a.cem_cl ? gr / a.cem_cl : gr;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
             float x = 0.f;
-            if (k < S) x = (gr < a.N && a.prev_state) ? a.prev_state[gr * S + k] : 0.f;
+            if (k < S) x = (gr < a.N && a.prev_state) ? a.prev_state[sr * S + k] : 0.f;
             else if (k == S + Ad) x = 1.f;
             else if (!WITH_ACTOR && k < S + Ad && gr < a.N && a.ext_actions) x = a.ext_actions[gr * Ad + (k - S)];
             v[j] = x;
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
             } break;
             case EPI_GRU: {
               const int n0 = ph.aux0, Ns = ph.Np;
-              const float* bold = (t == 0) ? a.prev_belief + grow * Be
+              const float* bold = (t == 0) ? a.prev_belief + (a.cem_cl ? grow / a.cem_cl : grow) * Be
                                            : a.beliefs + ((long long)(t - 1) * a.N + grow) * Be;
               float* bnew = a.beliefs + orow * Be;
               // previous belief (fp32 master copy) for this thread's columns: issued before the wait
@@ -528,16 +533,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
             case EPI_PRIOR_OUT: {
               const int Sp = ph.Np;    // mean at [0,Sp), raw std at [Sp, 2Sp)
               const int c = half * 16;
+              // row of this thread in the state-noise tensor
+              const long long erow = a.cem_cl
+                  ? (long long)t * ((a.N / a.cem_cl) * a.cem_c) + (grow / a.cem_cl) * a.cem_c + a.cem_c0 + grow % a.cem_cl
+                  : orow;
               float eps[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) eps[j] = (rvalid && c + j < S) ? a.eps_s[orow * S + c + j] : 0.f;
+              for (int j = 0; j < 16; ++j) eps[j] = (rvalid && c + j < S) ? a.eps_s[erow * S + c + j] : 0.f;
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
               for (int cc = c, it = 0; cc < Sp; cc += 32, ++it) {
                 if (it > 0) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[orow * S + cc + j] : 0.f;
+                  for (int j = 0; j < 16; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[erow * S + cc + j] : 0.f;
                 }
                 float m_[16], s_[16];
                 tmem_ld16(tacc + cc, m_);
@@ -549,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   if (col < S) {
                     const float sd = softplusf_(s_[j]) + a.min_std;
                     const float st = fmaf(sd, eps[j], m_[j]);
-                    if (rvalid) {
+                    if (rvalid && a.means) {
                       a.means[orow * S + col] = m_[j];
                       a.stds[orow * S + col] = sd;
                       a.states[orow * S + col] = st;

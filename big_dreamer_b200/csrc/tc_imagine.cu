@@ -238,6 +238,139 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared by CEM and TransitionModel.forward (prior-only): embed -> GRU slices -> prior phases
+// ---------------------------------------------------------------------------------------------
+static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp_sa, int Kp_hid, int Kp_x,
+                                  bool save) {
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Nh = r16(Hi), Nb = r16(Be), Sp = r16(S);
+  {
+    uint32_t w = b.add_pack(r.embed.w, S + A, 0, Be, Nb, Kp_sa, 0, S + A, r.embed.b, S + A);
+    int d = b.dcol();
+    b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
+    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, save ? 1 : 0, TILE_H);
+  }
+  int slice = 0;
+  for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
+    const int nv = min(64, Be - n0), Ns = r16(nv);
+    int d = b.dcol();
+    uint32_t w[6];
+    for (int g = 0; g < 3; ++g) {
+      w[2 * g] = b.add_pack(r.w_ih, Be, g * Be + n0, nv, Ns, Kp_x, 0, Be, r.b_ih, Be);
+      w[2 * g + 1] = b.add_pack(r.w_hh, Be, g * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
+    }
+    b.add_gemm(w[0], Ns, Kp_x, TILE_H, 0, d, 0);
+    b.add_gemm(w[1], Ns, Kp_b, TILE_BCUR, 0, d, 1);
+    b.add_gemm(w[2], Ns, Kp_x, TILE_H, 0, d + Ns, 0);
+    b.add_gemm(w[3], Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
+    b.add_gemm(w[4], Ns, Kp_x, TILE_H, 0, d + 2 * Ns, 0);
+    b.add_gemm(w[5], Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);
+    b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
+  }
+  {
+    uint32_t w1 = b.add_pack(r.prior1.w, Be, 0, Hi, Nh, Kp_b, 0, Be, r.prior1.b, Be);
+    int d = b.dcol();
+    b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
+    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, save ? 2 : 0, TILE_H);
+    uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+    uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+    d = b.dcol();
+    b.add_gemm(wm, Sp, Kp_hid, TILE_H, 0, d, 0);
+    b.add_gemm(wsd, Sp, Kp_hid, TILE_H, 0, d + Sp, 0);
+    b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
+  }
+}
+
+bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision) {
+  if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
+  if (!(r.activation == BD_ACT_ELU || r.activation == BD_ACT_RELU || r.activation == BD_ACT_TANH ||
+        r.activation == BD_ACT_IDENTITY) || reward.activation != r.activation) return false;
+  if (r.belief_size + 1 > 256 || r.hidden_size + 1 > 256 || r.state_size > 128 || r.action_size > 16) return false;
+  if (reward.n_layers < 2 || reward.layer[reward.n_layers - 1].out_features != 1) return false;
+  for (int l = 0; l + 1 < reward.n_layers; ++l)
+    if (reward.layer[l].out_features + 1 > 256) return false;
+  // the 5-slice GRU + head programs must fit the job tables
+  return (r.belief_size + 63) / 64 * 6 + 2 * reward.n_layers + 6 <= kMaxPackJobs;
+}
+size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long rows, int H) {
+  return imagine_pack_bytes(r, reward) + mlp_pack_bytes(reward) +
+         ((size_t)H * rows * r.belief_size + (size_t)H * rows) * sizeof(float) + 8192;
+}
+
+// Candidate evaluation of one CEM iteration on the rollout engine: actions are given, the reward
+// head is fused into every step, only the per-step rewards leave the SM (plus the fp32 belief).
+// a->actions must already hold the sampled local actions (H, B, Cl, A).
+int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,
+                bd_stream_t stream) {
+  const bd_rssm& r = a->rssm;
+  const bd_mlp& hd = a->reward;
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1), Ks = r16(S);
+  int Kp_h = max(Kp_hid, Kp_x);
+  const int Cl = a->c_end - a->c_begin;
+  const long long rows = (long long)a->B * Cl;
+  Builder b;
+  add_transition_phases(b, r, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
+  // reward head on (b', s'): DenseModel (src/planner.py:68-72)
+  for (int l = 0; l < hd.n_layers; ++l) {
+    const bd_linear& L = hd.layer[l];
+    const bool last = (l == hd.n_layers - 1);
+    const int n = L.out_features, Np = r16(n);
+    const int d = b.dcol();
+    if (l == 0) {
+      uint32_t wb = b.add_pack(L.w, Be + S, 0, n, Np, Kp_b, 0, Be, L.b, Be);
+      uint32_t wsx = b.add_pack(L.w, Be + S, 0, n, Np, Ks, Be, S, nullptr, -1);
+      b.add_gemm(wb, Np, Kp_b, TILE_BNXT, 0, d, 0);
+      b.add_gemm(wsx, Np, Ks, TILE_SA, 0, d, 1);
+    } else {
+      const int kin = L.in_features, Kp = r16(kin + 1);
+      uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
+      b.add_gemm(w, Np, Kp, TILE_H, 0, d, 0);
+    }
+    if (last) b.end_phase(EPI_HEAD_OUT, 1, 1, Np, 0, d, 0, TILE_H);
+    else { b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H); Kp_h = max(Kp_h, r16(n + 1)); }
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core CEM: program too large");
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p_ = base + off; off += (bytes + 255) & ~size_t(255); return p_; };
+  uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
+  float* beliefs = reinterpret_cast<float*>(take((size_t)a->H * rows * Be * sizeof(float)));
+  if (off > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core CEM: workspace %zu < %zu", ws_bytes, off);
+
+  RolloutArgs ra{};
+  if (!plan_smem(Kp_b, Kp_sa, Kp_h, b.max_stage, ra.sm))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core CEM: tiles do not fit shared memory");
+  b.finalize_blocks(ra.sm.stage_bytes);
+  ra.prog = b.prog;
+  ra.wpack = wpack;
+  ra.N = rows; ra.T = a->H; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = 0;
+  ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
+  ra.prev_state = a->state; ra.prev_belief = a->belief; ra.eps_s = a->eps_s;
+  ra.beliefs = beliefs; ra.states = nullptr; ra.means = nullptr; ra.stds = nullptr;
+  ra.head_out[0] = rew_out; ra.ext_actions = a->actions; ra.has_b1 = 1;
+  ra.cem_cl = Cl; ra.cem_c = a->C; ra.cem_c0 = a->c_begin;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long max_img = 0;
+  for (int i = 0; i < b.pack.njobs; ++i)
+    max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+  long long pgx = (max_img + 255) / 256;
+  if (pgx > 64) pgx = 64;
+  dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+  const long long ntiles = (rows + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+  BD_CUDA_LAUNCH_CHECK();
+  ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
+  return launch_rollout(fmt, r.activation, false, false, grid, ra, s);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BPTT of the imagination rollout on the tensor-core engine (tc_bptt.cuh)
 // ---------------------------------------------------------------------------------------------
 static uint32_t add_pack_T(Builder& b, const float* w, int ld, int n_valid, int Np, int Kp, int nseg,
