@@ -49,9 +49,10 @@ struct BpttArgs {
   float *d_prev_state, *d_prev_belief;
   float *scr_carry, *scr_gtot;   // per-CTA scratch, [gridDim.x][128][Kb] fp32
   const unsigned int* amax_bits;
+  PrefetchPlan pf;
 };
 
-template <int FMT>
+template <int FMT, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const BpttArgs& a = A_;
@@ -63,9 +64,9 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
   const Program& P = a.prog;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh);
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf);
   } else if (warp == 1) {
-    issuer_role<FMT, false>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, nullptr);
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof);
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
@@ -74,8 +75,11 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
     const int Be = a.Be, S = a.S, Ad = a.A, Kb = a.Kb;
     uint8_t* Ht = smem + a.sm.off_tile[TILE_H];
     uint8_t* D2 = smem + a.sm.off_tile[TILE_D2];
-    float* carry = a.scr_carry + ((size_t)blockIdx.x * kTileRows + row) * Kb;
-    float* gtot = a.scr_gtot + ((size_t)blockIdx.x * kTileRows + row) * Kb;
+    // per-CTA fp32 scratch, stored as [col/4][row][4] so a warp's float4 accesses are contiguous;
+    // SIDX(col) (col a multiple of 4) is this thread's float4 slot
+    float* carry = a.scr_carry + (size_t)blockIdx.x * kTileRows * Kb + row * 4;
+    float* gtot = a.scr_gtot + (size_t)blockIdx.x * kTileRows * Kb + row * 4;
+#define SIDX(col) ((size_t)((col) >> 2) * (kTileRows * 4))
     float inv_scale;
     const float scale = grad_scale(a.amax_bits, &inv_scale);
     uint32_t Ge = 0, Gm = 0;
@@ -90,12 +94,58 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
         const size_t tl = (size_t)t * ntiles + tile;          // (t, tile) index of the saved images
         for (int pi = 0; pi < P.n_phases; ++pi) {
           const Phase ph = P.p[pi];
-          mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);
-          tc_fence_after_sync();
+          long long e0 = 0, e1 = 0;
+          if (PROF) e0 = clock64();
+          // Gate stages after the first do not read their own phase's accumulator: they only need
+          // the slab they overwrite to be free, i.e. the PREVIOUS phase's MMAs done (Kp_out = 1).
+          const uint32_t Gw = Gm - ((ph.epi == EPI_P_GATE && ph.Kp_out) ? 1u : 0u);
+#define BD_WAIT_ACC()                                         \
+  do {                                                        \
+    mbar_wait(&sh.acc_full[Gw & 3], (Gw >> 2) & 1);           \
+    tc_fence_after_sync();                                    \
+    if (PROF) e1 = clock64();                                 \
+  } while (0)
           switch (ph.epi) {
             case EPI_P_DPRE2: {
               const int Sp = a.Sp;
+              // branch-free clamped loads of everything that does not depend on TMEM; the first
+              // chunk's loads are issued before the accumulator wait
+              const long long lrow = rvalid ? orow : (long long)t * a.N;       // any valid row
+              float sd_[16], ep_[16], gs_[16], gm_[16], gd_[16];
+              auto load_chunk = [&](int c) {
+                if ((S & 1) == 0) {     // rows are 8-byte aligned: 64-bit loads, clamped inside the row
+#pragma unroll
+                  for (int j = 0; j < 16; j += 2) {
+                    const long long o = lrow * S + min(c + j, S - 2);
+                    const float2 x0 = *reinterpret_cast<const float2*>(a.stds + o);
+                    const float2 x1 = *reinterpret_cast<const float2*>(a.eps_s + o);
+                    sd_[j] = x0.x; sd_[j + 1] = x0.y; ep_[j] = x1.x; ep_[j + 1] = x1.y;
+                    float2 y = make_float2(0.f, 0.f);
+                    if (a.g_states) y = *reinterpret_cast<const float2*>(a.g_states + o);
+                    gs_[j] = y.x; gs_[j + 1] = y.y;
+                    y = make_float2(0.f, 0.f);
+                    if (a.g_means) y = *reinterpret_cast<const float2*>(a.g_means + o);
+                    gm_[j] = y.x; gm_[j + 1] = y.y;
+                    y = make_float2(0.f, 0.f);
+                    if (a.g_stds) y = *reinterpret_cast<const float2*>(a.g_stds + o);
+                    gd_[j] = y.x; gd_[j + 1] = y.y;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const long long o = lrow * S + min(c + j, S - 1);
+                    sd_[j] = a.stds[o];
+                    ep_[j] = a.eps_s[o];
+                    gs_[j] = a.g_states ? a.g_states[o] : 0.f;
+                    gm_[j] = a.g_means ? a.g_means[o] : 0.f;
+                    gd_[j] = a.g_stds ? a.g_stds[o] : 0.f;
+                  }
+                }
+              };
+              if (half * 16 < Sp) load_chunk(half * 16);
+              BD_WAIT_ACC();
               for (int c = half * 16; c < Sp; c += 32) {
+                if (c != half * 16) load_chunk(c);
                 float cs[16], m_[16], s_[16];
                 if (i > 0) {
                   tmem_ld16(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA
@@ -106,17 +156,13 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  const int col = c + j;
-                  float dmu = 0.f, draw = 0.f;
-                  if (col < S && rvalid) {
-                    const long long o = orow * S + col;
-                    const float gs = cs[j] + (a.g_states ? a.g_states[o] * scale : 0.f);
-                    dmu = gs + (a.g_means ? a.g_means[o] * scale : 0.f);
-                    const float sd = a.stds[o];
-                    const float dsd = gs * a.eps_s[o] + (a.g_stds ? a.g_stds[o] * scale : 0.f);
-                    draw = dsd * (1.f - __expf(-(sd - a.min_std)));   // softplus' = 1 - exp(-softplus)
-                  }
-                  m_[j] = dmu; s_[j] = draw;
+                  const bool ok = (c + j < S) && rvalid;
+                  const float gs = cs[j] + gs_[j] * scale;
+                  const float dmu = gs + gm_[j] * scale;
+                  const float dsd = gs * ep_[j] + gd_[j] * scale;
+                  const float draw = dsd * (1.f - fast_exp(-(sd_[j] - a.min_std)));   // softplus'
+                  m_[j] = ok ? dmu : 0.f;
+                  s_[j] = ok ? draw : 0.f;
                 }
                 uint8_t* p = D2 + (c >> 3) * kLboA + rowoff;
                 store8<FMT>(p, m_);
@@ -138,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8)
                   if (g8 < ngroups) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
+                if (c == half * 32) BD_WAIT_ACC();
                 if (two) tmem_ld32(tacc + c, v);
                 else tmem_ld16(tacc + c, v);
                 tmem_ld_wait();
@@ -159,50 +206,121 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               uint8_t* slab = smem + a.sm.off_tile[ph.out_tile];
               const uint16_t* gimg = a.sv_gate + tl * 5 * kTileRows * Kb + row * 8;
               const size_t plane = (size_t)kTileRows * Kb;
+              // pass A: upstream belief gradient and the carried z.G of the later step, fetched
+              // (branch-free, clamped) before the accumulator wait
+              float pre[2][16];
+              long long q0 = 0, q1 = 0, q2 = 0;
+              if (PROF) q0 = clock64();
+              if (!passB) {
+                // issue every load first (in-order issue would otherwise serialise one round trip
+                // per load pair), then combine
+                const float* gbrow = a.g_beliefs ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
+                float4 cin4[2][4], gb4[2][4];
+                const bool vec = ((Be & 3) == 0);
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                  const int c = half * 16 + it * 32;
+                  const int col0 = n0 + min(c, Ns - 16);
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cb = col0 + j4 * 4;
+                    cin4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    gb4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i > 0) cin4[it][j4] = *reinterpret_cast<const float4*>(carry + SIDX(cb));
+                    if (gbrow) {
+                      if (vec) gb4[it][j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
+                      else {
+                        gb4[it][j4].x = gbrow[min(cb, Be - 1)]; gb4[it][j4].y = gbrow[min(cb + 1, Be - 1)];
+                        gb4[it][j4].z = gbrow[min(cb + 2, Be - 1)]; gb4[it][j4].w = gbrow[min(cb + 3, Be - 1)];
+                      }
+                    }
+                  }
+                }
+                const float sc = rvalid ? scale : 0.f;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                  const int c = half * 16 + it * 32;
+                  const int col0 = n0 + min(c, Ns - 16);
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const int cb = col0 + j4 * 4;
+                    float4 gb = gb4[it][j4];
+                    if (cb >= Be) gb.x = 0.f;          // columns past Be (padding of the last slice)
+                    if (cb + 1 >= Be) gb.y = 0.f;
+                    if (cb + 2 >= Be) gb.z = 0.f;
+                    if (cb + 3 >= Be) gb.w = 0.f;
+                    pre[it][j4 * 4] = cin4[it][j4].x + gb.x * sc; pre[it][j4 * 4 + 1] = cin4[it][j4].y + gb.y * sc;
+                    pre[it][j4 * 4 + 2] = cin4[it][j4].z + gb.z * sc; pre[it][j4 * 4 + 3] = cin4[it][j4].w + gb.w * sc;
+                  }
+                }
+              }
+              if (PROF) q1 = clock64();
+              const int pl3 = passB ? 3 : 2;
+              uint4 cf[4][2];
+              auto load_planes = [&](int c) {
+                const uint16_t* gp = gimg + (size_t)((n0 + c) >> 3) * kTileRows * 8;
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  cf[0][g8] = *reinterpret_cast<const uint4*>(gp + 0 * plane + (size_t)g8 * kTileRows * 8);
+                  cf[1][g8] = *reinterpret_cast<const uint4*>(gp + 1 * plane + (size_t)g8 * kTileRows * 8);
+                  cf[2][g8] = *reinterpret_cast<const uint4*>(gp + pl3 * plane + (size_t)g8 * kTileRows * 8);
+                  if (!passB) cf[3][g8] = *reinterpret_cast<const uint4*>(gp + 4 * plane + (size_t)g8 * kTileRows * 8);
+                }
+              };
+              float Gb[16];
+              if (half * 16 < Ns) {
+                load_planes(half * 16);
+                if (passB) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(gtot + SIDX(n0 + half * 16 + j4 * 4));
+                    Gb[j4 * 4] = g4.x; Gb[j4 * 4 + 1] = g4.y; Gb[j4 * 4 + 2] = g4.z; Gb[j4 * 4 + 3] = g4.w;
+                  }
+                }
+              }
+              if (PROF) q2 = clock64();
+              BD_WAIT_ACC();
+              if (PROF && blockIdx.x == 0 && lane == 0 && warp == 2) {
+                a.prof[(20 + pi) * 8 + 0] += q1 - q0;    // upstream-gradient / carry fetch + combine
+                a.prof[(20 + pi) * 8 + 1] += q2 - q1;    // coefficient-plane loads issued
+                a.prof[(20 + pi) * 8 + 2] += e1 - q2;    // accumulator wait proper
+              }
 #pragma unroll
               for (int it = 0; it < 2; ++it) {
                 const int c = half * 16 + it * 32;
                 if (c < Ns) {
                   const int col0 = n0 + c;
                   float G[16];
+                  if (it > 0) load_planes(c);
                   if (!passB) {
                     tmem_ld16(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
                     tmem_ld_wait();
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                      float4 cin = make_float4(0.f, 0.f, 0.f, 0.f);
-                      if (i > 0) cin = *reinterpret_cast<const float4*>(carry + col0 + j4 * 4);
-                      float gb[4] = {0.f, 0.f, 0.f, 0.f};
-                      if (a.g_beliefs && rvalid) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                          if (col0 + j4 * 4 + j < Be) gb[j] = a.g_beliefs[orow * Be + col0 + j4 * 4 + j] * scale;
-                      }
-                      G[j4 * 4] += cin.x + gb[0]; G[j4 * 4 + 1] += cin.y + gb[1];
-                      G[j4 * 4 + 2] += cin.z + gb[2]; G[j4 * 4 + 3] += cin.w + gb[3];
-                      *reinterpret_cast<float4*>(gtot + col0 + j4 * 4) =
+                      G[j4 * 4] += pre[it][j4 * 4]; G[j4 * 4 + 1] += pre[it][j4 * 4 + 1];
+                      G[j4 * 4 + 2] += pre[it][j4 * 4 + 2]; G[j4 * 4 + 3] += pre[it][j4 * 4 + 3];
+                      *reinterpret_cast<float4*>(gtot + SIDX(col0 + j4 * 4)) =
                           make_float4(G[j4 * 4], G[j4 * 4 + 1], G[j4 * 4 + 2], G[j4 * 4 + 3]);
                     }
+                  } else if (it == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) G[j] = Gb[j];
                   } else {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                      const float4 g4 = *reinterpret_cast<const float4*>(gtot + col0 + j4 * 4);
+                      const float4 g4 = *reinterpret_cast<const float4*>(gtot + SIDX(col0 + j4 * 4));
                       G[j4 * 4] = g4.x; G[j4 * 4 + 1] = g4.y; G[j4 * 4 + 2] = g4.z; G[j4 * 4 + 3] = g4.w;
                     }
                   }
-                  const uint16_t* gp = gimg + (size_t)(col0 >> 3) * kTileRows * 8;
-                  // planes: 0 c_r, 1 c_z, 2 c_n, 3 c_nr, 4 z
-                  const int pl3 = passB ? 3 : 2;
 #pragma unroll
                   for (int part = 0; part < 3; ++part) {
-                    const int pl = part == 0 ? 0 : (part == 1 ? 1 : pl3);
                     float o[16];
 #pragma unroll
                     for (int g8 = 0; g8 < 2; ++g8) {
-                      float cf[8];
-                      unpack8<FMT>(*reinterpret_cast<const uint4*>(gp + pl * plane + (size_t)g8 * kTileRows * 8), cf);
+                      float c8[8];
+                      unpack8<FMT>(cf[part][g8], c8);
 #pragma unroll
-                      for (int j = 0; j < 8; ++j) o[g8 * 8 + j] = G[g8 * 8 + j] * cf[j];
+                      for (int j = 0; j < 8; ++j) o[g8 * 8 + j] = G[g8 * 8 + j] * c8[j];
                     }
                     uint8_t* p = slab + ((part * Ns + c) >> 3) * kLboA + rowoff;
                     store8<FMT>(p, o);
@@ -212,10 +330,10 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
 #pragma unroll
                     for (int g8 = 0; g8 < 2; ++g8) {
                       float zf[8];
-                      unpack8<FMT>(*reinterpret_cast<const uint4*>(gp + 4 * plane + (size_t)g8 * kTileRows * 8), zf);
-                      *reinterpret_cast<float4*>(carry + col0 + g8 * 8) =
+                      unpack8<FMT>(cf[3][g8], zf);
+                      *reinterpret_cast<float4*>(carry + SIDX(col0 + g8 * 8)) =
                           make_float4(G[g8 * 8] * zf[0], G[g8 * 8 + 1] * zf[1], G[g8 * 8 + 2] * zf[2], G[g8 * 8 + 3] * zf[3]);
-                      *reinterpret_cast<float4*>(carry + col0 + g8 * 8 + 4) =
+                      *reinterpret_cast<float4*>(carry + SIDX(col0 + g8 * 8 + 4)) =
                           make_float4(G[g8 * 8 + 4] * zf[4], G[g8 * 8 + 5] * zf[5], G[g8 * 8 + 6] * zf[6], G[g8 * 8 + 7] * zf[7]);
                     }
                   }
@@ -223,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
             } break;
             case EPI_P_DSA: {
+              BD_WAIT_ACC();
               const uint32_t tacc = trow + 256;
               if (half == 0) {
                 const int c0 = (S >> 4) << 4;
@@ -273,23 +392,30 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                     if (rvalid) {
 #pragma unroll
                       for (int j = 0; j < 16; ++j)
-                        if (c + j < Be) a.d_prev_belief[grow * Be + c + j] = (v[j] + carry[c + j]) * inv_scale;
+                        if (c + j < Be) a.d_prev_belief[grow * Be + c + j] = (v[j] + carry[SIDX((c + j) & ~3) + ((c + j) & 3)]) * inv_scale;
                     }
                   }
                 }
               }
             } break;
-            default: break;
+            default: BD_WAIT_ACC(); break;
           }
+#undef BD_WAIT_ACC
           tc_fence_before_sync();
           fence_proxy_async_smem();
           mbar_arrive(&sh.epi_done[Ge & 3]);
+          if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
+            const int o = pi * 8 + (warp == 2 ? 3 : 5);
+            a.prof[o] += e1 - e0;
+            a.prof[o + 1] += clock64() - e1;
+          }
           ++Ge;
           ++Gm;
         }
       }
     }
   }
+#undef SIDX
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);

@@ -156,16 +156,40 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
   return sh.tmem_holder;
 }
 
+// Per-(tile, step) global inputs of the epilogues that the producer warp pulls into L2 one step
+// ahead (prefetch.global.L2), so the epilogues see L2 latency instead of first-touch DRAM latency.
+struct PrefetchPlan {
+  int n;                     // number of ranges (0 = off)
+  int reverse;               // 1: the kernel walks time backwards (step index i -> t = T-1-i)
+  const char* base[6];
+  long long step_stride[6];  // bytes between consecutive t
+  long long tile_stride[6];  // bytes between consecutive tiles
+  unsigned int bytes[6];     // bytes per (tile, step)
+};
+__device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long tile, int t) {
+  const int lane = threadIdx.x & 31;
+  for (int r = 0; r < pf.n; ++r) {
+    const char* p = pf.base[r] + t * pf.step_stride[r] + tile * pf.tile_stride[r];
+    for (unsigned int o = lane * 128u; o < pf.bytes[r]; o += 32u * 128u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  }
+}
+
 // The whole warp walks the program so every address stays in uniform registers; one elected
 // lane issues the copies.
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
                                               const uint16_t* wpack, long long ntiles, int T,
-                                              uint8_t* smem, EngineShared& sh) {
+                                              uint8_t* smem, EngineShared& sh,
+                                              const PrefetchPlan* pf = nullptr) {
   uint8_t* ring = smem + sm.off_ring;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, ph = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-    for (int t = 0; t < T; ++t)
+    for (int t = 0; t < T; ++t) {
+      if (pf && pf->n) {      // inputs of the NEXT step (and of step 0 when a tile starts)
+        if (t == 0) prefetch_step(*pf, tile, pf->reverse ? T - 1 : 0);
+        if (t + 1 < T) prefetch_step(*pf, tile, pf->reverse ? T - 2 - t : t + 1);
+      }
       for (int gi = 0; gi < P.n_gemms; ++gi) {
         const Gemm g = P.g[gi];
         const uint16_t* src = wpack + g.w_off;
@@ -181,6 +205,7 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
           if (++st == nstage) { st = 0; ph ^= 1; }
         }
       }
+    }
 }
 
 // Ge counts epilogue completions (incl. the per-tile init pseudo-phase, which has no MMAs); Gm
@@ -556,7 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 for (int j = 0; j < 16; ++j) {
                   const int col = cc + j;
                   if (col < S) {
-                    const float sd = softplusf_(s_[j]) + a.min_std;
+                    // softplus(x) = max(x,0) + log(1 + exp(-|x|)) with single-MUFU exp / log
+                    const float sd = fmaxf(s_[j], 0.f) + __logf(1.f + fast_exp(-fabsf(s_[j]))) + a.min_std;
                     const float st = fmaf(sd, eps[j], m_[j]);
                     if (rvalid && a.means) {
                       a.means[orow * S + col] = m_[j];

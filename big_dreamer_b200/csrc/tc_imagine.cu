@@ -424,6 +424,8 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   auto gate_phase = [&](int sl, bool passB) {
     b.end_phase(EPI_P_GATE, 1, nvs[sl], nss[sl], 0, 0, n0s[sl], slab ? TILE_SLAB1 : TILE_SLAB0);
     b.prog.p[b.prog.n_phases - 1].pad = passB ? 1 : 0;
+    // every gate stage except the very first may start as soon as the previous phase's MMAs are done
+    b.prog.p[b.prog.n_phases - 1].Kp_out = (passB || sl > 0) ? 1 : 0;
   };
   gate_phase(0, false);
   for (int pass = 0; pass < 2; ++pass) {
@@ -523,13 +525,52 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   ba.g_entropy = a->g_entropy;
   ba.d_raw = d_raw; ba.d_prev_state = a->d_prev_state; ba.d_prev_belief = a->d_prev_belief;
   ba.scr_carry = scr_carry; ba.scr_gtot = scr_gtot; ba.amax_bits = amax;
+  {
+    // next-step inputs the producer warp prefetches into L2 (per tile and time step)
+    PrefetchPlan& pf = ba.pf;
+    pf.n = 0; pf.reverse = 1;
+    auto add = [&](const void* p, long long step_stride, long long tile_stride, size_t bytes) {
+      if (!p || pf.n >= 6) return;
+      pf.base[pf.n] = static_cast<const char*>(p); pf.step_stride[pf.n] = step_stride;
+      pf.tile_stride[pf.n] = tile_stride; pf.bytes[pf.n] = (unsigned int)bytes; ++pf.n;
+    };
+    const long long nt = ntiles;
+    add(ba.sv_gate, nt * 5LL * kTileRows * Kb * 2, 5LL * kTileRows * Kb * 2, (size_t)5 * kTileRows * Kb * 2);
+    add(ba.sv_xa, nt * (long long)kTileRows * Kb * 2, (long long)kTileRows * Kb * 2, (size_t)kTileRows * Kb * 2);
+    add(ba.sv_ha, nt * (long long)kTileRows * Kh * 2, (long long)kTileRows * Kh * 2, (size_t)kTileRows * Kh * 2);
+    add(a->g_beliefs, f.N * (long long)Be * 4, (long long)kTileRows * Be * 4, (size_t)kTileRows * Be * 4);
+    add(a->g_states, f.N * (long long)S * 4, (long long)kTileRows * S * 4, (size_t)kTileRows * S * 4);
+    add(f.stds, f.N * (long long)S * 4, (long long)kTileRows * S * 4, (size_t)kTileRows * S * 4);
+  }
   ProfScope ps(BD_PROF_BPTT, s);
-  if (fmt == 0) {
-    cudaFuncSetAttribute(bptt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
-    bptt_kernel<0><<<grid, kThreads, ba.sm.total, s>>>(ba);
+  if (getenv("BD_TC_PROF") && fmt == 0 && off + kMaxPhases * 64 + 4096 <= ws_bytes) {
+    // debug: per-phase cycle counters of CTA 0 (printed by scripts/prof_bptt.py)
+    ba.prof = reinterpret_cast<long long*>(base + ((off + 4095) & ~size_t(4095)));
+    cudaMemsetAsync(ba.prof, 0, kMaxPhases * 64, s);
+    cudaFuncSetAttribute(bptt_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
+    bptt_kernel<0, true><<<grid, kThreads, ba.sm.total, s>>>(ba);
+    static long long* host_prof = nullptr;
+    if (!host_prof) cudaMallocHost(&host_prof, kMaxPhases * 64);
+    cudaMemcpyAsync(host_prof, ba.prof, kMaxPhases * 64, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "bptt phase   iss_dep iss_wwait iss_issue | epi0_wait epi0_work | epi1_wait epi1_work  (cycles/step, CTA0)\n");
+    long long tot[7] = {0};
+    for (int pi = 0; pi < b.prog.n_phases; ++pi) {
+      fprintf(stderr, "p%-2d epi=%d ", pi, (int)b.prog.p[pi].epi);
+      for (int k = 0; k < 7; ++k) { fprintf(stderr, "%9lld", host_prof[pi * 8 + k] / f.T); tot[k] += host_prof[pi * 8 + k] / f.T; }
+      if (pi < 20) fprintf(stderr, "   | pre %lld planes %lld accwait %lld", host_prof[(20 + pi) * 8] / f.T,
+                           host_prof[(20 + pi) * 8 + 1] / f.T, host_prof[(20 + pi) * 8 + 2] / f.T);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "total     ");
+    for (int k = 0; k < 7; ++k) fprintf(stderr, "%9lld", tot[k]);
+    fprintf(stderr, "\n");
+  } else if (fmt == 0) {
+    cudaFuncSetAttribute(bptt_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
+    bptt_kernel<0, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
   } else {
-    cudaFuncSetAttribute(bptt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
-    bptt_kernel<1><<<grid, kThreads, ba.sm.total, s>>>(ba);
+    cudaFuncSetAttribute(bptt_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ba.sm.total);
+    bptt_kernel<1, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
   }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
