@@ -138,12 +138,19 @@ int bd_lambda_return_backward(const float* d_returns, int T, int64_t N, double d
 }
 
 size_t bd_transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
-  return r ? f32::transition_workspace_bytes(r, L, B, observe, backward) : 0;
+  if (!r) return 0;
+  size_t f = f32::transition_workspace_bytes(r, L, B, observe, backward);
+  bd_mlp none{};
+  size_t t = tc::imagine_pack_bytes(*r, none);
+  return f > t ? f : t;
 }
 int bd_transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, int precision,
                           bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
+  if (a->B > 0 && tc::transition_supported(*a, precision) && a->init_state && a->init_belief &&
+      a->actions && a->eps_prior && a->beliefs && a->prior_states && a->prior_means && a->prior_stds)
+    return tc::transition_forward(a, ws, ws_bytes, precision, stream);
   return f32::transition_forward(a, ws, ws_bytes, stream);
 }
 int bd_transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, int precision,

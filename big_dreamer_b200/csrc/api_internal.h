@@ -47,6 +47,9 @@ size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
 size_t bptt_workspace_bytes(const bd_rssm& r);
 int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
                  bd_stream_t stream);
+bool transition_supported(const bd_transition_args& a, int precision);
+int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, int precision,
+                       bd_stream_t stream);
 bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision);
 size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long rows, int H);
 int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,

@@ -370,6 +370,58 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   return launch_rollout(fmt, r.activation, false, false, grid, ra, s);
 }
 
+// TransitionModel.forward, prior-only mode without a nonterminal mask (src/models.py:239-260), on the
+// rollout engine: actions are given, outputs are the reference's four (L,B,.) tensors.
+bool transition_supported(const bd_transition_args& a, int precision) {
+  if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
+  if (a.embeddings || a.nonterminals) return false;
+  const bd_rssm& r = a.rssm;
+  if (!(r.activation == BD_ACT_ELU || r.activation == BD_ACT_RELU || r.activation == BD_ACT_TANH ||
+        r.activation == BD_ACT_IDENTITY)) return false;
+  return r.belief_size + 1 <= 256 && r.hidden_size + 1 <= 256 && r.state_size <= 128 && r.action_size <= 16;
+}
+int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, int precision,
+                       bd_stream_t stream) {
+  const bd_rssm& r = a->rssm;
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1);
+  Builder b;
+  add_transition_phases(b, r, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core transition_forward: program too large");
+  if ((size_t)b.w_elems * 2 > ws_bytes)
+    BD_FAIL(BD_ERR_WORKSPACE, "tensor-core transition_forward: workspace %zu too small", ws_bytes);
+  RolloutArgs ra{};
+  if (!plan_smem(Kp_b, Kp_sa, max(Kp_hid, Kp_x), b.max_stage, ra.sm))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core transition_forward: tiles do not fit shared memory");
+  b.finalize_blocks(ra.sm.stage_bytes);
+  ra.prog = b.prog;
+  ra.wpack = static_cast<const uint16_t*>(ws);
+  ra.N = a->B; ra.T = a->L; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi;
+  ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = max(Kp_hid, Kp_x); ra.act = r.activation;
+  ra.min_std = r.min_std_dev;
+  ra.prev_state = a->init_state; ra.prev_belief = a->init_belief; ra.eps_s = a->eps_prior;
+  ra.beliefs = a->beliefs; ra.states = a->prior_states; ra.means = a->prior_means; ra.stds = a->prior_stds;
+  ra.ext_actions = a->actions; ra.has_b1 = 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long max_img = 0;
+  for (int i = 0; i < b.pack.njobs; ++i)
+    max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+  long long pgx = (max_img + 255) / 256;
+  if (pgx > 64) pgx = 64;
+  dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+  const long long ntiles = (a->B + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  BD_CUDA_LAUNCH_CHECK();
+  ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
+  return launch_rollout(fmt, r.activation, false, false, grid, ra, s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // BPTT of the imagination rollout on the tensor-core engine (tc_bptt.cuh)
 // ---------------------------------------------------------------------------------------------

@@ -158,3 +158,26 @@ def test_cem_tc(d):
         inter = len(set(got[b].tolist()) & set(trace[0]["topk"][b].tolist()))
         assert inter >= 0.9 * d["K"], inter
     assert float((out.cpu() - ref).abs().max()) < 5e-2
+
+
+def test_transition_prior_only_tc():
+    """TransitionModel.forward (prior-only) on the rollout engine; the autograd backward of this
+    entry point stays on the fp32 kernels."""
+    from oracle import rssm_oracle as orc
+    d = dict(Be=200, Hi=200, S=30, A=2, E=8, act="ELU")
+    trans, _, _, _ = orc.make_models(4, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    L, B = 12, 1000
+    g = torch.Generator().manual_seed(2)
+    s0, b0 = orc.make_latents(4, B, d["Be"], d["S"])
+    actions = torch.rand(L, B, d["A"], generator=g) * 2 - 1
+    ep = torch.randn(L, B, d["S"], generator=g)
+    dd = torch.float64
+    with torch.no_grad():
+        r = orc.transition_forward({k: v.to(dd) for k, v in trans.items()}, "ELU", 0.1, s0.to(dd),
+                                   actions.to(dd), b0.to(dd), ep.to(dd))
+        tm = pu.build_gpu_models(d, trans).transition
+        bd.set_precision("fp16")
+        o = tm(s0.cuda(), actions.cuda(), b0.cuda(), noise=dict(eps_prior=ep.cuda()))
+    assert o[3] is None and o[0].shape == (L, B, 200)
+    for got, ref in ((o[0], r[0]), (o[1], r[1]), (o[2][0], r[2][0]), (o[2][1], r[2][1])):
+        assert pu.relerr(got, ref.float()) < TOL
