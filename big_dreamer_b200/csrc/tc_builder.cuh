@@ -28,6 +28,16 @@ struct Builder {
     w_elems += (long long)Np * Kp;
     return off;
   }
+  // image whose rows are stacked from up to three source row ranges (same column mapping)
+  uint32_t add_pack_rows(const float* w, int ld, int nrseg, const PackSeg* rsegs, int Np, int Kp,
+                         int src_c0, int len, const float* bias, int bias_k) {
+    uint32_t off = add_pack(w, ld, 0, 0, Np, Kp, src_c0, len, bias, bias_k);
+    if (!ok) return off;
+    PackJob& j = pack.job[pack.njobs - 1];
+    j.nrseg = nrseg;
+    for (int i = 0; i < nrseg; ++i) j.rseg[i] = rsegs[i];
+    return off;
+  }
   void add_gemm(uint32_t w_off, int Np, int Kp, int a_tile, int a_k0, int d_col, int accumulate) {
     if (prog.n_gemms >= kMaxGemms) { ok = false; return; }
     Gemm& g = prog.g[prog.n_gemms++];

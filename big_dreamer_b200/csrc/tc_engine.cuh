@@ -490,9 +490,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 const int c = half * 16 + it * 32;
                 if (c < Ns) {
                   float r_[16], z_[16], in_[16], hn_[16], o[16];
-                  tmem_ld16(tacc + c, r_);
-                  tmem_ld16(tacc + Ns + c, z_);
-                  tmem_ld16(tacc + 2 * Ns + c, in_);
+                  tmem_ld16(tacc + c, in_);              // accumulator columns: IN | R | Z | HN
+                  tmem_ld16(tacc + Ns + c, r_);
+                  tmem_ld16(tacc + 2 * Ns + c, z_);
                   tmem_ld16(tacc + 3 * Ns + c, hn_);
                   tmem_ld_wait();
                   const int col0 = n0 + c;

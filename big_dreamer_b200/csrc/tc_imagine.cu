@@ -146,17 +146,16 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
       const int nv = min(64, Be - n0), Ns = r16(nv);
       int d = b.dcol();
-      uint32_t w[6];
-      for (int g = 0; g < 3; ++g) {
-        w[2 * g] = b.add_pack(r.w_ih, Be, g * Be + n0, nv, Ns, Kp_x, 0, Be, r.b_ih, Be);
-        w[2 * g + 1] = b.add_pack(r.w_hh, Be, g * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-      }
-      b.add_gemm(w[0], Ns, Kp_x, TILE_H, 0, d, 0);             // R  = x W_ir^T + b_ir
-      b.add_gemm(w[1], Ns, Kp_b, TILE_BCUR, 0, d, 1);          //    + h W_hr^T + b_hr
-      b.add_gemm(w[2], Ns, Kp_x, TILE_H, 0, d + Ns, 0);        // Z
-      b.add_gemm(w[3], Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
-      b.add_gemm(w[4], Ns, Kp_x, TILE_H, 0, d + 2 * Ns, 0);    // IN = x W_in^T + b_in
-      b.add_gemm(w[5], Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0); // HN = h W_hn^T + b_hn
+      // stacked gate images: 3 GEMMs per slice instead of 6, so the A tiles (x, h) are fetched from
+      // shared memory half as often.  Accumulator columns: IN | R | Z | HN, each Ns wide.
+      PackSeg rx[3] = {{0, 2 * Be + n0, nv}, {Ns, n0, nv}, {2 * Ns, Be + n0, nv}};      // W_in, W_ir, W_iz
+      PackSeg rh[2] = {{0, n0, nv}, {Ns, Be + n0, nv}};                                 // W_hr, W_hz
+      uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
+      uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
+      uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
+      b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);               // [IN | R | Z] = x W_i*^T + b_i*
+      b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);       // [R | Z]    += h W_h{r,z}^T + b_h{r,z}
+      b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);       // HN          = h W_hn^T + b_hn
       b.end_phase(EPI_GRU, (slice == 0 || getenv("BD_TC_SERIAL")) ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
     }
   }
@@ -254,17 +253,14 @@ static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp
   for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
     const int nv = min(64, Be - n0), Ns = r16(nv);
     int d = b.dcol();
-    uint32_t w[6];
-    for (int g = 0; g < 3; ++g) {
-      w[2 * g] = b.add_pack(r.w_ih, Be, g * Be + n0, nv, Ns, Kp_x, 0, Be, r.b_ih, Be);
-      w[2 * g + 1] = b.add_pack(r.w_hh, Be, g * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-    }
-    b.add_gemm(w[0], Ns, Kp_x, TILE_H, 0, d, 0);
-    b.add_gemm(w[1], Ns, Kp_b, TILE_BCUR, 0, d, 1);
-    b.add_gemm(w[2], Ns, Kp_x, TILE_H, 0, d + Ns, 0);
-    b.add_gemm(w[3], Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
-    b.add_gemm(w[4], Ns, Kp_x, TILE_H, 0, d + 2 * Ns, 0);
-    b.add_gemm(w[5], Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);
+    PackSeg rx[3] = {{0, 2 * Be + n0, nv}, {Ns, n0, nv}, {2 * Ns, Be + n0, nv}};
+    PackSeg rh[2] = {{0, n0, nv}, {Ns, Be + n0, nv}};
+    uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
+    uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
+    uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
+    b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);
+    b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
+    b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);
     b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
   }
   {

@@ -20,6 +20,8 @@ struct PackJob {
   int nseg;
   PackSeg seg[3];
   int transpose;        // 1: packed(n, k) = w[(src row = k-mapped), (src col = row0 + n)]  (dgrad)
+  int nrseg;            // > 0: image rows are stacked from several source row ranges (GRU gates)
+  PackSeg rseg[3];      // dst rows [dst_k0, +len) <- src rows [src_c0, +len)   (fields reused)
 };
 constexpr int kMaxPackJobs = 48;
 struct PackTable { int njobs; PackJob job[kMaxPackJobs]; };
@@ -37,14 +39,23 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, uint1
     int rem = (int)(i - (long long)kg * per_kgroup);
     int n = rem >> 3, k = kg * 8 + (rem & 7);
     float v = 0.f;
-    if (n < j.N) {
-      if (k == j.bias_k && j.bias) v = j.bias[j.row0 + n];
+    int srow = -1;                       // source row of image row n
+    if (j.nrseg > 0) {
+      for (int s = 0; s < j.nrseg; ++s) {
+        int c = n - j.rseg[s].dst_k0;
+        if (c >= 0 && c < j.rseg[s].len) srow = j.rseg[s].src_c0 + c;
+      }
+    } else if (n < j.N) {
+      srow = j.row0 + n;
+    }
+    if (srow >= 0) {
+      if (k == j.bias_k && j.bias) v = j.bias[srow];
       for (int s = 0; s < j.nseg; ++s) {
         int c = k - j.seg[s].dst_k0;
         if (c >= 0 && c < j.seg[s].len) {
           int sc = j.seg[s].src_c0 + c;
-          v = j.transpose ? j.w[(long long)sc * j.ld + j.row0 + n]
-                          : j.w[(long long)(j.row0 + n) * j.ld + sc];
+          v = j.transpose ? j.w[(long long)sc * j.ld + srow]
+                          : j.w[(long long)srow * j.ld + sc];
         }
       }
     }
