@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
-      mbar_arrive(&sh.epi_done[Ge & 3]);   // nothing to initialise per tile
+      mbar_arrive(&sh.epi_done[Ge & 7]);   // nothing to initialise per tile
       ++Ge;
       for (int i = 0; i < a.T; ++i) {
         const int t = a.T - 1 - i;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
 #undef BD_WAIT_ACC
           tc_fence_before_sync();
           fence_proxy_async_smem();
-          mbar_arrive(&sh.epi_done[Ge & 3]);
+          mbar_arrive(&sh.epi_done[Ge & 7]);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
             a.prof[o] += e1 - e0;

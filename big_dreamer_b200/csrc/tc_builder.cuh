@@ -2,6 +2,8 @@
 // entry points).
 #pragma once
 #include "tc_engine.cuh"
+#include <stdlib.h>
+#include <vector>
 
 namespace bd {
 namespace tc {
@@ -43,7 +45,7 @@ struct Builder {
     Gemm& g = prog.g[prog.n_gemms++];
     g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
     g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
-    g.kc = 32; g.pad = 0;
+    g.kc = 32; g.pad = 0; g.dep_back = 1;
     max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
   }
   // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
@@ -63,10 +65,33 @@ struct Builder {
     p.g0 = (uint8_t)cur_phase_g0; p.ng = (uint8_t)(prog.n_gemms - cur_phase_g0); p.epi = (uint8_t)epi;
     p.dep_back = (uint8_t)dep_back; p.n_valid = (uint16_t)n_valid; p.Np = (uint16_t)Np;
     p.Kp_out = (uint16_t)Kp_out; p.d_col = (uint16_t)d_col; p.aux0 = (uint16_t)aux0;
-    p.out_tile = (uint8_t)out_tile; p.pad = 0;
+    p.out_tile = (uint8_t)out_tile; p.pad = 0; p.n_sub = 1; p.pad2 = 0; p.split = 0;
+    for (int gi = cur_phase_g0; gi < prog.n_gemms; ++gi) prog.g[gi].dep_back = (uint8_t)dep_back;
+    for (int gi : chained) prog.g[gi].dep_back = 2;     // the previous phase published 2 sub-epilogues
+    chained.clear();
     cur_phase_g0 = prog.n_gemms;
   }
   int dcol() const { return (prog.n_phases & 1) * 256; }
+
+  // Sub-epilogue pipelining between two chained layers.  Call right after end_phase() of an ACT
+  // epilogue that writes an operand tile of Kp_out columns: it will publish columns [0, split)
+  // first.  chain_gemm() then adds the consumer GEMM as two K-slabs, the first of which only
+  // depends on that early publication.
+  int split_last_phase() {
+    Phase& p = prog.p[prog.n_phases - 1];
+    const int split = (p.Kp_out / 2 + 31) / 32 * 32;
+    if (getenv("BD_TC_NOSPLIT") || p.Kp_out < 96 || split >= p.Kp_out) return 0;
+    p.n_sub = 2; p.split = (uint16_t)split;
+    return split;
+  }
+  // consumer of the operand tile written by the previous phase (K = Kp columns from a_tile)
+  void chain_gemm(uint32_t w_off, int Np, int Kp, int a_tile, int d_col, int split) {
+    if (split <= 0 || split >= Kp) { add_gemm(w_off, Np, Kp, a_tile, 0, d_col, 0); return; }
+    add_gemm(w_off, Np, split, a_tile, 0, d_col, 0);
+    chained.push_back(prog.n_gemms - 1);
+    add_gemm(w_off + (uint32_t)split * Np, Np, Kp - split, a_tile, split, d_col, 1);
+  }
+  std::vector<int> chained;   // GEMMs that may start after the FIRST sub-epilogue of the previous phase
 };
 
 

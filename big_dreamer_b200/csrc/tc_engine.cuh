@@ -15,7 +15,8 @@
 // producer / issuer / epilogue hand-offs structurally consistent:
 //     w_full[s] / w_empty[s]   producer <-> issuer, one ring stage = one K-block of the weight image
 //     acc_full[Gm & 3]         issuer -> epilogue, tcgen05.commit after the last GEMM of phase Gm
-//     epi_done[Ge & 3]         epilogue -> issuer, 256 arrivals when epilogue Ge is done
+//     epi_done[Ge & 7]         epilogue -> issuer, 256 arrivals when (sub-)epilogue Ge is done;
+//                              every GEMM names the completion it depends on (dep_back)
 // A phase names how far back its dependency is (dep_back = 1: previous phase; 2: the one before,
 // which lets independent phases -- the GRU's N-slices -- overlap MMA with the previous epilogue
 // using the two TMEM halves).
@@ -52,7 +53,8 @@ struct Gemm {
   uint8_t a_tile;     // TileId
   uint8_t accumulate; // 1: continue a running sum in D; 2: only from the second time step on
   uint16_t kc;        // K columns per weight-ring stage (mult of 16): Np*kc*2 <= stage bytes
-  uint16_t pad;
+  uint8_t dep_back;   // this GEMM may start once epilogue completion (Ge_at_phase_start - dep_back) is in
+  uint8_t pad;
 };
 struct Phase {
   uint8_t g0, ng;     // GEMM range
@@ -65,6 +67,9 @@ struct Phase {
   uint16_t aux0;      // EPI_GRU: first belief column of the slice; EPI_HEAD_OUT: head index
   uint8_t out_tile;   // TileId written by EPI_ACT_H
   uint8_t pad;
+  uint8_t n_sub;      // sub-epilogues (1 or 2): an ACT epilogue may publish columns [0, split) early
+  uint8_t pad2;
+  uint16_t split;     // first column of the second sub-epilogue (multiple of 32)
 };
 struct Program {
   int n_gemms, n_phases;
@@ -138,7 +143,7 @@ __device__ __forceinline__ void store1(uint8_t* tile, int row, int col, float v)
 // Shared skeleton of every kernel on this path: barrier setup, the weight-producer warp and the
 // MMA-issuer warp.  Kernels differ only in their tile initialisation and epilogues.
 struct EngineShared {
-  uint64_t w_full[8], w_empty[8], acc_full[4], epi_done[4];
+  uint64_t w_full[8], w_empty[8], acc_full[4], epi_done[8];
   uint32_t tmem_holder;
 };
 
@@ -146,7 +151,8 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&sh.acc_full[i], 1); mbar_init(&sh.epi_done[i], kEpiThreads); }
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&sh.epi_done[i], kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&sh.tmem_holder);
@@ -217,6 +223,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
   const int lane = threadIdx.x & 31;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
+  uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
   const uint32_t ring_addr = smem_u32(smem + sm.off_ring);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
@@ -224,16 +231,22 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
       const int par = t & 1;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
-        long long c0 = 0, c1 = 0, wsum = 0;
+        long long c0 = 0, c1 = 0, wsum = 0, dsum = 0;
         if (PROF) c0 = clock64();
-        {
-          const uint32_t D = Ge - ph.dep_back;
-          mbar_wait(&sh.epi_done[D & 3], (D >> 2) & 1);
-          tc_fence_after_sync();
-        }
         if (PROF) c1 = clock64();
         for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
           const Gemm g = P.g[gi];
+          {   // per-GEMM dependency (sub-epilogue pipelining); older completions are implied
+            const uint32_t D = Ge - g.dep_back;
+            if ((int)(D - waited) > 0) {
+              long long d0 = 0;
+              if (PROF) d0 = clock64();
+              mbar_wait(&sh.epi_done[D & 7], (D >> 3) & 1);
+              tc_fence_after_sync();
+              waited = D;
+              if (PROF) dsum += clock64() - d0;
+            }
+          }
           uint32_t tile_id = g.a_tile;
           if (tile_id < 2) tile_id ^= par;
           const uint64_t a_desc0 =
@@ -268,12 +281,12 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
         if (elect_one()) umma_commit(&sh.acc_full[Gm & 3]);
         __syncwarp();
         if (PROF && blockIdx.x == 0 && lane == 0) {
-          prof[pi * 8 + 0] += c1 - c0;               // issuer: wait for the dependency epilogue
+          prof[pi * 8 + 0] += c1 - c0 + dsum;        // issuer: wait for the dependency epilogue(s)
           prof[pi * 8 + 1] += wsum;                  // issuer: wait for weight stages
-          prof[pi * 8 + 2] += clock64() - c1 - wsum; // issuer: issue time
+          prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum; // issuer: issue time
         }
         ++Gm;
-        ++Ge;
+        Ge += ph.n_sub;
       }
     }
   }
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           *reinterpret_cast<uint4*>(H + kg * kLboA + r * 16) = make_uint4(0, 0, 0, 0);
         }
         fence_proxy_async_smem();
-        mbar_arrive(&epi_done[Ge & 3]);
+        mbar_arrive(&epi_done[Ge & 7]);
         ++Ge;
       }
       for (int t = 0; t < a.T; ++t) {
@@ -410,7 +423,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               if (PROF) e1 = clock64();
               uint8_t* out = smem + a.sm.off_tile[ph.out_tile] + (row >> 3) * 128 + (row & 7) * 16;
               const int nv = ph.n_valid;
-              for (int c = half * 32; c < ph.Kp_out; c += 64) {
+              for (int sub = 0; sub < ph.n_sub; ++sub) {
+              const int c_lo = sub == 0 ? 0 : ph.split;
+              const int c_hi = (sub == ph.n_sub - 1) ? ph.Kp_out : ph.split;
+              if (sub > 0) {   // publish the first column range: the next layer's K-slab 0 may start
+                tc_fence_before_sync();
+                fence_proxy_async_smem();
+                mbar_arrive(&epi_done[Ge & 7]);
+                ++Ge;
+              }
+              for (int c = c_lo + half * 32; c < c_hi; c += 64) {
                 float v[32];
                 const bool two = (c + 16) < ph.Kp_out;
                 if (c + 32 <= ph.Np) {
@@ -454,6 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                     }
                   }
                 }
+              }
               }
             } break;
             case EPI_GRU: {
@@ -659,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           }
           tc_fence_before_sync();
           fence_proxy_async_smem();
-          mbar_arrive(&epi_done[Ge & 3]);
+          mbar_arrive(&epi_done[Ge & 7]);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
             a.prof[o] += e1 - e0;                          // epilogue: wait for the accumulator

@@ -118,19 +118,21 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     b.add_gemm(w0b, Nh, Kp_b, TILE_BCUR, 0, d, 0);
     b.add_gemm(w0s, Nh, Ks, TILE_SA, 0, d, 1);
     b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+    int sp = b.split_last_phase();
     for (int l = 1; l + 1 < ac.n_layers; ++l) {
       const bd_linear& L = ac.layer[l];
       uint32_t w = b.add_pack(L.w, Hi, 0, Hi, Nh, Kp_hid, 0, Hi, L.b, Hi);
       d = b.dcol();
-      b.add_gemm(w, Nh, Kp_hid, TILE_H, 0, d, 0);
+      b.chain_gemm(w, Nh, Kp_hid, TILE_H, d, sp);
       b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
+      sp = b.split_last_phase();
     }
     const bd_linear& Lo = ac.layer[ac.n_layers - 1];
     uint32_t wm = b.add_pack(Lo.w, Hi, 0, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
     uint32_t wsd = b.add_pack(Lo.w, Hi, A, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
     d = b.dcol();
-    b.add_gemm(wm, Ap, Kp_hid, TILE_H, 0, d, 0);
-    b.add_gemm(wsd, Ap, Kp_hid, TILE_H, 0, d + Ap, 0);
+    b.chain_gemm(wm, Ap, Kp_hid, TILE_H, d, sp);
+    b.chain_gemm(wsd, Ap, Kp_hid, TILE_H, d + Ap, sp);
     b.end_phase(EPI_ACTOR_OUT, 1, 2 * A, Ap, 0, d, 0, TILE_SA);
   }
   // ---- embed: x = act(W_sa [s ; a] + b)
@@ -140,6 +142,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
     b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, 1, TILE_H);      // aux0 = 1: save act'(x)
   }
+  int sp_x = b.split_last_phase();
   // ---- GRUCell in N-slices of <= 64 belief columns: accumulators R | Z | IN | HN per slice
   {
     int slice = 0;
@@ -153,7 +156,8 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
       uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
       uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
       uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-      b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);               // [IN | R | Z] = x W_i*^T + b_i*
+      if (slice == 0) b.chain_gemm(wx, 3 * Ns, Kp_x, TILE_H, d, sp_x);
+      else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);          // [IN | R | Z] = x W_i*^T + b_i*
       b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);       // [R | Z]    += h W_h{r,z}^T + b_h{r,z}
       b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);       // HN          = h W_hn^T + b_hn
       b.end_phase(EPI_GRU, (slice == 0 || getenv("BD_TC_SERIAL")) ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
@@ -165,11 +169,12 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     int d = b.dcol();
     b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
     b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 2, TILE_H);    // aux0 = 2: save act'(h)
+    const int sp_h = b.split_last_phase();
     uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     d = b.dcol();
-    b.add_gemm(wm, Sp, Kp_hid, TILE_H, 0, d, 0);
-    b.add_gemm(wsd, Sp, Kp_hid, TILE_H, 0, d + Sp, 0);
+    b.chain_gemm(wm, Sp, Kp_hid, TILE_H, d, sp_h);
+    b.chain_gemm(wsd, Sp, Kp_hid, TILE_H, d + Sp, sp_h);
     b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
   }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: program too large");
@@ -249,6 +254,7 @@ static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp
     b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
     b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, save ? 1 : 0, TILE_H);
   }
+  const int sp_x = b.split_last_phase();
   int slice = 0;
   for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
     const int nv = min(64, Be - n0), Ns = r16(nv);
@@ -258,7 +264,8 @@ static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp
     uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
     uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
     uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-    b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);
+    if (slice == 0) b.chain_gemm(wx, 3 * Ns, Kp_x, TILE_H, d, sp_x);
+    else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);
     b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
     b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);
     b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
@@ -268,11 +275,12 @@ static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp
     int d = b.dcol();
     b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
     b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, save ? 2 : 0, TILE_H);
+    const int sp_h = b.split_last_phase();
     uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
     d = b.dcol();
-    b.add_gemm(wm, Sp, Kp_hid, TILE_H, 0, d, 0);
-    b.add_gemm(wsd, Sp, Kp_hid, TILE_H, 0, d + Sp, 0);
+    b.chain_gemm(wm, Sp, Kp_hid, TILE_H, d, sp_h);
+    b.chain_gemm(wsd, Sp, Kp_hid, TILE_H, d + Sp, sp_h);
     b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
   }
 }
@@ -308,6 +316,7 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   Builder b;
   add_transition_phases(b, r, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
   // reward head on (b', s'): DenseModel (src/planner.py:68-72)
+  int sp_hd = 0;
   for (int l = 0; l < hd.n_layers; ++l) {
     const bd_linear& L = hd.layer[l];
     const bool last = (l == hd.n_layers - 1);
@@ -321,10 +330,14 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
     } else {
       const int kin = L.in_features, Kp = r16(kin + 1);
       uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
-      b.add_gemm(w, Np, Kp, TILE_H, 0, d, 0);
+      b.chain_gemm(w, Np, Kp, TILE_H, d, sp_hd);
     }
     if (last) b.end_phase(EPI_HEAD_OUT, 1, 1, Np, 0, d, 0, TILE_H);
-    else { b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H); Kp_h = max(Kp_h, r16(n + 1)); }
+    else {
+      b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H);
+      sp_hd = b.split_last_phase();
+      Kp_h = max(Kp_h, r16(n + 1));
+    }
   }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core CEM: program too large");
   char* base = static_cast<char*>(ws);
@@ -649,7 +662,7 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: sizes/activation not supported");
   Builder b;
   const int Kp_b = r16(k1 + 1), Ks = k2 > 0 ? r16(k2) : 0;
-  int Kp_h = 16;
+  int Kp_h = 16, sp_m = 0;
   for (int l = 0; l < m->n_layers; ++l) {
     const bd_linear& L = m->layer[l];
     const bool last = (l == m->n_layers - 1);
@@ -665,11 +678,12 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
     } else {
       const int kin = L.in_features, Kp = r16(kin + 1);
       uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
-      b.add_gemm(w, Np, Kp, TILE_H, 0, d, 0);
+      b.chain_gemm(w, Np, Kp, TILE_H, d, sp_m);
     }
     if (last) b.end_phase(EPI_STORE_OUT, 1, n, Np, 0, d, 0, TILE_H);
     else {
       b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H);
+      sp_m = b.split_last_phase();
       Kp_h = max(Kp_h, r16(n + 1));
     }
   }

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             *reinterpret_cast<uint4*>(a.x0s + (size_t)tile * kTileRows * a.Ks + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
         fence_proxy_async_smem();
-        mbar_arrive(&sh.epi_done[Ge & 3]);
+        mbar_arrive(&sh.epi_done[Ge & 7]);
         ++Ge;
       }
       for (int pi = 0; pi < P.n_phases; ++pi) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         }
         tc_fence_before_sync();
         fence_proxy_async_smem();
-        mbar_arrive(&sh.epi_done[Ge & 3]);
+        mbar_arrive(&sh.epi_done[Ge & 7]);
         ++Ge;
         ++Gm;
       }
