@@ -160,7 +160,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
       else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);          // [IN | R | Z] = x W_i*^T + b_i*
       b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);       // [R | Z]    += h W_h{r,z}^T + b_h{r,z}
       b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);       // HN          = h W_hn^T + b_hn
-      b.end_phase(EPI_GRU, (slice == 0 || getenv("BD_TC_SERIAL")) ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
+      b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
     }
   }
   // ---- prior: h = act(W_p1 b' + b), (mean | raw std) = W_p2 h + b

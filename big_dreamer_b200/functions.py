@@ -16,7 +16,6 @@ from . import _lib
 from ._lib import BdError
 
 _precision = "fp32"
-_debug_last = None
 
 
 def set_precision(name: str) -> None:
@@ -325,8 +324,6 @@ class ImagineFunction(torch.autograd.Function):
         ctx.save_for_backward(s0, b0, ea, ee, es, beliefs, states, means, stds, entropy, actions,
                               actor_raw, dent, *AP, *RP[:10])
         ctx.mark_non_differentiable(actions)
-        global _debug_last
-        _debug_last = dict(actor_raw=actor_raw, dent=dent)
         return beliefs, states, means, stds, entropy, actions
 
     @staticmethod
