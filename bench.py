@@ -371,7 +371,11 @@ def run_ours(args):
                 "d2h_bytes_per_step": 8, "ms_per_step": total_e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak,
+                     # DRAM read+write bytes of that kernel per launch from the committed ncu --set
+                     # full capture (profiles/r01_summary.md), valid for the default workload only
+                     "traffic": ({"rollout_fwd": 96.8e6, "bptt": 162.9e6}.get(dom)
+                                 if (rows == ROWS_DEFAULT and args.precision == "fp16") else None),
                      "step_frac": step_tflops / peak, "note": note},
         "kernels": kernels,
         "clocks": clocks,

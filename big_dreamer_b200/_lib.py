@@ -55,7 +55,8 @@ class ActorCfg(C.Structure):
 class MlpBwdArgs(C.Structure):
     _fields_ = [("x1", C.c_void_p), ("k1", C.c_int), ("x2", C.c_void_p), ("k2", C.c_int),
                 ("rows", C.c_int64), ("dy", C.c_void_p), ("dx1", C.c_void_p), ("dx2", C.c_void_p),
-                ("dw", C.c_void_p * BD_MAX_LAYERS), ("db", C.c_void_p * BD_MAX_LAYERS)]
+                ("dw", C.c_void_p * BD_MAX_LAYERS), ("db", C.c_void_p * BD_MAX_LAYERS),
+                ("saved", C.c_void_p)]
 
 
 class TransitionArgs(C.Structure):
@@ -118,6 +119,10 @@ SIGNATURES = {
     "bd_mlp_forward": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                  C.c_void_p]),
+    "bd_mlp_saved_bytes": (C.c_size_t, [C.POINTER(Mlp), C.c_int, C.c_int, C.c_int64, C.c_int]),
+    "bd_mlp_forward_save": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_int, C.c_void_p]),
     "bd_mlp_backward": (C.c_int, [C.POINTER(Mlp), C.POINTER(MlpBwdArgs), C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p]),
     "bd_lambda_return_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,

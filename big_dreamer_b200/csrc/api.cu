@@ -110,6 +110,23 @@ int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, in
     return tc::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, precision, stream);
   return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
 }
+size_t bd_mlp_saved_bytes(const bd_mlp* m, int k1, int k2, int64_t rows, int precision) {
+  if (!m || !tc::mlp_backward_supported(*m, k1, k2, precision)) return 0;
+  return tc::mlp_saved_bytes(*m, rows);
+}
+int bd_mlp_forward_save(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2,
+                        int64_t rows, float* y, void* saved, void* ws, size_t ws_bytes,
+                        int precision, bd_stream_t stream) {
+  BD_NEED(m, "mlp");
+  if (rows == 0) return BD_OK;
+  BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
+  BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward_save: bad k1/k2/x2");
+  BD_ONLY_FP32(precision);
+  if (tc::mlp_supported(*m, k1, k2, precision))
+    return tc::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, precision, stream,
+                           tc::mlp_backward_supported(*m, k1, k2, precision) ? saved : nullptr);
+  return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
+}
 int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
                     int precision, bd_stream_t stream) {
   BD_NEED(m, "mlp"); BD_NEED(a, "args");

@@ -57,7 +57,9 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
 bool mlp_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_pack_bytes(const bd_mlp& m);
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
-                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream);
+                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream,
+                void* saved = nullptr);
+size_t mlp_saved_bytes(const bd_mlp& m, int64_t rows);
 bool mlp_backward_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t rows);
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,

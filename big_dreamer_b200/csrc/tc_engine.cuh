@@ -103,6 +103,7 @@ struct RolloutArgs {
   // saved for the tensor-core BPTT (16-bit tile images, see tc_bptt.cuh); null = do not save
   uint16_t *sv_gate, *sv_xa, *sv_ha;
   int kb_sv, kh_sv;
+  uint16_t* sv_mlp[BD_MAX_LAYERS];   // MLP forward: image of hidden layer l (cols = its Kp_out)
   int has_b1;                 // 0: single belief tile (MLP forward), 1: ping-pong
   // CEM: rows are (batch row, local candidate); start latents are per batch row and the state
   // noise is indexed by the GLOBAL candidate (src/planner.py:37-39, 53-65)
@@ -458,7 +459,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   store8<FMT>(p + 2 * kLboA, v + 16);
                   store8<FMT>(p + 3 * kLboA, v + 24);
                 }
-                if (ph.aux0 && a.sv_xa) {   // act'(output) for the backward pass (1: embed x, 2: prior h)
+                if (ph.aux0 >= 3 && a.sv_mlp[ph.aux0 - 3]) {   // MLP forward: keep the hidden image itself
+                  uint16_t* img = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * ph.Kp_out + row * 8;
+#pragma unroll
+                  for (int g8 = 0; g8 < 4; ++g8) {
+                    const int cg = c + g8 * 8;
+                    if (cg < ph.Kp_out) {
+                      float hv[8];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) hv[j] = rvalid ? v[g8 * 8 + j] : 0.f;
+                      *reinterpret_cast<uint4*>(img + (size_t)(cg >> 3) * kTileRows * 8) =
+                          make_uint4(Half16<FMT>::pack2(hv[0], hv[1]), Half16<FMT>::pack2(hv[2], hv[3]),
+                                     Half16<FMT>::pack2(hv[4], hv[5]), Half16<FMT>::pack2(hv[6], hv[7]));
+                    }
+                  }
+                } else if (ph.aux0 && ph.aux0 < 3 && a.sv_xa) {   // act'(output) for BPTT (1: embed x, 2: prior h)
                   const int kp = ph.aux0 == 1 ? a.kb_sv : a.kh_sv;
                   uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) +
                                   ((size_t)t * ntiles + tile) * kTileRows * kp + row * 8;

@@ -656,8 +656,14 @@ size_t mlp_pack_bytes(const bd_mlp& m) {
   return e * 2 + 4096;
 }
 
+size_t mlp_saved_bytes(const bd_mlp& m, int64_t rows) {
+  size_t per_tile = 0;
+  for (int l = 0; l + 1 < m.n_layers; ++l) per_tile += (size_t)kTileRows * r16(m.layer[l].out_features + 1) * 2;
+  return (size_t)((rows + kTileRows - 1) / kTileRows) * per_tile + 256;
+}
+
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
-                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
+                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream, void* saved) {
   if (!mlp_supported(*m, k1, k2, precision))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: sizes/activation not supported");
   Builder b;
@@ -682,7 +688,7 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
     }
     if (last) b.end_phase(EPI_STORE_OUT, 1, n, Np, 0, d, 0, TILE_H);
     else {
-      b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H);
+      b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, saved ? 3 + l : 0, TILE_H);
       sp_m = b.split_last_phase();
       Kp_h = max(Kp_h, r16(n + 1));
     }
@@ -700,6 +706,14 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
   ra.N = rows; ra.T = 1; ra.Be = k1; ra.S = k2; ra.A = 0; ra.Hi = 0; ra.J = 0;
   ra.Kp_b = Kp_b; ra.Kp_sa = max(Ks, 16); ra.Kp_h = Kp_h; ra.act = m->activation;
   ra.prev_belief = x1; ra.prev_state = x2; ra.mlp_out = y; ra.has_b1 = 0;
+  if (saved) {   // hidden images, layer after layer, each [tiles][128 x Kp_l] (same layout mlp_backward reads)
+    const size_t tiles = (size_t)((rows + kTileRows - 1) / kTileRows);
+    char* sb = static_cast<char*>(saved);
+    for (int l = 0; l + 1 < m->n_layers; ++l) {
+      ra.sv_mlp[l] = reinterpret_cast<uint16_t*>(sb);
+      sb += tiles * kTileRows * r16(m->layer[l].out_features + 1) * 2;
+    }
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long max_img = 0;
   for (int i = 0; i < b.pack.njobs; ++i)

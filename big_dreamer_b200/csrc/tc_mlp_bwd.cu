@@ -84,8 +84,11 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   bool want_w = false;
   for (int l = 0; l < L; ++l) want_w |= (a->dw[l] != nullptr) || (a->db[l] != nullptr);
   const bool want_dx = a->dx1 || a->dx2;
+  const bool have_saved = a->saved != nullptr;   // hidden images from bd_mlp_forward_save: no recompute
   BwdPlan p;
   make_plan(*m, k1, k2, want_w, p);
+  if (have_saved)
+    for (int l = 0; l + 1 < L; ++l) p.per_tile_bytes -= 128 * p.kp_xs[l] * 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
 
@@ -94,7 +97,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   for (int l = 0; l < L; ++l) {
     const bd_linear& Lr = m->layer[l];
     const int n = Lr.out_features, Np = r16(n);
-    if (l + 1 < L) {
+    if (l + 1 < L && !have_saved) {
       const int d = b.dcol();
       if (l == 0) {
         uint32_t wb = b.add_pack(Lr.w, k1 + k2, 0, n, Np, p.Kp_b, 0, k1, Lr.b, k1);
@@ -220,7 +223,16 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     // scratch images for this chunk
     size_t so = 0;
     auto st = [&](size_t bytes) { char* r = scratch + so; so += bytes; return reinterpret_cast<uint16_t*>(r); };
-    for (int l = 0; l + 1 < L; ++l) ba.xs[l] = st((size_t)nt * 128 * p.kp_xs[l] * 2);
+    if (have_saved) {
+      const size_t all_tiles = (size_t)total_tiles;
+      const char* sb = static_cast<const char*>(a->saved);
+      for (int l = 0; l + 1 < L; ++l) {
+        ba.xs[l] = reinterpret_cast<uint16_t*>(const_cast<char*>(sb) + (size_t)t0 * 128 * p.kp_xs[l] * 2);
+        sb += all_tiles * 128 * p.kp_xs[l] * 2;
+      }
+    } else {
+      for (int l = 0; l + 1 < L; ++l) ba.xs[l] = st((size_t)nt * 128 * p.kp_xs[l] * 2);
+    }
     for (int l = 0; l < L; ++l) ba.ds[l] = want_w ? st((size_t)nt * 128 * p.kp_ds[l] * 2) : nullptr;
     if (!want_w) ba.ds[L - 1] = nullptr;
     ba.x0b = want_w ? st((size_t)nt * 128 * p.Kp_b * 2) : nullptr;

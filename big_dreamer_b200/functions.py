@@ -66,10 +66,16 @@ class MlpFunction(torch.autograd.Function):
         y = torch.empty(rows, out, device=a1.device, dtype=torch.float32)
         nbytes = lib.bd_mlp_workspace_bytes(C.byref(mlp), rows, 0)
         ws = _lib.workspace(nbytes, a1.device)
-        _lib.check(lib.bd_mlp_forward(C.byref(mlp), _lib.ptr(a1), a1.shape[1], _lib.ptr(a2),
-                                      a2.shape[1] if a2 is not None else 0, rows, _lib.ptr(y),
-                                      ws.data_ptr(), ws.numel(), _prec(), _lib.stream_ptr()),
-                   "bd_mlp_forward")
+        k2 = a2.shape[1] if a2 is not None else 0
+        # tensor-core modes: keep the hidden-activation images so the backward skips recomputing them
+        nsaved = lib.bd_mlp_saved_bytes(C.byref(mlp), a1.shape[1], k2, rows, _prec()) \
+            if (rows and any(ctx.needs_input_grad)) else 0
+        saved = torch.empty(nsaved, dtype=torch.uint8, device=a1.device) if nsaved else None
+        _lib.check(lib.bd_mlp_forward_save(C.byref(mlp), _lib.ptr(a1), a1.shape[1], _lib.ptr(a2), k2,
+                                           rows, _lib.ptr(y), saved.data_ptr() if nsaved else None,
+                                           ws.data_ptr(), ws.numel(), _prec(), _lib.stream_ptr()),
+                   "bd_mlp_forward_save")
+        ctx.mlp_saved, ctx.prec = saved, _prec()
         ctx.act_id, ctx.has_x2 = act_id, x2 is not None
         ctx.x1_shape = x1.shape
         ctx.x2_shape = x2.shape if x2 is not None else None
@@ -99,10 +105,12 @@ class MlpFunction(torch.autograd.Function):
         args.dx1, args.dx2 = _lib.ptr(dx1), _lib.ptr(dx2)
         for i in range(n):
             args.dw[i], args.db[i] = _lib.ptr(dws[i]), _lib.ptr(dbs[i])
+        if ctx.mlp_saved is not None:
+            args.saved = ctx.mlp_saved.data_ptr()
         nbytes = lib.bd_mlp_workspace_bytes(C.byref(mlp), rows, 1)
         ws = _lib.workspace(nbytes, a1.device)
         _lib.check(lib.bd_mlp_backward(C.byref(mlp), C.byref(args), ws.data_ptr(), ws.numel(),
-                                       _prec(), _lib.stream_ptr()), "bd_mlp_backward")
+                                       ctx.prec, _lib.stream_ptr()), "bd_mlp_backward")
         grads: List[Optional[torch.Tensor]] = [None,
                                                dx1.reshape(ctx.x1_shape) if dx1 is not None else None,
                                                dx2.reshape(ctx.x2_shape) if dx2 is not None else None]

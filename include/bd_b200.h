@@ -135,8 +135,15 @@ typedef struct {
   float* dx2;                 /* (rows,k2) optional, overwritten               */
   float* dw[BD_MAX_LAYERS];   /* optional, accumulated (+=)                    */
   float* db[BD_MAX_LAYERS];   /* optional, accumulated (+=)                    */
+  const void* saved;          /* optional: buffer written by bd_mlp_forward_save (tensor-core modes) */
 } bd_mlp_bwd_args;
-/* hidden activations are recomputed from the inputs (nothing is saved by forward) */
+/* Tensor-core modes: the forward can leave 16-bit images of its hidden activations in a caller
+ * buffer of bd_mlp_saved_bytes() bytes; the backward then skips their recomputation.  Without it
+ * (saved == NULL, or fp32 mode) hidden activations are recomputed from the inputs. */
+size_t bd_mlp_saved_bytes(const bd_mlp* m, int k1, int k2, int64_t rows, int precision);
+int bd_mlp_forward_save(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2,
+                        int64_t rows, float* y, void* saved, void* ws, size_t ws_bytes,
+                        int precision, bd_stream_t stream);
 int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
                     int precision, bd_stream_t stream);
 
