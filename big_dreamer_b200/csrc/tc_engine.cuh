@@ -83,6 +83,25 @@ struct SmemPlan {
   uint32_t total;
 };
 
+// Per-(tile, step) global inputs of the epilogues that the producer warp pulls into L2 one step
+// ahead (prefetch.global.L2), so the epilogues see L2 latency instead of first-touch DRAM latency.
+struct PrefetchPlan {
+  int n;                     // number of ranges (0 = off)
+  int reverse;               // 1: the kernel walks time backwards (step index i -> t = T-1-i)
+  const char* base[6];
+  long long step_stride[6];  // bytes between consecutive t
+  long long tile_stride[6];  // bytes between consecutive tiles
+  unsigned int bytes[6];     // bytes per (tile, step)
+};
+__device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long tile, int t) {
+  const int lane = threadIdx.x & 31;
+  for (int r = 0; r < pf.n; ++r) {
+    const char* p = pf.base[r] + t * pf.step_stride[r] + tile * pf.tile_stride[r];
+    for (unsigned int o = lane * 128u; o < pf.bytes[r]; o += 32u * 128u)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  }
+}
+
 struct RolloutArgs {
   Program prog;
   SmemPlan sm;
@@ -108,6 +127,7 @@ struct RolloutArgs {
   // CEM: rows are (batch row, local candidate); start latents are per batch row and the state
   // noise is indexed by the GLOBAL candidate (src/planner.py:37-39, 53-65)
   int cem_cl, cem_c, cem_c0;  // local candidates per batch row (0 = off), global candidates, first
+  PrefetchPlan pf;            // next tile's / step's epilogue inputs (producer-warp L2 prefetch)
 };
 
 // fast-math activations for the 16-bit path (the result is rounded to 10 / 7 mantissa bits anyway)
@@ -163,25 +183,6 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
   return sh.tmem_holder;
 }
 
-// Per-(tile, step) global inputs of the epilogues that the producer warp pulls into L2 one step
-// ahead (prefetch.global.L2), so the epilogues see L2 latency instead of first-touch DRAM latency.
-struct PrefetchPlan {
-  int n;                     // number of ranges (0 = off)
-  int reverse;               // 1: the kernel walks time backwards (step index i -> t = T-1-i)
-  const char* base[6];
-  long long step_stride[6];  // bytes between consecutive t
-  long long tile_stride[6];  // bytes between consecutive tiles
-  unsigned int bytes[6];     // bytes per (tile, step)
-};
-__device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long tile, int t) {
-  const int lane = threadIdx.x & 31;
-  for (int r = 0; r < pf.n; ++r) {
-    const char* p = pf.base[r] + t * pf.step_stride[r] + tile * pf.tile_stride[r];
-    for (unsigned int o = lane * 128u; o < pf.bytes[r]; o += 32u * 128u)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-  }
-}
-
 // The whole warp walks the program so every address stays in uniform registers; one elected
 // lane issues the copies.
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
@@ -194,8 +195,9 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     for (int t = 0; t < T; ++t) {
       if (pf && pf->n) {      // inputs of the NEXT step (and of step 0 when a tile starts)
-        if (t == 0) prefetch_step(*pf, tile, pf->reverse ? T - 1 : 0);
+        if (t == 0 && tile == (long long)blockIdx.x) prefetch_step(*pf, tile, pf->reverse ? T - 1 : 0);
         if (t + 1 < T) prefetch_step(*pf, tile, pf->reverse ? T - 2 - t : t + 1);
+        else if (tile + gridDim.x < ntiles) prefetch_step(*pf, tile + gridDim.x, pf->reverse ? T - 1 : 0);
       }
       for (int gi = 0; gi < P.n_gemms; ++gi) {
         const Gemm g = P.g[gi];
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   const Program& P = a.prog;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh);
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf);
   } else if (warp == 1) {
     issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof);
   } else {

@@ -706,6 +706,16 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
   ra.N = rows; ra.T = 1; ra.Be = k1; ra.S = k2; ra.A = 0; ra.Hi = 0; ra.J = 0;
   ra.Kp_b = Kp_b; ra.Kp_sa = max(Ks, 16); ra.Kp_h = Kp_h; ra.act = m->activation;
   ra.prev_belief = x1; ra.prev_state = x2; ra.mlp_out = y; ra.has_b1 = 0;
+  {   // next tile's input rows -> L2 while the current tile computes
+    PrefetchPlan& pf = ra.pf;
+    pf.n = 0; pf.reverse = 0;
+    pf.base[0] = reinterpret_cast<const char*>(x1); pf.step_stride[0] = 0;
+    pf.tile_stride[0] = (long long)kTileRows * k1 * 4; pf.bytes[0] = (unsigned)(kTileRows * k1 * 4); pf.n = 1;
+    if (x2 && k2 > 0) {
+      pf.base[1] = reinterpret_cast<const char*>(x2); pf.step_stride[1] = 0;
+      pf.tile_stride[1] = (long long)kTileRows * k2 * 4; pf.bytes[1] = (unsigned)(kTileRows * k2 * 4); pf.n = 2;
+    }
+  }
   if (saved) {   // hidden images, layer after layer, each [tiles][128 x Kp_l] (same layout mlp_backward reads)
     const size_t tiles = (size_t)((rows + kTileRows - 1) / kTileRows);
     char* sb = static_cast<char*>(saved);

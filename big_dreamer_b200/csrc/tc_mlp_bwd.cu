@@ -245,6 +245,21 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
     const unsigned grid = (unsigned)(nt < sms ? nt : sms);
     {
+      // the producer warp pulls the NEXT tile's inputs (rows of x1 / x2 / dy, saved hidden images) into L2
+      PrefetchPlan& pf = ba.pf;
+      pf.n = 0; pf.reverse = 0;
+      auto add = [&](const void* ptr, size_t tile_bytes) {
+        if (!ptr || pf.n >= 6) return;
+        pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
+        pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
+      };
+      add(ba.x1, (size_t)128 * k1 * 4);
+      add(ba.x2, (size_t)128 * k2 * 4);
+      add(ba.dy, (size_t)128 * out * 4);
+      if (have_saved)
+        for (int l = 0; l + 1 < L && pf.n < 6; ++l) add(ba.xs[l], (size_t)128 * p.kp_xs[l] * 2);
+    }
+    {
       ProfScope ps(BD_PROF_MLP_BWD, s);
       if (fmt == 0) BD_TRY(launch_bwd_act<0>(m->activation, grid, ba, s));
       else BD_TRY(launch_bwd_act<1>(m->activation, grid, ba, s));

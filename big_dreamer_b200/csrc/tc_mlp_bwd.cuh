@@ -36,6 +36,7 @@ struct MlpBwdArgs {
   uint16_t *x0b, *x0s;          // images of [x1 | 1] and x2
   int kp_xs[BD_MAX_LAYERS], kp_ds[BD_MAX_LAYERS];
   const unsigned int* amax_bits;  // device: bit pattern of max|dy| (see grad_scale)
+  PrefetchPlan pf;                // next tile's inputs, pulled into L2 by the producer warp
 };
 
 // Gradients reach this kernel scaled by 1/(T*N) and can sit far below fp16's normal range, so the
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   const Program& P = a.prog;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, 1, smem, sh);
+    producer_role(P, a.sm, a.wpack, ntiles, 1, smem, sh, &a.pf);
   } else if (warp == 1) {
     issuer_role<FMT, false>(P, a.sm, ntiles, 1, smem, sh, tmem_base, nullptr);
   } else {
@@ -159,10 +160,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
         const uint32_t tacc = trow + ph.d_col;
-        mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);
-        tc_fence_after_sync();
+#define BD_WAIT_ACC()                                        \
+  do {                                                       \
+    mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);          \
+    tc_fence_after_sync();                                   \
+  } while (0)
         switch (ph.epi) {
           case EPI_B_ACT_SAVE: {
+            BD_WAIT_ACC();
             const int l = ph.aux0, nv = ph.n_valid;
             uint16_t* img = a.xs[l] + (size_t)tile * kTileRows * ph.Kp_out;
             for (int c = half * 32; c < ph.Kp_out; c += 64) {
@@ -201,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             }
           } break;
           case EPI_B_LOAD_DY: {
+            BD_WAIT_ACC();
             const int l = a.n_layers - 1, kp = a.kp_ds[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
             for (int c = half * 8; c < kp; c += 16) {
@@ -218,15 +224,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             const int nv = ph.n_valid, kp = a.kp_ds[l];
             const uint16_t* himg = a.xs[l] + (size_t)tile * kTileRows * a.kp_xs[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
-            for (int c = half * 32; c < kp; c += 64) {
-              float v[32];
-              const bool two = (c + 16) < kp;
-              const int ngroups = two ? 4 : 2;
-              uint4 hu[4];
+            uint4 hu[4];
+            auto load_h = [&](int c) {
+              const int ngroups = ((c + 16) < kp) ? 4 : 2;
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8)
                 if (g8 < ngroups)
                   hu[g8] = *reinterpret_cast<const uint4*>(himg + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8);
+            };
+            if (half * 32 < kp) load_h(half * 32);      // issued before the accumulator wait
+            BD_WAIT_ACC();
+            for (int c = half * 32; c < kp; c += 64) {
+              float v[32];
+              const bool two = (c + 16) < kp;
+              const int ngroups = two ? 4 : 2;
+              if (c != half * 32) load_h(c);
               if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
               else {
                 if (c < ph.Np) tmem_ld16(tacc + c, v);
@@ -252,23 +264,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             }
           } break;
           case EPI_B_DX: {
+            BD_WAIT_ACC();
             const int nin = a.k1 + a.k2;
+            const bool v4 = ((a.k1 & 3) == 0);
             for (int c = half * 16; c < ph.Np; c += 32) {
               float v[16];
               tmem_ld16(tacc + c, v);
               tmem_ld_wait();
               if (rvalid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int col = c + j;
-                  if (col < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + col] = v[j] * inv_scale; }
-                  else if (col < nin) { if (a.dx2) a.dx2[grow * a.k2 + (col - a.k1)] = v[j] * inv_scale; }
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const int col = c + j4 * 4;
+                  if (v4 && col + 3 < a.k1) {        // whole float4 inside dx1 (rows are 16-byte aligned)
+                    if (a.dx1)
+                      *reinterpret_cast<float4*>(a.dx1 + grow * a.k1 + col) =
+                          make_float4(v[j4 * 4] * inv_scale, v[j4 * 4 + 1] * inv_scale,
+                                      v[j4 * 4 + 2] * inv_scale, v[j4 * 4 + 3] * inv_scale);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const int cc = col + j;
+                      if (cc < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + cc] = v[j4 * 4 + j] * inv_scale; }
+                      else if (cc < nin) { if (a.dx2) a.dx2[grow * a.k2 + (cc - a.k1)] = v[j4 * 4 + j] * inv_scale; }
+                    }
+                  }
                 }
               }
             }
           } break;
-          default: break;
+          default: BD_WAIT_ACC(); break;
         }
+#undef BD_WAIT_ACC
         tc_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(&sh.epi_done[Ge & 7]);
