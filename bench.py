@@ -268,17 +268,30 @@ def run_ours(args):
     noise = bd.draw_imagine_noise(T, rows, d["S"], d["A"], dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
+    CHUNK = 131072   # rows per forward/backward pass: rows are independent, so a large batch is
+                     # processed in slices (bounds the saved-for-backward state); grads accumulate
+
     def step(s0_, b0_, noise_):
         for p in actor_params:
             p.grad = None
-        beliefs, states, _, entropy = bd.imagine_ahead(agent, s0_[None], b0_[None], noise_)
-        rew = mods.reward(beliefs, states)
-        val = mods.critic(beliefs, states)
-        ret = bd.lambda_return(rew, val, val[-1], DISCOUNT, LAMBDA)
-        loss = -(ret + ENT_W * entropy.unsqueeze(-1)).mean()
-        loss.backward()
+        total, ents = None, []
+        n = s0_.shape[0]
+        for lo in range(0, n, CHUNK):
+            hi = min(n, lo + CHUNK)
+            nz = None if noise_ is None else {"eps_a": noise_["eps_a"][:, lo:hi], "eps_s": noise_["eps_s"][:, lo:hi],
+                                              "eps_e": noise_["eps_e"][:, :, lo:hi]}
+            if nz is not None and (lo > 0 or hi < n):
+                nz = {k: v.contiguous() for k, v in nz.items()}
+            beliefs, states, _, entropy = bd.imagine_ahead(agent, s0_[None, lo:hi], b0_[None, lo:hi], nz)
+            rew = mods.reward(beliefs, states)
+            val = mods.critic(beliefs, states)
+            ret = bd.lambda_return(rew, val, val[-1], DISCOUNT, LAMBDA)
+            loss = -(ret + ENT_W * entropy.unsqueeze(-1)).sum() / (T * n)     # = slice of the global mean
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+            ents.append(entropy.detach().mean() * ((hi - lo) / n))
         D_.allreduce_grads(actor_params)
-        return loss, entropy
+        return total, torch.stack(ents).sum()
 
     def barrier():
         if world > 1:
@@ -326,7 +339,7 @@ def run_ours(args):
         s = s0_h.to(dev, non_blocking=True)
         b = b0_h.to(dev, non_blocking=True)
         loss, ent = step(s, b, None)
-        return float(loss.item()), float(ent.mean().item())
+        return float(loss.item()), float(ent.item())
     ms_e2e, _ = timed(e2e_step, args.steps, warmup)
     clocks = sampler.stop() if sampler else None
 
