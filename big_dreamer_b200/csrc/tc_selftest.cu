@@ -43,8 +43,28 @@ selftest_kernel(const float* __restrict__ x, int K, int Kp, int Np, const uint16
   __syncthreads();
   tc_fence_after_sync();
   const int d_col = swap_lbo_sbo >> 8;   // test hook: accumulator column offset
+  const bool a_in_tmem = (swap_lbo_sbo & 2) != 0;   // test hook: A operand from tensor memory (TS mode)
   swap_lbo_sbo &= 1;
   const uint32_t tmem_base = tmem_base_holder + d_col;
+  const uint32_t a_tmem = tmem_base_holder + 384;   // A image: Kp/2 columns (<= 128)
+  if (a_in_tmem) {
+    // row = tid = TMEM lane; one 32-bit column holds two K-adjacent 16-bit elements
+    for (int k0 = 0; k0 < Kp; k0 += 16) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int k = k0 + 2 * j;
+        float v0 = k < K ? x[tid * K + k] : (k == K ? 1.f : 0.f);
+        float v1 = (k + 1) < K ? x[tid * K + k + 1] : ((k + 1) == K ? 1.f : 0.f);
+        pk[j] = Half16<FMT>::pack2(v0, v1);
+      }
+      tmem_st8(a_tmem + ((uint32_t)(warp * 32) << 16) + (k0 >> 1), pk);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+  }
 
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)Np * Kp * 2;
@@ -59,7 +79,8 @@ selftest_kernel(const float* __restrict__ x, int K, int Kp, int Np, const uint16
       uint32_t b_addr = smem_u32(b_tile) + ks * 2 * lbo_b;
       uint64_t ad = swap_lbo_sbo ? make_smem_desc(a_addr, sbo, lbo_a) : make_smem_desc(a_addr, lbo_a, sbo);
       uint64_t bd_ = swap_lbo_sbo ? make_smem_desc(b_addr, sbo, lbo_b) : make_smem_desc(b_addr, lbo_b, sbo);
-      umma_f16(tmem_base, ad, bd_, idesc, ks > 0 ? 1u : 0u);
+      if (a_in_tmem) umma_f16_ts(tmem_base, a_tmem + ks * 8, bd_, idesc, ks > 0 ? 1u : 0u);
+      else umma_f16(tmem_base, ad, bd_, idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(&bar_mma);
   }

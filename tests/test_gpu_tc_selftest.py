@@ -39,3 +39,13 @@ def test_tc_accumulator_column_offsets(d_col, N):
     y, ref = run(200, N, 0, swap=d_col << 8)
     err = float((y - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, (d_col, N, err)
+
+
+@pytest.mark.parametrize("K,N", [(200, 200), (47, 64), (230, 208)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_tc_a_operand_from_tmem(K, N, fmt):
+    """TS mode: the A operand is written to tensor memory with tcgen05.st and read by the MMA from
+    there (the round-2 plan for chain layers); same numerics as the shared-memory operand."""
+    y, ref = run(K, N, fmt, swap=2)
+    err = float((y - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
