@@ -208,6 +208,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   ba.wpack = wpack; ba.T = 1; ba.prof = nullptr; ba.amax_bits = amax;
   ba.k1 = k1; ba.k2 = k2; ba.out = m->layer[L - 1].out_features; ba.n_layers = L; ba.act = m->activation;
   ba.Kp_b = p.Kp_b; ba.Ks = p.Ks; ba.Kp_h = p.Kp_h; ba.Kp_g = p.Kp_g; ba.want_images = want_w ? 1 : 0;
+  ba.need_x = (want_w || !have_saved) ? 1 : 0;
   for (int l = 0; l < L; ++l) { ba.kp_xs[l] = p.kp_xs[l]; ba.kp_ds[l] = p.kp_ds[l]; }
 
   int dev = 0, sms = 148;
@@ -253,8 +254,10 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
         pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
         pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
       };
-      add(ba.x1, (size_t)128 * k1 * 4);
-      add(ba.x2, (size_t)128 * k2 * 4);
+      if (ba.need_x) {
+        add(ba.x1, (size_t)128 * k1 * 4);
+        add(ba.x2, (size_t)128 * k2 * 4);
+      }
       add(ba.dy, (size_t)128 * out * 4);
       if (have_saved)
         for (int l = 0; l + 1 < L && pf.n < 6; ++l) add(ba.xs[l], (size_t)128 * p.kp_xs[l] * 2);

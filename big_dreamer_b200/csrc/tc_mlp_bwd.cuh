@@ -29,6 +29,7 @@ struct MlpBwdArgs {
   int k1, k2, out, n_layers, act;
   int Kp_b, Ks, Kp_h, Kp_g;
   int want_images;              // 1: also dump X / dY images for wgrad
+  int need_x;                   // 0: inputs are not needed (saved hidden images, no wgrad): skip tile init
   const float *x1, *x2, *dy;
   float *dx1, *dx2;
   uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
       // ---------------- init: B0 <- [x1 | 1], SA <- x2 (and their images for wgrad)
-      {
+      if (a.need_x) {
         const int gb = a.Kp_b >> 3;
         for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
@@ -154,9 +155,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             *reinterpret_cast<uint4*>(a.x0s + (size_t)tile * kTileRows * a.Ks + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
         fence_proxy_async_smem();
-        mbar_arrive(&sh.epi_done[Ge & 7]);
-        ++Ge;
       }
+      mbar_arrive(&sh.epi_done[Ge & 7]);
+      ++Ge;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
         const uint32_t tacc = trow + ph.d_col;
@@ -224,21 +225,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             const int nv = ph.n_valid, kp = a.kp_ds[l];
             const uint16_t* himg = a.xs[l] + (size_t)tile * kTileRows * a.kp_xs[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
-            uint4 hu[4];
-            auto load_h = [&](int c) {
+            uint4 hu[4], hn[4];
+            auto load_h = [&](int c, uint4* dst) {
               const int ngroups = ((c + 16) < kp) ? 4 : 2;
 #pragma unroll
               for (int g8 = 0; g8 < 4; ++g8)
                 if (g8 < ngroups)
-                  hu[g8] = *reinterpret_cast<const uint4*>(himg + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8);
+                  dst[g8] = *reinterpret_cast<const uint4*>(himg + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8);
             };
-            if (half * 32 < kp) load_h(half * 32);      // issued before the accumulator wait
+            if (half * 32 < kp) load_h(half * 32, hn);      // issued before the accumulator wait
             BD_WAIT_ACC();
             for (int c = half * 32; c < kp; c += 64) {
               float v[32];
               const bool two = (c + 16) < kp;
               const int ngroups = two ? 4 : 2;
-              if (c != half * 32) load_h(c);
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) hu[g8] = hn[g8];
+              if (c + 64 < kp) load_h(c + 64, hn);          // next chunk's image while this one is processed
               if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
               else {
                 if (c < ph.Np) tmem_ld16(tacc + c, v);
