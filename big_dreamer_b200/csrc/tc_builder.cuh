@@ -49,7 +49,8 @@ struct Builder {
     max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
   }
   // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
-  void finalize_blocks(uint32_t stage_bytes) {
+  void finalize_blocks(uint32_t stage_bytes) { finalize_blocks_of(prog, stage_bytes); }
+  static void finalize_blocks_of(Program& prog, uint32_t stage_bytes) {
     for (int i = 0; i < prog.n_gemms; ++i) {
       Gemm& g = prog.g[i];
       uint32_t kc = stage_bytes / (g.Np * 2u) / 16u * 16u;
@@ -65,13 +66,22 @@ struct Builder {
     p.g0 = (uint8_t)cur_phase_g0; p.ng = (uint8_t)(prog.n_gemms - cur_phase_g0); p.epi = (uint8_t)epi;
     p.dep_back = (uint8_t)dep_back; p.n_valid = (uint16_t)n_valid; p.Np = (uint16_t)Np;
     p.Kp_out = (uint16_t)Kp_out; p.d_col = (uint16_t)d_col; p.aux0 = (uint16_t)aux0;
-    p.out_tile = (uint8_t)out_tile; p.pad = 0; p.n_sub = 1; p.pad2 = 0; p.split = 0;
+    p.out_tile = (uint8_t)out_tile; p.pad = 0; p.n_sub = 1; p.pad2 = 0; p.split = 0; p.col0 = 0; p.pad3 = 0;
     for (int gi = cur_phase_g0; gi < prog.n_gemms; ++gi) prog.g[gi].dep_back = (uint8_t)dep_back;
     for (int gi : chained) prog.g[gi].dep_back = 2;     // the previous phase published 2 sub-epilogues
     chained.clear();
     cur_phase_g0 = prog.n_gemms;
   }
   int dcol() const { return (prog.n_phases & 1) * 256; }
+
+  // ---- column-split (cluster) builds: one program per rank, shared pack table / weight buffer
+  Program ranks[kMaxRanks];
+  void end_rank(int r) {
+    ranks[r] = prog;
+    prog = Program{};
+    cur_phase_g0 = 0;
+    chained.clear();
+  }
 
   // Sub-epilogue pipelining between two chained layers.  Call right after end_phase() of an ACT
   // epilogue that writes an operand tile of Kp_out columns: it will publish columns [0, split)

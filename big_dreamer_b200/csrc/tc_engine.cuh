@@ -20,6 +20,14 @@
 // A phase names how far back its dependency is (dep_back = 1: previous phase; 2: the one before,
 // which lets independent phases -- the GRU's N-slices -- overlap MMA with the previous epilogue
 // using the two TMEM halves).
+//
+// Column-split mode (nranks = 2 or 4, small row counts): the CTAs of a thread-block cluster share
+// ONE row tile.  Every rank runs its own program over a slice of each layer's output columns
+// (its own weight rows, so the weight stream and the epilogue work are divided by nranks) and
+// writes its slice of the next operand tile into every rank's shared memory.  The barriers then
+// become cluster-wide: tcgen05.commit multicasts to acc_full of every rank (an epilogue may only
+// overwrite operand columns once NO rank's MMAs still read them) and every epilogue warp arrives
+// on epi_done of every rank.  Narrow phases (actor / prior / head outputs) are replicated.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -32,6 +40,7 @@ constexpr int kTileRows = 128;
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int kMaxGemms = 64, kMaxPhases = 40;
+constexpr int kMaxRanks = 4;            // CTAs per cluster in column-split mode (1 = off)
 constexpr uint32_t kLboA = kTileRows * 16;   // bytes between 8-column groups of an activation tile
 
 enum TileId : uint8_t { TILE_BCUR = 0, TILE_BNXT = 1, TILE_SA = 2, TILE_H = 3, TILE_H2 = 4,
@@ -70,6 +79,8 @@ struct Phase {
   uint8_t n_sub;      // sub-epilogues (1 or 2): an ACT epilogue may publish columns [0, split) early
   uint8_t pad2;
   uint16_t split;     // first column of the second sub-epilogue (multiple of 32)
+  uint16_t col0;      // column-split mode: first (global) output column of this rank; Kp_out is its end
+  uint16_t pad3;
 };
 struct Program {
   int n_gemms, n_phases;
@@ -103,7 +114,8 @@ __device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long 
 }
 
 struct RolloutArgs {
-  Program prog;
+  Program prog[kMaxRanks];   // one program per cluster rank (column-split mode); [0] when nranks == 1
+  int nranks;
   SmemPlan sm;
   const uint16_t* wpack;
   long long N;            // rows
@@ -168,18 +180,19 @@ struct EngineShared {
   uint32_t tmem_holder;
 };
 
-__device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage) {
+__device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], 1);
-    for (int i = 0; i < 8; ++i) mbar_init(&sh.epi_done[i], kEpiThreads);
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], R);
+    for (int i = 0; i < 8; ++i) mbar_init(&sh.epi_done[i], R == 1 ? kEpiThreads : (kEpiThreads / 32) * R);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&sh.tmem_holder);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (R > 1) cluster_sync_all();   // peers' barriers are initialised before anyone arrives remotely
   return sh.tmem_holder;
 }
 
@@ -188,16 +201,17 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
                                               const uint16_t* wpack, long long ntiles, int T,
                                               uint8_t* smem, EngineShared& sh,
-                                              const PrefetchPlan* pf = nullptr) {
+                                              const PrefetchPlan* pf = nullptr, uint32_t R = 1) {
   uint8_t* ring = smem + sm.off_ring;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, ph = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
+  for (long long tile = tile0; tile < ntiles; tile += tstride)
     for (int t = 0; t < T; ++t) {
       if (pf && pf->n) {      // inputs of the NEXT step (and of step 0 when a tile starts)
-        if (t == 0 && tile == (long long)blockIdx.x) prefetch_step(*pf, tile, pf->reverse ? T - 1 : 0);
+        if (t == 0 && tile == tile0) prefetch_step(*pf, tile, pf->reverse ? T - 1 : 0);
         if (t + 1 < T) prefetch_step(*pf, tile, pf->reverse ? T - 2 - t : t + 1);
-        else if (tile + gridDim.x < ntiles) prefetch_step(*pf, tile + gridDim.x, pf->reverse ? T - 1 : 0);
+        else if (tile + tstride < ntiles) prefetch_step(*pf, tile + tstride, pf->reverse ? T - 1 : 0);
       }
       for (int gi = 0; gi < P.n_gemms; ++gi) {
         const Gemm g = P.g[gi];
@@ -222,13 +236,13 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
 template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
-                                            uint32_t tmem_base, long long* prof) {
+                                            uint32_t tmem_base, long long* prof, uint32_t R = 1) {
   const int lane = threadIdx.x & 31;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
   uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
   const uint32_t ring_addr = smem_u32(smem + sm.off_ring);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long long tile = blockIdx.x / R; tile < ntiles; tile += gridDim.x / R) {
     ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
     for (int t = 0; t < T; ++t) {
       const int par = t & 1;
@@ -244,7 +258,12 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             if ((int)(D - waited) > 0) {
               long long d0 = 0;
               if (PROF) d0 = clock64();
-              mbar_wait(&sh.epi_done[D & 7], (D >> 3) & 1);
+              if (R > 1) {     // peers wrote their column slices of the operand tiles (generic proxy)
+                mbar_wait_cluster(&sh.epi_done[D & 7], (D >> 3) & 1);
+                fence_proxy_async_all();
+              } else {
+                mbar_wait(&sh.epi_done[D & 7], (D >> 3) & 1);
+              }
               tc_fence_after_sync();
               waited = D;
               if (PROF) dsum += clock64() - d0;
@@ -281,7 +300,10 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(&sh.acc_full[Gm & 3]);
+        if (elect_one()) {
+          if (R > 1) umma_commit_mc(&sh.acc_full[Gm & 3], (uint16_t)((1u << R) - 1));
+          else umma_commit(&sh.acc_full[Gm & 3]);
+        }
         __syncwarp();
         if (PROF && blockIdx.x == 0 && lane == 0) {
           prof[pi * 8 + 0] += c1 - c0 + dsum;        // issuer: wait for the dependency epilogue(s)
@@ -325,14 +347,16 @@ __device__ __forceinline__ void store8(uint8_t* p, const float* v) {
                  Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
 }
 
-template <int FMT, int ACT, bool WITH_ACTOR, bool PROF>
+template <int FMT, int ACT, bool WITH_ACTOR, bool PROF, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_constant__ RolloutArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RolloutArgs& a = A_;
   uint8_t* smem = smem_raw;
   __shared__ EngineShared sh;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
+  const uint32_t R = CLUSTER ? (uint32_t)a.nranks : 1u;   // compile-time 1 keeps the single-CTA path lean
+  const uint32_t rank = R > 1 ? cluster_ctarank() : 0u;
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;
   long long prof_c0 = 0, prof_g0 = 0;
@@ -342,12 +366,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   }
 
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
-  const Program& P = a.prog;
+  const Program& P = CLUSTER ? a.prog[rank] : a.prog[0];
+  const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf);
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R);
   } else if (warp == 1) {
-    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof);
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R);
   } else {
     // =========================================================== epilogue warps
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -356,8 +381,32 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
     const int etid = tid - 64;
     const int Be = a.Be, S = a.S, Ad = a.A;
     const bool be4 = (Be & 3) == 0;
+    const bool wr0 = rank == 0;       // replicated phases: only rank 0 writes the global outputs
+    // 16 B of an operand tile (8 columns of one row): local store, mirrored into every peer's
+    // shared memory in column-split mode
+    auto put8 = [&](uint8_t* p, const float* v) {
+      const uint4 u = make_uint4(Half16<FMT>::pack2(v[0], v[1]), Half16<FMT>::pack2(v[2], v[3]),
+                                 Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
+      if (R == 1) {
+        *reinterpret_cast<uint4*>(p) = u;
+      } else {
+        const uint32_t la = smem_u32(p);
+        for (uint32_t k = 0; k < R; ++k) st_cluster_v4(mapa_u32(la, k), u);
+      }
+    };
+    // publish epilogue completion Ge: 256 local arrivals, or one arrival per warp on every rank
+    auto epi_arrive = [&](uint32_t ge) {
+      if (R == 1) {
+        fence_proxy_async_smem();
+        mbar_arrive(&epi_done[ge & 7]);
+      } else {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane < (int)R) mbar_arrive_cluster(mapa_u32(smem_u32(&epi_done[ge & 7]), (uint32_t)lane));
+      }
+    };
     uint32_t Ge = 0, Gm = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (long long tile = tile0; tile < ntiles; tile += tstride) {
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
       // ---------------- tile initialisation: B0 <- prev_belief | 1, B1 <- 0 | 1, SA <- prev_state | . | 1
@@ -405,8 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           *reinterpret_cast<uint4*>(H + kg * kLboA + r * 16) = make_uint4(0, 0, 0, 0);
         }
-        fence_proxy_async_smem();
-        mbar_arrive(&epi_done[Ge & 7]);
+        epi_arrive(Ge);
         ++Ge;
       }
       for (int t = 0; t < a.T; ++t) {
@@ -427,22 +475,24 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               uint8_t* out = smem + a.sm.off_tile[ph.out_tile] + (row >> 3) * 128 + (row & 7) * 16;
               const int nv = ph.n_valid;
               for (int sub = 0; sub < ph.n_sub; ++sub) {
-              const int c_lo = sub == 0 ? 0 : ph.split;
+              // this rank's columns are [col0, Kp_out) (col0 = 0 unless column-split); the
+              // accumulator holds them at TMEM columns [0, Np)
+              const int c_lo = sub == 0 ? ph.col0 : ph.split;
               const int c_hi = (sub == ph.n_sub - 1) ? ph.Kp_out : ph.split;
               if (sub > 0) {   // publish the first column range: the next layer's K-slab 0 may start
                 tc_fence_before_sync();
-                fence_proxy_async_smem();
-                mbar_arrive(&epi_done[Ge & 7]);
+                epi_arrive(Ge);
                 ++Ge;
               }
               for (int c = c_lo + half * 32; c < c_hi; c += 64) {
                 float v[32];
                 const bool two = (c + 16) < ph.Kp_out;
-                if (c + 32 <= ph.Np) {
-                  tmem_ld32(tacc + c, v);
+                const int ca = c - ph.col0;           // accumulator column
+                if (ca + 32 <= ph.Np) {
+                  tmem_ld32(tacc + ca, v);
                 } else {
-                  if (c < ph.Np) tmem_ld16(tacc + c, v);
-                  if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
+                  if (ca < ph.Np) tmem_ld16(tacc + ca, v);
+                  if (ca + 16 < ph.Np) tmem_ld16(tacc + ca + 16, v + 16);
                 }
                 tmem_ld_wait();
 #pragma unroll
@@ -455,11 +505,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   }
                 }
                 uint8_t* p = out + (c >> 3) * kLboA;
-                store8<FMT>(p, v);
-                store8<FMT>(p + kLboA, v + 8);
+                put8(p, v);
+                put8(p + kLboA, v + 8);
                 if (two) {
-                  store8<FMT>(p + 2 * kLboA, v + 16);
-                  store8<FMT>(p + 3 * kLboA, v + 24);
+                  put8(p + 2 * kLboA, v + 16);
+                  put8(p + 3 * kLboA, v + 24);
                 }
                 if (ph.aux0 >= 3 && a.sv_mlp[ph.aux0 - 3]) {   // MLP forward: keep the hidden image itself
                   uint16_t* img = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * ph.Kp_out + row * 8;
@@ -482,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
 #pragma unroll
                   for (int g8 = 0; g8 < 4; ++g8) {
                     const int cg = c + g8 * 8;
-                    if (cg < kp) {
+                    if (cg < kp && cg < ph.Kp_out) {
                       float dv[8];
 #pragma unroll
                       for (int j = 0; j < 8; ++j)
@@ -589,8 +639,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   }
                   if (col0 < a.Kp_b) {
                     uint8_t* p = Bnxt + (col0 >> 3) * kLboA + (row >> 3) * 128 + (row & 7) * 16;
-                    store8<FMT>(p, o);
-                    store8<FMT>(p + kLboA, o + 8);
+                    put8(p, o);
+                    put8(p + kLboA, o + 8);
                   }
                 }
               }
@@ -624,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                     // softplus(x) = max(x,0) + log(1 + exp(-|x|)) with single-MUFU exp / log
                     const float sd = fmaxf(s_[j], 0.f) + __logf(1.f + fast_exp(-fabsf(s_[j]))) + a.min_std;
                     const float st = fmaf(sd, eps[j], m_[j]);
-                    if (rvalid && a.means) {
+                    if (rvalid && a.means && wr0) {
                       a.means[orow * S + col] = m_[j];
                       a.stds[orow * S + col] = sd;
                       a.states[orow * S + col] = st;
@@ -656,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                     const float ea = rvalid ? a.eps_a[orow * Ad + j] : 0.f;
                     const float act = tanhf(mean + ea * sd);
                     store1<FMT>(SAt, row, S + j, act);
-                    if (rvalid) {
+                    if (rvalid && wr0) {
                       a.actions[orow * Ad + j] = act;
                       a.actor_raw[orow * 2 * Ad + j] = m_[j];
                       a.actor_raw[orow * 2 * Ad + Ad + j] = s_[j];
@@ -673,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 float v[16];
                 tmem_ld16(tacc, v);
                 tmem_ld_wait();
-                if (rvalid && a.head_out[ph.aux0]) a.head_out[ph.aux0][orow] = v[0];
+                if (rvalid && wr0 && a.head_out[ph.aux0]) a.head_out[ph.aux0][orow] = v[0];
               }
             } break;
             case EPI_STORE_OUT: {
@@ -685,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                 float v[16];
                 tmem_ld16(tacc + c, v);
                 tmem_ld_wait();
-                if (rvalid) {
+                if (rvalid && wr0) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j)
                     if (c + j < nv) a.mlp_out[orow * nv + c + j] = v[j];
@@ -698,8 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
             } break;
           }
           tc_fence_before_sync();
-          fence_proxy_async_smem();
-          mbar_arrive(&epi_done[Ge & 7]);
+          epi_arrive(Ge);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
             a.prof[o] += e1 - e0;                          // epilogue: wait for the accumulator
@@ -728,6 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
       a.prof[40 * 8 + blockIdx.x * 3 + 2] = smid;
     }
   }
+  if (R > 1) cluster_sync_all();   // no rank leaves while peers may still write to / arrive on it
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 

@@ -45,6 +45,8 @@ size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor) {
   e += (size_t)8 * 6 * 64 * r16(r.belief_size + 1);       // GRU slices (<= 8 slices of 64)
   img(r.hidden_size, r.belief_size);
   img(2 * r.state_size + 32, r.hidden_size);
+  // narrow output layers are replicated per cluster rank in column-split mode
+  e += (size_t)kMaxRanks * (2 * 16 + 2 * r16(r.state_size) + 32) * r16(max(r.hidden_size, r.belief_size) + 1);
   return e * 2 + 4096;
 }
 
@@ -65,36 +67,146 @@ static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& s
   return true;
 }
 
-template <int FMT, int ACT, bool WITH_ACTOR>
-static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s) {
-  if (prof && FMT == 0 && ACT == BD_ACT_ELU) {
-    cudaFuncSetAttribute(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
-    rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, true><<<grid, kThreads, ra.sm.total, s>>>(ra);
+
+// ---------------------------------------------------------------------------------------------
+// Column-split (cluster) mode helpers: rank `rank` of R owns 16-column groups
+// [G*rank/R, G*(rank+1)/R) of a G-group output.
+// ---------------------------------------------------------------------------------------------
+static inline void split_cols(int groups, int rank, int R, int& c0, int& c1) {
+  c0 = groups * rank / R * 16;
+  c1 = groups * (rank + 1) / R * 16;
+}
+// every rank must own at least one accumulator group of an n-wide layer written to a Kp_out tile
+static bool split_ok_act(int n, int Kp_out, int R) {
+  const int G = Kp_out / 16;
+  if (G < R) return false;
+  for (int k = 0; k < R; ++k) {
+    int c0, c1;
+    split_cols(G, k, R, c0, c1);
+    if (c1 <= c0 || c0 >= r16(n)) return false;
+  }
+  return true;
+}
+static bool split_ok_gru(int Be, int R) {
+  const int G = r16(Be) / 16;
+  const int ns = ((G + R - 1) / R + 3) / 4;
+  return G / R >= ns && G / R >= 1;
+}
+// cluster size for `ntiles` row tiles: split the columns of a tile over 2 or 4 SMs while that
+// still leaves every cluster its own SMs (BD_TC_CLUSTER=1|2|4 forces a size, for tests)
+static int pick_ranks(long long ntiles, const int* act_n, const int* act_kp, int nact, int Be) {
+  int want = ntiles <= 32 ? 4 : (ntiles <= 70 ? 2 : 1);
+  if (const char* e = getenv("BD_TC_CLUSTER")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) want = v;
+  }
+  for (int R = want; R > 1; R >>= 1) {
+    bool ok = Be <= 0 || split_ok_gru(Be, R);
+    for (int i = 0; i < nact && ok; ++i) ok = split_ok_act(act_n[i], act_kp[i], R);
+    if (ok) return R;
+  }
+  return 1;
+}
+
+struct ActSrc { const float* w; int ld, src_c0, len, Kp, a_tile; const float* bias; int bias_k; };
+// act(sum_i A_i W_i^T + b) -> operand tile out_tile (Kp_out columns).  R == 1: the whole layer,
+// its first GEMM chained on the previous phase's early publication when chain_split > 0 (returns
+// this phase's own split).  R > 1: this rank's column slice of the layer (weight rows [c0, c1)).
+static int add_act_phase(Builder& b, int rank, int R, const ActSrc* src, int nsrc, int n, int Kp_out,
+                         int aux0, int out_tile, int chain_split) {
+  const int Np = r16(n);
+  int c0 = 0, c1 = Kp_out;
+  if (R > 1) split_cols(Kp_out / 16, rank, R, c0, c1);
+  const int Nr = max(0, min(c1, Np) - c0);
+  const int nvr = max(0, min(n - c0, Nr));
+  const int d = b.dcol();
+  for (int i = 0; i < nsrc && Nr > 0; ++i) {
+    const ActSrc& x = src[i];
+    uint32_t off = b.add_pack(x.w, x.ld, c0, nvr, Nr, x.Kp, x.src_c0, x.len, x.bias, x.bias_k);
+    if (i == 0 && R == 1 && chain_split > 0) b.chain_gemm(off, Nr, x.Kp, x.a_tile, d, chain_split);
+    else b.add_gemm(off, Nr, x.Kp, x.a_tile, 0, d, i > 0 ? 1 : 0);
+  }
+  b.end_phase(EPI_ACT_H, 1, n, Nr, c1, d, aux0, out_tile);
+  if (b.ok) b.prog.p[b.prog.n_phases - 1].col0 = (uint16_t)c0;
+  return R == 1 ? b.split_last_phase() : 0;
+}
+// GRUCell in N-slices of <= 64 belief columns: accumulators IN | R | Z | HN per slice.  Stacked
+// gate images: 3 GEMMs per slice instead of 6, so the A tiles (x, h) are fetched from shared
+// memory half as often.  R > 1: only this rank's belief columns, in evenly sized slices.
+static void add_gru_phases(Builder& b, const bd_rssm& r, int rank, int R, int Kp_x, int Kp_b, int sp_x) {
+  const int Be = r.belief_size;
+  int n0s[8], nss[8], ns = 0;
+  if (R == 1) {
+    for (int n0 = 0; n0 < Be && ns < 8; n0 += 64, ++ns) { n0s[ns] = n0; nss[ns] = r16(min(64, Be - n0)); }
   } else {
-    cudaFuncSetAttribute(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
-    rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false><<<grid, kThreads, ra.sm.total, s>>>(ra);
+    const int G = r16(Be) / 16;
+    ns = ((G + R - 1) / R + 3) / 4;
+    const int g0 = G * rank / R, ng = G * (rank + 1) / R - g0;
+    for (int sl = 0; sl < ns; ++sl) {
+      const int ga = g0 + ng * sl / ns, gb = g0 + ng * (sl + 1) / ns;
+      n0s[sl] = ga * 16; nss[sl] = (gb - ga) * 16;
+    }
   }
-  BD_CUDA_LAUNCH_CHECK();
-  return BD_OK;
-}
-template <int FMT, bool WITH_ACTOR>
-static int launch_rollout_a(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s) {
-  switch (act) {
-    case BD_ACT_ELU: return launch_rollout_t<FMT, BD_ACT_ELU, WITH_ACTOR>(prof, grid, ra, s);
-    case BD_ACT_RELU: return launch_rollout_t<FMT, BD_ACT_RELU, WITH_ACTOR>(prof, grid, ra, s);
-    case BD_ACT_TANH: return launch_rollout_t<FMT, BD_ACT_TANH, WITH_ACTOR>(prof, grid, ra, s);
-    default: return launch_rollout_t<FMT, BD_ACT_IDENTITY, WITH_ACTOR>(prof, grid, ra, s);
+  for (int slice = 0; slice < ns; ++slice) {
+    const int n0 = n0s[slice], Ns = nss[slice];
+    const int nv = max(0, min(Ns, Be - n0));
+    int d = b.dcol();
+    if (Ns > 0) {
+      PackSeg rx[3] = {{0, 2 * Be + n0, nv}, {Ns, n0, nv}, {2 * Ns, Be + n0, nv}};      // W_in, W_ir, W_iz
+      PackSeg rh[2] = {{0, n0, nv}, {Ns, Be + n0, nv}};                                 // W_hr, W_hz
+      uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
+      uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
+      uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
+      if (slice == 0) b.chain_gemm(wx, 3 * Ns, Kp_x, TILE_H, d, sp_x);
+      else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);          // [IN | R | Z] = x W_i*^T + b_i*
+      b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);       // [R | Z]    += h W_h{r,z}^T + b_h{r,z}
+      b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);       // HN          = h W_hn^T + b_hn
+    }
+    b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
   }
 }
+// embed -> GRU -> prior of one transition step (shared by imagine, CEM, TransitionModel.forward)
+static void add_transition_phases(Builder& b, const bd_rssm& r, int rank, int R, int Kp_b, int Kp_sa,
+                                  int Kp_hid, int Kp_x, bool save) {
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Sp = r16(S);
+  // x = act(W_sa [s ; a] + b)
+  ActSrc se{r.embed.w, S + A, 0, S + A, Kp_sa, TILE_SA, r.embed.b, S + A};
+  const int sp_x = add_act_phase(b, rank, R, &se, 1, Be, Kp_x, save ? 1 : 0, TILE_H, 0);   // aux0 = 1: save act'(x)
+  add_gru_phases(b, r, rank, R, Kp_x, Kp_b, sp_x);
+  // prior: h = act(W_p1 b' + b), (mean | raw std) = W_p2 h + b   (output phase replicated on every rank)
+  ActSrc sp1{r.prior1.w, Be, 0, Be, Kp_b, TILE_BNXT, r.prior1.b, Be};
+  const int sp_h = add_act_phase(b, rank, R, &sp1, 1, Hi, Kp_hid, save ? 2 : 0, TILE_H, 0);  // aux0 = 2: save act'(h)
+  uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+  uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
+  const int d = b.dcol();
+  b.chain_gemm(wm, Sp, Kp_hid, TILE_H, d, sp_h);
+  b.chain_gemm(wsd, Sp, Kp_hid, TILE_H, d + Sp, sp_h);
+  b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
+}
+
+static void set_programs(RolloutArgs& ra, Builder& b, int R) {
+  ra.nranks = R;
+  if (R == 1) {
+    b.finalize_blocks(ra.sm.stage_bytes);
+    ra.prog[0] = b.prog;
+  } else {
+    for (int k = 0; k < R; ++k) {
+      Builder::finalize_blocks_of(b.ranks[k], ra.sm.stage_bytes);
+      ra.prog[k] = b.ranks[k];
+    }
+  }
+}
+
+// kernel instantiations live in tc_rollout_f{0,1}{a,n}.cu (compiled in parallel)
+int launch_rollout_f0a(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s);
+int launch_rollout_f0n(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s);
+int launch_rollout_f1a(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s);
+int launch_rollout_f1n(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s);
 static int launch_rollout(int fmt, int act, bool with_actor, bool prof, unsigned grid,
                           const RolloutArgs& ra, cudaStream_t s) {
-  if (fmt == 0)
-    return with_actor ? launch_rollout_a<0, true>(act, prof, grid, ra, s)
-                      : launch_rollout_a<0, false>(act, prof, grid, ra, s);
-  return with_actor ? launch_rollout_a<1, true>(act, prof, grid, ra, s)
-                    : launch_rollout_a<1, false>(act, prof, grid, ra, s);
+  if (fmt == 0) return with_actor ? launch_rollout_f0a(act, prof, grid, ra, s) : launch_rollout_f0n(act, prof, grid, ra, s);
+  return with_actor ? launch_rollout_f1a(act, prof, grid, ra, s) : launch_rollout_f1n(act, prof, grid, ra, s);
 }
 
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
@@ -108,74 +220,35 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1);
   const int Kp_h = max(Kp_hid, Kp_x), Ks = r16(S);
   const int Nh = r16(Hi), Nb = r16(Be), Ap = 16, Sp = r16(S);
+  const long long ntiles = (a->N + kTileRows - 1) / kTileRows;
+  const int act_n[2] = {Hi, Be}, act_kp[2] = {Kp_hid, Kp_x};
+  int R = pick_ranks(ntiles, act_n, act_kp, 2, Be);
   Builder b;
-  // ---- actor (src/models.py:506-517): L0 on [b ; s], hidden layers, output (mean | std)
-  {
+  for (;; R = 1, b = Builder()) {     // a column-split build that overflows the tables falls back to R = 1
+  for (int rank = 0; rank < R; ++rank) {
+    // ---- actor (src/models.py:506-517): L0 on [b ; s], hidden layers, output (mean | std)
     const bd_linear& L0 = ac.layer[0];
-    uint32_t w0b = b.add_pack(L0.w, Be + S, 0, Hi, Nh, Kp_b, 0, Be, L0.b, Be);
-    uint32_t w0s = b.add_pack(L0.w, Be + S, 0, Hi, Nh, Ks, Be, S, nullptr, -1);
-    int d = b.dcol();
-    b.add_gemm(w0b, Nh, Kp_b, TILE_BCUR, 0, d, 0);
-    b.add_gemm(w0s, Nh, Ks, TILE_SA, 0, d, 1);
-    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
-    int sp = b.split_last_phase();
+    ActSrc s0[2] = {{L0.w, Be + S, 0, Be, Kp_b, TILE_BCUR, L0.b, Be},
+                    {L0.w, Be + S, Be, S, Ks, TILE_SA, nullptr, -1}};
+    int sp = add_act_phase(b, rank, R, s0, 2, Hi, Kp_hid, 0, TILE_H, 0);
     for (int l = 1; l + 1 < ac.n_layers; ++l) {
       const bd_linear& L = ac.layer[l];
-      uint32_t w = b.add_pack(L.w, Hi, 0, Hi, Nh, Kp_hid, 0, Hi, L.b, Hi);
-      d = b.dcol();
-      b.chain_gemm(w, Nh, Kp_hid, TILE_H, d, sp);
-      b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 0, TILE_H);
-      sp = b.split_last_phase();
+      ActSrc sl{L.w, Hi, 0, Hi, Kp_hid, TILE_H, L.b, Hi};
+      sp = add_act_phase(b, rank, R, &sl, 1, Hi, Kp_hid, 0, TILE_H, sp);
     }
-    const bd_linear& Lo = ac.layer[ac.n_layers - 1];
-    uint32_t wm = b.add_pack(Lo.w, Hi, 0, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
-    uint32_t wsd = b.add_pack(Lo.w, Hi, A, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
-    d = b.dcol();
-    b.chain_gemm(wm, Ap, Kp_hid, TILE_H, d, sp);
-    b.chain_gemm(wsd, Ap, Kp_hid, TILE_H, d + Ap, sp);
-    b.end_phase(EPI_ACTOR_OUT, 1, 2 * A, Ap, 0, d, 0, TILE_SA);
-  }
-  // ---- embed: x = act(W_sa [s ; a] + b)
-  {
-    uint32_t w = b.add_pack(r.embed.w, S + A, 0, Be, Nb, Kp_sa, 0, S + A, r.embed.b, S + A);
-    int d = b.dcol();
-    b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, 1, TILE_H);      // aux0 = 1: save act'(x)
-  }
-  int sp_x = b.split_last_phase();
-  // ---- GRUCell in N-slices of <= 64 belief columns: accumulators R | Z | IN | HN per slice
-  {
-    int slice = 0;
-    for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
-      const int nv = min(64, Be - n0), Ns = r16(nv);
-      int d = b.dcol();
-      // stacked gate images: 3 GEMMs per slice instead of 6, so the A tiles (x, h) are fetched from
-      // shared memory half as often.  Accumulator columns: IN | R | Z | HN, each Ns wide.
-      PackSeg rx[3] = {{0, 2 * Be + n0, nv}, {Ns, n0, nv}, {2 * Ns, Be + n0, nv}};      // W_in, W_ir, W_iz
-      PackSeg rh[2] = {{0, n0, nv}, {Ns, Be + n0, nv}};                                 // W_hr, W_hz
-      uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
-      uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
-      uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-      if (slice == 0) b.chain_gemm(wx, 3 * Ns, Kp_x, TILE_H, d, sp_x);
-      else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);          // [IN | R | Z] = x W_i*^T + b_i*
-      b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);       // [R | Z]    += h W_h{r,z}^T + b_h{r,z}
-      b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);       // HN          = h W_hn^T + b_hn
-      b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
+    {   // output layer: narrow, replicated on every rank in column-split mode
+      const bd_linear& Lo = ac.layer[ac.n_layers - 1];
+      uint32_t wm = b.add_pack(Lo.w, Hi, 0, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
+      uint32_t wsd = b.add_pack(Lo.w, Hi, A, A, Ap, Kp_hid, 0, Hi, Lo.b, Hi);
+      const int d = b.dcol();
+      b.chain_gemm(wm, Ap, Kp_hid, TILE_H, d, sp);
+      b.chain_gemm(wsd, Ap, Kp_hid, TILE_H, d + Ap, sp);
+      b.end_phase(EPI_ACTOR_OUT, 1, 2 * A, Ap, 0, d, 0, TILE_SA);
     }
+    add_transition_phases(b, r, rank, R, Kp_b, Kp_sa, Kp_hid, Kp_x, true);
+    if (R > 1) b.end_rank(rank);
   }
-  // ---- prior: h = act(W_p1 b' + b), (mean | raw std) = W_p2 h + b
-  {
-    uint32_t w1 = b.add_pack(r.prior1.w, Be, 0, Hi, Nh, Kp_b, 0, Be, r.prior1.b, Be);
-    int d = b.dcol();
-    b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, 2, TILE_H);    // aux0 = 2: save act'(h)
-    const int sp_h = b.split_last_phase();
-    uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
-    uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
-    d = b.dcol();
-    b.chain_gemm(wm, Sp, Kp_hid, TILE_H, d, sp_h);
-    b.chain_gemm(wsd, Sp, Kp_hid, TILE_H, d + Sp, sp_h);
-    b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
+  if (b.ok || R == 1) break;
   }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: program too large");
   const size_t pack_bytes = (size_t)b.w_elems * 2;
@@ -183,11 +256,9 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
     BD_FAIL(BD_ERR_WORKSPACE, "tensor-core imagine_forward: workspace %zu < %zu", ws_bytes, pack_bytes);
 
   RolloutArgs ra{};
-  ra.prog = b.prog;
   if (!plan_smem(Kp_b, Kp_sa, Kp_h, b.max_stage, ra.sm))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core imagine_forward: tiles do not fit shared memory");
-  b.finalize_blocks(ra.sm.stage_bytes);
-  ra.prog = b.prog;
+  set_programs(ra, b, R);
   ra.wpack = static_cast<const uint16_t*>(ws);
   ra.N = a->N; ra.T = a->T; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = a->actor_cfg.entropy_samples;
   ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
@@ -219,7 +290,6 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   long long pgx = (max_img + 255) / 256;
   if (pgx > 64) pgx = 64;
   dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
-  const long long ntiles = (a->N + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -239,50 +309,6 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
                                              a->dent);
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Shared by CEM and TransitionModel.forward (prior-only): embed -> GRU slices -> prior phases
-// ---------------------------------------------------------------------------------------------
-static void add_transition_phases(Builder& b, const bd_rssm& r, int Kp_b, int Kp_sa, int Kp_hid, int Kp_x,
-                                  bool save) {
-  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
-  const int Nh = r16(Hi), Nb = r16(Be), Sp = r16(S);
-  {
-    uint32_t w = b.add_pack(r.embed.w, S + A, 0, Be, Nb, Kp_sa, 0, S + A, r.embed.b, S + A);
-    int d = b.dcol();
-    b.add_gemm(w, Nb, Kp_sa, TILE_SA, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Be, Nb, Kp_x, d, save ? 1 : 0, TILE_H);
-  }
-  const int sp_x = b.split_last_phase();
-  int slice = 0;
-  for (int n0 = 0; n0 < Be; n0 += 64, ++slice) {
-    const int nv = min(64, Be - n0), Ns = r16(nv);
-    int d = b.dcol();
-    PackSeg rx[3] = {{0, 2 * Be + n0, nv}, {Ns, n0, nv}, {2 * Ns, Be + n0, nv}};
-    PackSeg rh[2] = {{0, n0, nv}, {Ns, Be + n0, nv}};
-    uint32_t wx = b.add_pack_rows(r.w_ih, Be, 3, rx, 3 * Ns, Kp_x, 0, Be, r.b_ih, Be);
-    uint32_t wh = b.add_pack_rows(r.w_hh, Be, 2, rh, 2 * Ns, Kp_b, 0, Be, r.b_hh, Be);
-    uint32_t wn = b.add_pack(r.w_hh, Be, 2 * Be + n0, nv, Ns, Kp_b, 0, Be, r.b_hh, Be);
-    if (slice == 0) b.chain_gemm(wx, 3 * Ns, Kp_x, TILE_H, d, sp_x);
-    else b.add_gemm(wx, 3 * Ns, Kp_x, TILE_H, 0, d, 0);
-    b.add_gemm(wh, 2 * Ns, Kp_b, TILE_BCUR, 0, d + Ns, 1);
-    b.add_gemm(wn, Ns, Kp_b, TILE_BCUR, 0, d + 3 * Ns, 0);
-    b.end_phase(EPI_GRU, slice == 0 ? 1 : 2, nv, Ns, 0, d, n0, TILE_BNXT);
-  }
-  {
-    uint32_t w1 = b.add_pack(r.prior1.w, Be, 0, Hi, Nh, Kp_b, 0, Be, r.prior1.b, Be);
-    int d = b.dcol();
-    b.add_gemm(w1, Nh, Kp_b, TILE_BNXT, 0, d, 0);
-    b.end_phase(EPI_ACT_H, 1, Hi, Nh, Kp_hid, d, save ? 2 : 0, TILE_H);
-    const int sp_h = b.split_last_phase();
-    uint32_t wm = b.add_pack(r.prior2.w, Hi, 0, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
-    uint32_t wsd = b.add_pack(r.prior2.w, Hi, S, S, Sp, Kp_hid, 0, Hi, r.prior2.b, Hi);
-    d = b.dcol();
-    b.chain_gemm(wm, Sp, Kp_hid, TILE_H, d, sp_h);
-    b.chain_gemm(wsd, Sp, Kp_hid, TILE_H, d + Sp, sp_h);
-    b.end_phase(EPI_PRIOR_OUT, 1, 2 * S, Sp, 0, d, 0, TILE_SA);
-  }
 }
 
 bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision) {
@@ -313,31 +339,44 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   int Kp_h = max(Kp_hid, Kp_x);
   const int Cl = a->c_end - a->c_begin;
   const long long rows = (long long)a->B * Cl;
+  const long long ntiles = (rows + kTileRows - 1) / kTileRows;
+  int act_n[2 + BD_MAX_LAYERS] = {Hi, Be}, act_kp[2 + BD_MAX_LAYERS] = {Kp_hid, Kp_x}, nact = 2;
+  for (int l = 0; l + 1 < hd.n_layers; ++l) {
+    act_n[nact] = hd.layer[l].out_features; act_kp[nact] = r16(hd.layer[l].out_features + 1); ++nact;
+    Kp_h = max(Kp_h, r16(hd.layer[l].out_features + 1));
+  }
+  int R = pick_ranks(ntiles, act_n, act_kp, nact, Be);
   Builder b;
-  add_transition_phases(b, r, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
-  // reward head on (b', s'): DenseModel (src/planner.py:68-72)
-  int sp_hd = 0;
-  for (int l = 0; l < hd.n_layers; ++l) {
-    const bd_linear& L = hd.layer[l];
-    const bool last = (l == hd.n_layers - 1);
-    const int n = L.out_features, Np = r16(n);
-    const int d = b.dcol();
-    if (l == 0) {
-      uint32_t wb = b.add_pack(L.w, Be + S, 0, n, Np, Kp_b, 0, Be, L.b, Be);
-      uint32_t wsx = b.add_pack(L.w, Be + S, 0, n, Np, Ks, Be, S, nullptr, -1);
-      b.add_gemm(wb, Np, Kp_b, TILE_BNXT, 0, d, 0);
-      b.add_gemm(wsx, Np, Ks, TILE_SA, 0, d, 1);
-    } else {
-      const int kin = L.in_features, Kp = r16(kin + 1);
-      uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
-      b.chain_gemm(w, Np, Kp, TILE_H, d, sp_hd);
+  for (;; R = 1, b = Builder()) {
+  for (int rank = 0; rank < R; ++rank) {
+    add_transition_phases(b, r, rank, R, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
+    // reward head on (b', s'): DenseModel (src/planner.py:68-72)
+    int sp_hd = 0;
+    for (int l = 0; l < hd.n_layers; ++l) {
+      const bd_linear& L = hd.layer[l];
+      const bool last = (l == hd.n_layers - 1);
+      const int n = L.out_features;
+      if (!last) {
+        if (l == 0) {
+          ActSrc s0[2] = {{L.w, Be + S, 0, Be, Kp_b, TILE_BNXT, L.b, Be},
+                          {L.w, Be + S, Be, S, Ks, TILE_SA, nullptr, -1}};
+          sp_hd = add_act_phase(b, rank, R, s0, 2, n, r16(n + 1), 0, TILE_H, 0);
+        } else {
+          const int kin = L.in_features;
+          ActSrc sl{L.w, kin, 0, kin, r16(kin + 1), TILE_H, L.b, kin};
+          sp_hd = add_act_phase(b, rank, R, &sl, 1, n, r16(n + 1), 0, TILE_H, sp_hd);
+        }
+      } else {   // scalar output: replicated
+        const int kin = L.in_features, Kp = r16(kin + 1), Np = r16(n);
+        const int d = b.dcol();
+        uint32_t w = b.add_pack(L.w, kin, 0, n, Np, Kp, 0, kin, L.b, kin);
+        b.chain_gemm(w, Np, Kp, TILE_H, d, sp_hd);
+        b.end_phase(EPI_HEAD_OUT, 1, 1, Np, 0, d, 0, TILE_H);
+      }
     }
-    if (last) b.end_phase(EPI_HEAD_OUT, 1, 1, Np, 0, d, 0, TILE_H);
-    else {
-      b.end_phase(EPI_ACT_H, 1, n, Np, r16(n + 1), d, 0, TILE_H);
-      sp_hd = b.split_last_phase();
-      Kp_h = max(Kp_h, r16(n + 1));
-    }
+    if (R > 1) b.end_rank(rank);
+  }
+  if (b.ok || R == 1) break;
   }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core CEM: program too large");
   char* base = static_cast<char*>(ws);
@@ -350,8 +389,7 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   RolloutArgs ra{};
   if (!plan_smem(Kp_b, Kp_sa, Kp_h, b.max_stage, ra.sm))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core CEM: tiles do not fit shared memory");
-  b.finalize_blocks(ra.sm.stage_bytes);
-  ra.prog = b.prog;
+  set_programs(ra, b, R);
   ra.wpack = wpack;
   ra.N = rows; ra.T = a->H; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = 0;
   ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
@@ -366,7 +404,6 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   long long pgx = (max_img + 255) / 256;
   if (pgx > 64) pgx = 64;
   dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
-  const long long ntiles = (rows + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -394,16 +431,21 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, i
   const bd_rssm& r = a->rssm;
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
   const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1);
+  const long long ntiles = (a->B + kTileRows - 1) / kTileRows;
+  const int act_n[2] = {Hi, Be}, act_kp[2] = {Kp_hid, Kp_x};
+  const int R = pick_ranks(ntiles, act_n, act_kp, 2, Be);
   Builder b;
-  add_transition_phases(b, r, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
+  for (int rank = 0; rank < R; ++rank) {
+    add_transition_phases(b, r, rank, R, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
+    if (R > 1) b.end_rank(rank);
+  }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core transition_forward: program too large");
   if ((size_t)b.w_elems * 2 > ws_bytes)
     BD_FAIL(BD_ERR_WORKSPACE, "tensor-core transition_forward: workspace %zu too small", ws_bytes);
   RolloutArgs ra{};
   if (!plan_smem(Kp_b, Kp_sa, max(Kp_hid, Kp_x), b.max_stage, ra.sm))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core transition_forward: tiles do not fit shared memory");
-  b.finalize_blocks(ra.sm.stage_bytes);
-  ra.prog = b.prog;
+  set_programs(ra, b, R);
   ra.wpack = static_cast<const uint16_t*>(ws);
   ra.N = a->B; ra.T = a->L; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi;
   ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = max(Kp_hid, Kp_x); ra.act = r.activation;
@@ -418,7 +460,6 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, i
   long long pgx = (max_img + 255) / 256;
   if (pgx > 64) pgx = 64;
   dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
-  const long long ntiles = (a->B + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -700,8 +741,7 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
   RolloutArgs ra{};
   if (!plan_smem(Kp_b, max(Ks, 16), Kp_h, b.max_stage, ra.sm, false))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_forward: tiles do not fit shared memory");
-  b.finalize_blocks(ra.sm.stage_bytes);
-  ra.prog = b.prog;
+  set_programs(ra, b, 1);
   ra.wpack = static_cast<const uint16_t*>(ws);
   ra.N = rows; ra.T = 1; ra.Be = k1; ra.S = k2; ra.A = 0; ra.Hi = 0; ra.J = 0;
   ra.Kp_b = Kp_b; ra.Kp_sa = max(Ks, 16); ra.Kp_h = Kp_h; ra.act = m->activation;

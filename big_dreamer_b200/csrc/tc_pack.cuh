@@ -23,7 +23,7 @@ struct PackJob {
   int nrseg;            // > 0: image rows are stacked from several source row ranges (GRU gates)
   PackSeg rseg[3];      // dst rows [dst_k0, +len) <- src rows [src_c0, +len)   (fields reused)
 };
-constexpr int kMaxPackJobs = 48;
+constexpr int kMaxPackJobs = 64;
 struct PackTable { int njobs; PackJob job[kMaxPackJobs]; };
 
 template <int FMT>

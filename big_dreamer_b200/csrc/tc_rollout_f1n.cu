@@ -1,0 +1,9 @@
+// rollout engine kernels: format bf16, without the fused actor
+#include "tc_rollout_launch.cuh"
+namespace bd {
+namespace tc {
+int launch_rollout_f1n(int act, bool prof, unsigned grid, const RolloutArgs& ra, cudaStream_t s) {
+  return launch_rollout_a<1, false>(act, prof, grid, ra, s);
+}
+}  // namespace tc
+}  // namespace bd

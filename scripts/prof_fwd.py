@@ -31,10 +31,13 @@ if os.environ.get("BD_TC_PROF"):
         v = np.frombuffer(raw[off:off + 40 * 64].tobytes(), dtype=np.int64).reshape(40, 8)
         if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[:12, 7].sum() == 0:
             names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed", "gru0", "gru1", "gru2", "gru3", "prior1", "priorOut"]
-            print("phase      iss_dep  iss_wwait iss_issue | epi0_wait epi0_work | epi1_wait epi1_work   (cycles per step, CTA 0, 2 launches x 14 steps)")
+            nph = int((v[:20, 2] > 0).sum())
+            if nph != 12:
+                names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed"] + ["gru%d" % i for i in range(nph - 8)] + ["prior1", "priorOut"]
+            print("phase      iss_dep  iss_wwait iss_issue | epi0_wait epi0_work | epi1_wait epi1_work   (cycles per step, CTA 0, last launch, 14 steps)")
             for i, n in enumerate(names):
-                print(f"{n:9s}", " ".join(f"{int(x)//28:9d}" for x in v[i, :7]))
-            tot = v[:12, :7].sum(0) // 28
+                print(f"{n:9s}", " ".join(f"{int(x)//14:9d}" for x in v[i, :7]))
+            tot = v[:12, :7].sum(0) // 14
             print("total    ", " ".join(f"{int(x):9d}" for x in tot))
             w = np.frombuffer(raw[off + 40 * 64: off + 40 * 64 + 160 * 24].tobytes(), dtype=np.int64).reshape(160, 3)
             w = w[w[:, 0] > 0]
@@ -43,5 +46,5 @@ if os.environ.get("BD_TC_PROF"):
             dur = (w[:, 1] - w[:, 0]) / 1e3
             print("per-CTA duration us: min %.0f median %.0f max %.0f" % (dur.min(), np.median(dur), dur.max()), "distinct SMs", len(set(w[:, 2].tolist())))
             print("first 12 durations", dur[:12].round().tolist())
-            print("CTA0 kernel cycles per launch", int(v[39, 0]) // 2, "ns", int(v[39, 1]) // 2, "-> GHz", v[39, 0] / max(1, v[39, 1]))
+            print("CTA0 kernel cycles per launch", int(v[39, 0]), "ns", int(v[39, 1]), "-> GHz", v[39, 0] / max(1, v[39, 1]))
             break

@@ -181,3 +181,18 @@ def test_transition_prior_only_tc():
     assert o[3] is None and o[0].shape == (L, B, 200)
     for got, ref in ((o[0], r[0]), (o[1], r[1]), (o[2][0], r[2][0]), (o[2][1], r[2][1])):
         assert pu.relerr(got, ref.float()) < TOL
+
+
+@pytest.mark.parametrize("R", [1, 2, 4])
+def test_column_split_cluster_sizes(R, monkeypatch):
+    """Column-split mode of the rollout engine (tc_engine.cuh): a cluster of R CTAs shares one row
+    tile.  Forced through BD_TC_CLUSTER; every size must meet the same parity bound as the
+    single-CTA path on imagine (values + actor grads), CEM and TransitionModel.forward."""
+    monkeypatch.setenv("BD_TC_CLUSTER", str(R))
+    for d in (dict(Be=200, Hi=200, S=30, A=1, E=8, N=300, H=15, act="ELU"),
+              dict(Be=96, Hi=72, S=20, A=2, E=8, N=129, H=5, act="Tanh")):
+        res = pu.run_imagine_case(d, seed=5, precision="fp16", oracle_dtype=torch.float64)
+        for k, e in res["errors"].items():
+            assert e < TOL, (R, d, res["errors"])
+    test_cem_tc(dict(Be=200, Hi=200, S=30, A=1, E=8, B=2, C=300, K=30, H=6, iters=2, act="ELU"))
+    test_transition_prior_only_tc()
