@@ -233,23 +233,34 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
 
 // Ge counts epilogue completions (incl. the per-tile init pseudo-phase, which has no MMAs); Gm
 // counts phases with MMAs.  Each indexes its own barrier ring so generations stay in step.
+//
+// The whole warp walks the program converged: every lane executes the barrier waits and the
+// descriptor arithmetic on warp-uniform values, and each tcgen05.mma / tcgen05.commit is a single
+// instruction predicated on the elected lane (umma_f16_elect).  Wrapping the MMAs of a ring stage
+// in an `if (elected)` region instead costs ~300 cycles per region (operands are moved into
+// uniform registers again) -- measured with scripts/mmabench2.py: 216 vs 79 cycles per MMA.
 template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
-                                            uint32_t tmem_base, long long* prof, uint32_t R = 1) {
+                                            uint32_t tmem_base_, long long* prof, uint32_t R = 1) {
   const int lane = threadIdx.x & 31;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
   uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
-  const uint32_t ring_addr = smem_u32(smem + sm.off_ring);
+  // provably warp-uniform copies (lane 0's value) of everything that feeds an MMA operand
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_, 0);
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+  const uint32_t ring_addr = smem_base + sm.off_ring;
+  const uint32_t bar_w_empty = __shfl_sync(0xffffffffu, smem_u32(&sh.w_empty[0]), 0);
+  const uint32_t bar_acc_full = __shfl_sync(0xffffffffu, smem_u32(&sh.acc_full[0]), 0);
+  const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 0, 128) >> 32);   // SBO = 128, version, no swizzle
   for (long long tile = blockIdx.x / R; tile < ntiles; tile += gridDim.x / R) {
     ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
     for (int t = 0; t < T; ++t) {
       const int par = t & 1;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
-        long long c0 = 0, c1 = 0, wsum = 0, dsum = 0;
-        if (PROF) c0 = clock64();
+        long long c1 = 0, wsum = 0, dsum = 0;
         if (PROF) c1 = clock64();
         for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
           const Gemm g = P.g[gi];
@@ -264,6 +275,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               } else {
                 mbar_wait(&sh.epi_done[D & 7], (D >> 3) & 1);
               }
+              __syncwarp();      // lanes leave the spin loop at different times: reconverge before elect.sync
               tc_fence_after_sync();
               waited = D;
               if (PROF) dsum += clock64() - d0;
@@ -271,11 +283,13 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           }
           uint32_t tile_id = g.a_tile;
           if (tile_id < 2) tile_id ^= par;
-          const uint64_t a_desc0 =
-              make_smem_desc(smem_u32(smem + sm.off_tile[tile_id]) + (g.a_k0 >> 3) * kLboA, kLboA, 128);
+          // descriptor low words: start address >> 4 in [0,14), LBO >> 4 in [16,30)
+          // (in a cluster launch the shared-window address carries the CTA rank in its upper bits:
+          // the descriptor takes only the 18-bit offset)
+          uint32_t a_lo = ((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) + (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4)) |
+                          ((kLboA >> 4) << 16);
           const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
           const uint32_t lbo_b = (uint32_t)g.Np * 16;
-          const uint64_t b_desc0 = make_smem_desc(0, lbo_b, 128);
           const uint32_t d_tmem = tmem_base + g.d_col;
           uint32_t acc = g.accumulate == 2 ? (t > 0 ? 1u : 0u) : g.accumulate;
           for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
@@ -283,38 +297,34 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             long long w0 = 0;
             if (PROF) w0 = clock64();
             mbar_wait(&sh.w_full[st], wph);
+            __syncwarp();
             tc_fence_after_sync();
             if (PROF) wsum += clock64() - w0;
-            const uint64_t bd0 = b_desc0 | (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFF);
-            if (elect_one()) {
-              for (int ks = 0; ks < kc; ks += 16) {
-                // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
-                const uint64_t ad = a_desc0 + (uint64_t)(((k0 + ks) >> 3) * (kLboA >> 4));
-                const uint64_t bd_ = bd0 + (uint64_t)((ks >> 3) * (lbo_b >> 4));
-                umma_f16(d_tmem, ad, bd_, idesc, (acc | (uint32_t)ks) ? 1u : 0u);
-              }
-              umma_commit(&sh.w_empty[st]);
+            uint32_t b_lo = (((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu) | ((lbo_b >> 4) << 16);
+            for (int ks = 0; ks < kc; ks += 16) {
+              // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
+              umma_f16_elect(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc);
+              acc = 1;
+              a_lo += 2 * (kLboA >> 4);
+              b_lo += 2 * (lbo_b >> 4);
             }
-            __syncwarp();
-            acc = 1;
+            umma_commit_elect(bar_w_empty + st * 8);
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
         }
-        if (elect_one()) {
-          if (R > 1) umma_commit_mc(&sh.acc_full[Gm & 3], (uint16_t)((1u << R) - 1));
-          else umma_commit(&sh.acc_full[Gm & 3]);
-        }
-        __syncwarp();
+        if (R > 1) umma_commit_mc_elect(bar_acc_full + (Gm & 3) * 8, (uint16_t)((1u << R) - 1));
+        else umma_commit_elect(bar_acc_full + (Gm & 3) * 8);
         if (PROF && blockIdx.x == 0 && lane == 0) {
-          prof[pi * 8 + 0] += c1 - c0 + dsum;        // issuer: wait for the dependency epilogue(s)
-          prof[pi * 8 + 1] += wsum;                  // issuer: wait for weight stages
-          prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum; // issuer: issue time
+          prof[pi * 8 + 0] += dsum;                          // issuer: wait for the dependency epilogue(s)
+          prof[pi * 8 + 1] += wsum;                          // issuer: wait for weight stages
+          prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum;  // issuer: issue time
         }
         ++Gm;
         Ge += ph.n_sub;
       }
     }
   }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------

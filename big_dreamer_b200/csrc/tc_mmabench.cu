@@ -65,6 +65,126 @@ extern "C" int bd_tc_mmabench(int N, int nmma, int layout, int dep, long long* o
   return BD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Micro-benchmark: the same MMA chain as the engine issues for one layer (KM8 tiles, `ksteps`
+// distinct K=16 steps of A and B), optionally with a producer warp streaming bulk TMA copies into
+// a 4-slot ring at the same time (tma != 0) and epilogue-like warps hammering shared memory
+// with 16-byte stores (stw != 0).  Reports cycles for nrep passes over the K range.
+namespace bd {
+namespace tc {
+__global__ void __launch_bounds__(320, 1) mma_bench2_kernel(int N, int ksteps, int nrep, int tma, int stw,
+                                                            const uint8_t* gsrc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar, rbar[4];
+  __shared__ uint32_t holder;
+  __shared__ volatile int done;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* A = smem;                       // 128 x 208 x 2 = 53248
+  uint8_t* B = smem + 53248;               // up to 256 x 208 x 2 = 106496 -> cap N*ksteps*32
+  uint8_t* ring = smem + 53248 + 90112;    // 4 x 13312
+  uint8_t* scratch = ring + 4 * 13312;     // 16 KB for the store warps
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&rbar[i], 1);
+    fence_barrier_init();
+    done = 0;
+  }
+  if (warp == 1) tmem_alloc<512>(&holder);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = holder;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_f16(0, 128, N);
+    const uint64_t ad = make_smem_desc(smem_u32(A), 128 * 16, 128);
+    const uint64_t bdsc = make_smem_desc(smem_u32(B), N * 16, 128);
+    const uint32_t a_step = (2 * 128 * 16) >> 4, b_step = (2 * N * 16) >> 4;
+    const long long t0 = clock64();
+    for (int r = 0; r < nrep; ++r) {
+      // stw bits: 1 = store warps, 2 = commit to a dummy barrier every 2 MMAs, 4 = tcgen05 fence
+      // every 2 MMAs, 8 = elect + syncwarp every 2 MMAs (the engine's per-stage structure)
+      if (stw & 256) {          // CUTLASS style: warp-uniform descriptors, only the MMA itself elected
+        // values made provably warp-uniform (shfl from lane 0) so they live in uniform registers
+        const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t alo = __shfl_sync(0xffffffffu, (uint32_t)ad, 0), ahi = __shfl_sync(0xffffffffu, (uint32_t)(ad >> 32), 0);
+        const uint32_t blo = __shfl_sync(0xffffffffu, (uint32_t)bdsc, 0), bhi = __shfl_sync(0xffffffffu, (uint32_t)(bdsc >> 32), 0);
+        const uint32_t id_u = __shfl_sync(0xffffffffu, idesc, 0);
+        const uint32_t bar_u = __shfl_sync(0xffffffffu, smem_u32(&rbar[3]), 0);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          umma_f16_elect(tm_u + (uint32_t)((r & 1) * 256), alo + ks * a_step, ahi, blo + ks * b_step, bhi, id_u, ks > 0 ? 1u : 0u);
+          if ((stw & 2) && (ks & 1)) umma_commit_elect(bar_u);
+        }
+        __syncwarp();
+      } else if (stw & 0xE) {
+        const int grp = (stw >> 4) ? (stw >> 4) : 2;      // MMAs per elected block
+        for (int k0 = 0; k0 < ksteps; k0 += grp) {
+          if (stw & 4) tc_fence_after_sync();
+          if (elect_one()) {
+            for (int ks = k0; ks < min(k0 + grp, ksteps); ++ks)
+              umma_f16(tmem + (uint32_t)((r & 1) * 256), ad + (uint64_t)(ks * a_step), bdsc + (uint64_t)(ks * b_step), idesc, ks > 0 ? 1u : 0u);
+            if (stw & 2) umma_commit(&rbar[3]);
+          }
+          __syncwarp();
+        }
+      } else {
+        if (elect_one()) {
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16(tmem + (uint32_t)((r & 1) * 256), ad + (uint64_t)(ks * a_step), bdsc + (uint64_t)(ks * b_step), idesc, ks > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) umma_commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (tid == 0) { out[0] = t1 - t0; done = 1; }
+  } else if (warp == 2 && tma) {
+    uint32_t ph[4] = {0, 0, 0, 0};
+    int n = 0;
+    for (int it = 0; !done && it < 100000; ++it) {
+      const int s = it & 3;
+      if (it >= 4) { mbar_wait(&rbar[s], ph[s]); ph[s] ^= 1; }
+      if (elect_one()) {
+        mbar_expect_tx(&rbar[s], 13312);
+        tma_bulk_g2s(ring + s * 13312, gsrc + (size_t)(it % 64) * 13312, 13312, &rbar[s]);
+      }
+      __syncwarp();
+      ++n;
+    }
+    // drain
+    for (int k = 0; k < 4 && k < n; ++k) { const int s = (n - 1 - k) & 3; (void)s; }
+    if ((tid & 31) == 0) out[2] = n;
+    __nanosleep(20000);
+  } else if (warp >= 2 && (stw & 1) && !(warp == 2 && tma)) {
+    long long cnt = 0;
+    const int et = tid - 64;
+    for (int it = 0; !done && it < 1000000; ++it) {
+      *reinterpret_cast<uint4*>(scratch + ((et * 16 + it * 4096) & 16383)) = make_uint4(it, et, 0, 0);
+      ++cnt;
+    }
+    if (tid == 96) out[3] = cnt;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+}  // namespace tc
+}  // namespace bd
+
+extern "C" int bd_tc_mmabench2(int N, int ksteps, int nrep, int tma, int stw, const void* gsrc, long long* out, bd_stream_t stream) {
+  using namespace bd;
+  BD_CHECK_ARG(N >= 16 && N <= 256 && (N % 16) == 0 && ksteps >= 1 && ksteps <= 13 && (size_t)N * ksteps * 32 <= 90112 && out,
+               "bd_tc_mmabench2: bad args");
+  const int sm = 53248 + 90112 + 4 * 13312 + 16384;
+  cudaFuncSetAttribute(tc::mma_bench2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  tc::mma_bench2_kernel<<<1, 320, sm, static_cast<cudaStream_t>(stream)>>>(N, ksteps, nrep, tma, stw, static_cast<const uint8_t*>(gsrc), out);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Micro-benchmark: cost of exchanging an operand-tile slice between the CTAs of a cluster through
 // distributed shared memory.  mode 0: per-thread st.shared::cluster.v4 + per-warp remote arrive;

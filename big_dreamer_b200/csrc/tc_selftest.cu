@@ -44,6 +44,7 @@ selftest_kernel(const float* __restrict__ x, int K, int Kp, int Np, const uint16
   tc_fence_after_sync();
   const int d_col = swap_lbo_sbo >> 8;   // test hook: accumulator column offset
   const bool a_in_tmem = (swap_lbo_sbo & 2) != 0;   // test hook: A operand from tensor memory (TS mode)
+  const bool warp_issue = (swap_lbo_sbo & 4) != 0;  // test hook: whole-warp issue, elect-predicated instructions
   swap_lbo_sbo &= 1;
   const uint32_t tmem_base = tmem_base_holder + d_col;
   const uint32_t a_tmem = tmem_base_holder + 384;   // A image: Kp/2 columns (<= 128)
@@ -66,7 +67,32 @@ selftest_kernel(const float* __restrict__ x, int K, int Kp, int Np, const uint16
     tc_fence_after_sync();
   }
 
-  if (tid == 0) {
+  if (warp_issue) {
+    if (warp == 0) {     // the engine's issuer structure (tc_engine.cuh issuer_role)
+      const uint32_t bytes = (uint32_t)Np * Kp * 2;
+      if (tid == 0) {
+        mbar_expect_tx(&bar_w, bytes);
+        tma_bulk_g2s(b_tile, wp, bytes, &bar_w);
+      }
+      mbar_wait(&bar_w, 0);
+      __syncwarp();
+      tc_fence_after_sync();
+      const uint32_t idesc = make_idesc_f16(FMT, 128, Np);
+      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a0 = __shfl_sync(0xffffffffu, smem_u32(a_tile), 0), b0 = __shfl_sync(0xffffffffu, smem_u32(b_tile), 0);
+      const uint32_t bar_u = __shfl_sync(0xffffffffu, smem_u32(&bar_mma), 0);
+      const uint32_t hi = (uint32_t)(make_smem_desc(0, 0, 128) >> 32);
+      uint32_t a_lo = (a0 >> 4) | ((128u * 16u >> 4) << 16), b_lo = (b0 >> 4) | (((uint32_t)Np * 16u >> 4) << 16);
+      uint32_t acc = 0;
+      for (int ks = 0; ks < Kp / 16; ++ks) {
+        umma_f16_elect(tm_u, a_lo, hi, b_lo, hi, idesc, acc);
+        acc = 1;
+        a_lo += 2 * (128 * 16 >> 4);
+        b_lo += 2 * ((uint32_t)Np * 16 >> 4);
+      }
+      umma_commit_elect(bar_u);
+    }
+  } else if (tid == 0) {
     const uint32_t bytes = (uint32_t)Np * Kp * 2;
     mbar_expect_tx(&bar_w, bytes);
     tma_bulk_g2s(b_tile, wp, bytes, &bar_w);

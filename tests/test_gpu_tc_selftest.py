@@ -49,3 +49,13 @@ def test_tc_a_operand_from_tmem(K, N, fmt):
     y, ref = run(K, N, fmt, swap=2)
     err = float((y - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("K,N", [(200, 200), (47, 64), (230, 208), (31, 16)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_tc_warp_wide_elect_issue(K, N, fmt):
+    """The engine's issuer structure: the whole warp runs the loop on warp-uniform descriptors and
+    each tcgen05.mma / commit is one instruction predicated on the elected lane."""
+    y, ref = run(K, N, fmt, swap=4)
+    err = float((y - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
