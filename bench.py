@@ -227,6 +227,78 @@ def cem_block(bd, orc, pu, dev, precision, with_cpu):
     return out
 
 
+OBS_CFG = dict(L=49, B=50, E=1024)      # BASELINE configs[3]
+
+
+def observe_block(bd, orc, pu, dev, precision):
+    """Secondary: TransitionModel.forward with observations (posterior pass, BASELINE configs[3]),
+    forward + backward to all transition weights.  M = 50 rows: latency-bound, reported as time."""
+    d = dict(CFG, **OBS_CFG)
+    trans, _, _, _ = orc.make_models(0, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    tm = pu.build_gpu_models(d, trans, device=dev).transition
+    g = torch.Generator().manual_seed(0)
+    L, B = d["L"], d["B"]
+    s0, b0 = orc.make_latents(0, B, d["Be"], d["S"])
+    s0, b0 = s0.to(dev), b0.to(dev)
+    actions = (torch.rand(L, B, d["A"], generator=g) * 2 - 1).to(dev)
+    emb = torch.randn(L, B, d["E"], generator=g).to(dev)
+    nt = torch.ones(L, B, 1, device=dev)
+
+    def step():
+        for p_ in tm.parameters():
+            p_.grad = None
+        o = tm(s0, actions, b0, emb, nt)
+        loss = o[0].mean() + o[3].mean() + o[4][0].mean() + o[4][1].mean() + o[2][0].mean()
+        loss.backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "observe_row_steps_per_sec", "value": L * B / (ms * 1e-3), "unit": "row-steps/s",
+            "ms_per_pass": ms, "config": dict(OBS_CFG, belief_size=d["Be"], state_size=d["S"]),
+            "precision": "fp32 kernels (observe mode has no 16-bit path yet)", "pass": "fwd+bwd, full wgrad"}
+
+
+def value_update_block(bd, orc, pu, dev, precision, rows, T):
+    """Secondary: critic regression update on detached imagined (b, s): DenseModel
+    forward + backward with weight gradients (src/dreamer.py:369-391)."""
+    d = dict(CFG)
+    _, _, _, value = orc.make_models(0, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    critic = bd.DenseModel(d["Be"] + d["S"], d["Hi"], activation=d["act"]).to(dev)
+    critic.load_state_dict(value)
+    g = torch.Generator().manual_seed(0)
+    b = torch.tanh(torch.randn(T, rows, d["Be"], generator=g)).to(dev)
+    st = (0.5 * torch.randn(T, rows, d["S"], generator=g)).to(dev)
+    target = torch.randn(T, rows, 1, generator=g).to(dev)
+
+    def step():
+        for p_ in critic.parameters():
+            p_.grad = None
+        v = critic(b, st)
+        loss = 0.5 * ((v - target) ** 2).mean()          # -log N(target; v, 1) up to a constant
+        loss.backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "value_update_rows_per_sec", "value": rows * T / (ms * 1e-3), "unit": "rows/s",
+            "ms_per_update": ms, "rows": rows * T, "precision": precision}
+
+
 def workload_config(rows, precision):
     return {"workload": "BASELINE configs[1]: Dreamer default RSSM imagine_ahead + reward/value heads"
                         " + lambda_return, fwd + BPTT actor loss",
@@ -396,6 +468,8 @@ def run_ours(args):
     }
     if world == 1:
         out["cem"] = cem_block(bd, orc, pu, dev, args.precision, not args.no_cpu_baseline)
+        out["observe"] = observe_block(bd, orc, pu, dev, args.precision)
+        out["value_update"] = value_update_block(bd, orc, pu, dev, args.precision, min(rows, 131072), T)
     if world == 1 and not args.no_cpu_baseline:
         ts = time_cpu(d, rows, 5, 1)
         cores = torch.get_num_threads()

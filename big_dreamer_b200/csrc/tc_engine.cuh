@@ -335,7 +335,7 @@ __device__ __forceinline__ float fast_exp(float x) {   // single MUFU.EX2, flush
 }
 template <int ACT>
 __device__ __forceinline__ float tc_act_t(float x) {
-  if (ACT == BD_ACT_ELU) return fmaxf(x, 0.f) + fminf(fast_exp(x) - 1.f, 0.f);
+  if (ACT == BD_ACT_ELU) return fmaxf(x, fast_exp(fminf(x, 0.f)) - 1.f);   // e^min(x,0) - 1 >= x for x < 0, = 0 for x >= 0
   if (ACT == BD_ACT_RELU) return fmaxf(x, 0.f);
   if (ACT == BD_ACT_TANH) return fast_tanh(x);
   return x;

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(320, 1) mma_bench2_kernel(int N, int ksteps, i
         const uint32_t id_u = __shfl_sync(0xffffffffu, idesc, 0);
         const uint32_t bar_u = __shfl_sync(0xffffffffu, smem_u32(&rbar[3]), 0);
         for (int ks = 0; ks < ksteps; ++ks) {
-          umma_f16_elect(tm_u + (uint32_t)((r & 1) * 256), alo + ks * a_step, ahi, blo + ks * b_step, bhi, id_u, ks > 0 ? 1u : 0u);
+          umma_f16_elect(tm_u + (uint32_t)(((stw & 512) ? 0 : (r & 1)) * 256), alo + ks * a_step, ahi, blo + ks * b_step, bhi, id_u, ks > 0 ? 1u : 0u);
           if ((stw & 2) && (ks & 1)) umma_commit_elect(bar_u);
         }
         __syncwarp();
@@ -158,6 +158,21 @@ __global__ void __launch_bounds__(320, 1) mma_bench2_kernel(int N, int ksteps, i
     for (int k = 0; k < 4 && k < n; ++k) { const int s = (n - 1 - k) & 3; (void)s; }
     if ((tid & 31) == 0) out[2] = n;
     __nanosleep(20000);
+  } else if (warp >= 2 && (stw & 512)) {
+    // epilogue-like TMEM reads (of the accumulator half the MMAs are not writing) + ELU-like math
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+    float acc_ = 0.f;
+    long long cnt = 0;
+    for (int it = 0; !done && it < 1000000; ++it) {
+      float v[32];
+      tmem_ld32(trow + ((it & 3) * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc_ += v[j];
+      ++cnt;
+    }
+    if (acc_ == 1234.5f) out[1] = 1;
+    if (tid == 96) out[3] = cnt;
   } else if (warp >= 2 && (stw & 1) && !(warp == 2 && tma)) {
     long long cnt = 0;
     const int et = tid - 64;

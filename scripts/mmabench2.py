@@ -9,7 +9,7 @@ out = torch.zeros(4, dtype=torch.int64, device="cuda")
 src = torch.zeros(64 * 13312, dtype=torch.uint8, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
 for N in (208, 64):
-    for tma, stw in ((0, 0), (0, 8 + 16 * 2), (0, 256), (0, 256 + 2)):
+    for tma, stw in ((0, 0), (0, 256 + 2), (0, 256 + 2 + 512), (1, 256 + 2 + 512)):
         res = []
         for nrep in (4, 36):
             out.zero_()

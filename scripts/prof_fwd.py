@@ -29,7 +29,7 @@ if os.environ.get("BD_TC_PROF"):
     import struct
     for off in range(0, 4 << 20, 4096):
         v = np.frombuffer(raw[off:off + 40 * 64].tobytes(), dtype=np.int64).reshape(40, 8)
-        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[:12, 7].sum() == 0:
+        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[:12, 7].sum() == 0 and v[39, 0] > 0:
             names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed", "gru0", "gru1", "gru2", "gru3", "prior1", "priorOut"]
             nph = int((v[:20, 2] > 0).sum())
             if nph != 12:
