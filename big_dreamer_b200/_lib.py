@@ -154,6 +154,11 @@ SIGNATURES = {
                               C.c_void_p]),
     "bd_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    # debug micro-benchmarks (scripts/mmabench*.py, scripts/dsmembench.py)
+    "bd_tc_mmabench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_tc_mmabench2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "bd_tc_dsmembench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -13,6 +13,9 @@
  *                                           (+ get_action           src/dreamer.py:429-444,
  *                                              ActorModel.forward   src/models.py:506-517,
  *                                              SampleDist.entropy   src/models.py:725-733)
+ *   bd_mlp_forward_save (+ bd_mlp_saved_bytes, bd_imagine_saved_bytes): the same forwards, also
+ *                                           keeping 16-bit images for the tensor-core backward
+ *                                           (what autograd's saved tensors are in the reference)
  *   bd_lambda_return_forward / _backward    lambda_return           src/dreamer.py:447-471
  *   bd_cem_evaluate / bd_cem_refit / bd_cem_plan
  *                                           MPCPlanner.forward      src/planner.py:28-90
@@ -307,6 +310,14 @@ int bd_prof_read(int kernel, float* ms_total, int* launches);
  * bytes.  Used by the GPU tests to validate the UMMA descriptors / TMEM layout in isolation. */
 int bd_tc_selftest(const float* x, const float* w, const float* b, int K, int N, int fmt,
                    int swap_lbo_sbo, void* ws, size_t ws_bytes, float* y, bd_stream_t stream);
+
+/* Debug micro-benchmarks (not on the product path; scripts/mmabench*.py, scripts/dsmembench.py):
+ * cycles per tcgen05.mma for different operand layouts / issue structures / concurrent traffic,
+ * and the cost of exchanging an operand-tile slice between the CTAs of a cluster. */
+int bd_tc_mmabench(int N, int nmma, int layout, int dep, long long* out_cycles, bd_stream_t stream);
+int bd_tc_mmabench2(int N, int ksteps, int nrep, int tma, int mode, const void* gsrc, long long* out,
+                    bd_stream_t stream);
+int bd_tc_dsmembench(int R, int bytes, int mode, int iters, long long* out_cycles, bd_stream_t stream);
 
 #ifdef __cplusplus
 }
