@@ -668,6 +668,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
+              // The (mean, std, state) rows of a tile are one contiguous block of each fp32 output:
+              // stage them row-major in the H tile (dead during this epilogue: its last reader was
+              // this phase's MMA) and write them out coalesced, instead of 3*S strided scalar stores
+              // per thread.  Falls back to direct stores when the tile is too small.
+              const bool want_out = a.means != nullptr && wr0;
+              const bool staged = want_out && (3 * S * 4 <= a.Kp_h * 2);
+              float* stage = reinterpret_cast<float*>(smem + a.sm.off_tile[TILE_H]);
               for (int cc = c, it = 0; cc < Sp; cc += 32, ++it) {
                 if (it > 0) {
 #pragma unroll
@@ -684,12 +691,35 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                     // softplus(x) = max(x,0) + log(1 + exp(-|x|)) with single-MUFU exp / log
                     const float sd = fmaxf(s_[j], 0.f) + __logf(1.f + fast_exp(-fabsf(s_[j]))) + a.min_std;
                     const float st = fmaf(sd, eps[j], m_[j]);
-                    if (rvalid && a.means && wr0) {
+                    if (staged) {
+                      stage[row * S + col] = m_[j];
+                      stage[(kTileRows + row) * S + col] = sd;
+                      stage[(2 * kTileRows + row) * S + col] = st;
+                    } else if (rvalid && want_out) {
                       a.means[orow * S + col] = m_[j];
                       a.stds[orow * S + col] = sd;
                       a.states[orow * S + col] = st;
                     }
                     store1<FMT>(SAt, row, col, st);
+                  }
+                }
+              }
+              if (staged) {      // uniform per CTA: all 256 epilogue threads take part
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const long long row0 = tile * kTileRows;
+                const int nrows = (int)((a.N - row0) < kTileRows ? (a.N - row0) : kTileRows);
+                const int nfl = nrows * S;                                  // floats per output
+                const long long g0 = ((long long)t * a.N + row0) * S;
+                float* outs[3] = {a.means, a.stds, a.states};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  float* dst = outs[k] + g0;
+                  const float* src = stage + k * kTileRows * S;
+                  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nfl & 3) == 0) {
+                    for (int i = etid * 4; i < nfl; i += 256 * 4)
+                      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
+                  } else {
+                    for (int i = etid; i < nfl; i += 256) dst[i] = src[i];
                   }
                 }
               }

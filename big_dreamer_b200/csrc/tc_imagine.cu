@@ -593,11 +593,18 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     const float* gs[5] = {a->g_beliefs, a->g_states, a->g_means, a->g_stds, a->g_entropy};
     const long long ns[5] = {(long long)f.T * f.N * Be, (long long)f.T * f.N * S, (long long)f.T * f.N * S,
                              (long long)f.T * f.N * S, (long long)f.T * f.N};
+    AbsmaxJobs jobs{};
+    int nj = 0;
+    long long nmax = 0;
     for (int i = 0; i < 5; ++i) {
       if (!gs[i]) continue;
-      long long g = (ns[i] + 255) / 256;
-      if (g > 1184) g = 1184;
-      absmax_kernel<<<(unsigned)(g < 1 ? 1 : g), 256, 0, s>>>(gs[i], ns[i], amax);
+      jobs.x[nj] = gs[i]; jobs.n[nj] = ns[i]; ++nj;
+      nmax = max(nmax, ns[i]);
+    }
+    if (nj) {      // one launch for all upstream-gradient tensors
+      long long g = (nmax + 255) / 256;
+      if (g > 592) g = 592;
+      absmax_multi_kernel<<<dim3((unsigned)(g < 1 ? 1 : g), (unsigned)nj), 256, 0, s>>>(jobs, amax);
       BD_CUDA_LAUNCH_CHECK();
     }
   }

@@ -69,6 +69,22 @@ static __global__ void absmax_kernel(const float* __restrict__ x, long long n, u
   if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
+// several tensors in one launch (blockIdx.y selects the tensor): the BPTT's upstream gradients
+struct AbsmaxJobs { const float* x[6]; long long n[6]; };
+static __global__ void absmax_multi_kernel(const AbsmaxJobs jobs, unsigned int* out) {
+  const float* __restrict__ x = jobs.x[blockIdx.y];
+  const long long n = jobs.n[blockIdx.y];
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    if (v < 3.0e38f) m = fmaxf(m, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 template <int FMT>
 __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};

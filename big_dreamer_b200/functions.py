@@ -48,6 +48,22 @@ def _zeros_like_if(flag: bool, p: torch.Tensor) -> Optional[torch.Tensor]:
     return torch.zeros_like(p, memory_format=torch.contiguous_format) if flag else None
 
 
+def _zero_grads(flags, params):
+    """Zero-initialised gradient buffers for the flagged parameters, carved out of ONE flat
+    allocation (one fill kernel instead of one per parameter; the library accumulates into them)."""
+    sizes = [p.numel() if f else 0 for f, p in zip(flags, params)]
+    padded = [(n + 63) // 64 * 64 for n in sizes]          # keep every buffer 256-byte aligned
+    total = sum(padded)
+    if total == 0:
+        return [None] * len(params)
+    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+    out, off = [], 0
+    for n, m, p in zip(sizes, padded, params):
+        out.append(flat[off:off + n].view(p.shape) if n else None)
+        off += m
+    return out
+
+
 # =============================================================================
 # MLP  (DenseModel.forward, src/models.py:393-408)
 # =============================================================================
@@ -96,8 +112,9 @@ class MlpFunction(torch.autograd.Function):
         need = ctx.needs_input_grad  # (act_id, x1, x2, w0, b0, w1, b1, ...)
         dx1 = torch.empty_like(a1) if need[1] else None
         dx2 = torch.empty_like(a2) if (a2 is not None and need[2]) else None
-        dws = [_zeros_like_if(need[3 + 2 * i], ws_[i]) for i in range(n)]
-        dbs = [_zeros_like_if(need[4 + 2 * i], bs_[i]) for i in range(n)]
+        g = _zero_grads([need[3 + 2 * i] for i in range(n)] + [need[4 + 2 * i] for i in range(n)],
+                        list(ws_) + list(bs_))
+        dws, dbs = g[:n], g[n:]
         args = _lib.MlpBwdArgs()
         args.x1, args.k1 = _lib.ptr(a1), a1.shape[1]
         args.x2, args.k2 = _lib.ptr(a2), (a2.shape[1] if a2 is not None else 0)
@@ -367,12 +384,9 @@ class ImagineFunction(torch.autograd.Function):
         d_s0 = torch.empty_like(s0) if need[3] else None
         d_b0 = torch.empty_like(b0) if need[4] else None
         a.d_prev_state, a.d_prev_belief = _lib.ptr(d_s0), _lib.ptr(d_b0)
-        dA = []
+        dA = _zero_grads([need[9 + j] for j in range(2 * n_actor)], list(AP[:2 * n_actor]))
         for i in range(n_actor):
-            dw = _zeros_like_if(need[9 + 2 * i], AP[2 * i])
-            db = _zeros_like_if(need[10 + 2 * i], AP[2 * i + 1])
-            a.actor_dw[i], a.actor_db[i] = _lib.ptr(dw), _lib.ptr(db)
-            dA += [dw, db]
+            a.actor_dw[i], a.actor_db[i] = _lib.ptr(dA[2 * i]), _lib.ptr(dA[2 * i + 1])
         nbytes = lib.bd_imagine_workspace_bytes(C.byref(f.rssm), C.byref(f.actor), T, N, 1)
         ws = _lib.workspace(nbytes, s0.device)
         _lib.check(lib.bd_imagine_backward(C.byref(a), ws.data_ptr(), ws.numel(), ctx.prec,
