@@ -185,7 +185,7 @@ size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, 
   if (backward) {   // tensor-core modes: d_raw (T,N,2A) + the larger of the BPTT / actor-MLP workspaces
     size_t mb = tc::mlp_backward_workspace_bytes(*actor, r->belief_size, r->state_size, (int64_t)T * N);
     size_t draw = ((size_t)T * N * 2 * r->action_size * sizeof(float) + 255) & ~size_t(255);
-    size_t bp = tc::bptt_workspace_bytes(*r);
+    size_t bp = tc::bptt_workspace_bytes(*r, T, N);
     if (bp > mb) mb = bp;
     t = draw + (mb > f ? mb : f);
   }

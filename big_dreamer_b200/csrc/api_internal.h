@@ -44,7 +44,7 @@ size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor);
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                     bd_stream_t stream);
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
-size_t bptt_workspace_bytes(const bd_rssm& r);
+size_t bptt_workspace_bytes(const bd_rssm& r, int T, long long N);
 int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
                  bd_stream_t stream);
 bool transition_supported(const bd_transition_args& a, int precision);

@@ -45,12 +45,44 @@ struct BpttArgs {
   const uint16_t *sv_gate, *sv_xa, *sv_ha;
   const float *stds, *eps_s, *eps_a, *actions, *actor_raw, *dent;
   const float *g_beliefs, *g_states, *g_means, *g_stds, *g_entropy;
+  const float* gbt;              // g_beliefs re-laid per (t, tile) as [col/4][row][4] (gb_tile_kernel), or null
   float* d_raw;
   float *d_prev_state, *d_prev_belief;
   float *scr_carry, *scr_gtot;   // per-CTA scratch, [gridDim.x][128][Kb] fp32
   const unsigned int* amax_bits;
   PrefetchPlan pf;
 };
+
+// Upstream belief gradients (T,N,Be) row-major -> per (t, tile) images [col/4][row][4] (zero padded),
+// the layout of the kernel's own fp32 scratch: with one thread per row, row-major reads touch 32
+// different 128-byte lines per warp instruction; this layout makes them 512 contiguous bytes.
+// Also folds in this tensor's contribution to the abs-max that sets the gradient scale.
+static __global__ void gb_tile_kernel(const float* __restrict__ g, long long N, int Be, int Kb,
+                                      long long ntiles, float* __restrict__ out, unsigned int* amax) {
+  __shared__ float sm_[kTileRows][65];
+  const long long tile = blockIdx.x;
+  const int t = blockIdx.y, p = blockIdx.z;
+  const long long row0 = tile * kTileRows;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < kTileRows * 64; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63, col = p * 64 + c;
+    const float v = (row0 + r < N && col < Be) ? g[((long long)t * N + row0 + r) * Be + col] : 0.f;
+    sm_[r][c] = v;
+    const float av = fabsf(v);
+    if (av < 3.0e38f) m = fmaxf(m, av);      // ignore inf / nan, as absmax_kernel does
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+  __syncthreads();
+  const int ngroups = min(16, (Kb - p * 64) >> 2);
+  float* o = out + ((long long)t * ntiles + tile) * kTileRows * Kb;
+  for (int i = threadIdx.x; i < ngroups * kTileRows; i += blockDim.x) {
+    const int cg = i >> 7, r = i & 127;
+    *reinterpret_cast<float4*>(o + ((size_t)(p * 16 + cg) * kTileRows + r) * 4) =
+        make_float4(sm_[r][cg * 4], sm_[r][cg * 4 + 1], sm_[r][cg * 4 + 2], sm_[r][cg * 4 + 3]);
+  }
+}
 
 template <int FMT, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
@@ -214,7 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               if (!passB) {
                 // issue every load first (in-order issue would otherwise serialise one round trip
                 // per load pair), then combine
-                const float* gbrow = a.g_beliefs ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
+                const float* gbrow = (a.g_beliefs && !a.gbt) ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
+                const float* gbt = a.gbt ? a.gbt + tl * kTileRows * Kb + row * 4 : nullptr;
                 float4 cin4[2][4], gb4[2][4];
                 const bool vec = ((Be & 3) == 0);
 #pragma unroll
@@ -227,7 +260,9 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                     cin4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     gb4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i > 0) cin4[it][j4] = *reinterpret_cast<const float4*>(carry + SIDX(cb));
-                    if (gbrow) {
+                    if (gbt) {
+                      gb4[it][j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
+                    } else if (gbrow) {
                       if (vec) gb4[it][j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
                       else {
                         gb4[it][j4].x = gbrow[min(cb, Be - 1)]; gb4[it][j4].y = gbrow[min(cb + 1, Be - 1)];

@@ -489,11 +489,12 @@ static uint32_t add_pack_T(Builder& b, const float* w, int ld, int n_valid, int 
   return off;
 }
 
-size_t bptt_workspace_bytes(const bd_rssm& r) {
+size_t bptt_workspace_bytes(const bd_rssm& r, int T, long long N) {
   const int Kb = r16(r.belief_size);
+  const size_t gbt = (size_t)T * ((N + kTileRows - 1) / kTileRows) * kTileRows * Kb * 4 + 256;   // tiled g_beliefs
   size_t pack = (size_t)r16(r.hidden_size) * 2 * r16(r.state_size) + (size_t)Kb * r16(r.hidden_size) +
                 (size_t)2 * Kb * 3 * (r.belief_size + 64) + (size_t)r16(r.state_size + r.action_size) * Kb;
-  return pack * 2 + 4096 + (size_t)2 * 160 * kTileRows * Kb * 4 + 65536;
+  return pack * 2 + 4096 + (size_t)2 * 160 * kTileRows * Kb * 4 + 65536 + gbt;
 }
 
 int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
@@ -587,17 +588,26 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   unsigned int* amax = reinterpret_cast<unsigned int*>(take(256));
   float* scr_carry = reinterpret_cast<float*>(take((size_t)grid * kTileRows * Kb * 4));
   float* scr_gtot = reinterpret_cast<float*>(take((size_t)grid * kTileRows * Kb * 4));
+  // tiled copy of the upstream belief gradients: pays off while the tensor stays L2-resident (an extra
+  // HBM round trip of T*N*Be*4 bytes costs more than the coalescing saves beyond that)
+  const bool tile_gb = a->g_beliefs && (size_t)f.T * f.N * Be * 4 <= ((size_t)48 << 20);
+  float* gbt = tile_gb ? reinterpret_cast<float*>(take((size_t)f.T * ntiles * kTileRows * Kb * 4)) : nullptr;
   if (off > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core BPTT: workspace %zu < %zu", ws_bytes, off);
   cudaMemsetAsync(amax, 0, 256, s);
   {
     const float* gs[5] = {a->g_beliefs, a->g_states, a->g_means, a->g_stds, a->g_entropy};
     const long long ns[5] = {(long long)f.T * f.N * Be, (long long)f.T * f.N * S, (long long)f.T * f.N * S,
                              (long long)f.T * f.N * S, (long long)f.T * f.N};
+    if (gbt) {     // upstream belief gradients in the kernel's tile layout (coalesced gate-stage reads)
+      gb_tile_kernel<<<dim3((unsigned)ntiles, (unsigned)f.T, (unsigned)((Kb + 63) / 64)), 256, 0, s>>>(
+          a->g_beliefs, f.N, Be, Kb, ntiles, gbt, amax);
+      BD_CUDA_LAUNCH_CHECK();
+    }
     AbsmaxJobs jobs{};
     int nj = 0;
     long long nmax = 0;
     for (int i = 0; i < 5; ++i) {
-      if (!gs[i]) continue;
+      if (!gs[i] || (i == 0 && gbt)) continue;      // g_beliefs: folded into gb_tile_kernel
       jobs.x[nj] = gs[i]; jobs.n[nj] = ns[i]; ++nj;
       nmax = max(nmax, ns[i]);
     }
@@ -634,6 +644,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   ba.g_entropy = a->g_entropy;
   ba.d_raw = d_raw; ba.d_prev_state = a->d_prev_state; ba.d_prev_belief = a->d_prev_belief;
   ba.scr_carry = scr_carry; ba.scr_gtot = scr_gtot; ba.amax_bits = amax;
+  ba.gbt = gbt;
   {
     // next-step inputs the producer warp prefetches into L2 (per tile and time step)
     PrefetchPlan& pf = ba.pf;
@@ -647,7 +658,8 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     add(ba.sv_gate, nt * 5LL * kTileRows * Kb * 2, 5LL * kTileRows * Kb * 2, (size_t)5 * kTileRows * Kb * 2);
     add(ba.sv_xa, nt * (long long)kTileRows * Kb * 2, (long long)kTileRows * Kb * 2, (size_t)kTileRows * Kb * 2);
     add(ba.sv_ha, nt * (long long)kTileRows * Kh * 2, (long long)kTileRows * Kh * 2, (size_t)kTileRows * Kh * 2);
-    add(a->g_beliefs, f.N * (long long)Be * 4, (long long)kTileRows * Be * 4, (size_t)kTileRows * Be * 4);
+    if (gbt) add(gbt, nt * (long long)kTileRows * Kb * 4, (long long)kTileRows * Kb * 4, (size_t)kTileRows * Kb * 4);
+    else add(a->g_beliefs, f.N * (long long)Be * 4, (long long)kTileRows * Be * 4, (size_t)kTileRows * Be * 4);
     add(a->g_states, f.N * (long long)S * 4, (long long)kTileRows * S * 4, (size_t)kTileRows * S * 4);
     add(f.stds, f.N * (long long)S * 4, (long long)kTileRows * S * 4, (size_t)kTileRows * S * 4);
   }
