@@ -285,29 +285,75 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
           case EPI_B_DX: {
             BD_WAIT_ACC();
             const int nin = a.k1 + a.k2;
+            // dX rows of a tile are one contiguous block of dx1 (and of dx2): stage the tile row-major
+            // in shared memory (every operand tile is dead once this phase's MMAs are done) and copy
+            // it out coalesced, instead of one 16-byte store per row per warp instruction.
+            const int st1 = a.k1 + ((12 - a.k1 % 8) % 8);          // row stride (floats): = 4 mod 8 -> conflict-free float4
+            const int st2 = a.k2 | 1;
+            float* stage1 = reinterpret_cast<float*>(smem + a.sm.off_tile[0]);
+            float* stage2 = stage1 + (size_t)kTileRows * st1;
+            const bool staged = (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);
             const bool v4 = ((a.k1 & 3) == 0);
-            for (int c = half * 16; c < ph.Np; c += 32) {
-              float v[16];
-              tmem_ld16(tacc + c, v);
+            for (int c = half * 32; c < ph.Np; c += 64) {
+              float v[32];
+              const bool two = c + 16 < ph.Np;
+              if (two) tmem_ld32(tacc + c, v);
+              else tmem_ld16(tacc + c, v);
               tmem_ld_wait();
-              if (rvalid) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const int col = c + j4 * 4;
-                  if (v4 && col + 3 < a.k1) {        // whole float4 inside dx1 (rows are 16-byte aligned)
-                    if (a.dx1)
-                      *reinterpret_cast<float4*>(a.dx1 + grow * a.k1 + col) =
-                          make_float4(v[j4 * 4] * inv_scale, v[j4 * 4 + 1] * inv_scale,
-                                      v[j4 * 4 + 2] * inv_scale, v[j4 * 4 + 3] * inv_scale);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const int col = c + j4 * 4;
+                if (j4 >= 4 && !two) break;
+                const float4 o = make_float4(v[j4 * 4] * inv_scale, v[j4 * 4 + 1] * inv_scale,
+                                             v[j4 * 4 + 2] * inv_scale, v[j4 * 4 + 3] * inv_scale);
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+                if (staged) {
+                  if (col + 3 < a.k1) {
+                    *reinterpret_cast<float4*>(stage1 + (size_t)row * st1 + col) = o;
                   } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const int cc = col + j;
-                      if (cc < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + cc] = v[j4 * 4 + j] * inv_scale; }
-                      else if (cc < nin) { if (a.dx2) a.dx2[grow * a.k2 + (cc - a.k1)] = v[j4 * 4 + j] * inv_scale; }
+                      if (cc < a.k1) stage1[(size_t)row * st1 + cc] = ov[j];
+                      else if (cc < nin) stage2[(size_t)row * st2 + (cc - a.k1)] = ov[j];
+                    }
+                  }
+                } else if (rvalid) {
+                  if (v4 && col + 3 < a.k1) {        // whole float4 inside dx1 (rows are 16-byte aligned)
+                    if (a.dx1) *reinterpret_cast<float4*>(a.dx1 + grow * a.k1 + col) = o;
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const int cc = col + j;
+                      if (cc < a.k1) { if (a.dx1) a.dx1[grow * a.k1 + cc] = ov[j]; }
+                      else if (cc < nin) { if (a.dx2) a.dx2[grow * a.k2 + (cc - a.k1)] = ov[j]; }
                     }
                   }
                 }
+              }
+            }
+            if (staged) {      // uniform per CTA
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              const long long row0 = tile * kTileRows;
+              const int nrows = (int)((a.N - row0) < kTileRows ? (a.N - row0) : kTileRows);
+              const int et = tid - 64;
+              if (a.dx1) {
+                float* dst = a.dx1 + row0 * a.k1;
+                if (v4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                  const int q4 = a.k1 >> 2, n4 = nrows * q4;
+                  for (int i = et; i < n4; i += 256) {
+                    const int r = i / q4, c4 = i - r * q4;
+                    reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(stage1 + (size_t)r * st1 + c4 * 4);
+                  }
+                } else {
+                  const int n = nrows * a.k1;
+                  for (int i = et; i < n; i += 256) { const int r = i / a.k1; dst[i] = stage1[(size_t)r * st1 + (i - r * a.k1)]; }
+                }
+              }
+              if (a.dx2 && a.k2 > 0) {
+                float* dst = a.dx2 + row0 * a.k2;
+                const int n = nrows * a.k2;
+                for (int i = et; i < n; i += 256) { const int r = i / a.k2; dst[i] = stage2[(size_t)r * st2 + (i - r * a.k2)]; }
               }
             }
           } break;
