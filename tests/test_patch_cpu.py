@@ -1,0 +1,110 @@
+"""Drop-in swap: `bd.patch()` rebinds the reference's model classes and functions, and the
+UNMODIFIED reference agent then constructs itself from the B200-backed modules (constructor
+signatures, `.parameters()` for its optimizers, `state_dict` layout).  CPU only: nothing is launched.
+Needs the reference tree (present in the build container, absent on the GPU box)."""
+import os
+import sys
+
+import pytest
+import torch
+
+import big_dreamer_b200 as bd
+from oracle import ref_harness as rh
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="reference tree not present")
+
+
+class FakeEnv:
+    action_size = 2
+    observation_size = (3, 64, 64)
+
+    def reset(self):
+        return torch.zeros(1, 3, 64, 64)
+
+    def step(self, action):
+        return torch.zeros(1, 3, 64, 64), 0.0, False
+
+    def sample_random_action(self):
+        return torch.zeros(self.action_size)
+
+    def close(self):
+        pass
+
+
+def _coerce(d):
+    """hydra/omegaconf parsed `2e-4` as a float; PyYAML reads it as a string."""
+    for k, v in list(d.items()):
+        if isinstance(v, dict):
+            _coerce(v)
+        elif isinstance(v, str):
+            try:
+                d[k] = float(v)
+            except ValueError:
+                pass
+    return d
+
+
+@pytest.fixture()
+def ref_agent_modules():
+    import yaml
+    rh.load()
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.pop(k, None) for k in ("typeguard", "torchtyping", "plotly", "gym")}
+    sys.path.insert(0, os.path.join(rh.REFERENCE_ROOT, "src"))
+    sys.path.insert(0, rh._SHIMS)
+    try:
+        import dreamer
+        import models
+        import planet
+        import planner
+        params = _coerce(yaml.safe_load(open(os.path.join(rh.REFERENCE_ROOT, "src/conf/config.yaml"))))
+        params["experience_size"] = 100
+        yield planet, dreamer, models, planner, params
+    finally:
+        bd.unpatch()
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
+
+
+def test_patch_rebinds_and_reference_agent_constructs(ref_agent_modules):
+    planet, dreamer, models, planner, params = ref_agent_modules
+    ref_tm, ref_dense, ref_planner = models.TransitionModel, models.DenseModel, planner.MPCPlanner
+    ref_imagine, ref_lambda = dreamer.Dreamer.imagine_ahead, dreamer.lambda_return
+    bd.patch()
+    # the classes themselves and every copy the agents took with `from models import ...`
+    # (src/planet.py:15,17, src/dreamer.py:13)
+    assert models.TransitionModel is bd.TransitionModel and planet.TransitionModel is bd.TransitionModel
+    for mod in (models, planet, dreamer):
+        assert mod.DenseModel is bd.DenseModel
+    assert planner.MPCPlanner is bd.MPCPlanner and planet.MPCPlanner is bd.MPCPlanner
+    assert dreamer.lambda_return is bd.lambda_return
+    assert dreamer.Dreamer.imagine_ahead is not ref_imagine
+
+    agent = dreamer.Dreamer(params, FakeEnv())           # the reference's own constructor, unmodified
+    assert isinstance(agent.transition_model, bd.TransitionModel)
+    assert isinstance(agent.reward_model, bd.DenseModel) and isinstance(agent.critic, bd.DenseModel)
+    assert isinstance(agent.planner, bd.MPCPlanner)
+    assert agent.planner.transition_model is agent.transition_model
+    # parameter layout identical to the reference's modules: its checkpoints load strictly
+    torch.manual_seed(0)
+    ref = ref_tm(params["belief_size"], params["state_size"], FakeEnv.action_size, params["hidden_size"],
+                 params["embedding_size"], params["dense_activation_function"])
+    agent.transition_model.load_state_dict(ref.state_dict())
+    agent.reward_model.load_state_dict(
+        ref_dense(params["belief_size"] + params["state_size"], params["hidden_size"],
+                  activation=params["dense_activation_function"]).state_dict())
+    n_model = sum(p.numel() for p in agent.model_params)
+    assert n_model > sum(p.numel() for p in agent.transition_model.parameters()) > 0
+    # the reference's loop-driven access path stays available (src/dreamer.py:219-223)
+    for name in ("fc_embed_state_action", "rnn", "belief_prior", "belief_posterior"):
+        assert isinstance(getattr(agent.transition_model, name), torch.nn.Module)
+    # no CPU fallback: the patched hot path refuses CPU tensors loudly
+    with pytest.raises(bd.BdError):
+        agent.reward_model(torch.zeros(3, params["belief_size"]), torch.zeros(3, params["state_size"]))
+
+    bd.unpatch()
+    assert models.TransitionModel is ref_tm and planet.DenseModel is ref_dense
+    assert planner.MPCPlanner is ref_planner and dreamer.lambda_return is ref_lambda
+    assert dreamer.Dreamer.imagine_ahead is ref_imagine
