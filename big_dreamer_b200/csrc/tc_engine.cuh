@@ -847,10 +847,13 @@ static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const
       const float y = tanhf(mean + e * sd);
       const float yc = fminf(fmaxf(y, -kClamp), kClamp);
       const float gate = (yc == y) ? 1.f : 0.f;
-      const float xh = 0.5f * logf((1.f + yc) / (1.f - yc));
+      // atanh(yc) = (la - lb) / 2 and the tanh log-det 2 (ln2 - x - softplus(-2x)) = ln(1 - yc^2)
+      // = la + lb share the two logarithms; tanh(atanh(yc)) = yc
+      const float la = __logf(1.f + yc), lb = __logf(1.f - yc);
+      const float xh = 0.5f * (la - lb);
       const float d = xh - mean;
-      lp_sum += -(d * d) / var2 - log_sd - kLogSqrt2Pi - 2.f * (kLog2 - xh - softplusf_(-2.f * xh));
-      const float dlp = -d * inv_var + 2.f * tanhf(xh);
+      lp_sum += -(d * d) / var2 - log_sd - kLogSqrt2Pi - (la + lb);
+      const float dlp = -d * inv_var + 2.f * yc;
       dm_sum += d * inv_var + gate * dlp;
       ds_sum += d * d * inv_var * inv_sd - inv_sd + gate * e * dlp;
     }
