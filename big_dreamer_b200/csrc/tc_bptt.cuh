@@ -376,6 +376,16 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
             } break;
             case EPI_P_DSA: {
+              // A = 1 (the common case): the per-row inputs of the action gradient are loaded before
+              // the accumulator wait; larger action spaces load them in the loop below
+              float pm = 0.f, ps = 0.f, pa = 0.f, pdm = 0.f, pds = 0.f, pe = 0.f, pge = 0.f;
+              const bool pre = half == 0 && rvalid && Ad == 1;
+              if (pre) {
+                pge = a.g_entropy ? a.g_entropy[orow] : 0.f;
+                pm = a.actor_raw[orow * 2]; ps = a.actor_raw[orow * 2 + 1];
+                pa = a.actions[orow]; pe = a.eps_a[orow];
+                pdm = a.dent[orow * 2]; pds = a.dent[orow * 2 + 1];
+              }
               BD_WAIT_ACC();
               const uint32_t tacc = trow + 256;
               if (half == 0) {
@@ -389,18 +399,19 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                 }
                 tmem_ld_wait();
                 if (rvalid) {
-                  const float ge = a.g_entropy ? a.g_entropy[orow] * scale : 0.f;
+                  const float ge = (pre ? pge : (a.g_entropy ? a.g_entropy[orow] : 0.f)) * scale;
                   for (int j = 0; j < Ad; ++j) {
                     const int idx = S - c0 + j;
                     float da = 0.f;
 #pragma unroll
                     for (int k = 0; k < 32; ++k) if (k == idx) da = vv[k];
                     const long long oa = orow * Ad + j;
-                    const float m_raw = a.actor_raw[orow * 2 * Ad + j], s_raw = a.actor_raw[orow * 2 * Ad + Ad + j];
-                    const float act = a.actions[oa];
+                    const float m_raw = pre ? pm : a.actor_raw[orow * 2 * Ad + j];
+                    const float s_raw = pre ? ps : a.actor_raw[orow * 2 * Ad + Ad + j];
+                    const float act = pre ? pa : a.actions[oa];
                     const float dy = da * (1.f - act * act);
-                    const float dmean = dy + ge * a.dent[orow * 2 * Ad + j];
-                    const float dsd = dy * a.eps_a[oa] + ge * a.dent[orow * 2 * Ad + Ad + j];
+                    const float dmean = dy + ge * (pre ? pdm : a.dent[orow * 2 * Ad + j]);
+                    const float dsd = dy * (pre ? pe : a.eps_a[oa]) + ge * (pre ? pds : a.dent[orow * 2 * Ad + Ad + j]);
                     const float th = tanhf(m_raw / a.cfg.mean_scale);
                     a.d_raw[orow * 2 * Ad + j] = dmean * (1.f - th * th) * inv_scale;
                     a.d_raw[orow * 2 * Ad + Ad + j] = dsd * softplus_gradf_(s_raw + a.cfg.raw_init_std) * inv_scale;

@@ -24,11 +24,17 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cud
     cfg.numAttrs = R > 1 ? 1 : 0;
     unsigned clusters = grid;
     if (R > 1) {
-      cfg.gridDim = dim3(R);
-      int maxc = 0;
-      if (cudaOccupancyMaxActiveClusters(&maxc, kernel, &cfg) != cudaSuccess || maxc < 1) {
-        cudaGetLastError();
-        BD_FAIL(BD_ERR_CUDA, "tensor-core rollout: a cluster of %u CTAs cannot be scheduled", R);
+      // co-resident clusters of this (kernel, cluster size, shared memory): queried once per variant
+      static thread_local int cached_maxc[5] = {0, 0, 0, 0, 0};
+      static thread_local uint32_t cached_smem[5] = {0, 0, 0, 0, 0};
+      int maxc = cached_maxc[R];
+      if (maxc == 0 || cached_smem[R] != ra.sm.total) {
+        cfg.gridDim = dim3(R);
+        if (cudaOccupancyMaxActiveClusters(&maxc, kernel, &cfg) != cudaSuccess || maxc < 1) {
+          cudaGetLastError();
+          BD_FAIL(BD_ERR_CUDA, "tensor-core rollout: a cluster of %u CTAs cannot be scheduled", R);
+        }
+        cached_maxc[R] = maxc; cached_smem[R] = ra.sm.total;
       }
       if (clusters > (unsigned)maxc) clusters = (unsigned)maxc;
     }
