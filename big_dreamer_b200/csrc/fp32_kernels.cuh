@@ -156,9 +156,105 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
   }
 }
 
+// Skinny variant for M <= 64 rows (one 50-row batch of the observe pass, src/models.py:239-271):
+// the 64x64 tiling above would leave 4-10 CTAs walking K in 16-column steps, one L2 round trip
+// each (25-32 us per GEMM).  Here a CTA owns all rows x 16 output columns (N/16 CTAs) and moves
+// K in 128-column chunks with the next chunk's loads in flight during the FMAs.
+constexpr int SK_BN = 16, SK_KC = 128;
+template <bool B_TRANS, int EPI>
+__global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
+  __shared__ float As[SK_KC][65];
+  __shared__ float Bs[SK_KC][SK_BN];
+  const int tid = threadIdx.x, n0 = blockIdx.x * SK_BN;
+  const int K = g.K1 + g.K2;
+  const int m = tid & 63, ng = tid >> 6;      // this thread's outputs: row m, columns n0 + 4 ng .. +3
+  const int lk = tid & 127, lh = tid >> 7;    // loader mapping: K offset inside the chunk, row parity
+  float ra[32], rb[8];
+  // Branch-free loads (clamped addresses, value selected afterwards) so that all 40 loads of a
+  // chunk are in flight together; nested `if`s around each load serialise them (22 us per GEMM).
+  auto load_chunk = [&](int k0) {
+    const int gk = k0 + lk;
+    const bool kok = gk < K;
+    const bool seg1 = gk < g.K1;
+    const int gkc = kok ? gk : K - 1;
+    const float* base = (seg1 || g.K2 == 0) ? g.A1 + min(gkc, g.K1 - 1) : g.A2 + (gkc - g.K1);
+    const long long ld = (seg1 || g.K2 == 0) ? g.lda1 : g.lda2;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int gm = lh + 2 * i;
+      const float v = base[(long long)min(gm, g.M - 1) * ld];
+      ra[i] = (kok && gm < g.M) ? v : 0.f;
+    }
+    if (g.rowscale1 && seg1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ra[i] *= g.rowscale1[min(lh + 2 * i, g.M - 1)];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n, k;
+      if (B_TRANS) { k = lk; n = lh + 2 * i; }
+      else         { n = tid & 15; k = (tid >> 4) + 16 * i; }
+      const int gn = n0 + n, gkb = k0 + k;
+      const int gnc = min(gn, g.N - 1), gkc2 = min(gkb, K - 1);
+      const float v = B_TRANS ? g.B[(long long)gnc * g.ldb + gkc2] : g.B[(long long)gkc2 * g.ldb + gnc];
+      rb[i] = (gn < g.N && gkb < K) ? v : 0.f;
+    }
+  };
+  auto store_chunk = [&]() {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) As[lk][lh + 2 * i] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (B_TRANS) Bs[lk][lh + 2 * i] = rb[i];
+      else Bs[(tid >> 4) + 16 * i][tid & 15] = rb[i];
+    }
+  };
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  load_chunk(0);
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    store_chunk();
+    __syncthreads();
+    if (k0 + SK_KC < K) load_chunk(k0 + SK_KC);
+    const int kc = min(SK_KC, K - k0);
+#pragma unroll 8
+    for (int k = 0; k < kc; ++k) {
+      const float a = As[k][m];
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][ng * 4]);
+      acc[0] = fmaf(a, b4.x, acc[0]); acc[1] = fmaf(a, b4.y, acc[1]);
+      acc[2] = fmaf(a, b4.z, acc[2]); acc[3] = fmaf(a, b4.w, acc[3]);
+    }
+    __syncthreads();
+  }
+  if (m >= g.M) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int gn = n0 + ng * 4 + j;
+    if (gn >= g.N) continue;
+    float v = acc[j];
+    float* c = g.C + (long long)m * g.ldc + gn;
+    if (EPI == EPI_BIAS_ACT) {
+      if (g.bias) v += g.bias[gn];
+      v = act_fwd(g.act, v);
+      if (g.beta) v += *c;
+      *c = v;
+    } else {
+      if (g.aux) v *= act_bwd_from_out(g.act, g.aux[(long long)m * g.ldaux + gn]);
+      if (g.beta) v += *c;
+      *c = v;
+    }
+  }
+}
+
 template <bool A_TRANS, bool B_TRANS, int EPI>
 inline int launch_gemm(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return BD_OK;
+  if constexpr (!A_TRANS && EPI != EPI_ATOMIC) {
+    if (g.M <= 64) {
+      sgemm_skinny_kernel<B_TRANS, EPI><<<(g.N + SK_BN - 1) / SK_BN, 256, 0, s>>>(g);
+      BD_CUDA_LAUNCH_CHECK();
+      return BD_OK;
+    }
+  }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, EPI == EPI_ATOMIC ? g.ksplit : 1);
   sgemm_kernel<A_TRANS, B_TRANS, EPI><<<grid, GEMM_THREADS, 0, s>>>(g);
   BD_CUDA_LAUNCH_CHECK();

@@ -22,3 +22,14 @@ for i in range(int(os.environ.get("REPS", 3))):
     (o[0].mean() + o[3].mean() + o[4][0].mean() + o[4][1].mean() + o[2][0].mean()).backward()
 torch.cuda.synchronize()
 print("ok")
+import time
+def one():
+    for p in tm.parameters():
+        p.grad = None
+    o = tm(s0, actions, b0, emb, nt)
+    (o[0].mean() + o[3].mean() + o[4][0].mean() + o[4][1].mean() + o[2][0].mean()).backward()
+for _ in range(2):
+    one()
+torch.cuda.synchronize()
+t0 = time.perf_counter(); one(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"host enqueue {1e3*(t1-t0):.2f} ms, total {1e3*(t2-t0):.2f} ms")
