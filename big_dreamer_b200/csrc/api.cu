@@ -198,7 +198,10 @@ size_t bd_imagine_saved_bytes(const bd_rssm* r, int T, int64_t N, int precision)
 int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                        bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
-  if (precision == BD_PREC_FP16 || precision == BD_PREC_BF16)
+  // 16-bit modes: the tensor-core rollout when the configuration fits it, else the fp32 kernels
+  // (higher precision, same device path; the backward makes the same decision)
+  if ((precision == BD_PREC_FP16 || precision == BD_PREC_BF16) &&
+      tc::imagine_supported(a->rssm, a->actor, precision))
     return tc::imagine_forward(a, ws, ws_bytes, precision, stream);
   BD_ONLY_FP32(precision);
   return f32::imagine_forward(a, ws, ws_bytes, stream);

@@ -23,6 +23,17 @@ static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
 }
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N) { return saved_layout(r, T, N).total + 256; }
 
+// Do the operand tiles of the rollout engine (two belief tiles, [s;a], one hidden tile) plus at
+// least two weight-ring stages fit the 227 KB of shared memory?  (Same arithmetic as plan_smem.)
+static bool rollout_tiles_fit(const bd_rssm& r, int extra_hidden) {
+  const int Kp_b = r16(r.belief_size + 1), Kp_sa = r16(r.state_size + r.action_size + 1);
+  const int Kp_h = max(max(r16(r.hidden_size + 1), Kp_b), r16(extra_hidden + 1));
+  const size_t tiles = (size_t)kTileRows * 2 * (2 * Kp_b + Kp_sa + Kp_h);
+  const int widest = max(max(r16(r.hidden_size), r16(r.belief_size)), max(192, r16(extra_hidden)));
+  const size_t stage = ((size_t)widest * 64 + 1023) & ~size_t(1023);
+  return tiles + 2 * stage <= (size_t)227 * 1024 - 2048;
+}
+
 bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
   if (precision != BD_PREC_FP16 && precision != BD_PREC_BF16) return false;
   if (!(r.activation == BD_ACT_ELU || r.activation == BD_ACT_RELU || r.activation == BD_ACT_TANH ||
@@ -33,7 +44,7 @@ bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
   if (actor.n_layers < 2) return false;
   for (int l = 0; l + 1 < actor.n_layers; ++l)
     if (actor.layer[l].out_features != r.hidden_size) return false;
-  return true;
+  return rollout_tiles_fit(r, 0);
 }
 
 size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor) {
@@ -317,8 +328,12 @@ bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision) {
         r.activation == BD_ACT_IDENTITY) || reward.activation != r.activation) return false;
   if (r.belief_size + 1 > 256 || r.hidden_size + 1 > 256 || r.state_size > 128 || r.action_size > 16) return false;
   if (reward.n_layers < 2 || reward.layer[reward.n_layers - 1].out_features != 1) return false;
-  for (int l = 0; l + 1 < reward.n_layers; ++l)
+  int widest = 0;
+  for (int l = 0; l + 1 < reward.n_layers; ++l) {
     if (reward.layer[l].out_features + 1 > 256) return false;
+    widest = max(widest, reward.layer[l].out_features);
+  }
+  if (!rollout_tiles_fit(r, widest)) return false;
   // the 5-slice GRU + head programs must fit the job tables
   return (r.belief_size + 63) / 64 * 6 + 2 * reward.n_layers + 6 <= kMaxPackJobs;
 }
@@ -424,7 +439,8 @@ bool transition_supported(const bd_transition_args& a, int precision) {
   const bd_rssm& r = a.rssm;
   if (!(r.activation == BD_ACT_ELU || r.activation == BD_ACT_RELU || r.activation == BD_ACT_TANH ||
         r.activation == BD_ACT_IDENTITY)) return false;
-  return r.belief_size + 1 <= 256 && r.hidden_size + 1 <= 256 && r.state_size <= 128 && r.action_size <= 16;
+  return r.belief_size + 1 <= 256 && r.hidden_size + 1 <= 256 && r.state_size <= 128 && r.action_size <= 16 &&
+         rollout_tiles_fit(r, 0);
 }
 int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, int precision,
                        bd_stream_t stream) {

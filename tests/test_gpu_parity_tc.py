@@ -196,3 +196,14 @@ def test_column_split_cluster_sizes(R, monkeypatch):
             assert e < TOL, (R, d, res["errors"])
     test_cem_tc(dict(Be=200, Hi=200, S=30, A=1, E=8, B=2, C=300, K=30, H=6, iters=2, act="ELU"))
     test_transition_prior_only_tc()
+
+
+@pytest.mark.parametrize("d", [dict(Be=240, Hi=240, S=30, A=2, E=8, N=100, H=4, act="ELU"),
+                               dict(Be=300, Hi=272, S=40, A=3, E=8, N=70, H=3, act="Tanh")])
+def test_16bit_mode_falls_back_to_fp32_kernels_when_tiles_do_not_fit(d):
+    """Configurations the tensor-core rollout cannot hold (operand tiles beyond 227 KB of shared
+    memory, widths above 255) still run in a 16-bit mode: on the fp32 CUDA kernels, never on the
+    CPU, forward and backward making the same choice."""
+    res = pu.run_imagine_case(d, seed=2, precision="fp16", oracle_dtype=torch.float64)
+    for k, e in res["errors"].items():
+        assert e < TOL, (d, res["errors"])
