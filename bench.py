@@ -407,11 +407,29 @@ def run_ours(args):
 
     # (2) end to end through the public API: host latents in pinned memory, H2D inside the timed
     # region, noise drawn by the API itself (as the reference does), D2H of the logged scalars
+    # Every step copies one step's latents H2D (2.3 MB) and reads the two logged scalars back in one
+    # D2H; the copy for step i+1 is enqueued on a copy stream while step i computes (what a training
+    # loop's batch prefetch does), so only its tail is exposed.
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            s = s0_h.to(dev, non_blocking=True)
+            b = b0_h.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return s, b, ev
+    nxt = [prefetch()]
+
     def e2e_step():
-        s = s0_h.to(dev, non_blocking=True)
-        b = b0_h.to(dev, non_blocking=True)
+        s, b, ev = nxt[0]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        s.record_stream(cur)
+        b.record_stream(cur)
         loss, ent = step(s, b, None)
-        return float(loss.item()), float(ent.item())
+        nxt[0] = prefetch()
+        return torch.stack([loss.detach(), ent.detach()]).tolist()
     ms_e2e, _ = timed(e2e_step, args.steps, warmup)
     clocks = sampler.stop() if sampler else None
 
@@ -453,7 +471,10 @@ def run_ours(args):
         "data": "synthetic", "config": workload_config(rows, args.precision),
         "e2e": {"value": e2e_value, "unit": "steps/s",
                 "h2d_bytes_per_step": int(s0_h.numel() * 4 + b0_h.numel() * 4),
-                "d2h_bytes_per_step": 8, "ms_per_step": total_e2e_ms / args.steps},
+                "d2h_bytes_per_step": 8, "ms_per_step": total_e2e_ms / args.steps,
+                "note": "per step: one H2D of the start latents from pinned memory (enqueued on a copy "
+                        "stream for the next step while this one computes), noise drawn by the API, "
+                        "one D2H of (loss, entropy)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak,
