@@ -364,10 +364,25 @@ static int step_backward(const bd_rssm& r, const StepBuf& w, int rows, const flo
 // -------------------------------------------------------------------------------------
 // TransitionModel.forward / backward
 // -------------------------------------------------------------------------------------
+// Weight / bias gradients of TransitionModel.forward batched over time: instead of 10 rank-B wgrad
+// GEMMs + 7 column sums PER STEP (B = 50 rows in the observe pass: 17 tiny launches x 49 steps), the
+// backward keeps every step's wgrad operands (L x B rows each) and runs ONE GEMM / column sum per
+// parameter after the time loop.  Used when the whole batch is one chunk and the buffers are small.
+constexpr size_t kTimeBatchMaxBytes = (size_t)512 << 20;
+static size_t time_batch_row_floats(const bd_rssm& r, bool observe) {
+  size_t Be = r.belief_size, Hi = r.hidden_size, S = r.state_size;
+  // x, h, d_pre, d_h, d_gi, d_gh, dx, masked previous state (+ hq, d_preq, d_hq)
+  return Be + Hi + 2 * S + Hi + 3 * Be + 3 * Be + Be + S + (observe ? Hi + 2 * S + Hi : 0);
+}
+static size_t time_batch_bytes(const bd_rssm& r, int L, int64_t B, bool observe) {
+  if (B <= 0 || B > kMaxChunkRows) return 0;
+  size_t b = (size_t)L * B * time_batch_row_floats(r, observe) * sizeof(float);
+  return b <= kTimeBatchMaxBytes ? b + 4096 : 0;
+}
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
-  (void)L;
   int64_t rows = B < kMaxChunkRows ? B : kMaxChunkRows;
-  return (size_t)(rows > 0 ? rows : 1) * step_row_floats(*r, observe != 0, backward != 0) * sizeof(float) + kSlackBytes;
+  size_t step = (size_t)(rows > 0 ? rows : 1) * step_row_floats(*r, observe != 0, backward != 0) * sizeof(float);
+  return step + (backward ? time_batch_bytes(*r, L, B, observe != 0) : 0) + kSlackBytes;
 }
 
 static int check_transition(const bd_transition_args& a) {
@@ -421,13 +436,32 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
   const bool observe = f.embeddings != nullptr;
   const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size, B = f.B;
   cudaStream_t s = S(stream);
+  const long long Hi = r.hidden_size;
+  const bd_rssm_grads& G = a->grads;
+  const bool any_wgrad = G.embed_w || G.embed_b || G.w_ih || G.w_hh || G.b_ih || G.b_hh || G.prior1_w ||
+                         G.prior1_b || G.prior2_w || G.prior2_b || G.post1_w || G.post1_b || G.post2_w ||
+                         G.post2_b;
+  const size_t tb_bytes = time_batch_bytes(r, f.L, B, observe);
+  const size_t step_bytes = (size_t)B * step_row_floats(r, observe, true) * sizeof(float);
+  // time-batched weight gradients: the whole batch is one chunk and the workspace holds the operands
+  const bool batched = any_wgrad && tb_bytes > 0 && ws_bytes >= step_bytes + tb_bytes + kSlackBytes;
   int chunk;
-  BD_TRY(chunk_rows_for(ws_bytes, step_row_floats(r, observe, true), B, &chunk));
+  BD_TRY(chunk_rows_for(batched ? ws_bytes - tb_bytes : ws_bytes, step_row_floats(r, observe, true), B, &chunk));
   for (long long r0 = 0; r0 < B; r0 += chunk) {
     int nr = (int)((B - r0) < chunk ? (B - r0) : chunk);
     Arena ar(ws, ws_bytes);
     StepBuf w;
     if (!carve_step(ar, r, chunk, observe, true, w)) BD_FAIL(BD_ERR_WORKSPACE, "transition_backward: workspace");
+    // per-step slices (t * B rows) of the wgrad operands
+    float *tx = nullptr, *th = nullptr, *tdpre = nullptr, *tdh = nullptr, *tdgi = nullptr, *tdgh = nullptr,
+          *tdx = nullptr, *tsx = nullptr, *thq = nullptr, *tdpreq = nullptr, *tdhq = nullptr;
+    const size_t LB = (size_t)f.L * B;
+    if (batched) {
+      tx = ar.f32(LB * Be); th = ar.f32(LB * Hi); tdpre = ar.f32(LB * 2 * Sz); tdh = ar.f32(LB * Hi);
+      tdgi = ar.f32(LB * 3 * Be); tdgh = ar.f32(LB * 3 * Be); tdx = ar.f32(LB * Be); tsx = ar.f32(LB * Sz);
+      if (observe) { thq = ar.f32(LB * Hi); tdpreq = ar.f32(LB * 2 * Sz); tdhq = ar.f32(LB * Hi); }
+      if (!ar.ok() || chunk != B) BD_FAIL(BD_ERR_WORKSPACE, "transition_backward: time-batch workspace");
+    }
     bool have_carry = false;
     for (int t = f.L - 1; t >= 0; --t) {
       const long long o = (long long)t * B + r0, op = (long long)(t - 1) * B + r0;
@@ -440,11 +474,23 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
           (long long)nr * Be);
       BD_CUDA_LAUNCH_CHECK();
       const float* carry_s = have_carry ? w.carry_s : nullptr;
+      StepBuf wt = w;
+      if (batched) {     // this step's wgrad operands land in their time-major slices
+        const size_t tb = (size_t)t * B;
+        wt.x = tx + tb * Be; wt.h = th + tb * Hi; wt.d_pre = tdpre + tb * 2 * Sz; wt.d_h = tdh + tb * Hi;
+        wt.d_gi = tdgi + tb * 3 * Be; wt.d_gh = tdgh + tb * 3 * Be; wt.dx = tdx + tb * Be;
+        if (observe) { wt.hq = thq + tb * Hi; wt.d_preq = tdpreq + tb * 2 * Sz; wt.d_hq = tdhq + tb * Hi; }
+        if (G.embed_w) {   // masked previous state = the embed layer's input (src/models.py:241-251)
+          slice_cols_kernel<<<grid1d((long long)nr * Sz), 256, 0, s>>>(
+              s_prev, Sz, 0, (int)Sz, f.nonterminals ? f.nonterminals + o : nullptr, tsx + tb * Sz, nr);
+          BD_CUDA_LAUNCH_CHECK();
+        }
+      }
       // the carried state gradient belongs to whichever sample fed the next step; it must be
       // consumed before step_backward overwrites w.carry_s, so stage it in w.dsa[:, :S]... the
       // sample-bwd kernels run before anything writes carry_s/dsa, so passing it directly is safe.
       BD_TRY(step_backward(
-          r, w, nr, s_prev, f.nonterminals ? f.nonterminals + o : nullptr, f.actions + o * A, b_prev,
+          r, wt, nr, s_prev, f.nonterminals ? f.nonterminals + o : nullptr, f.actions + o * A, b_prev,
           f.beliefs + o * Be, f.eps_prior + o * Sz, observe ? f.embeddings + o * E : nullptr,
           observe ? f.eps_post + o * Sz : nullptr,
           a->g_prior_states ? a->g_prior_states + o * Sz : nullptr, observe ? nullptr : carry_s,
@@ -454,13 +500,46 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
           observe ? carry_s : nullptr,
           (observe && a->g_post_means) ? a->g_post_means + o * Sz : nullptr,
           (observe && a->g_post_stds) ? a->g_post_stds + o * Sz : nullptr,
-          (observe && a->d_embeddings) ? a->d_embeddings + o * E : nullptr, &a->grads, s));
+          (observe && a->d_embeddings && !batched) ? a->d_embeddings + o * E : nullptr,
+          batched ? nullptr : &a->grads, s));
       if (a->d_actions) {
         slice_cols_kernel<<<grid1d((long long)nr * A), 256, 0, s>>>(w.dsa, Sz + A, (int)Sz, (int)A, nullptr,
                                                                     a->d_actions + o * A, nr);
         BD_CUDA_LAUNCH_CHECK();
       }
       have_carry = true;
+    }
+    if (batched) {     // one GEMM / column sum per parameter over all L*B rows
+      const int n = (int)LB, nB = (int)B;
+      if (observe) {
+        if (G.post2_b) BD_TRY(bias_grad(tdpreq, 2 * Sz, 2 * Sz, n, G.post2_b, s));
+        if (G.post2_w) BD_TRY(linear_wgrad(tdpreq, 2 * Sz, 2 * Sz, thq, Hi, Hi, n, G.post2_w, Hi, 0, s));
+        if (G.post1_b) BD_TRY(bias_grad(tdhq, Hi, Hi, n, G.post1_b, s));
+        if (G.post1_w) {
+          BD_TRY(linear_wgrad(tdhq, Hi, Hi, f.beliefs, Be, Be, n, G.post1_w, Be + E, 0, s));
+          BD_TRY(linear_wgrad(tdhq, Hi, Hi, f.embeddings, E, E, n, G.post1_w, Be + E, Be, s));
+        }
+        if (a->d_embeddings)
+          BD_TRY(linear_dgrad(tdhq, Hi, Hi, r.post1.w, Be + E, Be, E, n, a->d_embeddings, E,
+                              BD_ACT_IDENTITY, nullptr, 0, 0, s));
+      }
+      if (G.prior2_b) BD_TRY(bias_grad(tdpre, 2 * Sz, 2 * Sz, n, G.prior2_b, s));
+      if (G.prior2_w) BD_TRY(linear_wgrad(tdpre, 2 * Sz, 2 * Sz, th, Hi, Hi, n, G.prior2_w, Hi, 0, s));
+      if (G.prior1_b) BD_TRY(bias_grad(tdh, Hi, Hi, n, G.prior1_b, s));
+      if (G.prior1_w) BD_TRY(linear_wgrad(tdh, Hi, Hi, f.beliefs, Be, Be, n, G.prior1_w, Be, 0, s));
+      if (G.b_ih) BD_TRY(bias_grad(tdgi, 3 * Be, 3 * Be, n, G.b_ih, s));
+      if (G.b_hh) BD_TRY(bias_grad(tdgh, 3 * Be, 3 * Be, n, G.b_hh, s));
+      if (G.w_ih) BD_TRY(linear_wgrad(tdgi, 3 * Be, 3 * Be, tx, Be, Be, n, G.w_ih, Be, 0, s));
+      if (G.w_hh) {      // h_{t-1}: init_belief for t = 0, beliefs[t-1] after
+        BD_TRY(linear_wgrad(tdgh, 3 * Be, 3 * Be, f.init_belief, Be, Be, nB, G.w_hh, Be, 0, s));
+        if (f.L > 1)
+          BD_TRY(linear_wgrad(tdgh + (size_t)B * 3 * Be, 3 * Be, 3 * Be, f.beliefs, Be, Be, n - nB, G.w_hh, Be, 0, s));
+      }
+      if (G.embed_b) BD_TRY(bias_grad(tdx, Be, Be, n, G.embed_b, s));
+      if (G.embed_w) {
+        BD_TRY(linear_wgrad(tdx, Be, Be, tsx, Sz, Sz, n, G.embed_w, Sz + A, 0, s));
+        BD_TRY(linear_wgrad(tdx, Be, Be, f.actions, A, A, n, G.embed_w, Sz + A, Sz, s));
+      }
     }
     if (a->d_init_belief)
       cudaMemcpyAsync(a->d_init_belief + r0 * Be, w.carry_b, (size_t)nr * Be * sizeof(float),
