@@ -3,6 +3,8 @@
 // sized to the caller's workspace; all rows are independent.
 #include "api_internal.h"
 #include "fp32_kernels.cuh"
+#include "observe_persist.cuh"
+#include <stdlib.h>
 
 namespace bd {
 namespace f32 {
@@ -379,10 +381,266 @@ static size_t time_batch_bytes(const bd_rssm& r, int L, int64_t B, bool observe)
   size_t b = (size_t)L * B * time_batch_row_floats(r, observe) * sizeof(float);
   return b <= kTimeBatchMaxBytes ? b + 4096 : 0;
 }
+
+// the wgrad operands of every step, time-major (L*B rows each)
+struct TimeBatch {
+  float *tx, *th, *tdpre, *tdh, *tdgi, *tdgh, *tdx, *tsx, *thq, *tdpreq, *tdhq;
+};
+// one GEMM / column sum per parameter over all L*B rows (+ d embeddings)
+static int time_batched_param_grads(const bd_rssm& r, const bd_transition_args& f,
+                                    const bd_transition_bwd_args& a, const TimeBatch& tb, cudaStream_t s) {
+  const bd_rssm_grads& G = a.grads;
+  const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size,
+                  Hi = r.hidden_size, B = f.B;
+  const bool observe = f.embeddings != nullptr;
+  const int n = (int)((size_t)f.L * B), nB = (int)B;
+  if (observe) {
+    if (G.post2_b) BD_TRY(bias_grad(tb.tdpreq, 2 * Sz, 2 * Sz, n, G.post2_b, s));
+    if (G.post2_w) BD_TRY(linear_wgrad(tb.tdpreq, 2 * Sz, 2 * Sz, tb.thq, Hi, Hi, n, G.post2_w, Hi, 0, s));
+    if (G.post1_b) BD_TRY(bias_grad(tb.tdhq, Hi, Hi, n, G.post1_b, s));
+    if (G.post1_w) {
+      BD_TRY(linear_wgrad(tb.tdhq, Hi, Hi, f.beliefs, Be, Be, n, G.post1_w, Be + E, 0, s));
+      BD_TRY(linear_wgrad(tb.tdhq, Hi, Hi, f.embeddings, E, E, n, G.post1_w, Be + E, Be, s));
+    }
+    if (a.d_embeddings)
+      BD_TRY(linear_dgrad(tb.tdhq, Hi, Hi, r.post1.w, Be + E, Be, E, n, a.d_embeddings, E,
+                          BD_ACT_IDENTITY, nullptr, 0, 0, s));
+  }
+  if (G.prior2_b) BD_TRY(bias_grad(tb.tdpre, 2 * Sz, 2 * Sz, n, G.prior2_b, s));
+  if (G.prior2_w) BD_TRY(linear_wgrad(tb.tdpre, 2 * Sz, 2 * Sz, tb.th, Hi, Hi, n, G.prior2_w, Hi, 0, s));
+  if (G.prior1_b) BD_TRY(bias_grad(tb.tdh, Hi, Hi, n, G.prior1_b, s));
+  if (G.prior1_w) BD_TRY(linear_wgrad(tb.tdh, Hi, Hi, f.beliefs, Be, Be, n, G.prior1_w, Be, 0, s));
+  if (G.b_ih) BD_TRY(bias_grad(tb.tdgi, 3 * Be, 3 * Be, n, G.b_ih, s));
+  if (G.b_hh) BD_TRY(bias_grad(tb.tdgh, 3 * Be, 3 * Be, n, G.b_hh, s));
+  if (G.w_ih) BD_TRY(linear_wgrad(tb.tdgi, 3 * Be, 3 * Be, tb.tx, Be, Be, n, G.w_ih, Be, 0, s));
+  if (G.w_hh) {      // h_{t-1}: init_belief for t = 0, beliefs[t-1] after
+    BD_TRY(linear_wgrad(tb.tdgh, 3 * Be, 3 * Be, f.init_belief, Be, Be, nB, G.w_hh, Be, 0, s));
+    if (f.L > 1)
+      BD_TRY(linear_wgrad(tb.tdgh + (size_t)B * 3 * Be, 3 * Be, 3 * Be, f.beliefs, Be, Be, n - nB, G.w_hh, Be, 0, s));
+  }
+  if (G.embed_b) BD_TRY(bias_grad(tb.tdx, Be, Be, n, G.embed_b, s));
+  if (G.embed_w) {
+    BD_TRY(linear_wgrad(tb.tdx, Be, Be, tb.tsx, Sz, Sz, n, G.embed_w, Sz + A, 0, s));
+    BD_TRY(linear_wgrad(tb.tdx, Be, Be, f.actions, A, A, n, G.embed_w, Sz + A, Sz, s));
+  }
+  return BD_OK;
+}
+
+
+// -------------------------------------------------------------------------------------
+// Observe pass on the persistent cluster kernels (observe_persist.cuh)
+// -------------------------------------------------------------------------------------
+constexpr int64_t kPersistMaxRows = 8 * obs::kR;      // up to 8 clusters of 16 CTAs
+static bool persist_shape_ok(const bd_rssm& r, int L, int64_t B) {
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  return L >= 1 && B >= 1 && B <= kPersistMaxRows && Be <= 256 && Hi <= 1024 && S + A <= obs::kMaxSmallK &&
+         2 * S <= obs::kMaxSmallK && S <= 16 * obs::kC;
+}
+struct PersistOps { obs::OpDesc d[obs::OP_COUNT]; };
+static PersistOps persist_ops(const bd_rssm& r) {
+  const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
+  const int Bep = (Be + 3) & ~3;
+  PersistOps o;
+  o.d[obs::OP_EMB] = obs::make_op(S + A, (Be + 3) / 4);
+  o.d[obs::OP_GRU] = obs::make_op(2 * Be, Be);
+  o.d[obs::OP_Q1F] = obs::make_op(Be, (Hi + 3) / 4);
+  o.d[obs::OP_Q2F] = obs::make_op(Hi, S);
+  o.d[obs::OP_B1] = obs::make_op(2 * S, (Hi + 3) / 4);
+  o.d[obs::OP_B2] = obs::make_op(Hi, (Be + 3) / 4);
+  o.d[obs::OP_B3] = obs::make_op(4 * Be, 2 * Bep / 4);
+  o.d[obs::OP_B4] = obs::make_op(Be, (S + A + 3) / 4);
+  return o;
+}
+static size_t persist_ws_bytes(const bd_rssm& r, int L, int64_t B, bool backward) {
+  const size_t Be = r.belief_size, Hi = r.hidden_size, S = r.state_size;
+  const size_t n = (size_t)L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
+  const PersistOps o = persist_ops(r);
+  size_t bytes = 0;
+  auto add = [&](size_t floats) { bytes += pad256(floats); };
+  if (!backward) {
+    add(n * Hi); add(n * Hi); add(n * 2 * S);
+    for (int i = obs::OP_EMB; i <= obs::OP_Q2F; ++i) add(obs::op_floats(o.d[i]));
+    add(nch * obs::fwd_scratch_floats((int)Be, (int)Hi));
+  } else {
+    add(n * Be); add(n * Hi); add(n * 2 * S); add(n * Hi); add(n * 3 * Be); add(n * 3 * Be); add(n * Be);
+    add(n * S); add(n * Hi); add(n * 2 * S); add(n * Hi);                       // TimeBatch
+    add(n * 3 * Be); add(n * 3 * Be); add(n * 2 * S); add(n * 2 * S); add(n * Be);   // gi gh pre preq Gtot
+    for (int i = obs::OP_B1; i <= obs::OP_B4; ++i) add(obs::op_floats(o.d[i]));
+    add(nch * obs::bwd_scratch_floats((int)Be, (int)Hi, (int)S));
+  }
+  return bytes + 4096;
+}
+// Can a cluster of 16 CTAs with this much shared memory be scheduled?  (asked once per kernel)
+template <typename Kern>
+static bool persist_launchable(Kern kern) {
+  static int cached = -1;
+  if (cached >= 0) return cached != 0;
+  const char* env = getenv("BD_OBS_PERSIST");
+  if (env && env[0] == '0') { cached = 0; return false; }
+  cached = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, obs::kSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(obs::kC); cfg.blockDim = dim3(obs::kThreads); cfg.dynamicSmemBytes = obs::kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = obs::kC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  cached = nclusters >= 1 ? 1 : 0;
+  return cached != 0;
+}
+template <typename Kern, typename Args>
+static int persist_launch(Kern kern, const Args& args, int64_t B, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  const unsigned nch = (unsigned)((B + obs::kR - 1) / obs::kR);
+  cfg.gridDim = dim3(obs::kC * nch); cfg.blockDim = dim3(obs::kThreads);
+  cfg.dynamicSmemBytes = obs::kSmemBytes; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = obs::kC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args);
+  ++bd::g_launch_count;
+  if (e != cudaSuccess) BD_FAIL(BD_ERR_CUDA, "observe persistent kernel launch failed: %s", cudaGetErrorString(e));
+  return BD_OK;
+}
+static int persist_pack(const bd_rssm& r, PersistOps& o, int first, int count, Arena& ar, cudaStream_t s) {
+  obs::PackArgs p{};
+  int kmax = 1;
+  for (int i = 0; i < obs::OP_COUNT; ++i) { p.K[i] = o.d[i].K; p.NJ[i] = o.d[i].NJ; p.Wc[i] = o.d[i].Wc; }
+  for (int i = first; i < first + count; ++i) {
+    p.dst[i] = ar.f32(obs::op_floats(o.d[i]));
+    o.d[i].w = p.dst[i];
+    kmax = max(kmax, o.d[i].K);
+  }
+  if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "observe (persistent): workspace too small for packed weights");
+  p.first = first; p.count = count;
+  p.Be = r.belief_size; p.Bep = (r.belief_size + 3) & ~3; p.Hi = r.hidden_size; p.S = r.state_size;
+  p.A = r.action_size; p.E = r.embedding_size;
+  p.w_sa = r.embed.w; p.w_ih = r.w_ih; p.w_hh = r.w_hh; p.w_q1 = r.post1.w; p.w_q2 = r.post2.w;
+  dim3 grid((unsigned)(((size_t)obs::kC * kmax * obs::kRowFloats + 255) / 256), count);
+  obs::pack_ops_kernel<<<grid, 256, 0, s>>>(p);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const bd_rssm& r = a->rssm;
+  const long long Be = r.belief_size, Sz = r.state_size, E = r.embedding_size, Hi = r.hidden_size, B = a->B;
+  const size_t n = (size_t)a->L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
+  Arena ar(ws, ws_bytes);
+  float* PE = ar.f32(n * Hi);
+  float* h = ar.f32(n * Hi);
+  float* pre = ar.f32(n * 2 * Sz);
+  PersistOps o = persist_ops(r);
+  BD_TRY(persist_pack(r, o, obs::OP_EMB, 4, ar, s));
+  float* scratch = ar.f32(nch * obs::fwd_scratch_floats((int)Be, (int)Hi));
+  if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "observe forward (persistent): workspace too small");
+  // embedding half of the posterior's first layer for every step: PE = emb W_q1[:, Be:]^T + b_q1
+  {
+    GemmArgs g;
+    g.A1 = a->embeddings; g.lda1 = E; g.K1 = (int)E; g.B = r.post1.w + Be; g.ldb = Be + E;
+    g.C = PE; g.ldc = Hi; g.bias = r.post1.b; g.M = (int)n; g.N = (int)Hi; g.act = BD_ACT_IDENTITY;
+    BD_TRY((launch_gemm<false, true, EPI_BIAS_ACT>(g, s)));
+  }
+  obs::FwdArgs k{};
+  k.emb = o.d[obs::OP_EMB]; k.gru = o.d[obs::OP_GRU]; k.q1 = o.d[obs::OP_Q1F]; k.q2 = o.d[obs::OP_Q2F];
+  k.L = a->L; k.B = B; k.Be = (int)Be; k.Hi = (int)Hi; k.S = (int)Sz; k.A = r.action_size; k.act = r.activation;
+  k.min_std = r.min_std_dev;
+  k.init_state = a->init_state; k.init_belief = a->init_belief; k.actions = a->actions;
+  k.nonterm = a->nonterminals; k.eps_post = a->eps_post; k.PE = PE;
+  k.b_sa = r.embed.b; k.b_ih = r.b_ih; k.b_hh = r.b_hh; k.b_q2 = r.post2.b;
+  k.beliefs = a->beliefs; k.post_s = a->post_states; k.post_m = a->post_means; k.post_sd = a->post_stds;
+  k.scratch = scratch;
+  BD_TRY(persist_launch(obs::observe_fwd_kernel, k, B, s));
+  // prior branch: not fed back in observe mode -> batched over all L*B beliefs (src/models.py:256)
+  BD_TRY(linear_fwd(r.prior1, r.activation, a->beliefs, (int)Be, Be, nullptr, 0, 0, nullptr, (int)n, h, Hi, s));
+  BD_TRY(linear_fwd(r.prior2, BD_ACT_IDENTITY, h, (int)Hi, Hi, nullptr, 0, 0, nullptr, (int)n, pre, 2 * Sz, s));
+  belief_sample_fwd_kernel<<<grid1d((long long)n * Sz), 256, 0, s>>>(
+      pre, a->eps_prior, r.min_std_dev, a->prior_states, a->prior_means, a->prior_stds, (long long)n * Sz, (int)Sz);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const bd_transition_args& f = a->fwd;
+  const bd_rssm& r = f.rssm;
+  const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size,
+                  Hi = r.hidden_size, B = f.B;
+  const int L = f.L;
+  const size_t n = (size_t)L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
+  const int ni = (int)n, nB = (int)B;
+  Arena ar(ws, ws_bytes);
+  TimeBatch tb;
+  tb.tx = ar.f32(n * Be); tb.th = ar.f32(n * Hi); tb.tdpre = ar.f32(n * 2 * Sz); tb.tdh = ar.f32(n * Hi);
+  tb.tdgi = ar.f32(n * 3 * Be); tb.tdgh = ar.f32(n * 3 * Be); tb.tdx = ar.f32(n * Be); tb.tsx = ar.f32(n * Sz);
+  tb.thq = ar.f32(n * Hi); tb.tdpreq = ar.f32(n * 2 * Sz); tb.tdhq = ar.f32(n * Hi);
+  float* gi = ar.f32(n * 3 * Be);
+  float* gh = ar.f32(n * 3 * Be);
+  float* pre = ar.f32(n * 2 * Sz);
+  float* preq = ar.f32(n * 2 * Sz);
+  float* Gtot = ar.f32(n * Be);
+  PersistOps o = persist_ops(r);
+  BD_TRY(persist_pack(r, o, obs::OP_B1, 4, ar, s));
+  float* scratch = ar.f32(nch * obs::bwd_scratch_floats((int)Be, (int)Hi, (int)Sz));
+  if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "observe backward (persistent): workspace too small");
+  // ---- recompute every step's internals from the saved outputs, batched over time
+  slice_cols_kernel<<<grid1d(B * Sz), 256, 0, s>>>(f.init_state, Sz, 0, (int)Sz, f.nonterminals, tb.tsx, B);
+  BD_CUDA_LAUNCH_CHECK();
+  if (L > 1) {
+    slice_cols_kernel<<<grid1d((long long)(n - B) * Sz), 256, 0, s>>>(
+        f.post_states, Sz, 0, (int)Sz, f.nonterminals ? f.nonterminals + B : nullptr, tb.tsx + B * Sz,
+        (long long)(n - B));
+    BD_CUDA_LAUNCH_CHECK();
+  }
+  BD_TRY(linear_fwd(r.embed, r.activation, tb.tsx, (int)Sz, Sz, f.actions, (int)A, A, nullptr, ni, tb.tx, Be, s));
+  BD_TRY(matmul_nt_bias(tb.tx, (int)Be, Be, r.w_ih, r.b_ih, (int)(3 * Be), ni, gi, 3 * Be, s));
+  BD_TRY(matmul_nt_bias(f.init_belief, (int)Be, Be, r.w_hh, r.b_hh, (int)(3 * Be), nB, gh, 3 * Be, s));
+  if (L > 1)
+    BD_TRY(matmul_nt_bias(f.beliefs, (int)Be, Be, r.w_hh, r.b_hh, (int)(3 * Be), ni - nB, gh + B * 3 * Be, 3 * Be, s));
+  BD_TRY(linear_fwd(r.prior1, r.activation, f.beliefs, (int)Be, Be, nullptr, 0, 0, nullptr, ni, tb.th, Hi, s));
+  BD_TRY(linear_fwd(r.prior2, BD_ACT_IDENTITY, tb.th, (int)Hi, Hi, nullptr, 0, 0, nullptr, ni, pre, 2 * Sz, s));
+  BD_TRY(linear_fwd(r.post1, r.activation, f.beliefs, (int)Be, Be, f.embeddings, (int)E, E, nullptr, ni, tb.thq, Hi, s));
+  BD_TRY(linear_fwd(r.post2, BD_ACT_IDENTITY, tb.thq, (int)Hi, Hi, nullptr, 0, 0, nullptr, ni, preq, 2 * Sz, s));
+  // ---- prior branch backward (no recurrence in observe mode): d b_t += d_h W_p1
+  belief_sample_bwd_kernel<<<grid1d((long long)n * Sz), 256, 0, s>>>(
+      pre, f.eps_prior, a->g_prior_states, nullptr, a->g_prior_means, a->g_prior_stds, tb.tdpre, (long long)n * Sz, (int)Sz);
+  BD_CUDA_LAUNCH_CHECK();
+  BD_TRY(linear_dgrad(tb.tdpre, (int)(2 * Sz), 2 * Sz, r.prior2.w, (int)Hi, 0, (int)Hi, ni, tb.tdh, Hi, r.activation,
+                      tb.th, Hi, 0, s));
+  if (a->g_beliefs) cudaMemcpyAsync(Gtot, a->g_beliefs, n * Be * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  else cudaMemsetAsync(Gtot, 0, n * Be * sizeof(float), s);
+  BD_TRY(linear_dgrad(tb.tdh, (int)Hi, Hi, r.prior1.w, (int)Be, 0, (int)Be, ni, Gtot, Be, BD_ACT_IDENTITY, nullptr, 0, 1, s));
+  // ---- the recurrence
+  obs::BwdArgs k{};
+  k.b1 = o.d[obs::OP_B1]; k.b2 = o.d[obs::OP_B2]; k.b3 = o.d[obs::OP_B3]; k.b4 = o.d[obs::OP_B4];
+  k.L = L; k.B = B; k.Be = (int)Be; k.Bep = ((int)Be + 3) & ~3; k.Hi = (int)Hi; k.S = (int)Sz; k.A = (int)A;
+  k.act = r.activation;
+  k.nonterm = f.nonterminals; k.eps_post = f.eps_post;
+  k.g_post_s = a->g_post_states; k.g_post_m = a->g_post_means; k.g_post_sd = a->g_post_stds;
+  k.preq = preq; k.hq = tb.thq; k.x = tb.tx; k.gi = gi; k.gh = gh; k.init_belief = f.init_belief;
+  k.beliefs = f.beliefs; k.Gtot = Gtot;
+  k.tdpreq = tb.tdpreq; k.tdhq = tb.tdhq; k.tdgi = tb.tdgi; k.tdgh = tb.tdgh; k.tdx = tb.tdx;
+  k.d_actions = a->d_actions; k.d_init_state = a->d_init_state; k.d_init_belief = a->d_init_belief;
+  k.scratch = scratch;
+  BD_TRY(persist_launch(obs::observe_bwd_kernel, k, B, s));
+  // ---- parameter gradients and d embeddings, batched over time
+  return time_batched_param_grads(r, f, *a, tb, s);
+}
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
   int64_t rows = B < kMaxChunkRows ? B : kMaxChunkRows;
   size_t step = (size_t)(rows > 0 ? rows : 1) * step_row_floats(*r, observe != 0, backward != 0) * sizeof(float);
-  return step + (backward ? time_batch_bytes(*r, L, B, observe != 0) : 0) + kSlackBytes;
+  size_t total = step + (backward ? time_batch_bytes(*r, L, B, observe != 0) : 0) + kSlackBytes;
+  if (observe && persist_shape_ok(*r, L, B)) {
+    const size_t p = persist_ws_bytes(*r, L, B, backward != 0) + kSlackBytes;
+    if (p > total) total = p;
+  }
+  return total;
 }
 
 static int check_transition(const bd_transition_args& a) {
@@ -402,6 +660,9 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, b
   const bd_rssm& r = a->rssm;
   const bool observe = a->embeddings != nullptr;
   const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size, B = a->B;
+  if (observe && persist_shape_ok(r, a->L, B) && ws_bytes >= persist_ws_bytes(r, a->L, B, false) &&
+      persist_launchable(obs::observe_fwd_kernel))
+    return observe_forward_persist(a, ws, ws_bytes, S(stream));
   int chunk;
   BD_TRY(chunk_rows_for(ws_bytes, step_row_floats(r, observe, false), B, &chunk));
   for (long long r0 = 0; r0 < B; r0 += chunk) {
@@ -437,6 +698,9 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
   const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size, B = f.B;
   cudaStream_t s = S(stream);
   const long long Hi = r.hidden_size;
+  if (observe && persist_shape_ok(r, f.L, B) && ws_bytes >= persist_ws_bytes(r, f.L, B, true) &&
+      persist_launchable(obs::observe_bwd_kernel))
+    return observe_backward_persist(a, ws, ws_bytes, s);
   const bd_rssm_grads& G = a->grads;
   const bool any_wgrad = G.embed_w || G.embed_b || G.w_ih || G.w_hh || G.b_ih || G.b_hh || G.prior1_w ||
                          G.prior1_b || G.prior2_w || G.prior2_b || G.post1_w || G.post1_b || G.post2_w ||
@@ -510,36 +774,8 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
       have_carry = true;
     }
     if (batched) {     // one GEMM / column sum per parameter over all L*B rows
-      const int n = (int)LB, nB = (int)B;
-      if (observe) {
-        if (G.post2_b) BD_TRY(bias_grad(tdpreq, 2 * Sz, 2 * Sz, n, G.post2_b, s));
-        if (G.post2_w) BD_TRY(linear_wgrad(tdpreq, 2 * Sz, 2 * Sz, thq, Hi, Hi, n, G.post2_w, Hi, 0, s));
-        if (G.post1_b) BD_TRY(bias_grad(tdhq, Hi, Hi, n, G.post1_b, s));
-        if (G.post1_w) {
-          BD_TRY(linear_wgrad(tdhq, Hi, Hi, f.beliefs, Be, Be, n, G.post1_w, Be + E, 0, s));
-          BD_TRY(linear_wgrad(tdhq, Hi, Hi, f.embeddings, E, E, n, G.post1_w, Be + E, Be, s));
-        }
-        if (a->d_embeddings)
-          BD_TRY(linear_dgrad(tdhq, Hi, Hi, r.post1.w, Be + E, Be, E, n, a->d_embeddings, E,
-                              BD_ACT_IDENTITY, nullptr, 0, 0, s));
-      }
-      if (G.prior2_b) BD_TRY(bias_grad(tdpre, 2 * Sz, 2 * Sz, n, G.prior2_b, s));
-      if (G.prior2_w) BD_TRY(linear_wgrad(tdpre, 2 * Sz, 2 * Sz, th, Hi, Hi, n, G.prior2_w, Hi, 0, s));
-      if (G.prior1_b) BD_TRY(bias_grad(tdh, Hi, Hi, n, G.prior1_b, s));
-      if (G.prior1_w) BD_TRY(linear_wgrad(tdh, Hi, Hi, f.beliefs, Be, Be, n, G.prior1_w, Be, 0, s));
-      if (G.b_ih) BD_TRY(bias_grad(tdgi, 3 * Be, 3 * Be, n, G.b_ih, s));
-      if (G.b_hh) BD_TRY(bias_grad(tdgh, 3 * Be, 3 * Be, n, G.b_hh, s));
-      if (G.w_ih) BD_TRY(linear_wgrad(tdgi, 3 * Be, 3 * Be, tx, Be, Be, n, G.w_ih, Be, 0, s));
-      if (G.w_hh) {      // h_{t-1}: init_belief for t = 0, beliefs[t-1] after
-        BD_TRY(linear_wgrad(tdgh, 3 * Be, 3 * Be, f.init_belief, Be, Be, nB, G.w_hh, Be, 0, s));
-        if (f.L > 1)
-          BD_TRY(linear_wgrad(tdgh + (size_t)B * 3 * Be, 3 * Be, 3 * Be, f.beliefs, Be, Be, n - nB, G.w_hh, Be, 0, s));
-      }
-      if (G.embed_b) BD_TRY(bias_grad(tdx, Be, Be, n, G.embed_b, s));
-      if (G.embed_w) {
-        BD_TRY(linear_wgrad(tdx, Be, Be, tsx, Sz, Sz, n, G.embed_w, Sz + A, 0, s));
-        BD_TRY(linear_wgrad(tdx, Be, Be, f.actions, A, A, n, G.embed_w, Sz + A, Sz, s));
-      }
+      TimeBatch tb{tx, th, tdpre, tdh, tdgi, tdgh, tdx, tsx, thq, tdpreq, tdhq};
+      BD_TRY(time_batched_param_grads(r, f, *a, tb, s));
     }
     if (a->d_init_belief)
       cudaMemcpyAsync(a->d_init_belief + r0 * Be, w.carry_b, (size_t)nr * Be * sizeof(float),
