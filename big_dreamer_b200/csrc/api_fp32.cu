@@ -433,8 +433,13 @@ static int time_batched_param_grads(const bd_rssm& r, const bd_transition_args& 
 constexpr int64_t kPersistMaxRows = 8 * obs::kR;      // up to 8 clusters of 16 CTAs
 static bool persist_shape_ok(const bd_rssm& r, int L, int64_t B) {
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
-  return L >= 1 && B >= 1 && B <= kPersistMaxRows && Be <= 256 && Hi <= 1024 && S + A <= obs::kMaxSmallK &&
-         2 * S <= obs::kMaxSmallK && S <= 16 * obs::kC;
+  return L >= 1 && B >= 1 && B <= kPersistMaxRows && Be <= 256 && Hi <= 256 && S <= 128 && S + A <= obs::kMaxSmallK &&
+         2 * S <= obs::kMaxSmallK;
+}
+static int obs_prof_flag() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BD_OBS_PROF"); v = e ? atoi(e) : 0; }
+  return v;
 }
 struct PersistOps { obs::OpDesc d[obs::OP_COUNT]; };
 static PersistOps persist_ops(const bd_rssm& r) {
@@ -557,6 +562,7 @@ static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t
   k.b_sa = r.embed.b; k.b_ih = r.b_ih; k.b_hh = r.b_hh; k.b_q2 = r.post2.b;
   k.beliefs = a->beliefs; k.post_s = a->post_states; k.post_m = a->post_means; k.post_sd = a->post_stds;
   k.scratch = scratch;
+  k.prof = obs_prof_flag();
   BD_TRY(persist_launch(obs::observe_fwd_kernel, k, B, s));
   // prior branch: not fed back in observe mode -> batched over all L*B beliefs (src/models.py:256)
   BD_TRY(linear_fwd(r.prior1, r.activation, a->beliefs, (int)Be, Be, nullptr, 0, 0, nullptr, (int)n, h, Hi, s));
@@ -628,6 +634,8 @@ static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, s
   k.tdpreq = tb.tdpreq; k.tdhq = tb.tdhq; k.tdgi = tb.tdgi; k.tdgh = tb.tdgh; k.tdx = tb.tdx;
   k.d_actions = a->d_actions; k.d_init_state = a->d_init_state; k.d_init_belief = a->d_init_belief;
   k.scratch = scratch;
+  k.vec_h = ((reinterpret_cast<uintptr_t>(f.init_belief) | reinterpret_cast<uintptr_t>(f.beliefs)) & 15) == 0;
+  k.prof = obs_prof_flag();
   BD_TRY(persist_launch(obs::observe_bwd_kernel, k, B, s));
   // ---- parameter gradients and d embeddings, batched over time
   return time_batched_param_grads(r, f, *a, tb, s);

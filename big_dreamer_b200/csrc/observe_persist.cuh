@@ -11,11 +11,15 @@
 //     (pack_ops_kernel; constant over the steps, so their first ring stages are requested BEFORE
 //     the cluster barrier that waits for the other CTAs' activations);
 //   * phases are separated by the hardware cluster barrier (arrive.release / wait.acquire).
-// Thread tile: 4 consecutive rows x 4 "slots" of one slot group (one float4 of A, one float4 of W
-// per k: 16 FMA per 2 LDS.128).  A slot group is either the four pre-activations of one GRU unit
-// (r, z, gi_n, gh_n -- the x and h projections are ONE contraction over [x ; h]) or four adjacent
-// output columns of a plain layer.  Layers with few slot groups per CTA split K over the idle
-// threads (up to 4 ways) and reduce through shared memory.
+// Outputs are organised in "slot groups" of four: the four pre-activations of one GRU unit (r, z,
+// gi_n, gh_n -- the x and h projections are ONE contraction over [x ; h]), (mu_j, raw_j) of the
+// posterior, or four adjacent output columns of a plain layer.  Compute thread tile: 8 rows x 8 slots
+// (4 LDS.128 per 64 FMA = 1 B of shared-memory traffic per FMA, the balance point of 128 B/clk
+// against 128 FMA/clk; a 4 x 4 tile measured 90 cycles per k-row, LDS-bound).  A 64 x 64 output
+// tile only needs 64 such threads, so the k rows of every ring stage are dealt round-robin to 4-32
+// groups of threads ("k-groups") whose partial sums meet in shared memory; the epilogue then runs
+// one (row, slot group) item per thread over all 256 threads, with its constant inputs requested
+// before the cluster barrier.
 //
 // What is hoisted out of the recurrence (and runs as ordinary batched GEMMs over all L*B rows, see
 // api_fp32.cu): the embedding half of the posterior's first layer (K = 1024 of 1224), the whole
@@ -44,14 +48,17 @@ constexpr int kNS = 4;          // ring stages
 constexpr int kThreads = 256;
 constexpr int kRowFloats = 64;  // floats per k row of an A block (64 rows) and of a W image (16 x 4)
 constexpr int kStageFloats = kKC * kRowFloats;
-constexpr int kSmemBytes = (2 * kNS * kStageFloats + kThreads * 16) * (int)sizeof(float);   // 147 456
+constexpr int kRedFloats = 64 * 64 * 4;   // k-group partial sums: (KG * WP) x 64 rows x 4 slots, KG * WP <= 64
+constexpr int kSmemBytes = (2 * kNS * kStageFloats + kRedFloats) * (int)sizeof(float);   // 196 608
 constexpr int kMaxSmallK = kNS * kKC;   // in-place operands (embed input, d_preq) fit the A ring
 
 enum OpId { OP_EMB = 0, OP_GRU, OP_Q1F, OP_Q2F, OP_B1, OP_B2, OP_B3, OP_B4, OP_COUNT };
 
 struct OpDesc {
   const float* w;   // packed images: CTA c's image at w + c * K * 64
-  int K, NJ, Wc, WP, KS;
+  int K, NJ;        // contraction length, slot groups over the whole cluster
+  int Wc, WP;       // slot groups per CTA, rounded up to a power of two
+  int TS, KG, tgs;  // slots per compute thread (4 | 8), k-groups, log2(threads per k-group)
 };
 inline OpDesc make_op(int K, int NJ) {
   OpDesc d{};
@@ -59,7 +66,11 @@ inline OpDesc make_op(int K, int NJ) {
   d.Wc = (NJ + kC - 1) / kC;
   d.WP = 1;
   while (d.WP < d.Wc) d.WP <<= 1;
-  d.KS = 16 / d.WP < 4 ? 16 / d.WP : 4;
+  d.TS = d.WP >= 2 ? 8 : 4;
+  const int tg = 8 * (d.WP * 4 / d.TS);      // 8 row octets x slot tiles
+  d.KG = kThreads / tg;
+  d.tgs = 0;
+  while ((1 << d.tgs) < tg) ++d.tgs;
   return d;
 }
 inline size_t op_floats(const OpDesc& d) { return (size_t)kC * d.K * kRowFloats; }
@@ -142,8 +153,8 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 struct Segs { const float* a0; int K0; const float* a1; };   // transposed [K][64] blocks, a1 after K0 rows
 
 struct Ctx {
-  float *As, *Ws, *red;     // shared memory: A ring, W ring, split-K partials
-  int tid, rg, jl, crank;
+  float *As, *Ws, *red;     // shared memory: A ring, W ring, k-group partials
+  int tid, crank, nvalid;
 };
 
 __device__ __forceinline__ void issue_w(const Ctx& c, const OpDesc& d, int chunk) {
@@ -166,90 +177,134 @@ __device__ __forceinline__ void prefetch_w(const Ctx& c, const OpDesc& d) {
   const int nch = (d.K + kKC - 1) / kKC;
   for (int s = 0; s < kNS - 1 && s < nch; ++s) issue_w(c, d, s);
 }
-__device__ __forceinline__ void fma_rows(const float* __restrict__ As, const float* __restrict__ Ws,
-                                         int nrows, int ks, int KS, int js, int rg, float (&acc)[4][4]) {
-#pragma unroll 4
-  for (int k = ks; k < nrows; k += KS) {
-    const float4 a = *reinterpret_cast<const float4*>(As + k * kRowFloats + rg * 4);
-    const float4 b = *reinterpret_cast<const float4*>(Ws + k * kRowFloats + js * 4);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(av[r], bv[g], acc[r][g]);
-  }
-}
-// split-K partials -> owner threads (ks == 0); returns true for threads that own a result
-__device__ __forceinline__ bool reduce_splitk(const Ctx& c, const OpDesc& d, int js, int ks, float (&acc)[4][4]) {
-  if (d.KS > 1) {
-    float4* mine = reinterpret_cast<float4*>(c.red + c.tid * 16);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) mine[r] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-    __syncthreads();
-    if (ks == 0) {
-      for (int q = 1; q < d.KS; ++q) {
-        const float4* o = reinterpret_cast<const float4*>(c.red + ((q * d.WP + js) * 16 + c.rg) * 16);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float4 v = o[r];
-          acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
-        }
-      }
-    }
-  }
-  __syncthreads();    // ring stages and `red` are free for the next op
-  return ks == 0 && js < d.Wc && (c.crank * d.Wc + js) < d.NJ;
-}
-// streamed op: A from the transposed scratch blocks.  prefetch_w(d) must have been called.
-__device__ __forceinline__ bool op_run(const Ctx& c, const OpDesc& d, const Segs& s, float (&acc)[4][4], int* jglob) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
-  const int js = c.jl & (d.WP - 1), ks = c.jl / d.WP;
-  const int nch = (d.K + kKC - 1) / kKC;
-  for (int st = 0; st < kNS - 1; ++st) {
-    if (st < nch) issue_a(c, d, s, st);
-    cp_async_commit();
-  }
-  for (int ch = 0; ch < nch; ++ch) {
-    cp_async_wait<kNS - 2>();
-    __syncthreads();
-    const int nxt = ch + kNS - 1;
-    if (nxt < nch) { issue_w(c, d, nxt); issue_a(c, d, s, nxt); }
-    cp_async_commit();
-    if (ks < d.KS)
-      fma_rows(c.As + (ch % kNS) * kStageFloats, c.Ws + (ch % kNS) * kStageFloats, min(kKC, d.K - ch * kKC),
-               ks, d.KS, js, c.rg, acc);
-  }
-  cp_async_wait<0>();
-  *jglob = c.crank * d.Wc + js;
-  return reduce_splitk(c, d, js, ks, acc);
-}
-// in-place op: the caller has written A as [K][64] at the start of the A ring (K <= kMaxSmallK);
-// the whole weight image is loaded behind it.  Includes the barrier that publishes the caller's A.
-__device__ __forceinline__ bool op_small(const Ctx& c, const OpDesc& d, float (&acc)[4][4], int* jglob) {
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int g = 0; g < 4; ++g) acc[r][g] = 0.f;
-  const int js = c.jl & (d.WP - 1), ks = c.jl / d.WP;
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  if (ks < d.KS) fma_rows(c.As, c.Ws, d.K, ks, d.KS, js, c.rg, acc);
-  *jglob = c.crank * d.Wc + js;
-  return reduce_splitk(c, d, js, ks, acc);
-}
 __device__ __forceinline__ void load_w_small(const Ctx& c, const OpDesc& d) {
   const float* src = d.w + (size_t)c.crank * d.K * kRowFloats;
   for (int p = c.tid; p < d.K * 16; p += kThreads) cp_async16(c.Ws + p * 4, src + p * 4);
 }
-__device__ __forceinline__ void st4(float* p, float a, float b, float c_, float d) {
-  *reinterpret_cast<float4*>(p) = make_float4(a, b, c_, d);
+
+template <int TS>
+__device__ __forceinline__ void fma_rows(const float* __restrict__ ap, const float* __restrict__ bp,
+                                         int nrows, int kg, int KG, float (&acc)[8][8]) {
+#pragma unroll 2
+  for (int k = kg; k < nrows; k += KG) {
+    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * kRowFloats);
+    const float4 a1 = *reinterpret_cast<const float4*>(ap + k * kRowFloats + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bp + k * kRowFloats);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (TS == 8) {
+      const float4 b1 = *reinterpret_cast<const float4*>(bp + k * kRowFloats + 4);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int g = 0; g < 8; ++g) acc[r][g] = fmaf(av[r], bv[g], acc[r][g]);
+    } else {
+      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(av[r], bv[g], acc[r][g]);
+    }
+  }
+}
+
+// One contraction of the CTA's column slice: leaves the k-group partial sums in c.red
+// ([(kg * WP + js) * 64 + row] float4 = the four slots of slot group js) and ends with a
+// __syncthreads.  SMALL: the caller has written A as [K][64] at the start of the A ring
+// (K <= kMaxSmallK) and requested the whole weight image with load_w_small; otherwise A streams
+// from the transposed scratch blocks and prefetch_w(d) has been called.
+template <bool SMALL>
+__device__ __forceinline__ void op_compute(const Ctx& c, const OpDesc& d, const Segs& s) {
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) acc[r][g] = 0.f;
+  const int kg = c.tid >> d.tgs, u = c.tid & ((1 << d.tgs) - 1);
+  const int rr = u & 7, sg = u >> 3;
+  const bool active = rr * 8 < c.nvalid;
+  const int aoff = rr * 8, boff = sg * d.TS;
+  if (SMALL) {
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (active) {
+      if (d.TS == 8) fma_rows<8>(c.As + aoff, c.Ws + boff, d.K, kg, d.KG, acc);
+      else fma_rows<4>(c.As + aoff, c.Ws + boff, d.K, kg, d.KG, acc);
+    }
+  } else {
+    const int nch = (d.K + kKC - 1) / kKC;
+    for (int st = 0; st < kNS - 1; ++st) {
+      if (st < nch) issue_a(c, d, s, st);
+      cp_async_commit();
+    }
+    for (int ch = 0; ch < nch; ++ch) {
+      cp_async_wait<kNS - 2>();
+      __syncthreads();
+      const int nxt = ch + kNS - 1;
+      if (nxt < nch) { issue_w(c, d, nxt); issue_a(c, d, s, nxt); }
+      cp_async_commit();
+      if (active) {
+        const float* ap = c.As + (ch % kNS) * kStageFloats + aoff;
+        const float* bp = c.Ws + (ch % kNS) * kStageFloats + boff;
+        const int nrows = min(kKC, d.K - ch * kKC);
+        if (d.TS == 8) fma_rows<8>(ap, bp, nrows, kg, d.KG, acc);
+        else fma_rows<4>(ap, bp, nrows, kg, d.KG, acc);
+      }
+    }
+    cp_async_wait<0>();
+  }
+  if (active) {
+    float4* red4 = reinterpret_cast<float4*>(c.red);
+    const int js0 = sg * (d.TS >> 2);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      red4[(kg * d.WP + js0) * kR + aoff + r] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (d.TS == 8)
+        red4[(kg * d.WP + js0 + 1) * kR + aoff + r] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+    }
+  }
+  __syncthreads();
+}
+// the four slots of slot group js at one row, summed over the k-groups
+__device__ __forceinline__ float4 red_sum(const Ctx& c, const OpDesc& d, int js, int row) {
+  const float4* red4 = reinterpret_cast<const float4*>(c.red);
+  float4 v = red4[js * kR + row];
+  for (int kg = 1; kg < d.KG; ++kg) {
+    const float4 w = red4[(kg * d.WP + js) * kR + row];
+    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+  }
+  return v;
+}
+// epilogue item of a thread: (row, slot group); `it` < 64 * WP
+__device__ __forceinline__ bool item_of(const Ctx& c, const OpDesc& d, int it, int* row, int* js, int* jg) {
+  *row = it & 63; *js = it >> 6;
+  *jg = c.crank * d.Wc + *js;
+  return it < kR * d.WP && *row < c.nvalid && *js < d.Wc && *jg < d.NJ;
+}
+// four consecutive columns of a row-major row (vec: 16-byte aligned and ncols % 4 == 0)
+__device__ __forceinline__ float4 ldrow4(const float* rowp, int col, int ncols, bool vec) {
+  if (vec) return *reinterpret_cast<const float4*>(rowp + col);
+  float4 v;
+  v.x = rowp[min(col, ncols - 1)]; v.y = rowp[min(col + 1, ncols - 1)];
+  v.z = rowp[min(col + 2, ncols - 1)]; v.w = rowp[min(col + 3, ncols - 1)];
+  return v;
+}
+__device__ __forceinline__ void strow4(float* rowp, int col, int ncols, bool vec, float4 v) {
+  if (vec) { *reinterpret_cast<float4*>(rowp + col) = v; return; }
+  if (col < ncols) rowp[col] = v.x;
+  if (col + 1 < ncols) rowp[col + 1] = v.y;
+  if (col + 2 < ncols) rowp[col + 2] = v.z;
+  if (col + 3 < ncols) rowp[col + 3] = v.w;
 }
 
 // ------------------------------------------------------------------------------------------------
+#define OBS_T(i) do { if (a.prof) tm[i] = clock64(); } while (0)
+#define OBS_ACC(ph) do { if (a.prof) { pw[ph] += tm[1] - tm[0]; po[ph] += tm[2] - tm[1]; pe[ph] += tm[3] - tm[2]; } } while (0)
+#define OBS_REPORT(name) do { if (a.prof && c.tid == 0 && blockIdx.x < kC && (c.crank == 0 || c.crank == kC - 1)) \
+    for (int ph = 0; ph < 4; ++ph) printf("%s rank %d phase %d: wait %lld op %lld epi %lld cycles/step\n", name, c.crank, ph, \
+           pw[ph] / a.L, po[ph] / a.L, pe[ph] / a.L); } while (0)
+
 struct FwdArgs {
   OpDesc emb, gru, q1, q2;
   int L; long long B;
@@ -259,6 +314,7 @@ struct FwdArgs {
   const float *b_sa, *b_ih, *b_hh, *b_q2;
   float *beliefs, *post_s, *post_m, *post_sd;
   float* scratch;          // per cluster: xT [Be][64] | hT [2][Be][64] | hqT [Hi][64]
+  int prof;                // debug: print per-phase cycle counts of cluster ranks 0 and 15 (BD_OBS_PROF=1)
 };
 __host__ __device__ inline size_t fwd_scratch_floats(int Be, int Hi) { return (size_t)(3 * Be + Hi) * kRowFloats; }
 
@@ -266,114 +322,126 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
   extern __shared__ __align__(16) float smem[];
   Ctx c;
   c.As = smem; c.Ws = smem + kNS * kStageFloats; c.red = smem + 2 * kNS * kStageFloats;
-  c.tid = threadIdx.x; c.rg = c.tid & 15; c.jl = c.tid >> 4; c.crank = (int)cluster_ctarank();
+  c.tid = threadIdx.x; c.crank = (int)cluster_ctarank();
   const int Be = a.Be, Hi = a.Hi, S = a.S, Ad = a.A, SA = a.S + a.A;
   const long long B = a.B, row0 = (long long)(blockIdx.x / kC) * kR;
-  const int nvalid = (int)min((long long)kR, B - row0);
+  c.nvalid = (int)min((long long)kR, B - row0);
+  const int nvalid = c.nvalid;
   float* xT = a.scratch + (size_t)(blockIdx.x / kC) * fwd_scratch_floats(Be, Hi);
   float* hT = xT + (size_t)Be * kRowFloats;
   float* hqT = hT + (size_t)2 * Be * kRowFloats;
-  const int r0 = c.rg * 4;
+  const bool vecH = (Hi & 3) == 0;
   // h_0^T = init_belief^T (columns interleaved over the CTAs)
   for (int i = c.crank * kThreads + c.tid; i < Be * kR; i += kC * kThreads) {
     const int j = i >> 6, r = i & 63;
     hT[i] = r < nvalid ? a.init_belief[(row0 + r) * Be + j] : 0.f;
   }
   cluster_arrive();
-  float acc[4][4];
-  int jg;
+  long long tm[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0}, po[4] = {0, 0, 0, 0}, pe[4] = {0, 0, 0, 0};
+  int row, js, jg;
   for (int t = 0; t < a.L; ++t) {
     const int par = t & 1;
     const long long trow = (long long)t * B + row0;
     // ---------------------------------------------------------------- P1 embed
+    OBS_T(0);
     load_w_small(c, a.emb);
+    // in-place operand [s * nt ; a]^T: the action rows and the mask do not depend on the other CTAs
+    const int rme = c.tid & 63;
+    float ntr = 1.f;
+    if (a.nonterm && rme < nvalid) ntr = a.nonterm[trow + rme];
+    for (int i = S * kR + c.tid; i < SA * kR; i += kThreads)
+      c.As[i] = rme < nvalid ? a.actions[(trow + rme) * Ad + ((i >> 6) - S)] : 0.f;
     cluster_wait();
+    OBS_T(1);
     {
       const float* sp = t == 0 ? a.init_state + row0 * S : a.post_s + ((long long)(t - 1) * B + row0) * S;
-      for (int i = c.tid; i < SA * kR; i += kThreads) {
-        const int k = i >> 6, r = i & 63;
-        float v = 0.f;
-        if (r < nvalid) {
-          if (k < S) {
-            v = __ldcg(sp + (long long)r * S + k);
-            if (a.nonterm) v *= a.nonterm[trow + r];
-          } else v = a.actions[(trow + r) * Ad + (k - S)];
-        }
-        c.As[i] = v;
-      }
+      for (int i = c.tid; i < S * kR; i += kThreads)
+        c.As[i] = rme < nvalid ? __ldcg(sp + (long long)rme * S + (i >> 6)) * ntr : 0.f;
     }
-    if (op_small(c, a.emb, acc, &jg)) {
+    op_compute<true>(c, a.emb, Segs{});
+    OBS_T(2);
+    if (item_of(c, a.emb, c.tid, &row, &js, &jg)) {
+      const float4 v = red_sum(c, a.emb, js, row);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = 4 * jg + g;
-        if (col < Be) {
-          const float b = a.b_sa[col];
-          st4(xT + (size_t)col * kRowFloats + r0, act_fwd(a.act, acc[0][g] + b), act_fwd(a.act, acc[1][g] + b),
-              act_fwd(a.act, acc[2][g] + b), act_fwd(a.act, acc[3][g] + b));
-        }
+        if (col < Be) xT[(size_t)col * kRowFloats + row] = act_fwd(a.act, vv[g] + a.b_sa[col]);
       }
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(0);
     // ---------------------------------------------------------------- P2 GRU
+    OBS_T(0);
     prefetch_w(c, a.gru);
     cluster_wait();
+    OBS_T(1);
     const float* hprevT = hT + (size_t)par * Be * kRowFloats;
     float* hnewT = hT + (size_t)(par ^ 1) * Be * kRowFloats;
-    if (op_run(c, a.gru, Segs{xT, Be, hprevT}, acc, &jg)) {
-      const int j = jg;
-      const float4 h4 = ldcg4(hprevT + (size_t)j * kRowFloats + r0);
-      const float hp[4] = {h4.x, h4.y, h4.z, h4.w};
-      const float br = a.b_ih[j] + a.b_hh[j], bz = a.b_ih[Be + j] + a.b_hh[Be + j];
-      const float bin = a.b_ih[2 * Be + j], bhn = a.b_hh[2 * Be + j];
-      float hn[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float rr = sigmoidf_(acc[r][0] + br), z = sigmoidf_(acc[r][1] + bz);
-        const float n = tanhf(acc[r][2] + bin + rr * (acc[r][3] + bhn));
-        hn[r] = (1.f - z) * n + z * hp[r];
-        if (r0 + r < nvalid) a.beliefs[(trow + r0 + r) * Be + j] = hn[r];
+    op_compute<false>(c, a.gru, Segs{xT, Be, hprevT});
+    OBS_T(2);
+    for (int it = c.tid; it < kR * a.gru.WP; it += kThreads) {
+      if (item_of(c, a.gru, it, &row, &js, &jg)) {
+        const int j = jg;
+        const float hp = __ldcg(hprevT + (size_t)j * kRowFloats + row);
+        const float4 v = red_sum(c, a.gru, js, row);
+        const float rr = sigmoidf_(v.x + a.b_ih[j] + a.b_hh[j]);
+        const float z = sigmoidf_(v.y + a.b_ih[Be + j] + a.b_hh[Be + j]);
+        const float n = tanhf(v.z + a.b_ih[2 * Be + j] + rr * (v.w + a.b_hh[2 * Be + j]));
+        const float hn = (1.f - z) * n + z * hp;
+        a.beliefs[(trow + row) * Be + j] = hn;
+        hnewT[(size_t)j * kRowFloats + row] = hn;
       }
-      st4(hnewT + (size_t)j * kRowFloats + r0, hn[0], hn[1], hn[2], hn[3]);
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(1);
     // ---------------------------------------------------------------- P3 posterior hidden
+    OBS_T(0);
     prefetch_w(c, a.q1);
+    const bool own3 = item_of(c, a.q1, c.tid, &row, &js, &jg);
+    float4 pe4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (own3) pe4 = ldrow4(a.PE + (trow + row) * Hi, 4 * jg, Hi, vecH);
     cluster_wait();
-    if (op_run(c, a.q1, Segs{hnewT, Be, nullptr}, acc, &jg)) {
+    OBS_T(1);
+    op_compute<false>(c, a.q1, Segs{hnewT, Be, nullptr});
+    OBS_T(2);
+    if (own3) {
+      const float4 v = red_sum(c, a.q1, js, row);
+      const float vv[4] = {v.x + pe4.x, v.y + pe4.y, v.z + pe4.z, v.w + pe4.w};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = 4 * jg + g;
-        if (col < Hi) {
-          float v[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int rl = min(r0 + r, nvalid - 1);
-            v[r] = act_fwd(a.act, acc[r][g] + a.PE[(trow + rl) * Hi + col]);
-          }
-          st4(hqT + (size_t)col * kRowFloats + r0, v[0], v[1], v[2], v[3]);
-        }
+        if (col < Hi) hqT[(size_t)col * kRowFloats + row] = act_fwd(a.act, vv[g]);
       }
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(2);
     // ---------------------------------------------------------------- P4 posterior output + sample
+    OBS_T(0);
     prefetch_w(c, a.q2);
     cluster_wait();
-    if (op_run(c, a.q2, Segs{hqT, Hi, nullptr}, acc, &jg)) {
-      const int j = jg;
-      const float bm = a.b_q2[j], bs = a.b_q2[S + j];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (r0 + r < nvalid) {
-          const long long o = (trow + r0 + r) * S + j;
-          const float m = acc[r][0] + bm, sd = softplusf_(acc[r][1] + bs) + a.min_std;
-          a.post_m[o] = m;
-          a.post_sd[o] = sd;
-          a.post_s[o] = m + sd * a.eps_post[o];
-        }
+    OBS_T(1);
+    op_compute<false>(c, a.q2, Segs{hqT, Hi, nullptr});
+    OBS_T(2);
+    for (int it = c.tid; it < kR * a.q2.WP; it += kThreads) {
+      if (item_of(c, a.q2, it, &row, &js, &jg)) {
+        const int j = jg;
+        const float4 v = red_sum(c, a.q2, js, row);
+        const long long o = (trow + row) * S + j;
+        const float m = v.x + a.b_q2[j], sd = softplusf_(v.y + a.b_q2[S + j]) + a.min_std;
+        a.post_m[o] = m;
+        a.post_sd[o] = sd;
+        a.post_s[o] = m + sd * a.eps_post[o];
       }
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(3);
   }
+  OBS_REPORT("fwd");
   cluster_wait();
 }
 
@@ -387,6 +455,8 @@ struct BwdArgs {
   float *tdpreq, *tdhq, *tdgi, *tdgh, *tdx;                                 // (L*B, .) row-major, written
   float *d_actions, *d_init_state, *d_init_belief;
   float* scratch;   // per cluster: dhqT [Hi][64] | planesT [4 Be][64] | dxT [Be][64] | czT [Be][64] | cbT [Be][64] | csT [S][64]
+  int vec_h;        // init_belief / beliefs are 16-byte aligned (float4 loads of their rows)
+  int prof;
 };
 __host__ __device__ inline size_t bwd_scratch_floats(int Be, int Hi, int S) { return (size_t)(Hi + 7 * Be + S) * kRowFloats; }
 
@@ -394,36 +464,52 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
   extern __shared__ __align__(16) float smem[];
   Ctx c;
   c.As = smem; c.Ws = smem + kNS * kStageFloats; c.red = smem + 2 * kNS * kStageFloats;
-  c.tid = threadIdx.x; c.rg = c.tid & 15; c.jl = c.tid >> 4; c.crank = (int)cluster_ctarank();
+  c.tid = threadIdx.x; c.crank = (int)cluster_ctarank();
   const int Be = a.Be, Bep = a.Bep, Hi = a.Hi, S = a.S, Ad = a.A;
   const long long B = a.B, row0 = (long long)(blockIdx.x / kC) * kR;
-  const int nvalid = (int)min((long long)kR, B - row0);
+  c.nvalid = (int)min((long long)kR, B - row0);
+  const int nvalid = c.nvalid;
   float* dhqT = a.scratch + (size_t)(blockIdx.x / kC) * bwd_scratch_floats(Be, Hi, S);
   float* planesT = dhqT + (size_t)Hi * kRowFloats;
   float* dxT = planesT + (size_t)4 * Be * kRowFloats;
   float* czT = dxT + (size_t)Be * kRowFloats;
   float* cbT = czT + (size_t)Be * kRowFloats;
   float* csT = cbT + (size_t)Be * kRowFloats;
-  const int r0 = c.rg * 4;
+  const bool vecH = (Hi & 3) == 0, vecB = (Be & 3) == 0;
   cluster_arrive();
-  float acc[4][4];
-  int jg;
+  long long tm[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0}, po[4] = {0, 0, 0, 0}, pe[4] = {0, 0, 0, 0};
+  int row, js, jg;
   for (int i = 0; i < a.L; ++i) {
     const int t = a.L - 1 - i;
     const bool first = i == 0;
     const long long trow = (long long)t * B + row0;
     // ---------------------------------------------------------------- Q1 posterior output backward
+    OBS_T(0);
     load_w_small(c, a.b1);
-    cluster_wait();
+    const bool own1 = item_of(c, a.b1, c.tid, &row, &js, &jg);
+    float4 hq4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (own1) hq4 = ldrow4(a.hq + (trow + row) * Hi, 4 * jg, Hi, vecH);
+    // in-place operand d_preq^T: everything but the carried state gradient is known before the
+    // barrier.  dm = P0 + cs, draw = P1 + cs * Q with P0, P1 parked in the A ring and Q in `red`
+    // (both free here; every thread revisits only its own elements)
     for (int e = c.tid; e < S * kR; e += kThreads) {
       const int j = e >> 6, r = e & 63;
       const int rl = min(r, nvalid - 1);
       const long long o = (trow + rl) * S + j;
-      float gs = a.g_post_s ? a.g_post_s[o] : 0.f;
-      if (!first) gs += __ldcg(csT + e);
-      const float dm = gs + (a.g_post_m ? a.g_post_m[o] : 0.f);
-      const float dsd = gs * a.eps_post[o] + (a.g_post_sd ? a.g_post_sd[o] : 0.f);
-      const float draw = dsd * softplus_gradf_(a.preq[(trow + rl) * 2 * S + S + j]);
+      const float gsb = a.g_post_s ? a.g_post_s[o] : 0.f;
+      const float eps = a.eps_post[o];
+      const float spg = softplus_gradf_(a.preq[(trow + rl) * 2 * S + S + j]);
+      c.As[e] = gsb + (a.g_post_m ? a.g_post_m[o] : 0.f);
+      c.As[S * kR + e] = (gsb * eps + (a.g_post_sd ? a.g_post_sd[o] : 0.f)) * spg;
+      c.red[e] = eps * spg;
+    }
+    cluster_wait();
+    OBS_T(1);
+    for (int e = c.tid; e < S * kR; e += kThreads) {
+      const int j = e >> 6, r = e & 63;
+      const float cs = first ? 0.f : __ldcg(csT + e);
+      const float dm = r < nvalid ? c.As[e] + cs : 0.f;
+      const float draw = r < nvalid ? c.As[S * kR + e] + cs * c.red[e] : 0.f;
       c.As[e] = dm;
       c.As[S * kR + e] = draw;
       if (c.crank == 0 && r < nvalid) {
@@ -431,130 +517,152 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
         a.tdpreq[(trow + r) * 2 * S + S + j] = draw;
       }
     }
-    if (op_small(c, a.b1, acc, &jg)) {
+    op_compute<true>(c, a.b1, Segs{});
+    OBS_T(2);
+    if (own1) {
+      const float4 v = red_sum(c, a.b1, js, row);
+      float4 o;
+      o.x = v.x * act_bwd_from_out(a.act, hq4.x); o.y = v.y * act_bwd_from_out(a.act, hq4.y);
+      o.z = v.z * act_bwd_from_out(a.act, hq4.z); o.w = v.w * act_bwd_from_out(a.act, hq4.w);
+      const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = 4 * jg + g;
-        if (col < Hi) {
-          float v[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int rl = min(r0 + r, nvalid - 1);
-            v[r] = acc[r][g] * act_bwd_from_out(a.act, a.hq[(trow + rl) * Hi + col]);
-            if (r0 + r < nvalid) a.tdhq[(trow + r0 + r) * Hi + col] = v[r];
-          }
-          st4(dhqT + (size_t)col * kRowFloats + r0, v[0], v[1], v[2], v[3]);
-        }
-      }
+      for (int g = 0; g < 4; ++g)
+        if (4 * jg + g < Hi) dhqT[(size_t)(4 * jg + g) * kRowFloats + row] = ov[g];
+      strow4(a.tdhq + (trow + row) * Hi, 4 * jg, Hi, vecH, o);
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(0);
     // ---------------------------------------------------------------- Q2 belief gradient + GRU gates
+    OBS_T(0);
     prefetch_w(c, a.b2);
+    const bool own2 = item_of(c, a.b2, c.tid, &row, &js, &jg);
+    float4 G4, gir, giz, gin, ghr, ghz, ghn4, h4;
+    G4 = gir = giz = gin = ghr = ghz = ghn4 = h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (own2) {
+      const int col = 4 * jg;
+      const long long o3 = (trow + row) * 3 * Be;
+      G4 = ldrow4(a.Gtot + (trow + row) * Be, col, Be, vecB);
+      gir = ldrow4(a.gi + o3, col, Be, vecB); giz = ldrow4(a.gi + o3 + Be, col, Be, vecB);
+      gin = ldrow4(a.gi + o3 + 2 * Be, col, Be, vecB);
+      ghr = ldrow4(a.gh + o3, col, Be, vecB); ghz = ldrow4(a.gh + o3 + Be, col, Be, vecB);
+      ghn4 = ldrow4(a.gh + o3 + 2 * Be, col, Be, vecB);
+      h4 = t == 0 ? ldrow4(a.init_belief + (row0 + row) * Be, col, Be, vecB && a.vec_h)
+                  : ldrow4(a.beliefs + ((long long)(t - 1) * B + row0 + row) * Be, col, Be, vecB && a.vec_h);
+    }
     cluster_wait();
-    if (op_run(c, a.b2, Segs{dhqT, Hi, nullptr}, acc, &jg)) {
+    OBS_T(1);
+    op_compute<false>(c, a.b2, Segs{dhqT, Hi, nullptr});
+    OBS_T(2);
+    if (own2) {
+      const float4 v = red_sum(c, a.b2, js, row);
+      const float Gq[4] = {v.x, v.y, v.z, v.w}, Gt[4] = {G4.x, G4.y, G4.z, G4.w};
+      const float ir[4] = {gir.x, gir.y, gir.z, gir.w}, iz[4] = {giz.x, giz.y, giz.z, giz.w};
+      const float in_[4] = {gin.x, gin.y, gin.z, gin.w}, hr[4] = {ghr.x, ghr.y, ghr.z, ghr.w};
+      const float hz[4] = {ghz.x, ghz.y, ghz.z, ghz.w}, hn[4] = {ghn4.x, ghn4.y, ghn4.z, ghn4.w};
+      const float hp[4] = {h4.x, h4.y, h4.z, h4.w};
+      float dr[4], dz_[4], dn_[4], dnr[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = 4 * jg + g;
+        dr[g] = dz_[g] = dn_[g] = dnr[g] = 0.f;
         if (col < Be) {
-          float cb[4] = {0.f, 0.f, 0.f, 0.f};
-          if (!first) {
-            const float4 q = ldcg4(cbT + (size_t)col * kRowFloats + r0);
-            cb[0] = q.x; cb[1] = q.y; cb[2] = q.z; cb[3] = q.w;
-          }
-          float dr[4], dz_[4], dn_[4], dnr[4], cz[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int rl = min(r0 + r, nvalid - 1);
-            const long long row = trow + rl;
-            const long long o3 = row * 3 * Be;
-            const float G = a.Gtot[row * Be + col] + cb[r] + acc[r][g];
-            const float ghn = a.gh[o3 + 2 * Be + col];
-            const float rr = sigmoidf_(a.gi[o3 + col] + a.gh[o3 + col]);
-            const float z = sigmoidf_(a.gi[o3 + Be + col] + a.gh[o3 + Be + col]);
-            const float n = tanhf(a.gi[o3 + 2 * Be + col] + rr * ghn);
-            const float h = t == 0 ? a.init_belief[(row0 + rl) * Be + col]
-                                   : a.beliefs[((long long)(t - 1) * B + row0 + rl) * Be + col];
-            const float dn = G * (1.f - z), dzz = G * (h - n);
-            const float dpn = dn * (1.f - n * n);
-            const float dpr = dpn * ghn * rr * (1.f - rr);
-            const float dpz = dzz * z * (1.f - z);
-            dr[r] = dpr; dz_[r] = dpz; dn_[r] = dpn; dnr[r] = dpn * rr; cz[r] = G * z;
-            if (r0 + r < nvalid) {
-              float* gi_o = a.tdgi + o3;
-              float* gh_o = a.tdgh + o3;
-              gi_o[col] = dpr; gh_o[col] = dpr;
-              gi_o[Be + col] = dpz; gh_o[Be + col] = dpz;
-              gi_o[2 * Be + col] = dpn; gh_o[2 * Be + col] = dpn * rr;
-            }
-          }
-          st4(planesT + (size_t)col * kRowFloats + r0, dr[0], dr[1], dr[2], dr[3]);
-          st4(planesT + (size_t)(Be + col) * kRowFloats + r0, dz_[0], dz_[1], dz_[2], dz_[3]);
-          st4(planesT + (size_t)(2 * Be + col) * kRowFloats + r0, dn_[0], dn_[1], dn_[2], dn_[3]);
-          st4(planesT + (size_t)(3 * Be + col) * kRowFloats + r0, dnr[0], dnr[1], dnr[2], dnr[3]);
-          st4(czT + (size_t)col * kRowFloats + r0, cz[0], cz[1], cz[2], cz[3]);
+          const float cb = first ? 0.f : __ldcg(cbT + (size_t)col * kRowFloats + row);
+          const float G = Gt[g] + cb + Gq[g];
+          const float rr = sigmoidf_(ir[g] + hr[g]);
+          const float z = sigmoidf_(iz[g] + hz[g]);
+          const float n = tanhf(in_[g] + rr * hn[g]);
+          const float dn = G * (1.f - z), dzz = G * (hp[g] - n);
+          const float dpn = dn * (1.f - n * n);
+          dr[g] = dpn * hn[g] * rr * (1.f - rr);
+          dz_[g] = dzz * z * (1.f - z);
+          dn_[g] = dpn;
+          dnr[g] = dpn * rr;
+          planesT[(size_t)col * kRowFloats + row] = dr[g];
+          planesT[(size_t)(Be + col) * kRowFloats + row] = dz_[g];
+          planesT[(size_t)(2 * Be + col) * kRowFloats + row] = dn_[g];
+          planesT[(size_t)(3 * Be + col) * kRowFloats + row] = dnr[g];
+          czT[(size_t)col * kRowFloats + row] = G * z;
         }
       }
+      const long long o3 = (trow + row) * 3 * Be;
+      const float4 r4 = make_float4(dr[0], dr[1], dr[2], dr[3]), z4 = make_float4(dz_[0], dz_[1], dz_[2], dz_[3]);
+      strow4(a.tdgi + o3, 4 * jg, Be, vecB, r4);
+      strow4(a.tdgh + o3, 4 * jg, Be, vecB, r4);
+      strow4(a.tdgi + o3 + Be, 4 * jg, Be, vecB, z4);
+      strow4(a.tdgh + o3 + Be, 4 * jg, Be, vecB, z4);
+      strow4(a.tdgi + o3 + 2 * Be, 4 * jg, Be, vecB, make_float4(dn_[0], dn_[1], dn_[2], dn_[3]));
+      strow4(a.tdgh + o3 + 2 * Be, 4 * jg, Be, vecB, make_float4(dnr[0], dnr[1], dnr[2], dnr[3]));
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(1);
     // ---------------------------------------------------------------- Q3 GRU input / hidden dgrad
+    OBS_T(0);
     prefetch_w(c, a.b3);
     cluster_wait();
-    if (op_run(c, a.b3, Segs{planesT, 4 * Be, nullptr}, acc, &jg)) {
+    OBS_T(1);
+    op_compute<false>(c, a.b3, Segs{planesT, 4 * Be, nullptr});
+    OBS_T(2);
+    for (int it = c.tid; it < kR * a.b3.WP; it += kThreads) {
+      if (item_of(c, a.b3, it, &row, &js, &jg)) {
+        const float4 v = red_sum(c, a.b3, js, row);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const int col0 = 4 * jg;
+        if (col0 < Bep) {
+          const float4 x4 = ldrow4(a.x + (trow + row) * Be, col0, Be, vecB);
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+          float ov[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = 4 * jg + g;
-        if (col < Bep) {
-          if (col < Be) {
-            float v[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const int rl = min(r0 + r, nvalid - 1);
-              v[r] = acc[r][g] * act_bwd_from_out(a.act, a.x[(trow + rl) * Be + col]);
-              if (r0 + r < nvalid) a.tdx[(trow + r0 + r) * Be + col] = v[r];
-            }
-            st4(dxT + (size_t)col * kRowFloats + r0, v[0], v[1], v[2], v[3]);
+          for (int g = 0; g < 4; ++g) {
+            ov[g] = vv[g] * act_bwd_from_out(a.act, xv[g]);
+            if (col0 + g < Be) dxT[(size_t)(col0 + g) * kRowFloats + row] = ov[g];
           }
+          strow4(a.tdx + (trow + row) * Be, col0, Be, vecB, make_float4(ov[0], ov[1], ov[2], ov[3]));
         } else {
-          const int cc = col - Bep;
-          if (cc < Be) {
-            const float4 q = ldcg4(czT + (size_t)cc * kRowFloats + r0);
-            const float v[4] = {acc[0][g] + q.x, acc[1][g] + q.y, acc[2][g] + q.z, acc[3][g] + q.w};
-            st4(cbT + (size_t)cc * kRowFloats + r0, v[0], v[1], v[2], v[3]);
-            if (t == 0 && a.d_init_belief) {
 #pragma unroll
-              for (int r = 0; r < 4; ++r)
-                if (r0 + r < nvalid) a.d_init_belief[(row0 + r0 + r) * Be + cc] = v[r];
+          for (int g = 0; g < 4; ++g) {
+            const int cc = col0 - Bep + g;
+            if (cc < Be) {
+              const float o = vv[g] + __ldcg(czT + (size_t)cc * kRowFloats + row);
+              cbT[(size_t)cc * kRowFloats + row] = o;
+              if (t == 0 && a.d_init_belief) a.d_init_belief[(row0 + row) * Be + cc] = o;
             }
           }
         }
       }
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(2);
     // ---------------------------------------------------------------- Q4 embed dgrad
+    OBS_T(0);
     prefetch_w(c, a.b4);
     cluster_wait();
-    if (op_run(c, a.b4, Segs{dxT, Be, nullptr}, acc, &jg)) {
+    OBS_T(1);
+    op_compute<false>(c, a.b4, Segs{dxT, Be, nullptr});
+    OBS_T(2);
+    if (item_of(c, a.b4, c.tid, &row, &js, &jg)) {
+      const float4 v = red_sum(c, a.b4, js, row);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const float nt = a.nonterm ? a.nonterm[trow + row] : 1.f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = 4 * jg + g;
         if (col < S) {
-          float v[4];
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int rl = min(r0 + r, nvalid - 1);
-            v[r] = acc[r][g] * (a.nonterm ? a.nonterm[trow + rl] : 1.f);
-            if (t == 0 && a.d_init_state && r0 + r < nvalid) a.d_init_state[(row0 + r0 + r) * S + col] = v[r];
-          }
-          st4(csT + (size_t)col * kRowFloats + r0, v[0], v[1], v[2], v[3]);
+          const float o = vv[g] * nt;
+          csT[(size_t)col * kRowFloats + row] = o;
+          if (t == 0 && a.d_init_state) a.d_init_state[(row0 + row) * S + col] = o;
         } else if (col < S + Ad && a.d_actions) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if (r0 + r < nvalid) a.d_actions[(trow + r0 + r) * Ad + (col - S)] = acc[r][g];
+          a.d_actions[(trow + row) * Ad + (col - S)] = vv[g];
         }
       }
     }
     cluster_arrive();
+    OBS_T(3);
+    OBS_ACC(3);
   }
+  OBS_REPORT("bwd");
   cluster_wait();
 }
 

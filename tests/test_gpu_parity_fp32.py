@@ -221,6 +221,79 @@ def test_transition_c4_shape_observe():
         assert pu.relerr(got, ref) < TOL
 
 
+def _observe_case(d, L, B, seed, masked=True):
+    """TransitionModel.forward in observe mode, forward + backward into every input and parameter,
+    CUDA path vs the oracle under autograd (same weights, inputs, noise and cotangents)."""
+    trans = orc.make_models(seed, d["Be"], d["S"], d["A"], d["Hi"], d["E"])[0]
+    g = torch.Generator().manual_seed(seed + 11)
+    s0 = 0.5 * torch.randn(B, d["S"], generator=g)
+    b0 = torch.tanh(torch.randn(B, d["Be"], generator=g))
+    actions = torch.rand(L, B, d["A"], generator=g) * 2 - 1
+    emb = torch.randn(L, B, d["E"], generator=g)
+    nt = (torch.rand(L, B, 1, generator=g) > 0.1).float() if masked else None
+    ep, eq = torch.randn(L, B, d["S"], generator=g), torch.randn(L, B, d["S"], generator=g)
+    widths = [d["Be"], d["S"], d["S"], d["S"], d["S"], d["S"], d["S"]]
+    cts = [torch.randn(L, B, w, generator=g) / (L * B) for w in widths]
+
+    def flat(o):
+        return [o[0], o[1], o[2][0], o[2][1], o[3], o[4][0], o[4][1]]
+    # oracle
+    sd = {k: v.clone().requires_grad_(True) for k, v in trans.items()}
+    rs0, rb0, remb = (t.clone().requires_grad_(True) for t in (s0, b0, emb))
+    ref = flat(orc.transition_forward(sd, d["act"], 0.1, rs0, actions, rb0, ep, remb, nt, eq))
+    sum((t * ct).sum() for t, ct in zip(ref, cts)).backward()
+    # CUDA path
+    tm = pu.build_gpu_models(d, trans).transition
+    c = lambda t: None if t is None else t.cuda()
+    gs0, gb0, gemb = (t.cuda().requires_grad_(True) for t in (s0, b0, emb))
+    out = flat(tm(gs0, c(actions), gb0, gemb, c(nt), noise=dict(eps_prior=c(ep), eps_post=c(eq))))
+    sum((t * ct.cuda()).sum() for t, ct in zip(out, cts)).backward()
+    errs = {f"out{i}": pu.relerr(a, b) for i, (a, b) in enumerate(zip(out, ref))}
+    errs.update(d_s0=pu.relerr(gs0.grad, rs0.grad), d_b0=pu.relerr(gb0.grad, rb0.grad),
+                d_emb=pu.relerr(gemb.grad, remb.grad))
+    for k, p_ in tm.named_parameters():
+        errs["g:" + k] = pu.relerr(p_.grad, sd[k].grad)
+    return errs
+
+
+@pytest.mark.parametrize("d,L,B", [
+    (dict(Be=200, Hi=200, S=30, A=1, E=1024, act="ELU"), 49, 50),     # BASELINE configs[3]
+    (dict(Be=200, Hi=200, S=30, A=6, E=64, act="ELU"), 5, 130),       # 3 clusters, ragged last chunk
+    (dict(Be=48, Hi=40, S=10, A=3, E=24, act="Tanh"), 7, 64),         # exactly one full chunk
+    (dict(Be=50, Hi=36, S=7, A=2, E=16, act="ReLU"), 4, 9),           # widths that are not multiples of 4
+    (dict(Be=32, Hi=32, S=30, A=1, E=16, act="ELU"), 3, 600),         # more rows than the cluster path takes
+])
+def test_observe_fwd_bwd_vs_oracle(d, L, B):
+    """Observe pass (persistent cluster kernels for B <= 512, per-step kernels above): every output,
+    input gradient and parameter gradient against the oracle."""
+    errs = _observe_case(d, L, B, seed=3)
+    bad = {k: v for k, v in errs.items() if not v < 2e-4}
+    assert not bad, bad
+
+
+def test_observe_unmasked_and_partial_cotangents():
+    """nonterminals=None and gradients flowing from a subset of the outputs only."""
+    d = dict(Be=64, Hi=48, S=12, A=2, E=32, act="ELU")
+    errs = _observe_case(d, 6, 20, seed=5, masked=False)
+    assert all(v < 2e-4 for v in errs.values()), errs
+    trans = orc.make_models(1, d["Be"], d["S"], d["A"], d["Hi"], d["E"])[0]
+    tm = pu.build_gpu_models(d, trans).transition
+    g = torch.Generator().manual_seed(0)
+    L, B = 4, 10
+    args = [torch.randn(B, d["S"], generator=g), torch.rand(L, B, d["A"], generator=g),
+            torch.randn(B, d["Be"], generator=g), torch.randn(L, B, d["E"], generator=g)]
+    ep, eq = torch.randn(L, B, d["S"], generator=g), torch.randn(L, B, d["S"], generator=g)
+    sd = {k: v.clone().requires_grad_(True) for k, v in trans.items()}
+    r = orc.transition_forward(sd, d["act"], 0.1, args[0], args[1], args[2], ep, args[3], None, eq)
+    (r[3].sum() + r[0][-1].sum()).backward()                      # posterior states + last belief only
+    o = tm(*[t.cuda() for t in args], None, noise=dict(eps_prior=ep.cuda(), eps_post=eq.cuda()))
+    (o[3].sum() + o[0][-1].sum()).backward()
+    for k, p_ in tm.named_parameters():
+        ref = sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])
+        got = p_.grad if p_.grad is not None else torch.zeros_like(p_)
+        assert float((got.cpu() - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-7, k
+
+
 # ------------------------------------------------------------------ CEM
 @pytest.mark.parametrize("name", ["cem_small", "cem_c3_like"])
 def test_cem_vs_reference_fixture(name):
