@@ -14,8 +14,8 @@
 // Outputs are organised in "slot groups" of four: the four pre-activations of one GRU unit (r, z,
 // gi_n, gh_n -- the x and h projections are ONE contraction over [x ; h]), (mu_j, raw_j) of the
 // posterior, or four adjacent output columns of a plain layer.  Compute thread tile: 8 rows x 8 slots
-// (4 LDS.128 per 64 FMA = 1 B of shared-memory traffic per FMA, the balance point of 128 B/clk
-// against 128 FMA/clk; a 4 x 4 tile measured 90 cycles per k-row, LDS-bound).  A 64 x 64 output
+// (4 LDS.128 per 32 packed FFMA2 = 1 B of shared-memory traffic per FMA, the balance point of
+// 128 B/clk against 128 FMA/clk; a 4 x 4 tile measured 90 cycles per k-row, LDS-bound).  A 64 x 64 output
 // tile only needs 64 such threads, so the k rows of every ring stage are dealt round-robin to 4-32
 // groups of threads ("k-groups") whose partial sums meet in shared memory; the epilogue then runs
 // one (row, slot group) item per thread over all 256 threads, with its constant inputs requested
@@ -182,29 +182,48 @@ __device__ __forceinline__ void load_w_small(const Ctx& c, const OpDesc& d) {
   for (int p = c.tid; p < d.K * 16; p += kThreads) cp_async16(c.Ws + p * 4, src + p * 4);
 }
 
+// Packed fp32 FMA (sm_100 FFMA2): {d0, d1} += a * {b0, b1}, each lane rounded exactly like fmaf.
+// Scalar FFMA issues every other cycle per scheduler (64 FMA/clk/SM); the packed form is the
+// only way to the SM's 128 FMA/clk, and takes the row operand as a broadcast scalar.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  uint64_t d, av, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(av), "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+// Software-pipelined: the operands of k-row k + KG are requested before the FMAs of k-row k (the
+// plain loop left the 4 LDS.128 -> 64 FFMA dependency exposed every iteration: with two warps per
+// scheduler and the LDS pipe as busy as the FMA pipe it ran at half the issue rate).
 template <int TS>
 __device__ __forceinline__ void fma_rows(const float* __restrict__ ap, const float* __restrict__ bp,
                                          int nrows, int kg, int KG, float (&acc)[8][8]) {
-#pragma unroll 2
-  for (int k = kg; k < nrows; k += KG) {
-    const float4 a0 = *reinterpret_cast<const float4*>(ap + k * kRowFloats);
-    const float4 a1 = *reinterpret_cast<const float4*>(ap + k * kRowFloats + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bp + k * kRowFloats);
+  int k = kg;
+  if (k >= nrows) return;
+  float4 a0 = *reinterpret_cast<const float4*>(ap + k * kRowFloats);
+  float4 a1 = *reinterpret_cast<const float4*>(ap + k * kRowFloats + 32);
+  float4 b0 = *reinterpret_cast<const float4*>(bp + k * kRowFloats);
+  float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (TS == 8) b1 = *reinterpret_cast<const float4*>(bp + k * kRowFloats + 4);
+  for (;;) {
+    const int kn = k + KG;
+    const bool more = kn < nrows;
+    const int kl = more ? kn : k;                 // clamped: the loads are always issued
+    const float4 na0 = *reinterpret_cast<const float4*>(ap + kl * kRowFloats);
+    const float4 na1 = *reinterpret_cast<const float4*>(ap + kl * kRowFloats + 32);
+    const float4 nb0 = *reinterpret_cast<const float4*>(bp + kl * kRowFloats);
+    float4 nb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TS == 8) nb1 = *reinterpret_cast<const float4*>(bp + kl * kRowFloats + 4);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    if (TS == 8) {
-      const float4 b1 = *reinterpret_cast<const float4*>(bp + k * kRowFloats + 4);
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) acc[r][g] = fmaf(av[r], bv[g], acc[r][g]);
-    } else {
-      const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) acc[r][g] = fmaf(av[r], bv[g], acc[r][g]);
-    }
+      for (int g = 0; g < TS; g += 2) ffma2(acc[r][g], acc[r][g + 1], av[r], bv[g], bv[g + 1]);
+    if (!more) break;
+    a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+    k = kn;
   }
 }
 
@@ -222,8 +241,11 @@ __device__ __forceinline__ void op_compute(const Ctx& c, const OpDesc& d, const 
     for (int g = 0; g < 8; ++g) acc[r][g] = 0.f;
   const int kg = c.tid >> d.tgs, u = c.tid & ((1 << d.tgs) - 1);
   const int rr = u & 7, sg = u >> 3;
-  const bool active = rr * 8 < c.nvalid;
-  const int aoff = rr * 8, boff = sg * d.TS;
+  // rows of this thread: 4 rr .. 4 rr + 3 and 32 + 4 rr .. 32 + 4 rr + 3, so that the eight lanes of a
+  // quarter warp read 128 contiguous bytes per LDS.128 (8 consecutive rows per thread would put
+  // them 32 bytes apart: a 2-way bank conflict on every A load)
+  const bool active = rr * 4 < c.nvalid;
+  const int aoff = rr * 4, boff = sg * d.TS;
   if (SMALL) {
     cp_async_commit();
     cp_async_wait<0>();
@@ -259,9 +281,10 @@ __device__ __forceinline__ void op_compute(const Ctx& c, const OpDesc& d, const 
     const int js0 = sg * (d.TS >> 2);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      red4[(kg * d.WP + js0) * kR + aoff + r] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      const int row = aoff + (r < 4 ? r : 28 + r);
+      red4[(kg * d.WP + js0) * kR + row] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
       if (d.TS == 8)
-        red4[(kg * d.WP + js0 + 1) * kR + aoff + r] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        red4[(kg * d.WP + js0 + 1) * kR + row] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
     }
   }
   __syncthreads();
