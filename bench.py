@@ -344,7 +344,7 @@ def run_ours(args):
     CHUNK = 131072   # rows per forward/backward pass: rows are independent, so a large batch is
                      # processed in slices (bounds the saved-for-backward state); grads accumulate
 
-    def step(s0_, b0_, noise_):
+    def compute(s0_, b0_, noise_):
         for p in actor_params:
             p.grad = None
         total, ents = None, []
@@ -363,8 +363,12 @@ def run_ours(args):
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             ents.append(entropy.detach().mean() * ((hi - lo) / n))
-        D_.allreduce_grads(actor_params)
         return total, torch.stack(ents).sum()
+
+    def step(s0_, b0_, noise_):
+        out = compute(s0_, b0_, noise_)
+        D_.allreduce_grads(actor_params)
+        return out
 
     def barrier():
         if world > 1:
@@ -405,6 +409,21 @@ def run_ours(args):
         if n.value:
             kernels[name] = {"ms_per_step": ms.value / args.steps, "launches_per_step": n.value / args.steps}
     lib.bd_prof_enable(0)
+    ms_eager = list(ms_dev)
+
+    # (1b) the same step captured once as a CUDA graph (bd.CapturedStep) and replayed: one graph
+    # launch per step instead of ~45 kernel launches + host work.  The gradient all-reduce (N > 1)
+    # stays outside the graph.  This is the headline number; the eager pass above provides the
+    # per-kernel CUDA-event times and the launch count.
+    use_graph = not args.no_graph
+    if use_graph:
+        cap_dev = bd.CapturedStep(lambda: compute(s0, b0, noise))
+
+        def graph_step():
+            out = cap_dev.replay()
+            D_.allreduce_grads(actor_params)
+            return out
+        ms_dev, _ = timed(graph_step, args.steps, warmup)
 
     # (2) end to end through the public API: host latents in pinned memory, H2D inside the timed
     # region, noise drawn by the API itself (as the reference does), D2H of the logged scalars
@@ -422,12 +441,27 @@ def run_ours(args):
         return s, b, ev
     nxt = [prefetch()]
 
+    if use_graph:
+        s_in, b_in = torch.empty_like(s0), torch.empty_like(b0)
+
+        def e2e_fn():
+            loss, ent = compute(s_in, b_in, None)          # noise drawn inside the captured step
+            return torch.stack([loss.detach(), ent.detach()])
+        cap_e2e = bd.CapturedStep(e2e_fn)
+
     def e2e_step():
         s, b, ev = nxt[0]
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
         s.record_stream(cur)
         b.record_stream(cur)
+        if use_graph:
+            s_in.copy_(s, non_blocking=True)               # staged latents -> the graph's inputs
+            b_in.copy_(b, non_blocking=True)
+            res = cap_e2e.replay()
+            D_.allreduce_grads(actor_params)
+            nxt[0] = prefetch()
+            return res.tolist()
         loss, ent = step(s, b, None)
         nxt[0] = prefetch()
         return torch.stack([loss.detach(), ent.detach()]).tolist()
@@ -487,6 +521,9 @@ def run_ours(args):
         "kernels": kernels,
         "clocks": clocks,
         "ms_min": min(ms_dev), "ms_median": statistics.median(ms_dev),
+        "launch": ("one CUDA graph replay per step (bd.CapturedStep); gpu_launches counts the kernels inside "
+                   "the replayed graphs" if use_graph else "eager: one launch per kernel"),
+        "ms_per_step_eager": sum(ms_eager) / len(ms_eager),
     }
     if world == 1:
         out["cem"] = cem_block(bd, orc, pu, dev, args.precision, not args.no_cpu_baseline)
@@ -512,6 +549,7 @@ def main():
                     help="fp16 (default: tcgen05, fp16 operands / fp32 accumulate), bf16, or fp32 check mode")
     ap.add_argument("--rows", type=int, default=ROWS_DEFAULT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager (one launch per kernel) path only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,8 +12,9 @@ from .functions import get_precision, set_precision
 from .modules import (DenseModel, MPCPlanner, TransitionModel, build_mlp, draw_imagine_noise,
                       imagine_ahead, imagine_and_returns, lambda_return)
 from .patch import patch, unpatch
+from .graph import CapturedStep
 
 __all__ = ["BdError", "LIB_PATH", "load_library", "get_precision", "set_precision", "DenseModel",
            "MPCPlanner", "TransitionModel", "build_mlp", "draw_imagine_noise", "imagine_ahead",
-           "imagine_and_returns", "lambda_return", "patch", "unpatch"]
+           "imagine_and_returns", "lambda_return", "patch", "unpatch", "CapturedStep"]
 __version__ = "0.1.0"

@@ -102,3 +102,38 @@ def test_cem_plan_c3_size_invariants():
         for it in range(d["iters"]):
             assert len(set(topk[it, 0].tolist())) == d["K"]
             assert int(topk[it, 0].min()) >= 0 and int(topk[it, 0].max()) < d["C"]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "fp32"])
+def test_captured_step_matches_eager(prec):
+    """bd.CapturedStep: the whole actor-loss step (imagine_ahead + heads + lambda_return + backward)
+    replayed as one CUDA graph gives the bit-identical loss and the same actor gradients (up to the
+    order of the fp32 atomics that end the weight-gradient kernels) as the eager launches,
+    also after new start latents are copied into the graph's static inputs."""
+    bd.set_precision(prec)
+    N = 300
+    mods, s0, b0, noise = _setup(N)
+    agent = pu.agent_ns(mods, D["H"])
+    params = list(mods.actor.parameters())
+
+    def fn(s_, b_):
+        for p in params:
+            p.grad = None
+        beliefs, states, _, ent = bd.imagine_ahead(agent, s_[None], b_[None], noise)
+        rew, val = mods.reward(beliefs, states), mods.critic(beliefs, states)
+        ret = bd.lambda_return(rew, val, val[-1], 0.995, 0.95)
+        loss = -(ret + 1e-5 * ent.unsqueeze(-1)).mean()
+        loss.backward()
+        return loss.detach()
+
+    s_in, b_in = s0.clone(), b0.clone()
+    step = bd.CapturedStep(fn, [s_in, b_in])
+    for scale in (1.0, 0.5):
+        s1, b1 = s0 * scale, b0 * scale
+        loss_g = step(s1, b1).clone()
+        grads_g = [p.grad.clone() for p in params]
+        loss_e = fn(s1, b1)
+        torch.cuda.synchronize()
+        assert torch.equal(loss_g, loss_e)
+        for g, p in zip(grads_g, params):     # weight gradients end in fp32 atomics: order-dependent
+            assert pu.relerr(g, p.grad) < 1e-5
