@@ -125,6 +125,11 @@ SIGNATURES = {
                                       C.c_int, C.c_void_p]),
     "bd_mlp_backward": (C.c_int, [C.POINTER(Mlp), C.POINTER(MlpBwdArgs), C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p]),
+    "bd_kl_loss_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                     C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bd_kl_loss_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_lambda_return_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                            C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "bd_lambda_return_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_double,

@@ -154,6 +154,21 @@ int bd_lambda_return_backward(const float* d_returns, int T, int64_t N, double d
                                      d_bootstrap, stream);
 }
 
+int bd_kl_loss_forward(const float* post_mean, const float* post_std, const float* prior_mean,
+                       const float* prior_std, int64_t rows, int S, const float* free_nats,
+                       double balance, float* div, float* loss, bd_stream_t stream) {
+  return f32::kl_loss_forward(post_mean, post_std, prior_mean, prior_std, rows, S, free_nats, balance, div,
+                              loss, stream);
+}
+int bd_kl_loss_backward(const float* post_mean, const float* post_std, const float* prior_mean,
+                        const float* prior_std, int64_t rows, int S, const float* free_nats,
+                        double balance, const float* div, const float* loss, const float* g_loss,
+                        float* d_post_mean, float* d_post_std, float* d_prior_mean,
+                        float* d_prior_std, bd_stream_t stream) {
+  return f32::kl_loss_backward(post_mean, post_std, prior_mean, prior_std, rows, S, free_nats, balance, div,
+                               loss, g_loss, d_post_mean, d_post_std, d_prior_mean, d_prior_std, stream);
+}
+
 size_t bd_transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
   if (!r) return 0;
   size_t f = f32::transition_workspace_bytes(r, L, B, observe, backward);

@@ -194,6 +194,35 @@ int lambda_return_backward(const float* d_returns, int T, int64_t N, double disc
 }
 
 // -------------------------------------------------------------------------------------
+// KL loss of the dynamics update (src/planet.py:288-308, src/dreamer.py:111-146)
+// -------------------------------------------------------------------------------------
+int kl_loss_forward(const float* post_mean, const float* post_std, const float* prior_mean,
+                    const float* prior_std, int64_t rows, int Sz, const float* free_nats, double balance,
+                    float* div, float* loss, bd_stream_t stream) {
+  BD_CHECK_ARG(rows >= 1 && Sz >= 1, "kl_loss: bad rows/S");
+  BD_CHECK_ARG(post_mean && post_std && prior_mean && prior_std && free_nats && div && loss, "kl_loss: null pointer");
+  BD_CHECK_ARG(balance < 0.0 || balance <= 1.0, "kl_loss: kl_balance must be -1 or in [0, 1]");
+  kl_rows_kernel<<<grid1d(rows * 32), 256, 0, S(stream)>>>(post_mean, post_std, prior_mean, prior_std, rows, Sz, div);
+  BD_CUDA_LAUNCH_CHECK();
+  kl_finish_kernel<<<1, 1024, 0, S(stream)>>>(div, rows, Sz, free_nats, balance >= 0.0 ? 1 : 0, loss);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+int kl_loss_backward(const float* post_mean, const float* post_std, const float* prior_mean,
+                     const float* prior_std, int64_t rows, int Sz, const float* free_nats, double balance,
+                     const float* div, const float* loss, const float* g_loss, float* d_post_mean,
+                     float* d_post_std, float* d_prior_mean, float* d_prior_std, bd_stream_t stream) {
+  BD_CHECK_ARG(rows >= 1 && Sz >= 1, "kl_loss: bad rows/S");
+  BD_CHECK_ARG(post_mean && post_std && prior_mean && prior_std && free_nats && div && loss && g_loss,
+               "kl_loss backward: null pointer");
+  kl_bwd_kernel<<<grid1d(rows * Sz), 256, 0, S(stream)>>>(post_mean, post_std, prior_mean, prior_std, div, loss,
+                                                         free_nats, g_loss, rows, Sz, (float)balance, d_post_mean,
+                                                         d_post_std, d_prior_mean, d_prior_std);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
+// -------------------------------------------------------------------------------------
 // One RSSM transition step, forward and backward-with-recompute
 // -------------------------------------------------------------------------------------
 static int check_rssm(const bd_rssm& r, bool need_post) {

@@ -19,6 +19,13 @@ int lambda_return_forward(const float* reward, const float* value, const float* 
 int lambda_return_backward(const float* d_returns, int T, int64_t N, double discount,
                            double lambda_, float* d_reward, float* d_value, float* d_bootstrap,
                            bd_stream_t stream);
+int kl_loss_forward(const float* post_mean, const float* post_std, const float* prior_mean,
+                    const float* prior_std, int64_t rows, int S, const float* free_nats, double balance,
+                    float* div, float* loss, bd_stream_t stream);
+int kl_loss_backward(const float* post_mean, const float* post_std, const float* prior_mean,
+                     const float* prior_std, int64_t rows, int S, const float* free_nats, double balance,
+                     const float* div, const float* loss, const float* g_loss, float* d_post_mean,
+                     float* d_post_std, float* d_prior_mean, float* d_prior_std, bd_stream_t stream);
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward);
 int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
 int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes,

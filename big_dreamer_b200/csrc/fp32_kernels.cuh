@@ -404,6 +404,81 @@ __global__ void belief_sample_bwd_kernel(const float* __restrict__ pre, const fl
 }
 
 // =====================================================================================
+// KL(posterior || prior) loss of the dynamics update:
+// Planet._kl_loss src/planet.py:288-308 and Dreamer._kl_loss src/dreamer.py:111-146
+// (torch.distributions.kl._kl_normal_normal, free nats, optional KL balancing).
+//   kl_rows_kernel    one warp per (t, b) row: div[row] = sum_S KL
+//   kl_finish_kernel  one block, deterministic tree: loss = mean_rows max(div, free_nats)   (balance < 0)
+//                     or max(mean_elements KL, free_nats) (balanced: both detached variants
+//                     have the same VALUE; they differ in where the gradient goes)
+//   kl_bwd_kernel     one thread per element -> up to four gradients
+// torch.max(a, b) passes the gradient to the larger input and half of it on a tie.
+// =====================================================================================
+__device__ __forceinline__ float kl_normal(float mq, float sq, float mp, float sp) {
+  const float vr = (sq / sp) * (sq / sp), t1 = ((mq - mp) / sp) * ((mq - mp) / sp);
+  return 0.5f * (vr + t1 - 1.f - logf(vr));
+}
+__global__ void kl_rows_kernel(const float* __restrict__ mq, const float* __restrict__ sq,
+                               const float* __restrict__ mp, const float* __restrict__ sp,
+                               long long rows, int S, float* __restrict__ div) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int j = lane; j < S; j += 32) {
+    const long long o = row * S + j;
+    acc += kl_normal(mq[o], sq[o], mp[o], sp[o]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) div[row] = acc;
+}
+__device__ __forceinline__ float max_grad_factor(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+__global__ void __launch_bounds__(1024) kl_finish_kernel(const float* __restrict__ div, long long rows, int S,
+                                                         const float* __restrict__ free_nats, int balanced,
+                                                         float* __restrict__ loss) {
+  __shared__ float red[1024];
+  const float fn = free_nats[0];
+  float acc = 0.f;
+  for (long long r = threadIdx.x; r < rows; r += 1024) acc += balanced ? div[r] : fmaxf(div[r], fn);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // loss[1] keeps the mean element KL for the backward of the balanced form
+    if (balanced) { const float m = red[0] / ((float)rows * (float)S); loss[0] = fmaxf(m, fn); loss[1] = m; }
+    else { loss[0] = red[0] / (float)rows; loss[1] = 0.f; }
+  }
+}
+__global__ void kl_bwd_kernel(const float* __restrict__ mq, const float* __restrict__ sq,
+                              const float* __restrict__ mp, const float* __restrict__ sp,
+                              const float* __restrict__ div, const float* __restrict__ loss,
+                              const float* __restrict__ free_nats, const float* __restrict__ g_loss,
+                              long long rows, int S, float balance, float* __restrict__ d_mq,
+                              float* __restrict__ d_sq, float* __restrict__ d_mp, float* __restrict__ d_sp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * S) return;
+  const float fn = free_nats[0], g = g_loss[0];
+  float wq, wp;     // weights of the posterior-side / prior-side gradients
+  if (balance < 0.f) {
+    wq = wp = g * max_grad_factor(div[i / S], fn) / (float)rows;
+  } else {
+    const float w = g * max_grad_factor(loss[1], fn) / ((float)rows * (float)S);
+    wp = balance * w;            // kl_lhs: posterior detached
+    wq = (1.f - balance) * w;    // kl_rhs: prior detached
+  }
+  const float a = mq[i], b = sq[i], c = mp[i], d = sp[i];
+  const float diff = a - c, inv_var = 1.f / (d * d);
+  if (d_mq) d_mq[i] = wq * diff * inv_var;
+  if (d_sq) d_sq[i] = wq * (b * inv_var - 1.f / b);
+  if (d_mp) d_mp[i] = -wp * diff * inv_var;
+  if (d_sp) d_sp[i] = wp * (1.f / d - (b * b + diff * diff) * inv_var / d);
+}
+
+// =====================================================================================
 // Actor head: ActorModel squash (src/models.py:513-516), tanh-Normal rsample
 // (src/dreamer.py:435-443) and the J-sample Monte-Carlo entropy (src/models.py:725-733,
 // 656-673).  One thread per row.  Also emits d entropy / d(mean,std) for backward.

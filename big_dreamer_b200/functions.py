@@ -392,3 +392,45 @@ class ImagineFunction(torch.autograd.Function):
         _lib.check(lib.bd_imagine_backward(C.byref(a), ws.data_ptr(), ws.numel(), ctx.prec,
                                            _lib.stream_ptr()), "bd_imagine_backward")
         return (None, None, None, d_s0, d_b0, None, None, None, None, *dA, *([None] * 10))
+
+
+# =============================================================================
+# KL loss (Planet._kl_loss src/planet.py:288-308, Dreamer._kl_loss src/dreamer.py:111-146)
+# =============================================================================
+class KlLossFunction(torch.autograd.Function):
+    """(post_mean, post_std, prior_mean, prior_std) each (L,B,S), free_nats (1,) device tensor,
+    balance (-1 = off) -> scalar loss.  Two kernels forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, post_mean, post_std, prior_mean, prior_std, free_nats, balance: float):
+        lib = _lib.load()
+        mq, sq, mp, sp = (_f32c(t) for t in (post_mean, post_std, prior_mean, prior_std))
+        if not (mq.shape == sq.shape == mp.shape == sp.shape) or mq.dim() < 2:
+            raise BdError("kl_loss: parameter tensors must share one (..., S) shape")
+        fn = _f32c(free_nats).reshape(-1)[:1]
+        S = mq.shape[-1]
+        rows = mq.numel() // S
+        div = torch.empty(rows, device=mq.device, dtype=torch.float32)
+        loss = torch.empty(2, device=mq.device, dtype=torch.float32)
+        _lib.check(lib.bd_kl_loss_forward(_lib.ptr(mq), _lib.ptr(sq), _lib.ptr(mp), _lib.ptr(sp), rows, S,
+                                          _lib.ptr(fn), float(balance), _lib.ptr(div), _lib.ptr(loss),
+                                          _lib.stream_ptr()), "bd_kl_loss_forward")
+        ctx.save_for_backward(mq, sq, mp, sp, fn, div, loss)
+        ctx.balance, ctx.shape = float(balance), post_mean.shape
+        # the reference returns a 0-dim tensor without balancing and shape (1,) with it
+        return loss[0].clone() if balance < 0 else loss[:1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        mq, sq, mp, sp, fn, div, loss = ctx.saved_tensors
+        S = mq.shape[-1]
+        rows = mq.numel() // S
+        need = ctx.needs_input_grad
+        outs = [torch.empty_like(t) if n else None for t, n in zip((mq, sq, mp, sp), need[:4])]
+        gl = _f32c(g).reshape(-1)[:1]
+        _lib.check(lib.bd_kl_loss_backward(_lib.ptr(mq), _lib.ptr(sq), _lib.ptr(mp), _lib.ptr(sp), rows, S,
+                                           _lib.ptr(fn), ctx.balance, _lib.ptr(div), _lib.ptr(loss),
+                                           _lib.ptr(gl), *(_lib.ptr(o) for o in outs), _lib.stream_ptr()),
+                   "bd_kl_loss_backward")
+        return (*(o.reshape(ctx.shape) if o is not None else None for o in outs), None, None)

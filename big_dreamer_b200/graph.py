@@ -12,7 +12,8 @@ the host work (ctypes calls, autograd bookkeeping) from the step.
 Rules (those of torch.cuda.graph): shapes are fixed; ``fn`` must not synchronise or read values on
 the host; random draws inside ``fn`` use torch's graph-safe generator; gradients produced by
 ``fn`` live in the graph's private pool and are overwritten by every replay (set ``p.grad = None``
-inside ``fn`` so the backward allocates them during capture).
+inside ``fn`` so the backward allocates them during capture; return the ``.grad`` tensors from ``fn`` if
+other code may rebind ``p.grad`` between replays).
 """
 from __future__ import annotations
 

@@ -245,6 +245,24 @@ def lambda_return(imged_reward: Tensor, value_pred: Tensor, bootstrap: Tensor,
     return F_.LambdaReturnFunction.apply(imged_reward, value_pred, bootstrap, discount, lambda_)
 
 
+def kl_loss(posterior_params, prior_params, free_nats, kl_balance: float = -1) -> Tensor:
+    """Fused KL(posterior || prior) loss with free nats and optional KL balancing
+    (Planet._kl_loss src/planet.py:288-308; Dreamer._kl_loss src/dreamer.py:111-146).
+    posterior_params / prior_params: (means, std_devs) each (L,B,S); free_nats: float or the
+    reference's (1,) tensor.  Returns a 0-dim tensor (no balancing) or shape (1,) (balancing), as
+    the reference does."""
+    qm, qs = posterior_params
+    pm, ps = prior_params
+    if not isinstance(free_nats, torch.Tensor):
+        free_nats = torch.full((1,), float(free_nats), device=qm.device, dtype=torch.float32)
+    return F_.KlLossFunction.apply(qm, qs, pm, ps, free_nats, float(kl_balance))
+
+
+def _kl_loss_method(self, posterior_params, prior_params):
+    """Bound by patch() as Planet._kl_loss / Dreamer._kl_loss (Gaussian latents)."""
+    return kl_loss(posterior_params, prior_params, self.free_nats, getattr(self, "kl_balance", -1))
+
+
 def imagine_and_returns(self, prev_state: Tensor, prev_belief: Tensor, reward_model, value_model,
                         discount: float, lambda_: float,
                         noise: Optional[Dict[str, Tensor]] = None):

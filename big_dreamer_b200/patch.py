@@ -26,8 +26,8 @@ def _get(name):
 
 def patch(fused: bool = False) -> None:
     """Rebind models.TransitionModel / DenseModel, planner.MPCPlanner (and the copies
-    ``planet`` / ``dreamer`` took with ``from ... import``), Dreamer.imagine_ahead and
-    dreamer.lambda_return."""
+    ``planet`` / ``dreamer`` took with ``from ... import``), Dreamer.imagine_ahead,
+    dreamer.lambda_return and Planet/Dreamer._kl_loss."""
     if _saved:
         return
     models, planner = _get("models"), _get("planner")
@@ -47,6 +47,17 @@ def patch(fused: bool = False) -> None:
     cls = dreamer.Dreamer
     _saved[("dreamer.Dreamer", "imagine_ahead")] = (cls, cls.imagine_ahead)
     cls.imagine_ahead = M.imagine_ahead
+    # dynamics-update KL (Gaussian latents; the Categorical path keeps the reference's method)
+    for owner in (planet.Planet, cls):
+        if "_kl_loss" in vars(owner):
+            orig = owner._kl_loss
+            _saved[(owner.__module__ + "." + owner.__name__, "_kl_loss")] = (owner, orig)
+
+            def _kl(self, posterior_params, prior_params, _orig=orig):
+                if getattr(self, "latent_distribution", "Gaussian") != "Gaussian":
+                    return _orig(self, posterior_params, prior_params)
+                return M._kl_loss_method(self, posterior_params, prior_params)
+            owner._kl_loss = _kl
     if fused:
         cls.imagine_and_returns = M.imagine_and_returns
 

@@ -17,6 +17,8 @@
  *                                           keeping 16-bit images for the tensor-core backward
  *                                           (what autograd's saved tensors are in the reference)
  *   bd_lambda_return_forward / _backward    lambda_return           src/dreamer.py:447-471
+ *   bd_kl_loss_forward / _backward          Planet/Dreamer._kl_loss src/planet.py:288-308,
+ *                                                                   src/dreamer.py:111-146
  *   bd_cem_evaluate / bd_cem_refit / bd_cem_plan
  *                                           MPCPlanner.forward      src/planner.py:28-90
  *
@@ -161,6 +163,26 @@ int bd_lambda_return_forward(const float* reward, const float* value, const floa
 int bd_lambda_return_backward(const float* d_returns, int T, int64_t N, double discount,
                               double lambda_, float* d_reward, float* d_value, float* d_bootstrap,
                               bd_stream_t stream);
+
+/* ------------------------------------------------------------- KL loss ---- */
+/* KL(posterior || prior) of the dynamics update, summed over the S latent dimensions, with the
+ * free-nats floor: Planet._kl_loss (src/planet.py:288-308) and Dreamer._kl_loss
+ * (src/dreamer.py:111-146).  All four parameter tensors are (rows, S) with rows = L*B.
+ *   balance < 0 : loss = mean_rows max(sum_S KL, free_nats)                (kl_balance == -1)
+ *   balance >= 0: loss = balance * max(mean KL(sg(post) || prior), free_nats)
+ *                      + (1 - balance) * max(mean KL(post || sg(prior)), free_nats)
+ * free_nats: device pointer to one float (the reference keeps it as a (1,) tensor).
+ * div (rows) and loss (2 floats: the loss, and the mean element KL of the balanced form) are
+ * outputs the backward needs again.  g_loss: device pointer to dL/dloss (one float).
+ * Any of the four gradient outputs may be NULL. */
+int bd_kl_loss_forward(const float* post_mean, const float* post_std, const float* prior_mean,
+                       const float* prior_std, int64_t rows, int S, const float* free_nats,
+                       double balance, float* div, float* loss, bd_stream_t stream);
+int bd_kl_loss_backward(const float* post_mean, const float* post_std, const float* prior_mean,
+                        const float* prior_std, int64_t rows, int S, const float* free_nats,
+                        double balance, const float* div, const float* loss, const float* g_loss,
+                        float* d_post_mean, float* d_post_std, float* d_prior_mean,
+                        float* d_prior_std, bd_stream_t stream);
 
 /* ----------------------------------------------- TransitionModel.forward ---- */
 typedef struct {

@@ -118,8 +118,31 @@ def cem_case(name, Be, Hi, S, A, E, B, C, K, H, iters, act="ELU", seed=2):
     print(name, out.flatten()[:4])
 
 
+def kl_case(name="kl_loss", L=7, B=9, S=30, seed=4):
+    """Reference _kl_loss values and gradients: Planet form, Dreamer without and with balancing;
+    free_nats chosen so that some rows sit below the floor and some above."""
+    g = torch.Generator().manual_seed(seed)
+    mk = lambda: torch.randn(L, B, S, generator=g) * 0.3
+    sd = lambda: torch.rand(L, B, S, generator=g) * 0.5 + 0.4
+    base = dict(post_mean=mk(), post_std=sd(), prior_mean=mk(), prior_std=sd())
+    fx = dict(inputs=base, cases=[])
+    for agent, fn, bal in (("planet", 3.0, -1), ("dreamer", 3.0, -1), ("dreamer", 0.05, 0.8),
+                           ("dreamer", 3.0, 0.8), ("dreamer", 0.1, 0.3)):
+        t = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        loss = rh.ref_kl_loss(agent, (t["post_mean"], t["post_std"]), (t["prior_mean"], t["prior_std"]), fn, bal)
+        (loss.sum() * 1.7).backward()
+        fx["cases"].append(dict(agent=agent, free_nats=fn, kl_balance=bal, loss=loss.detach().clone(),
+                                grads={k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v))
+                                       for k, v in t.items()}))
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, [float(c["loss"].sum()) for c in fx["cases"]])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if os.environ.get("BD_GOLDEN_ONLY") == "kl":
+        return kl_case()
+    kl_case()
     # c1 (README Pendulum sizes), well-conditioned entropy + default-init entropy
     imagine_case("imagine_c1", 32, 32, 30, 1, 64, 48, "ELU", 15, small_std=True)
     imagine_case("imagine_c1_init", 32, 32, 30, 1, 64, 32, "ELU", 15, small_std=False)

@@ -202,3 +202,15 @@ def ref_cem(mods, action_size, planning_horizon, iters, candidates, top, belief,
 
 def ref_lambda_return(*a, **k):
     return load().dreamer.lambda_return(*a, **k)
+
+
+def ref_kl_loss(agent: str, posterior_params, prior_params, free_nats: float, kl_balance: float = -1):
+    """The reference's own ``_kl_loss`` (agent = "planet": src/planet.py:288-308; "dreamer":
+    src/dreamer.py:111-146) called on a stand-in ``self`` carrying the attributes it reads."""
+    m = load()
+    ns = types.SimpleNamespace(latent_distribution="Gaussian", kl_balance=kl_balance,
+                               free_nats=torch.full((1,), free_nats, dtype=posterior_params[0].dtype))
+    if agent == "planet":
+        return sys.modules["planet"].Planet._kl_loss(ns, posterior_params, prior_params)
+    ns._get_dist = types.MethodType(m.dreamer.Dreamer._get_dist, ns)
+    return m.dreamer.Dreamer._kl_loss(ns, posterior_params, prior_params)

@@ -146,6 +146,29 @@ def transition_forward(sd: SD, act: str, min_std: float, init_state: Tensor, act
 
 
 # ----------------------------------------------------------------------------
+# KL loss of the dynamics update
+# ----------------------------------------------------------------------------
+def kl_normal(mq: Tensor, sq: Tensor, mp: Tensor, sp: Tensor) -> Tensor:
+    """torch.distributions.kl._kl_normal_normal(Normal(mq, sq), Normal(mp, sp)), elementwise."""
+    var_ratio = (sq / sp) ** 2
+    t1 = ((mq - mp) / sp) ** 2
+    return 0.5 * (var_ratio + t1 - 1 - var_ratio.log())
+
+
+def kl_loss(posterior_params, prior_params, free_nats: Tensor, kl_balance: float = -1) -> Tensor:
+    """Planet._kl_loss (src/planet.py:288-308) when kl_balance == -1, else the balanced form of
+    Dreamer._kl_loss (src/dreamer.py:129-144).  free_nats: (1,) tensor as in src/planet.py:98."""
+    qm, qs = posterior_params
+    pm, ps = prior_params
+    if kl_balance == -1:
+        div = kl_normal(qm, qs, pm, ps).sum(dim=2)
+        return torch.max(div, free_nats).mean(dim=(0, 1))
+    lhs = kl_normal(qm.detach(), qs.detach(), pm, ps).mean()
+    rhs = kl_normal(qm, qs, pm.detach(), ps.detach()).mean()
+    return kl_balance * torch.max(lhs, free_nats) + (1 - kl_balance) * torch.max(rhs, free_nats)
+
+
+# ----------------------------------------------------------------------------
 # actor: ActorModel.forward + Dreamer.get_action + SampleDist.entropy
 # ----------------------------------------------------------------------------
 TANH_CLAMP = 0.99999997  # src/models.py:663 (rounds to 0.99999994 in fp32)

@@ -294,6 +294,40 @@ def test_observe_unmasked_and_partial_cotangents():
         assert float((got.cpu() - ref).abs().max()) <= 2e-4 * float(ref.abs().max()) + 1e-7, k
 
 
+# ------------------------------------------------------------------ KL loss
+def test_kl_loss_vs_reference_fixture():
+    """bd.kl_loss (two fused kernels forward, one backward) against the values and gradients of the
+    reference's Planet._kl_loss / Dreamer._kl_loss frozen in tests/golden/kl_loss.pt."""
+    fx = load("kl_loss")
+    for c in fx["cases"]:
+        t = {k: v.cuda().requires_grad_(True) for k, v in fx["inputs"].items()}
+        loss = bd.kl_loss((t["post_mean"], t["post_std"]), (t["prior_mean"], t["prior_std"]),
+                          torch.full((1,), c["free_nats"], device="cuda"), c["kl_balance"])
+        assert loss.shape == c["loss"].shape
+        assert pu.relerr(loss, c["loss"]) < 1e-5, c["agent"]
+        (loss.sum() * 1.7).backward()
+        for k, g in c["grads"].items():
+            scale = float(g.abs().max())
+            assert float((t[k].grad.cpu() - g).abs().max()) <= 1e-4 * scale + 1e-9, (c["agent"], c["kl_balance"], k)
+
+
+def test_kl_loss_large_and_partial_grads():
+    """c4-sized parameters (49 x 50 x 30) vs the oracle; gradients only into the posterior side."""
+    g = torch.Generator().manual_seed(1)
+    L, B, S = 49, 50, 30
+    qm, pm = torch.randn(L, B, S, generator=g) * 0.5, torch.randn(L, B, S, generator=g) * 0.5
+    qs, ps = torch.rand(L, B, S, generator=g) + 0.2, torch.rand(L, B, S, generator=g) + 0.2
+    for bal, fn in ((-1, 3.0), (0.8, 0.1)):
+        a = [qm.clone().requires_grad_(True), qs.clone().requires_grad_(True)]
+        ref = orc.kl_loss((a[0], a[1]), (pm, ps), torch.full((1,), fn), bal)
+        ref.sum().backward()
+        b = [qm.cuda().requires_grad_(True), qs.cuda().requires_grad_(True)]
+        out = bd.kl_loss((b[0], b[1]), (pm.cuda(), ps.cuda()), fn, bal)
+        out.sum().backward()
+        assert pu.relerr(out, ref) < 1e-5
+        assert pu.relerr(b[0].grad, a[0].grad) < 1e-4 and pu.relerr(b[1].grad, a[1].grad) < 1e-4
+
+
 # ------------------------------------------------------------------ CEM
 @pytest.mark.parametrize("name", ["cem_small", "cem_c3_like"])
 def test_cem_vs_reference_fixture(name):

@@ -77,3 +77,19 @@ def test_lambda_return_fixture():
     fx = load("lambda_return")
     o = orc.lambda_return(fx["reward"], fx["value"], fx["value"][-1], fx["discount"], fx["lambda_"])
     assert torch.equal(o, fx["returns"])
+
+
+def test_kl_loss_fixture():
+    """Oracle kl_loss against the reference's Planet/Dreamer._kl_loss values and gradients
+    (no balancing, balancing above the free-nats floor, balancing at the floor)."""
+    fx = load("kl_loss")
+    for c in fx["cases"]:
+        t = {k: v.clone().requires_grad_(True) for k, v in fx["inputs"].items()}
+        loss = orc.kl_loss((t["post_mean"], t["post_std"]), (t["prior_mean"], t["prior_std"]),
+                           torch.full((1,), c["free_nats"]), c["kl_balance"])
+        assert loss.shape == c["loss"].shape
+        assert relerr(loss, c["loss"]) < 1e-6
+        (loss.sum() * 1.7).backward()
+        for k, g in c["grads"].items():
+            got = t[k].grad if t[k].grad is not None else torch.zeros_like(t[k])
+            assert float((got - g).abs().max()) <= 1e-6 * float(g.abs().max()) + 1e-12, (c, k)

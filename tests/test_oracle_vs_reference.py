@@ -111,3 +111,24 @@ def test_cem(B):
                          iters, C, K, b0, s0, ea, es)
     assert r.shape == (B, A)
     assert relerr(o, r) < 1e-10
+
+
+@pytest.mark.parametrize("agent,free_nats,bal", [("planet", 3.0, -1), ("dreamer", 2.0, -1),
+                                                  ("dreamer", 0.05, 0.8), ("dreamer", 5.0, 0.5)])
+def test_kl_loss(agent, free_nats, bal):
+    """oracle.kl_loss vs the reference's own _kl_loss (src/planet.py:288-308, src/dreamer.py:111-146), fp64."""
+    g = torch.Generator().manual_seed(3)
+    d = torch.float64
+    base = [torch.randn(6, 5, 12, generator=g, dtype=d) * 0.4, torch.rand(6, 5, 12, generator=g, dtype=d) + 0.3,
+            torch.randn(6, 5, 12, generator=g, dtype=d) * 0.4, torch.rand(6, 5, 12, generator=g, dtype=d) + 0.3]
+    a = [t.clone().requires_grad_(True) for t in base]
+    b = [t.clone().requires_grad_(True) for t in base]
+    lr = rh.ref_kl_loss(agent, (a[0], a[1]), (a[2], a[3]), free_nats, bal)
+    lo = orc.kl_loss((b[0], b[1]), (b[2], b[3]), torch.full((1,), free_nats, dtype=d), bal)
+    assert lr.shape == lo.shape and relerr(lo, lr) < 1e-12
+    lr.sum().backward()
+    lo.sum().backward()
+    for x, y in zip(a, b):
+        gx = x.grad if x.grad is not None else torch.zeros_like(x)
+        gy = y.grad if y.grad is not None else torch.zeros_like(y)
+        assert float((gx - gy).abs().max()) < 1e-12

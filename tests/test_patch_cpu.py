@@ -72,7 +72,9 @@ def test_patch_rebinds_and_reference_agent_constructs(ref_agent_modules):
     planet, dreamer, models, planner, params = ref_agent_modules
     ref_tm, ref_dense, ref_planner = models.TransitionModel, models.DenseModel, planner.MPCPlanner
     ref_imagine, ref_lambda = dreamer.Dreamer.imagine_ahead, dreamer.lambda_return
+    ref_kl_p, ref_kl_d = planet.Planet._kl_loss, dreamer.Dreamer._kl_loss
     bd.patch()
+    assert planet.Planet._kl_loss is not ref_kl_p and dreamer.Dreamer._kl_loss is not ref_kl_d
     # the classes themselves and every copy the agents took with `from models import ...`
     # (src/planet.py:15,17, src/dreamer.py:13)
     assert models.TransitionModel is bd.TransitionModel and planet.TransitionModel is bd.TransitionModel
@@ -108,3 +110,4 @@ def test_patch_rebinds_and_reference_agent_constructs(ref_agent_modules):
     assert models.TransitionModel is ref_tm and planet.DenseModel is ref_dense
     assert planner.MPCPlanner is ref_planner and dreamer.lambda_return is ref_lambda
     assert dreamer.Dreamer.imagine_ahead is ref_imagine
+    assert planet.Planet._kl_loss is ref_kl_p and dreamer.Dreamer._kl_loss is ref_kl_d
