@@ -362,6 +362,18 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
   cluster_arrive();
   long long tm[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0}, po[4] = {0, 0, 0, 0}, pe[4] = {0, 0, 0, 0};
   int row, js, jg;
+  // GRU epilogue items of this thread (up to 4 units j for its row): the gate biases never change
+  float gbias[4][4];
+  bool gown[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    gown[q] = item_of(c, a.gru, c.tid + q * kThreads, &row, &js, &jg);
+    const int j = gown[q] ? jg : 0;
+    gbias[q][0] = a.b_ih[j] + a.b_hh[j];
+    gbias[q][1] = a.b_ih[Be + j] + a.b_hh[Be + j];
+    gbias[q][2] = a.b_ih[2 * Be + j];
+    gbias[q][3] = a.b_hh[2 * Be + j];
+  }
   for (int t = 0; t < a.L; ++t) {
     const int par = t & 1;
     const long long trow = (long long)t * B + row0;
@@ -398,21 +410,33 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
     // ---------------------------------------------------------------- P2 GRU
     OBS_T(0);
     prefetch_w(c, a.gru);
-    cluster_wait();
-    OBS_T(1);
     const float* hprevT = hT + (size_t)par * Be * kRowFloats;
     float* hnewT = hT + (size_t)(par ^ 1) * Be * kRowFloats;
+    // h_{t-1} of this thread's items: written two phases ago (or by the prologue), so it can be
+    // requested before the barrier
+    float hprev[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hprev[q] = 0.f;
+      if (gown[q]) {
+        item_of(c, a.gru, c.tid + q * kThreads, &row, &js, &jg);
+        hprev[q] = __ldcg(hprevT + (size_t)jg * kRowFloats + row);
+      }
+    }
+    cluster_wait();
+    OBS_T(1);
     op_compute<false>(c, a.gru, Segs{xT, Be, hprevT});
     OBS_T(2);
-    for (int it = c.tid; it < kR * a.gru.WP; it += kThreads) {
-      if (item_of(c, a.gru, it, &row, &js, &jg)) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (gown[q]) {
+        item_of(c, a.gru, c.tid + q * kThreads, &row, &js, &jg);
         const int j = jg;
-        const float hp = __ldcg(hprevT + (size_t)j * kRowFloats + row);
         const float4 v = red_sum(c, a.gru, js, row);
-        const float rr = sigmoidf_(v.x + a.b_ih[j] + a.b_hh[j]);
-        const float z = sigmoidf_(v.y + a.b_ih[Be + j] + a.b_hh[Be + j]);
-        const float n = tanhf(v.z + a.b_ih[2 * Be + j] + rr * (v.w + a.b_hh[2 * Be + j]));
-        const float hn = (1.f - z) * n + z * hp;
+        const float rr = sigmoidf_(v.x + gbias[q][0]);
+        const float z = sigmoidf_(v.y + gbias[q][1]);
+        const float n = tanhf(v.z + gbias[q][2] + rr * (v.w + gbias[q][3]));
+        const float hn = (1.f - z) * n + z * hprev[q];
         a.beliefs[(trow + row) * Be + j] = hn;
         hnewT[(size_t)j * kRowFloats + row] = hn;
       }
@@ -561,6 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
     prefetch_w(c, a.b2);
     const bool own2 = item_of(c, a.b2, c.tid, &row, &js, &jg);
     float4 G4, gir, giz, gin, ghr, ghz, ghn4, h4;
+    float cbv[4] = {0.f, 0.f, 0.f, 0.f};
     G4 = gir = giz = gin = ghr = ghz = ghn4 = h4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (own2) {
       const int col = 4 * jg;
@@ -572,6 +597,11 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
       ghn4 = ldrow4(a.gh + o3 + 2 * Be, col, Be, vecB);
       h4 = t == 0 ? ldrow4(a.init_belief + (row0 + row) * Be, col, Be, vecB && a.vec_h)
                   : ldrow4(a.beliefs + ((long long)(t - 1) * B + row0 + row) * Be, col, Be, vecB && a.vec_h);
+      if (!first) {     // carry_b of step t + 1: written in its Q3, two barriers ago
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (col + g < Be) cbv[g] = __ldcg(cbT + (size_t)(col + g) * kRowFloats + row);
+      }
     }
     cluster_wait();
     OBS_T(1);
@@ -590,8 +620,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
         const int col = 4 * jg + g;
         dr[g] = dz_[g] = dn_[g] = dnr[g] = 0.f;
         if (col < Be) {
-          const float cb = first ? 0.f : __ldcg(cbT + (size_t)col * kRowFloats + row);
-          const float G = Gt[g] + cb + Gq[g];
+          const float G = Gt[g] + cbv[g] + Gq[g];
           const float rr = sigmoidf_(ir[g] + hr[g]);
           const float z = sigmoidf_(iz[g] + hz[g]);
           const float n = tanhf(in_[g] + rr * hn[g]);

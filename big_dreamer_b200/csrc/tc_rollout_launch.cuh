@@ -12,7 +12,7 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cud
   // `grid` counts row tiles (clusters); column-split mode launches nranks CTAs per tile
   const unsigned R = ra.nranks > 1 ? (unsigned)ra.nranks : 1u;
   auto go = [&](auto kernel) -> int {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ra.sm.total);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = ra.sm.total;
