@@ -1,11 +1,27 @@
 // extern "C" surface of libbd_b200.so (include/bd_b200.h): argument checks that are common to
 // all arithmetic modes and dispatch on bd_precision.  No CPU fallback anywhere: a precision
 // that this build does not implement returns BD_ERR_UNSUPPORTED.
+#include <mutex>
+#include <unordered_map>
+#include <stdlib.h>
 #include "api_internal.h"
 
 namespace bd {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launch_count = 0;
+
+void grow_smem_attr(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cur;
+  static const bool always_max = [] { const char* e = getenv("BD_SMEM_ATTR"); return e && e[0] == 'm'; }();
+  if (always_max) bytes = kMaxOptinSmem;
+  std::lock_guard<std::mutex> lock(mu);
+  int& c = cur[kernel];
+  if (bytes > c) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    c = bytes;
+  }
+}
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -38,13 +38,15 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
     if (rc__ != BD_OK) return rc__; \
   } while (0)
 
-// Dynamic shared-memory limit set on every kernel that needs more than 48 KB: always the device's
-// opt-in maximum (227 KB) less the 2 KB the kernels keep for static barriers -- the same budget the
-// shared-memory planners use -- never the size of the launch at hand.  The attribute is per-function
-// global state; setting it per launch made it depend on the LAST launch, which breaks any tool or
-// graph path that re-issues an earlier, larger launch of the same kernel (seen with ncu's per-node
-// profiling of a replayed CUDA graph: LaunchFailed on the heads' mlp_bwd_kernel).
-constexpr int kMaxOptinSmem = 227 * 1024 - 2048;
+// Dynamic shared-memory limit of a kernel that needs more than 48 KB.  The attribute is per-function
+// global state: setting it to the size of every launch made it depend on the LAST launch, which
+// breaks any tool or graph path that re-issues an earlier, larger launch of the same kernel (seen
+// with ncu's per-node profiling of a replayed CUDA graph: LaunchFailed on the heads'
+// mlp_bwd_kernel after the smaller actor launch).  It only ever grows here.
+constexpr int kMaxOptinSmem = 227 * 1024 - 2048;     // device opt-in maximum less static barriers
+void grow_smem_attr(const void* kernel, int bytes);  // api.cu
+template <typename K>
+inline void set_smem_attr(K kernel, size_t bytes) { grow_smem_attr(reinterpret_cast<const void*>(kernel), (int)bytes); }
 
 // ---------------------------------------------------------------- optional per-kernel timing
 bool prof_enabled();

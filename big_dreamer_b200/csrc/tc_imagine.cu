@@ -684,7 +684,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     // debug: per-phase cycle counters of CTA 0 (printed by scripts/prof_bptt.py)
     ba.prof = reinterpret_cast<long long*>(base + ((off + 4095) & ~size_t(4095)));
     cudaMemsetAsync(ba.prof, 0, kMaxPhases * 64, s);
-    cudaFuncSetAttribute(bptt_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+    set_smem_attr(bptt_kernel<0, true>, ba.sm.total);
     bptt_kernel<0, true><<<grid, kThreads, ba.sm.total, s>>>(ba);
     static long long* host_prof = nullptr;
     if (!host_prof) cudaMallocHost(&host_prof, kMaxPhases * 64);
@@ -703,10 +703,10 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     for (int k = 0; k < 7; ++k) fprintf(stderr, "%9lld", tot[k]);
     fprintf(stderr, "\n");
   } else if (fmt == 0) {
-    cudaFuncSetAttribute(bptt_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+    set_smem_attr(bptt_kernel<0, false>, ba.sm.total);
     bptt_kernel<0, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
   } else {
-    cudaFuncSetAttribute(bptt_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+    set_smem_attr(bptt_kernel<1, false>, ba.sm.total);
     bptt_kernel<1, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
   }
   BD_CUDA_LAUNCH_CHECK();

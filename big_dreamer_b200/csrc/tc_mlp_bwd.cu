@@ -61,8 +61,7 @@ template <int FMT>
 static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStream_t s) {
 #define BD_LAUNCH_BWD(ACTV)                                                                          \
   do {                                                                                               \
-    cudaFuncSetAttribute(mlp_bwd_kernel<FMT, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                         kMaxOptinSmem);                                                             \
+    set_smem_attr(mlp_bwd_kernel<FMT, ACTV>, ba.sm.total);                                           \
     mlp_bwd_kernel<FMT, ACTV><<<grid, kThreads, ba.sm.total, s>>>(ba);                               \
   } while (0)
   switch (act) {
@@ -295,10 +294,10 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
         dim3 wgrid((unsigned)per, (unsigned)nj);
         ProfScope ps(BD_PROF_WGRAD, s);
         if (fmt == 0) {
-          cudaFuncSetAttribute(wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+          set_smem_attr(wgrad_kernel<0>, smem);
           wgrad_kernel<0><<<wgrid, 128, smem, s>>>(wa);
         } else {
-          cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+          set_smem_attr(wgrad_kernel<1>, smem);
           wgrad_kernel<1><<<wgrid, 128, smem, s>>>(wa);
         }
         BD_CUDA_LAUNCH_CHECK();

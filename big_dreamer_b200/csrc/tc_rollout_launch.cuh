@@ -12,7 +12,7 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cud
   // `grid` counts row tiles (clusters); column-split mode launches nranks CTAs per tile
   const unsigned R = ra.nranks > 1 ? (unsigned)ra.nranks : 1u;
   auto go = [&](auto kernel) -> int {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmem);
+    set_smem_attr(kernel, ra.sm.total);
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = ra.sm.total;
