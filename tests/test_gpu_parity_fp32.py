@@ -164,6 +164,45 @@ def test_imagine_requires_frozen_transition():
     assert out[0].shape == (2, 4, 16)
 
 
+def test_actor_loss_with_discount_model():
+    """`use_discount=True` (src/dreamer.py:323-326, 347-352): the discount head is one more
+    DenseModel on the imagined latents and the cumulated, rounded discounts weight the objective.
+    Runs through the same drop-in pieces; actor gradients against the oracle."""
+    d = dict(Be=48, Hi=40, S=10, A=2, E=8, N=37, H=7, act="ELU")
+    trans, actor, reward, value = orc.make_models(2, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    actor["model.8.bias"][d["A"]:] -= 6.0
+    disc = orc.make_models(9, d["Be"], d["S"], d["A"], d["Hi"], d["E"])[2]      # another head
+    disc["model.8.bias"] += 0.3
+    s0, b0 = orc.make_latents(2, d["N"], d["Be"], d["S"])
+    ea, ee, es = orc.make_imagine_noise(2, d["H"] - 1, d["N"], d["S"], d["A"])
+    gamma, lam, ew = 0.99, 0.95, 1e-5
+
+    def weights(logits):                      # src/dreamer.py:324-326, 350-351
+        arr = gamma * torch.round(torch.sigmoid(logits))
+        arr[:, 0, 0] = 1.0
+        return torch.cumprod(arr, 0)
+
+    asd = {k: v.clone().requires_grad_(True) for k, v in actor.items()}
+    b, s_, _, ent, _ = orc.imagine_ahead(trans, asd, d["act"], 0.1, d["H"], s0[None], b0[None], ea, ee, es)
+    ret = orc.lambda_return(orc.dense(reward, d["act"], b, s_), v := orc.dense(value, d["act"], b, s_), v[-1], gamma, lam)
+    ref = -(weights(orc.dense(disc, d["act"], b, s_)) * (ret + ew * ent.unsqueeze(-1))).mean()
+    ref.backward()
+
+    mods = pu.build_gpu_models(d, trans, actor, reward, value)
+    dm = bd.DenseModel(d["Be"] + d["S"], d["Hi"], activation=d["act"]).cuda()
+    dm.load_state_dict(disc)
+    pu.freeze(mods.transition, mods.reward, mods.critic, dm)
+    gb, gs, _, gent = bd.imagine_ahead(pu.agent_ns(mods, d["H"]), s0.cuda()[None], b0.cuda()[None],
+                                       dict(eps_a=ea.cuda(), eps_e=ee.cuda(), eps_s=es.cuda()))
+    gv = mods.critic(gb, gs)
+    gret = bd.lambda_return(mods.reward(gb, gs), gv, gv[-1], gamma, lam)
+    out = -(weights(dm(gb, gs)) * (gret + ew * gent.unsqueeze(-1))).mean()
+    out.backward()
+    assert pu.relerr(out, ref) < TOL
+    for k, p_ in mods.actor.named_parameters():
+        assert pu.relerr(p_.grad, asd[k].grad) < 2e-4, k
+
+
 # ------------------------------------------------------------------ TransitionModel.forward
 @pytest.mark.parametrize("name", ["transition_c1", "transition_odd"])
 def test_transition_vs_reference_fixture(name):
