@@ -58,6 +58,18 @@ struct ProfScope {
   ~ProfScope() { prof_end(k, s); }
 };
 
+// Packed fp32 FMA (sm_100 FFMA2): {d0, d1} += a * {b0, b1}, each lane rounded exactly like fmaf.
+// Scalar FFMA issues every other cycle per scheduler (64 FMA/clk/SM); the packed form is the
+// only way to the SM's 128 FMA/clk, and takes the row operand as a broadcast scalar.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  uint64_t d, av, bv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(av), "l"(bv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // ---------------------------------------------------------------- activations
 // torch semantics: ELU(alpha=1) uses expm1; softplus(beta=1, threshold=20).
 __device__ __forceinline__ float act_fwd(int act, float x) {

@@ -119,9 +119,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
       float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
       float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) {     // packed FFMA2: twice the issue rate of scalar FFMA on sm_100
+        ffma2(acc[i][0], acc[i][1], a[i], b[0], b[1]);
+        ffma2(acc[i][2], acc[i][3], a[i], b[2], b[3]);
+      }
     }
     if (more) {
       store_tile(buf ^ 1);
@@ -220,8 +221,8 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
     for (int k = 0; k < kc; ++k) {
       const float a = As[k][m];
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][ng * 4]);
-      acc[0] = fmaf(a, b4.x, acc[0]); acc[1] = fmaf(a, b4.y, acc[1]);
-      acc[2] = fmaf(a, b4.z, acc[2]); acc[3] = fmaf(a, b4.w, acc[3]);
+      ffma2(acc[0], acc[1], a, b4.x, b4.y);
+      ffma2(acc[2], acc[3], a, b4.z, b4.w);
     }
     __syncthreads();
   }

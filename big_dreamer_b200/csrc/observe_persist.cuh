@@ -182,17 +182,6 @@ __device__ __forceinline__ void load_w_small(const Ctx& c, const OpDesc& d) {
   for (int p = c.tid; p < d.K * 16; p += kThreads) cp_async16(c.Ws + p * 4, src + p * 4);
 }
 
-// Packed fp32 FMA (sm_100 FFMA2): {d0, d1} += a * {b0, b1}, each lane rounded exactly like fmaf.
-// Scalar FFMA issues every other cycle per scheduler (64 FMA/clk/SM); the packed form is the
-// only way to the SM's 128 FMA/clk, and takes the row operand as a broadcast scalar.
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
-  uint64_t d, av, bv;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(av), "l"(bv));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
-}
 // Software-pipelined: the operands of k-row k + KG are requested before the FMAs of k-row k (the
 // plain loop left the 4 LDS.128 -> 64 FFMA dependency exposed every iteration: with two warps per
 // scheduler and the LDS pipe as busy as the FMA pipe it ran at half the issue rate).
