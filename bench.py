@@ -263,8 +263,9 @@ def observe_block(bd, orc, pu, dev, precision):
     ms = e0.elapsed_time(e1) / reps
     return {"metric": "observe_row_steps_per_sec", "value": L * B / (ms * 1e-3), "unit": "row-steps/s",
             "ms_per_pass": ms, "config": dict(OBS_CFG, belief_size=d["Be"], state_size=d["S"]),
-            "precision": "fp32 (persistent 16-CTA cluster kernels for the recurrence, packed FFMA2; observe mode has "
-                         "no 16-bit path yet)", "pass": "fwd+bwd, full wgrad"}
+            "precision": ("fp32 everywhere (persistent 16-CTA cluster kernels, packed FFMA2)" if precision == "fp32" else
+                          "fp32 state and small layers; the two big contractions of the persistent cluster kernels on "
+                          "TF32 mma.sync"), "pass": "fwd+bwd, full wgrad"}
 
 
 def value_update_block(bd, orc, pu, dev, precision, rows, T):

@@ -199,13 +199,13 @@ int bd_transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes
   if (a->B > 0 && tc::transition_supported(*a, precision) && a->init_state && a->init_belief &&
       a->actions && a->eps_prior && a->beliefs && a->prior_states && a->prior_means && a->prior_stds)
     return tc::transition_forward(a, ws, ws_bytes, precision, stream);
-  return f32::transition_forward(a, ws, ws_bytes, stream);
+  return f32::transition_forward(a, ws, ws_bytes, stream, precision);
 }
 int bd_transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, int precision,
                            bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
-  return f32::transition_backward(a, ws, ws_bytes, stream);
+  return f32::transition_backward(a, ws, ws_bytes, stream, precision);
 }
 
 size_t bd_imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N,

@@ -471,7 +471,7 @@ static int obs_prof_flag() {
   return v;
 }
 struct PersistOps { obs::OpDesc d[obs::OP_COUNT]; };
-static PersistOps persist_ops(const bd_rssm& r) {
+static PersistOps persist_ops(const bd_rssm& r, bool tc = false) {
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
   const int Bep = (Be + 3) & ~3;
   PersistOps o;
@@ -483,6 +483,10 @@ static PersistOps persist_ops(const bd_rssm& r) {
   o.d[obs::OP_B2] = obs::make_op(Hi, (Be + 3) / 4);
   o.d[obs::OP_B3] = obs::make_op(4 * Be, 2 * Bep / 4);
   o.d[obs::OP_B4] = obs::make_op(Be, (S + A + 3) / 4);
+  if (tc && (Be & 3) == 0) {      // TF32 mma.sync for the two big contractions (K % 8 == 0, 32 or 64 slots)
+    for (int i : {(int)obs::OP_GRU, (int)obs::OP_B3})
+      if (o.d[i].WP == 8 || o.d[i].WP == 16) { o.d[i].tc = 1; o.d[i].KG = 4; }
+  }
   return o;
 }
 static size_t persist_ws_bytes(const bd_rssm& r, int L, int64_t B, bool backward) {
@@ -563,7 +567,7 @@ static int persist_pack(const bd_rssm& r, PersistOps& o, int first, int count, A
   return BD_OK;
 }
 
-static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t ws_bytes, bool tc, cudaStream_t s) {
   const bd_rssm& r = a->rssm;
   const long long Be = r.belief_size, Sz = r.state_size, E = r.embedding_size, Hi = r.hidden_size, B = a->B;
   const size_t n = (size_t)a->L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
@@ -571,7 +575,7 @@ static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t
   float* PE = ar.f32(n * Hi);
   float* h = ar.f32(n * Hi);
   float* pre = ar.f32(n * 2 * Sz);
-  PersistOps o = persist_ops(r);
+  PersistOps o = persist_ops(r, tc);
   BD_TRY(persist_pack(r, o, obs::OP_EMB, 4, ar, s));
   float* scratch = ar.f32(nch * obs::fwd_scratch_floats((int)Be, (int)Hi));
   if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "observe forward (persistent): workspace too small");
@@ -602,7 +606,7 @@ static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t
   return BD_OK;
 }
 
-static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, cudaStream_t s) {
+static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes, bool tc, cudaStream_t s) {
   const bd_transition_args& f = a->fwd;
   const bd_rssm& r = f.rssm;
   const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size,
@@ -620,7 +624,7 @@ static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, s
   float* pre = ar.f32(n * 2 * Sz);
   float* preq = ar.f32(n * 2 * Sz);
   float* Gtot = ar.f32(n * Be);
-  PersistOps o = persist_ops(r);
+  PersistOps o = persist_ops(r, tc);
   BD_TRY(persist_pack(r, o, obs::OP_B1, 4, ar, s));
   float* scratch = ar.f32(nch * obs::bwd_scratch_floats((int)Be, (int)Hi, (int)Sz));
   if (!ar.ok()) BD_FAIL(BD_ERR_WORKSPACE, "observe backward (persistent): workspace too small");
@@ -691,7 +695,7 @@ static int check_transition(const bd_transition_args& a) {
   return BD_OK;
 }
 
-int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream) {
+int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream, int precision) {
   BD_TRY(check_transition(*a));
   if (a->B == 0) return BD_OK;
   const bd_rssm& r = a->rssm;
@@ -699,7 +703,7 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, b
   const long long Be = r.belief_size, Sz = r.state_size, A = r.action_size, E = r.embedding_size, B = a->B;
   if (observe && persist_shape_ok(r, a->L, B) && ws_bytes >= persist_ws_bytes(r, a->L, B, false) &&
       persist_launchable(obs::observe_fwd_kernel))
-    return observe_forward_persist(a, ws, ws_bytes, S(stream));
+    return observe_forward_persist(a, ws, ws_bytes, precision != BD_PREC_FP32, S(stream));
   int chunk;
   BD_TRY(chunk_rows_for(ws_bytes, step_row_floats(r, observe, false), B, &chunk));
   for (long long r0 = 0; r0 < B; r0 += chunk) {
@@ -726,7 +730,7 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, b
 }
 
 int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes,
-                        bd_stream_t stream) {
+                        bd_stream_t stream, int precision) {
   const bd_transition_args& f = a->fwd;
   BD_TRY(check_transition(f));
   if (f.B == 0) return BD_OK;
@@ -737,7 +741,7 @@ int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_byt
   const long long Hi = r.hidden_size;
   if (observe && persist_shape_ok(r, f.L, B) && ws_bytes >= persist_ws_bytes(r, f.L, B, true) &&
       persist_launchable(obs::observe_bwd_kernel))
-    return observe_backward_persist(a, ws, ws_bytes, s);
+    return observe_backward_persist(a, ws, ws_bytes, precision != BD_PREC_FP32, s);
   const bd_rssm_grads& G = a->grads;
   const bool any_wgrad = G.embed_w || G.embed_b || G.w_ih || G.w_hh || G.b_ih || G.b_hh || G.prior1_w ||
                          G.prior1_b || G.prior2_w || G.prior2_b || G.post1_w || G.post1_b || G.post2_w ||

@@ -27,9 +27,10 @@ int kl_loss_backward(const float* post_mean, const float* post_std, const float*
                      const float* div, const float* loss, const float* g_loss, float* d_post_mean,
                      float* d_post_std, float* d_prior_mean, float* d_prior_std, bd_stream_t stream);
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward);
-int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
+int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
+                       int precision = BD_PREC_FP32);
 int transition_backward(const bd_transition_bwd_args* a, void* ws, size_t ws_bytes,
-                        bd_stream_t stream);
+                        bd_stream_t stream, int precision = BD_PREC_FP32);
 size_t imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int64_t N, int backward);
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);
 int imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, bd_stream_t stream);

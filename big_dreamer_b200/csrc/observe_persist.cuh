@@ -47,9 +47,11 @@ constexpr int kKC = 64;         // k rows per ring stage
 constexpr int kNS = 4;          // ring stages
 constexpr int kThreads = 256;
 constexpr int kRowFloats = 64;  // floats per k row of an A block (64 rows) and of a W image (16 x 4)
-constexpr int kStageFloats = kKC * kRowFloats;
+constexpr int kLds = 72;        // floats between k rows in SHARED memory: 64 + 8 keeps the mma.sync fragment loads
+                                // (4 k rows x 8 columns per instruction) on 32 different banks
+constexpr int kStageFloats = kKC * kLds;
 constexpr int kRedFloats = 64 * 64 * 4;   // k-group partial sums: (KG * WP) x 64 rows x 4 slots, KG * WP <= 64
-constexpr int kSmemBytes = (2 * kNS * kStageFloats + kRedFloats) * (int)sizeof(float);   // 196 608
+constexpr int kSmemBytes = (2 * kNS * kStageFloats + kRedFloats) * (int)sizeof(float);   // 212 992
 constexpr int kMaxSmallK = kNS * kKC;   // in-place operands (embed input, d_preq) fit the A ring
 
 enum OpId { OP_EMB = 0, OP_GRU, OP_Q1F, OP_Q2F, OP_B1, OP_B2, OP_B3, OP_B4, OP_COUNT };
@@ -59,6 +61,7 @@ struct OpDesc {
   int K, NJ;        // contraction length, slot groups over the whole cluster
   int Wc, WP;       // slot groups per CTA, rounded up to a power of two
   int TS, KG, tgs;  // slots per compute thread (4 | 8), k-groups, log2(threads per k-group)
+  int tc;           // 1: TF32 mma.sync contraction (16-bit precision modes, WP = 8 | 16, K % 8 == 0; KG = 4)
 };
 inline OpDesc make_op(int K, int NJ) {
   OpDesc d{};
@@ -161,7 +164,7 @@ __device__ __forceinline__ void issue_w(const Ctx& c, const OpDesc& d, int chunk
   const int k0 = chunk * kKC, nrows = min(kKC, d.K - k0);
   const float* src = d.w + ((size_t)c.crank * d.K + k0) * kRowFloats;
   float* dst = c.Ws + (chunk % kNS) * kStageFloats;
-  for (int p = c.tid; p < nrows * 16; p += kThreads) cp_async16(dst + p * 4, src + p * 4);
+  for (int p = c.tid; p < nrows * 16; p += kThreads) cp_async16(dst + (p >> 4) * kLds + (p & 15) * 4, src + p * 4);
 }
 __device__ __forceinline__ void issue_a(const Ctx& c, const OpDesc& d, const Segs& s, int chunk) {
   const int k0 = chunk * kKC, nrows = min(kKC, d.K - k0);
@@ -169,7 +172,7 @@ __device__ __forceinline__ void issue_a(const Ctx& c, const OpDesc& d, const Seg
   for (int p = c.tid; p < nrows * 16; p += kThreads) {
     const int k = k0 + (p >> 4);
     const float* src = (k < s.K0 ? s.a0 + (size_t)k * kRowFloats : s.a1 + (size_t)(k - s.K0) * kRowFloats) + (p & 15) * 4;
-    cp_async16(dst + p * 4, src);
+    cp_async16(dst + (p >> 4) * kLds + (p & 15) * 4, src);
   }
 }
 // weights of the first ring stages: independent of the other CTAs, requested before the barrier wait
@@ -179,7 +182,7 @@ __device__ __forceinline__ void prefetch_w(const Ctx& c, const OpDesc& d) {
 }
 __device__ __forceinline__ void load_w_small(const Ctx& c, const OpDesc& d) {
   const float* src = d.w + (size_t)c.crank * d.K * kRowFloats;
-  for (int p = c.tid; p < d.K * 16; p += kThreads) cp_async16(c.Ws + p * 4, src + p * 4);
+  for (int p = c.tid; p < d.K * 16; p += kThreads) cp_async16(c.Ws + (p >> 4) * kLds + (p & 15) * 4, src + p * 4);
 }
 
 // Software-pipelined: the operands of k-row k + KG are requested before the FMAs of k-row k (the
@@ -190,20 +193,20 @@ __device__ __forceinline__ void fma_rows(const float* __restrict__ ap, const flo
                                          int nrows, int kg, int KG, float (&acc)[8][8]) {
   int k = kg;
   if (k >= nrows) return;
-  float4 a0 = *reinterpret_cast<const float4*>(ap + k * kRowFloats);
-  float4 a1 = *reinterpret_cast<const float4*>(ap + k * kRowFloats + 32);
-  float4 b0 = *reinterpret_cast<const float4*>(bp + k * kRowFloats);
+  float4 a0 = *reinterpret_cast<const float4*>(ap + k * kLds);
+  float4 a1 = *reinterpret_cast<const float4*>(ap + k * kLds + 32);
+  float4 b0 = *reinterpret_cast<const float4*>(bp + k * kLds);
   float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (TS == 8) b1 = *reinterpret_cast<const float4*>(bp + k * kRowFloats + 4);
+  if (TS == 8) b1 = *reinterpret_cast<const float4*>(bp + k * kLds + 4);
   for (;;) {
     const int kn = k + KG;
     const bool more = kn < nrows;
     const int kl = more ? kn : k;                 // clamped: the loads are always issued
-    const float4 na0 = *reinterpret_cast<const float4*>(ap + kl * kRowFloats);
-    const float4 na1 = *reinterpret_cast<const float4*>(ap + kl * kRowFloats + 32);
-    const float4 nb0 = *reinterpret_cast<const float4*>(bp + kl * kRowFloats);
+    const float4 na0 = *reinterpret_cast<const float4*>(ap + kl * kLds);
+    const float4 na1 = *reinterpret_cast<const float4*>(ap + kl * kLds + 32);
+    const float4 nb0 = *reinterpret_cast<const float4*>(bp + kl * kLds);
     float4 nb1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (TS == 8) nb1 = *reinterpret_cast<const float4*>(bp + kl * kRowFloats + 4);
+    if (TS == 8) nb1 = *reinterpret_cast<const float4*>(bp + kl * kLds + 4);
     const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
     const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -214,6 +217,88 @@ __device__ __forceinline__ void fma_rows(const float* __restrict__ ap, const flo
     a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
     k = kn;
   }
+}
+
+// ---- TF32 tensor-core variant of the contraction (precision modes other than fp32) ----------------
+// Legacy mma.sync m16n8k8 issues every 8 cycles per scheduler on sm_100a = 512 MAC/clk/SM, 4x the packed
+// FFMA2 rate (scripts/mma_tf32_bench.cu); the operands stay the fp32 blocks of the fp32 path (rounded to
+// TF32 with cvt.rna at fragment load), so nothing else changes.  Warp (kg, half): k-group kg takes every
+// fourth k8 step, `half` selects the lower / upper half of the CTA's slots; 4 m tiles x NT n tiles.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+template <int NT>
+__device__ __forceinline__ void mma_rows(const float* __restrict__ As, const float* __restrict__ Ws, int nrows,
+                                         int kg, int n0, int lane, int nvalid, float (&acc)[4][NT][4]) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int k0 = kg * 8; k0 < nrows; k0 += 32) {
+    uint32_t af[4][4], bf[NT][2];
+    const float* ab = As + (k0 + t) * kLds + g;
+    const float* bb = Ws + (k0 + t) * kLds + n0 + g;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      af[mt][0] = to_tf32(ab[16 * mt]);
+      af[mt][1] = to_tf32(ab[16 * mt + 8]);
+      af[mt][2] = to_tf32(ab[4 * kLds + 16 * mt]);
+      af[mt][3] = to_tf32(ab[4 * kLds + 16 * mt + 8]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      bf[nt][0] = to_tf32(bb[8 * nt]);
+      bf[nt][1] = to_tf32(bb[4 * kLds + 8 * nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      if (16 * mt < nvalid) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                       : "r"(af[mt][0]), "r"(af[mt][1]), "r"(af[mt][2]), "r"(af[mt][3]), "r"(bf[nt][0]), "r"(bf[nt][1]));
+      }
+    }
+  }
+}
+// streamed contraction on mma.sync; same contract as op_compute<false> (partials in c.red, KG = 4)
+template <int NT>
+__device__ __forceinline__ void op_compute_tc(const Ctx& c, const OpDesc& d, const Segs& s) {
+  float acc[4][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  const int warp = c.tid >> 5, lane = c.tid & 31;
+  const int kg = warp >> 1, n0 = (warp & 1) * 8 * NT;
+  const int nch = (d.K + kKC - 1) / kKC;
+  for (int st = 0; st < kNS - 1; ++st) {
+    if (st < nch) issue_a(c, d, s, st);
+    cp_async_commit();
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_async_wait<kNS - 2>();
+    __syncthreads();
+    const int nxt = ch + kNS - 1;
+    if (nxt < nch) { issue_w(c, d, nxt); issue_a(c, d, s, nxt); }
+    cp_async_commit();
+    mma_rows<NT>(c.As + (ch % kNS) * kStageFloats, c.Ws + (ch % kNS) * kStageFloats, min(kKC, d.K - ch * kKC), kg,
+                 n0, lane, c.nvalid, acc);
+  }
+  cp_async_wait<0>();
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int slot = n0 + 8 * nt + 2 * t;
+      float* r0p = c.red + ((size_t)((kg * d.WP + (slot >> 2)) * kR + 16 * mt + g)) * 4 + (slot & 3);
+      *reinterpret_cast<float2*>(r0p) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(r0p + 8 * 4) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+  __syncthreads();
 }
 
 // One contraction of the CTA's column slice: leaves the k-group partial sums in c.red
@@ -374,13 +459,13 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
     float ntr = 1.f;
     if (a.nonterm && rme < nvalid) ntr = a.nonterm[trow + rme];
     for (int i = S * kR + c.tid; i < SA * kR; i += kThreads)
-      c.As[i] = rme < nvalid ? a.actions[(trow + rme) * Ad + ((i >> 6) - S)] : 0.f;
+      c.As[(i >> 6) * kLds + rme] = rme < nvalid ? a.actions[(trow + rme) * Ad + ((i >> 6) - S)] : 0.f;
     cluster_wait();
     OBS_T(1);
     {
       const float* sp = t == 0 ? a.init_state + row0 * S : a.post_s + ((long long)(t - 1) * B + row0) * S;
       for (int i = c.tid; i < S * kR; i += kThreads)
-        c.As[i] = rme < nvalid ? __ldcg(sp + (long long)rme * S + (i >> 6)) * ntr : 0.f;
+        c.As[(i >> 6) * kLds + rme] = rme < nvalid ? __ldcg(sp + (long long)rme * S + (i >> 6)) * ntr : 0.f;
     }
     op_compute<true>(c, a.emb, Segs{});
     OBS_T(2);
@@ -414,7 +499,12 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
     }
     cluster_wait();
     OBS_T(1);
-    op_compute<false>(c, a.gru, Segs{xT, Be, hprevT});
+    if (a.gru.tc) {
+      if (a.gru.WP == 16) op_compute_tc<4>(c, a.gru, Segs{xT, Be, hprevT});
+      else op_compute_tc<2>(c, a.gru, Segs{xT, Be, hprevT});
+    } else {
+      op_compute<false>(c, a.gru, Segs{xT, Be, hprevT});
+    }
     OBS_T(2);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -535,8 +625,8 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
       const float gsb = a.g_post_s ? a.g_post_s[o] : 0.f;
       const float eps = a.eps_post[o];
       const float spg = softplus_gradf_(a.preq[(trow + rl) * 2 * S + S + j]);
-      c.As[e] = gsb + (a.g_post_m ? a.g_post_m[o] : 0.f);
-      c.As[S * kR + e] = (gsb * eps + (a.g_post_sd ? a.g_post_sd[o] : 0.f)) * spg;
+      c.As[j * kLds + r] = gsb + (a.g_post_m ? a.g_post_m[o] : 0.f);
+      c.As[(S + j) * kLds + r] = (gsb * eps + (a.g_post_sd ? a.g_post_sd[o] : 0.f)) * spg;
       c.red[e] = eps * spg;
     }
     cluster_wait();
@@ -544,10 +634,10 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
     for (int e = c.tid; e < S * kR; e += kThreads) {
       const int j = e >> 6, r = e & 63;
       const float cs = first ? 0.f : __ldcg(csT + e);
-      const float dm = r < nvalid ? c.As[e] + cs : 0.f;
-      const float draw = r < nvalid ? c.As[S * kR + e] + cs * c.red[e] : 0.f;
-      c.As[e] = dm;
-      c.As[S * kR + e] = draw;
+      const float dm = r < nvalid ? c.As[j * kLds + r] + cs : 0.f;
+      const float draw = r < nvalid ? c.As[(S + j) * kLds + r] + cs * c.red[e] : 0.f;
+      c.As[j * kLds + r] = dm;
+      c.As[(S + j) * kLds + r] = draw;
       if (c.crank == 0 && r < nvalid) {
         a.tdpreq[(trow + r) * 2 * S + j] = dm;
         a.tdpreq[(trow + r) * 2 * S + S + j] = draw;
@@ -643,7 +733,12 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
     prefetch_w(c, a.b3);
     cluster_wait();
     OBS_T(1);
-    op_compute<false>(c, a.b3, Segs{planesT, 4 * Be, nullptr});
+    if (a.b3.tc) {
+      if (a.b3.WP == 16) op_compute_tc<4>(c, a.b3, Segs{planesT, 4 * Be, nullptr});
+      else op_compute_tc<2>(c, a.b3, Segs{planesT, 4 * Be, nullptr});
+    } else {
+      op_compute<false>(c, a.b3, Segs{planesT, 4 * Be, nullptr});
+    }
     OBS_T(2);
     for (int it = c.tid; it < kR * a.b3.WP; it += kThreads) {
       if (item_of(c, a.b3, it, &row, &js, &jg)) {

@@ -207,3 +207,22 @@ def test_16bit_mode_falls_back_to_fp32_kernels_when_tiles_do_not_fit(d):
     res = pu.run_imagine_case(d, seed=2, precision="fp16", oracle_dtype=torch.float64)
     for k, e in res["errors"].items():
         assert e < TOL, (d, res["errors"])
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("d,L,B", [
+    (dict(Be=200, Hi=200, S=30, A=1, E=1024, act="ELU"), 49, 50),     # BASELINE configs[3]
+    (dict(Be=200, Hi=200, S=30, A=6, E=64, act="ELU"), 5, 130),       # 3 clusters, ragged last chunk
+    (dict(Be=128, Hi=96, S=20, A=2, E=48, act="Tanh"), 9, 40),        # WP = 8 / 8 slot tiles
+])
+def test_observe_tensor_core_modes(d, L, B, prec):
+    """Observe pass in the 16-bit precision modes: the two big contractions of the persistent cluster
+    kernels (GRU forward, GRU dgrad) run on TF32 mma.sync, everything else stays fp32.  Outputs, input
+    gradients and parameter gradients against the fp32 oracle within the north_star bound for
+    reduced-precision MMAs (max rel err <= 1e-2)."""
+    from tests.test_gpu_parity_fp32 import _observe_case
+    bd.set_precision(prec)
+    errs = _observe_case(d, L, B, seed=3)
+    print(prec, {k: f"{v:.1e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
