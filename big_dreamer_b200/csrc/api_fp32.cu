@@ -1060,7 +1060,9 @@ int cem_refit(const float* returns, const float* actions, int B, int C, int K, i
               int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream) {
   BD_CHECK_ARG(B >= 1 && C >= 1 && K >= 1 && K <= C && H >= 1 && A >= 1, "cem_refit: bad sizes");
   BD_CHECK_ARG(returns && actions && action_mean && action_std, "cem_refit: null pointer");
-  size_t smem = (size_t)C * (sizeof(float) + sizeof(int)) + (size_t)K * sizeof(int);
+  size_t P = 1;
+  while (P < (size_t)C) P <<= 1;
+  size_t smem = P * sizeof(unsigned long long) + (size_t)C * sizeof(int) + (size_t)K * sizeof(int);
   BD_CHECK_ARG(smem <= 200 * 1024, "cem_refit: candidates=%d too large for one CTA", C);
   static bool attr_set = false;
   if (!attr_set) {
