@@ -984,7 +984,7 @@ size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_
 }
 
 int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
-                 int precision) {
+                 int precision, bool weights_packed) {
   const bd_rssm& r = a->rssm;
   BD_TRY(check_rssm(r, false));
   BD_TRY(check_mlp(a->reward, r.belief_size + r.state_size));
@@ -1006,7 +1006,7 @@ int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream
     cem_sample_kernel<<<grid1d((long long)H * rows * A), 256, 0, s>>>(
         a->action_mean, a->action_std, a->eps_act, H, B, C, a->c_begin, Cl, A, a->actions);
     BD_CUDA_LAUNCH_CHECK();
-    BD_TRY(tc::cem_rollout(a, ar.base + ar.off, ar.cap - ar.off, precision, rew, stream));
+    BD_TRY(tc::cem_rollout(a, ar.base + ar.off, ar.cap - ar.off, precision, rew, stream, weights_packed));
     cem_sum_rewards_kernel<<<grid1d(rows), 256, 0, s>>>(rew, H, rows, a->returns);
     BD_CUDA_LAUNCH_CHECK();
     return BD_OK;
@@ -1113,7 +1113,8 @@ int cem_plan(const bd_cem_plan_args* a, void* ws, size_t ws_bytes, bd_stream_t s
     e.eps_act = a->eps_act + (long long)it * H * B * C * A;
     e.eps_s = a->eps_s + (long long)it * H * B * C * r.state_size;
     e.actions = actions; e.returns = returns;
-    BD_TRY(cem_evaluate(&e, sub, sub_bytes, stream, precision));
+    // the weights do not change inside a plan: their 16-bit images are packed by the first iteration only
+    BD_TRY(cem_evaluate(&e, sub, sub_bytes, stream, precision, it > 0));
     if (a->returns_trace)
       cudaMemcpyAsync(a->returns_trace + (long long)it * B * C, returns, (size_t)B * C * sizeof(float),
                       cudaMemcpyDeviceToDevice, s);

@@ -38,7 +38,7 @@ int imagine_backward_ex(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
                         float* d_raw_all);
 size_t cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H);
 int cem_evaluate(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
-                 int precision = BD_PREC_FP32);
+                 int precision = BD_PREC_FP32, bool weights_packed = false);
 int cem_refit(const float* returns, const float* actions, int B, int C, int K, int H, int A,
               int64_t* topk_idx, float* action_mean, float* action_std, bd_stream_t stream);
 size_t cem_plan_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C, int K, int H);
@@ -61,7 +61,7 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, i
 bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision);
 size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long rows, int H);
 int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,
-                bd_stream_t stream);
+                bd_stream_t stream, bool weights_packed = false);
 bool mlp_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_pack_bytes(const bd_mlp& m);
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,

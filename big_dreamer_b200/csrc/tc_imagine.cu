@@ -346,7 +346,7 @@ size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long 
 // head is fused into every step, only the per-step rewards leave the SM (plus the fp32 belief).
 // a->actions must already hold the sampled local actions (H, B, Cl, A).
 int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,
-                bd_stream_t stream) {
+                bd_stream_t stream, bool weights_packed) {
   const bd_rssm& r = a->rssm;
   const bd_mlp& hd = a->reward;
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
@@ -424,9 +424,11 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
   const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
-  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
-  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
-  BD_CUDA_LAUNCH_CHECK();
+  if (!weights_packed) {     // bd_cem_plan: iterations after the first reuse the images at `wpack`
+    if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    BD_CUDA_LAUNCH_CHECK();
+  }
   ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
   return launch_rollout(fmt, r.activation, false, false, grid, ra, s);
 }

@@ -416,3 +416,29 @@ def test_cem_refit_exact_on_reference_returns():
         best = actions[:, torch.arange(B)[:, None], t["topk"]]            # (H,B,K,A)
         assert pu.relerr(mean, best.mean(2)) < 1e-5
         assert pu.relerr(std, best.std(2, unbiased=False)) < 1e-5
+
+
+def test_cem_refit_sizes_and_ties():
+    """Elite selection kernel (bitonic sort of (value, index) keys) on candidate counts that are not powers
+    of two, above one element per thread, with many exact ties and signed zeros: identical elite SETS to a
+    stable descending sort (value desc, index asc = torch.topk's tie order on CPU for these inputs)."""
+    import ctypes as C
+    from big_dreamer_b200 import _lib
+    lib = bd.load_library()
+    g = torch.Generator().manual_seed(5)
+    for B, Cn, K, H, A in ((3, 1500, 37, 4, 2), (2, 2048, 2048, 2, 1), (1, 7, 3, 3, 1), (2, 3000, 100, 2, 3)):
+        ret = torch.randn(B, Cn, generator=g)
+        ret[:, ::3] = torch.round(ret[:, ::3] * 2) / 2          # many exact ties
+        ret[0, :4] = torch.tensor([0.0, -0.0, 0.0, -0.0])[:min(4, Cn)]
+        actions = torch.randn(H, B, Cn, A, generator=g)
+        order = torch.sort(ret.double() + 0.0, dim=1, descending=True, stable=True)[1][:, :K]
+        want = torch.sort(order, dim=1)[0]
+        idx = torch.empty(B, K, dtype=torch.int64, device="cuda")
+        mean, std = torch.empty(H, B, A, device="cuda"), torch.empty(H, B, A, device="cuda")
+        rc, ac = ret.cuda(), actions.cuda()
+        _lib.check(lib.bd_cem_refit(rc.data_ptr(), ac.data_ptr(), B, Cn, K, H, A, idx.data_ptr(),
+                                    mean.data_ptr(), std.data_ptr(), _lib.stream_ptr()), "refit")
+        assert torch.equal(idx.cpu(), want), (B, Cn, K)
+        best = actions[:, torch.arange(B)[:, None], want]                 # (H,B,K,A)
+        assert pu.relerr(mean, best.mean(2)) < 1e-5
+        assert float((std.cpu() - best.std(2, unbiased=False)).abs().max()) < 1e-5
