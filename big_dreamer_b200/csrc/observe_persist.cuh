@@ -464,8 +464,17 @@ __global__ void __launch_bounds__(kThreads, 1) observe_fwd_kernel(const __grid_c
     OBS_T(1);
     {
       const float* sp = t == 0 ? a.init_state + row0 * S : a.post_s + ((long long)(t - 1) * B + row0) * S;
-      for (int i = c.tid; i < S * kR; i += kThreads)
-        c.As[(i >> 6) * kLds + rme] = rme < nvalid ? __ldcg(sp + (long long)rme * S + (i >> 6)) * ntr : 0.f;
+      const int rl = min(rme, nvalid - 1);
+      for (int i0 = c.tid; i0 < S * kR; i0 += 8 * kThreads) {     // eight independent loads in flight
+        float sv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sv[q] = __ldcg(sp + (long long)rl * S + min((i0 >> 6) + 4 * q, S - 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int k = (i0 >> 6) + 4 * q;
+          if (k < S) c.As[k * kLds + rme] = rme < nvalid ? sv[q] * ntr : 0.f;
+        }
+      }
     }
     op_compute<true>(c, a.emb, Segs{});
     OBS_T(2);
@@ -618,29 +627,54 @@ __global__ void __launch_bounds__(kThreads, 1) observe_bwd_kernel(const __grid_c
     // in-place operand d_preq^T: everything but the carried state gradient is known before the
     // barrier.  dm = P0 + cs, draw = P1 + cs * Q with P0, P1 parked in the A ring and Q in `red`
     // (both free here; every thread revisits only its own elements)
-    for (int e = c.tid; e < S * kR; e += kThreads) {
-      const int j = e >> 6, r = e & 63;
-      const int rl = min(r, nvalid - 1);
-      const long long o = (trow + rl) * S + j;
-      const float gsb = a.g_post_s ? a.g_post_s[o] : 0.f;
-      const float eps = a.eps_post[o];
-      const float spg = softplus_gradf_(a.preq[(trow + rl) * 2 * S + S + j]);
-      c.As[j * kLds + r] = gsb + (a.g_post_m ? a.g_post_m[o] : 0.f);
-      c.As[(S + j) * kLds + r] = (gsb * eps + (a.g_post_sd ? a.g_post_sd[o] : 0.f)) * spg;
-      c.red[e] = eps * spg;
+    // (loads of eight elements are issued together: one loop iteration per element left an L2 round
+    // trip per iteration exposed -- 7.7 K cycles for 7.5 elements per thread)
+    const int nel = S * kR;
+    for (int e0 = c.tid; e0 < nel; e0 += 8 * kThreads) {
+      float gs_[8], gm_[8], gd_[8], ep_[8], pq_[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = min(e0 + q * kThreads, nel - 1);
+        const int j = e >> 6, rl = min(e & 63, nvalid - 1);
+        const long long o = (trow + rl) * S + j;
+        gs_[q] = a.g_post_s ? a.g_post_s[o] : 0.f;
+        gm_[q] = a.g_post_m ? a.g_post_m[o] : 0.f;
+        gd_[q] = a.g_post_sd ? a.g_post_sd[o] : 0.f;
+        ep_[q] = a.eps_post[o];
+        pq_[q] = a.preq[(trow + rl) * 2 * S + S + j];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + q * kThreads;
+        if (e < nel) {
+          const int j = e >> 6, r = e & 63;
+          const float spg = softplus_gradf_(pq_[q]);
+          c.As[j * kLds + r] = gs_[q] + gm_[q];
+          c.As[(S + j) * kLds + r] = (gs_[q] * ep_[q] + gd_[q]) * spg;
+          c.red[e] = ep_[q] * spg;
+        }
+      }
     }
     cluster_wait();
     OBS_T(1);
-    for (int e = c.tid; e < S * kR; e += kThreads) {
-      const int j = e >> 6, r = e & 63;
-      const float cs = first ? 0.f : __ldcg(csT + e);
-      const float dm = r < nvalid ? c.As[j * kLds + r] + cs : 0.f;
-      const float draw = r < nvalid ? c.As[(S + j) * kLds + r] + cs * c.red[e] : 0.f;
-      c.As[j * kLds + r] = dm;
-      c.As[(S + j) * kLds + r] = draw;
-      if (c.crank == 0 && r < nvalid) {
-        a.tdpreq[(trow + r) * 2 * S + j] = dm;
-        a.tdpreq[(trow + r) * 2 * S + S + j] = draw;
+    for (int e0 = c.tid; e0 < nel; e0 += 8 * kThreads) {
+      float cs_[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cs_[q] = first ? 0.f : __ldcg(csT + min(e0 + q * kThreads, nel - 1));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int e = e0 + q * kThreads;
+        if (e < nel) {
+          const int j = e >> 6, r = e & 63;
+          const float dm = r < nvalid ? c.As[j * kLds + r] + cs_[q] : 0.f;
+          const float draw = r < nvalid ? c.As[(S + j) * kLds + r] + cs_[q] * c.red[e] : 0.f;
+          c.As[j * kLds + r] = dm;
+          c.As[(S + j) * kLds + r] = draw;
+          if (c.crank == 0 && r < nvalid) {
+            a.tdpreq[(trow + r) * 2 * S + j] = dm;
+            a.tdpreq[(trow + r) * 2 * S + S + j] = draw;
+          }
+        }
       }
     }
     op_compute<true>(c, a.b1, Segs{});
