@@ -571,6 +571,7 @@ static int observe_forward_persist(const bd_transition_args* a, void* ws, size_t
   const bd_rssm& r = a->rssm;
   const long long Be = r.belief_size, Sz = r.state_size, E = r.embedding_size, Hi = r.hidden_size, B = a->B;
   const size_t n = (size_t)a->L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
+  Tf32Scope tf32_gemms(tc);      // 16-bit modes: the batched GEMMs below on TF32 mma.sync
   Arena ar(ws, ws_bytes);
   float* PE = ar.f32(n * Hi);
   float* h = ar.f32(n * Hi);
@@ -614,6 +615,7 @@ static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, s
   const int L = f.L;
   const size_t n = (size_t)L * B, nch = (size_t)((B + obs::kR - 1) / obs::kR);
   const int ni = (int)n, nB = (int)B;
+  Tf32Scope tf32_gemms(tc);
   Arena ar(ws, ws_bytes);
   TimeBatch tb;
   tb.tx = ar.f32(n * Be); tb.th = ar.f32(n * Hi); tb.tdpre = ar.f32(n * 2 * Sz); tb.tdh = ar.f32(n * Hi);

@@ -70,6 +70,12 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, f
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
 // ---------------------------------------------------------------- activations
 // torch semantics: ELU(alpha=1) uses expm1; softplus(beta=1, threshold=20).
 __device__ __forceinline__ float act_fwd(int act, float x) {

@@ -35,12 +35,23 @@ struct GemmArgs {
   int ksplit = 1;   // EPI_ATOMIC: K range split over gridDim.z
 };
 
+// 16-bit precision modes: the time-batched GEMMs of the observe pass (all L*B rows at once) run the
+// same tiling on TF32 mma.sync (set around those calls by Tf32Scope, api_fp32.cu); check mode never sets it.
+inline bool& gemm_tf32_flag() { static thread_local bool f = false; return f; }
+struct Tf32Scope {
+  bool prev;
+  explicit Tf32Scope(bool on) : prev(gemm_tf32_flag()) { gemm_tf32_flag() = on; }
+  ~Tf32Scope() { gemm_tf32_flag() = prev; }
+};
+
 constexpr int BM = 64, BN = 64, BK = 16, GEMM_THREADS = 256;
 
-template <bool A_TRANS, bool B_TRANS, int EPI>
+template <bool A_TRANS, bool B_TRANS, int EPI, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
-  __shared__ float As[2][BK][BM + 4];
-  __shared__ float Bs[2][BK][BN + 4];
+  // row stride 72: float4 rows stay 16-byte aligned and the mma.sync fragment loads of the TF32 variant
+  // (4 k rows x 8 columns per instruction) fall on 32 different banks
+  __shared__ __align__(16) float As[2][BK][BM + 8];
+  __shared__ __align__(16) float Bs[2][BK][BN + 8];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int K = g.K1 + g.K2;
@@ -100,6 +111,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
   };
 
   const int tx = tid % 16, ty = tid / 16;
+  // TF32 variant: warp w owns m tile (w >> 1) and n tiles 4 (w & 1) .. + 3 of the 64 x 64 block
+  const int lane = tid & 31, wrp = tid >> 5, fg = lane >> 2, ft = lane & 3;
+  const int mt0 = (wrp >> 1) * 16, nt0 = (wrp & 1) * 32;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -113,15 +127,36 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
     const bool more = k0 + BK < kend;
     if (more) load_tile(k0 + BK);
+    if (TF32) {
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      for (int ks = 0; ks < BK; ks += 8) {
+        uint32_t af[4], bf[4][2];
+        af[0] = f32_to_tf32(As[buf][ks + ft][mt0 + fg]);
+        af[1] = f32_to_tf32(As[buf][ks + ft][mt0 + fg + 8]);
+        af[2] = f32_to_tf32(As[buf][ks + ft + 4][mt0 + fg]);
+        af[3] = f32_to_tf32(As[buf][ks + ft + 4][mt0 + fg + 8]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {     // packed FFMA2: twice the issue rate of scalar FFMA on sm_100
-        ffma2(acc[i][0], acc[i][1], a[i], b[0], b[1]);
-        ffma2(acc[i][2], acc[i][3], a[i], b[2], b[3]);
+        for (int nt = 0; nt < 4; ++nt) {
+          bf[nt][0] = f32_to_tf32(Bs[buf][ks + ft][nt0 + 8 * nt + fg]);
+          bf[nt][1] = f32_to_tf32(Bs[buf][ks + ft + 4][nt0 + 8 * nt + fg]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                       : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(bf[nt][0]), "r"(bf[nt][1]));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {     // packed FFMA2: twice the issue rate of scalar FFMA on sm_100
+          ffma2(acc[i][0], acc[i][1], a[i], b[0], b[1]);
+          ffma2(acc[i][2], acc[i][3], a[i], b[2], b[3]);
+        }
       }
     }
     if (more) {
@@ -133,12 +168,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) sgemm_kernel(GemmArgs g) {
 
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int gm = m0 + ty * 4 + i;
-    if (gm >= g.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
-      if (gn >= g.N) continue;
+      // FFMA: thread (ty, tx) owns rows 4 ty + i, columns 4 tx + j; TF32: acc[i][j] is element j of the
+      // C fragment of n tile i (rows fg / fg + 8, columns 2 ft / 2 ft + 1)
+      const int gm = TF32 ? m0 + mt0 + fg + (j >= 2 ? 8 : 0) : m0 + ty * 4 + i;
+      const int gn = TF32 ? n0 + nt0 + 8 * i + 2 * ft + (j & 1) : n0 + tx * 4 + j;
+      if (gm >= g.M || gn >= g.N) continue;
       float v = acc[i][j];
       float* c = g.C + (long long)gm * g.ldc + gn;
       if (EPI == EPI_BIAS_ACT) {
@@ -257,7 +293,8 @@ inline int launch_gemm(const GemmArgs& g, cudaStream_t s) {
     }
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, EPI == EPI_ATOMIC ? g.ksplit : 1);
-  sgemm_kernel<A_TRANS, B_TRANS, EPI><<<grid, GEMM_THREADS, 0, s>>>(g);
+  if (gemm_tf32_flag()) sgemm_kernel<A_TRANS, B_TRANS, EPI, true><<<grid, GEMM_THREADS, 0, s>>>(g);
+  else sgemm_kernel<A_TRANS, B_TRANS, EPI, false><<<grid, GEMM_THREADS, 0, s>>>(g);
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
 }
