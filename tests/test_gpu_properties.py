@@ -136,3 +136,35 @@ def test_captured_step_matches_eager(prec):
         assert torch.equal(out_g[0], out_e[0])
         for g, e in zip(out_g[1:], out_e[1:]):     # weight gradients end in fp32 atomics: order-dependent
             assert pu.relerr(g, e) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_observe_pass_is_deterministic(prec):
+    """The persistent cluster kernels exchange activations between 16 CTAs through L2 behind cluster
+    barriers; a missing ordering would show up as run-to-run differences.  Forward outputs and the input
+    gradients (no atomics on their path) must be bit-identical across repeated runs; 3 clusters, ragged."""
+    bd.set_precision(prec)
+    d = dict(Be=200, Hi=200, S=30, A=2, E=96, act="ELU")
+    trans = orc.make_models(7, d["Be"], d["S"], d["A"], d["Hi"], d["E"])[0]
+    tm = pu.build_gpu_models(d, trans).transition
+    g = torch.Generator().manual_seed(1)
+    L, B = 12, 150
+    s0 = (0.5 * torch.randn(B, d["S"], generator=g)).cuda()
+    b0 = torch.tanh(torch.randn(B, d["Be"], generator=g)).cuda()
+    actions = (torch.rand(L, B, d["A"], generator=g) * 2 - 1).cuda()
+    emb = torch.randn(L, B, d["E"], generator=g).cuda()
+    nt = (torch.rand(L, B, 1, generator=g) > 0.1).float().cuda()
+    noise = dict(eps_prior=torch.randn(L, B, d["S"], generator=g).cuda(),
+                 eps_post=torch.randn(L, B, d["S"], generator=g).cuda())
+
+    def run():
+        a = [s0.clone().requires_grad_(True), b0.clone().requires_grad_(True), emb.clone().requires_grad_(True)]
+        o = tm(a[0], actions, a[1], a[2], nt, noise=noise)
+        outs = [o[0], o[1], o[2][0], o[2][1], o[3], o[4][0], o[4][1]]
+        sum(t.square().mean() for t in outs).backward()
+        return [t.detach().clone() for t in outs] + [a[0].grad.clone(), a[1].grad.clone()]
+
+    ref = run()
+    for _ in range(4):
+        for x, y in zip(run(), ref):
+            assert torch.equal(x, y)
