@@ -19,7 +19,9 @@
 // tile only needs 64 such threads, so the k rows of every ring stage are dealt round-robin to 4-32
 // groups of threads ("k-groups") whose partial sums meet in shared memory; the epilogue then runs
 // one (row, slot group) item per thread over all 256 threads, with its constant inputs requested
-// before the cluster barrier.
+// before the cluster barrier.  In the 16-bit precision modes the two big contractions (P2, Q3) run on
+// TF32 mma.sync m16n8k8 over the same shared-memory blocks (op_compute_tc: 4x the FFMA2 rate measured
+// on B200; everything else, including all state, stays fp32).
 //
 // What is hoisted out of the recurrence (and runs as ordinary batched GEMMs over all L*B rows, see
 // api_fp32.cu): the embedding half of the posterior's first layer (K = 1024 of 1224), the whole
@@ -224,11 +226,6 @@ __device__ __forceinline__ void fma_rows(const float* __restrict__ ap, const flo
 // FFMA2 rate (scripts/mma_tf32_bench.cu); the operands stay the fp32 blocks of the fp32 path (rounded to
 // TF32 with cvt.rna at fragment load), so nothing else changes.  Warp (kg, half): k-group kg takes every
 // fourth k8 step, `half` selects the lower / upper half of the CTA's slots; 4 m tiles x NT n tiles.
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 template <int NT>
 __device__ __forceinline__ void mma_rows(const float* __restrict__ As, const float* __restrict__ Ws, int nrows,
                                          int kg, int n0, int lane, int nvalid, float (&acc)[4][NT][4]) {
@@ -239,15 +236,15 @@ __device__ __forceinline__ void mma_rows(const float* __restrict__ As, const flo
     const float* bb = Ws + (k0 + t) * kLds + n0 + g;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-      af[mt][0] = to_tf32(ab[16 * mt]);
-      af[mt][1] = to_tf32(ab[16 * mt + 8]);
-      af[mt][2] = to_tf32(ab[4 * kLds + 16 * mt]);
-      af[mt][3] = to_tf32(ab[4 * kLds + 16 * mt + 8]);
+      af[mt][0] = f32_to_tf32(ab[16 * mt]);
+      af[mt][1] = f32_to_tf32(ab[16 * mt + 8]);
+      af[mt][2] = f32_to_tf32(ab[4 * kLds + 16 * mt]);
+      af[mt][3] = f32_to_tf32(ab[4 * kLds + 16 * mt + 8]);
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-      bf[nt][0] = to_tf32(bb[8 * nt]);
-      bf[nt][1] = to_tf32(bb[4 * kLds + 8 * nt]);
+      bf[nt][0] = f32_to_tf32(bb[8 * nt]);
+      bf[nt][1] = f32_to_tf32(bb[4 * kLds + 8 * nt]);
     }
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
