@@ -247,7 +247,7 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
   if (precision != BD_PREC_FP32 && want_actor && f.T >= 1 && f.N > 0 &&
       tc::mlp_backward_supported(f.actor, f.rssm.belief_size, f.rssm.state_size, precision)) {
     // BPTT dgrad chain (fp32 kernels) -> d_raw for every step; then the actor's recompute + dgrad +
-    // wgrad as two batched tensor-core MLP backwards (step 0 reads prev_*, steps 1.. read the outputs)
+    // wgrad as one batched tensor-core MLP backward
     const int A = f.rssm.action_size, Be = f.rssm.belief_size, S = f.rssm.state_size;
     const size_t draw_bytes = ((size_t)f.T * f.N * 2 * A * sizeof(float) + 255) & ~size_t(255);
     BD_CHECK_ARG(ws_bytes > draw_bytes + 65536, "bd_imagine_backward: workspace too small");
@@ -261,13 +261,10 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
     bd_mlp_bwd_args m{};
     m.k1 = Be; m.k2 = S;
     for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }
-    m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = f.N; m.dy = d_raw;
-    BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream));
-    if (f.T > 1) {
-      m.x1 = f.beliefs; m.x2 = f.states; m.rows = (int64_t)(f.T - 1) * f.N;
-      m.dy = d_raw + (size_t)f.N * 2 * A;
-      BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream));
-    }
+    // ONE batched backward over all T*N rows: step 0 reads (prev_belief, prev_state), steps 1.. read
+    // (beliefs, states)[t-1] -- a two-segment input (two passes cost a second, 20-CTA launch chain)
+    m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
+    BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N));
     return BD_OK;
   }
   return f32::imagine_backward(a, ws, ws_bytes, stream);

@@ -71,7 +71,7 @@ size_t mlp_saved_bytes(const bd_mlp& m, int64_t rows);
 bool mlp_backward_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t rows);
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
-                 bd_stream_t stream);
+                 bd_stream_t stream, const float* x1b = nullptr, const float* x2b = nullptr, int64_t split = -1);
 }  // namespace tc
 
 }  // namespace bd

@@ -76,7 +76,7 @@ static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStre
 }
 
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
-                 bd_stream_t stream) {
+                 bd_stream_t stream, const float* x1b, const float* x2b, int64_t split) {
   const int k1 = a->k1, k2 = a->k2, L = m->n_layers;
   if (!mlp_backward_supported(*m, k1, k2, precision))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: sizes/activation not supported");
@@ -240,6 +240,11 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     ba.N = nrows;
     ba.x1 = a->x1 + r0 * k1;
     ba.x2 = a->x2 ? a->x2 + r0 * k2 : nullptr;
+    // two-segment input: rows [0, split) from x1 / x2, the rest from x1b / x2b (chunk-relative here)
+    const bool two_seg = x1b != nullptr && split >= 0 && split < a->rows;
+    ba.split = two_seg ? (split > r0 ? split - r0 : 0) : nrows;
+    ba.x1b = two_seg ? x1b + (r0 > split ? (r0 - split) * k1 : 0) : ba.x1;
+    ba.x2b = (two_seg && x2b) ? x2b + (r0 > split ? (r0 - split) * k2 : 0) : ba.x2;
     ba.dy = a->dy + r0 * out;
     ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
@@ -253,7 +258,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
         pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
         pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
       };
-      if (ba.need_x) {
+      if (ba.need_x && !two_seg) {     // (the L2 prefetch assumes one contiguous input per tile index)
         add(ba.x1, (size_t)128 * k1 * 4);
         add(ba.x2, (size_t)128 * k2 * 4);
       }

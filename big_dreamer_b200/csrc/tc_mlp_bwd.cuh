@@ -31,6 +31,10 @@ struct MlpBwdArgs {
   int want_images;              // 1: also dump X / dY images for wgrad
   int need_x;                   // 0: inputs are not needed (saved hidden images, no wgrad): skip tile init
   const float *x1, *x2, *dy;
+  // optional second input segment: rows >= split come from x1b / x2b at (row - split).  The actor's
+  // inputs of imagine_ahead are (prev_belief, prev_state) for step 0 and (beliefs, states)[t-1] after.
+  const float *x1b, *x2b;
+  long long split;              // >= N when unused
   float *dx1, *dx2;
   uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
   uint16_t* ds[BD_MAX_LAYERS];  // ds[l]: images of dY_l (cols kp_ds[l]), l = 0..L-1
@@ -144,11 +148,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
+          const float* x1r = gr < a.split ? a.x1 + gr * a.k1 : a.x1b + (gr - a.split) * a.k1;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = (k < a.k1) ? ((gr < a.N) ? a.x1[gr * a.k1 + k] : 0.f) : ((k == a.k1 && gr < a.N) ? 1.f : 0.f);
+            v[j] = (k < a.k1) ? ((gr < a.N) ? x1r[k] : 0.f) : ((k == a.k1 && gr < a.N) ? 1.f : 0.f);
           }
           const uint4 u = pack8<FMT>(v);
           *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
@@ -159,11 +164,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
+          const float* x2r = gr < a.split ? a.x2 + gr * a.k2 : a.x2b + (gr - a.split) * a.k2;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = (k < a.k2 && gr < a.N) ? a.x2[gr * a.k2 + k] : 0.f;
+            v[j] = (k < a.k2 && gr < a.N) ? x2r[k] : 0.f;
           }
           const uint4 u = pack8<FMT>(v);
           *reinterpret_cast<uint4*>(SA + kg * kLboA + r * 16) = u;
