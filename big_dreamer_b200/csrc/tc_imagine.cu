@@ -315,9 +315,13 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   }
   ProfScope pe(BD_PROF_ENTROPY, s);
   // entropy + its gradient wrt (mean, std): independent of the recurrence -> separate parallel pass
-  dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
-  actor_entropy_kernel<<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy,
-                                             a->dent);
+  if ((long long)a->T * a->N <= (1 << 16)) {        // few row-steps: 8 lanes per row
+    dim3 egrid((unsigned)((a->N * 8 + 127) / 128), (unsigned)a->T);
+    actor_entropy_kernel<8><<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy, a->dent);
+  } else {
+    dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
+    actor_entropy_kernel<1><<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy, a->dent);
+  }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
 }
