@@ -168,3 +168,32 @@ def test_observe_pass_is_deterministic(prec):
     for _ in range(4):
         for x, y in zip(run(), ref):
             assert torch.equal(x, y)
+
+
+def test_actor_grads_add_over_row_slices_when_backward_is_chunked():
+    """40 000 start states x 14 steps = 560 000 actor rows: above the 2^18 rows the batched actor backward
+    takes per pass, so its two-segment input (start latents for step 0, rollout outputs after) is walked in
+    chunks.  Rows are independent, so the actor gradients of the whole batch must equal the sum over four
+    slices of 10 000 rows (each a single pass)."""
+    bd.set_precision("fp16")
+    N = 40000
+    mods, s0, b0, noise = _setup(N)
+    agent = pu.agent_ns(mods, D["H"])
+    params = list(mods.actor.parameters())
+
+    def grads(lo, hi):
+        for p in params:
+            p.grad = None
+        nz = {"eps_a": noise["eps_a"][:, lo:hi].contiguous(), "eps_s": noise["eps_s"][:, lo:hi].contiguous(),
+              "eps_e": noise["eps_e"][:, :, lo:hi].contiguous()}
+        b, s, _, ent = bd.imagine_ahead(agent, s0[None, lo:hi], b0[None, lo:hi], nz)
+        rew, val = mods.reward(b, s), mods.critic(b, s)
+        ret = bd.lambda_return(rew, val, val[-1], 0.995, 0.95)
+        (-(ret + 1e-5 * ent.unsqueeze(-1)).sum() / (14 * N)).backward()
+        return [p.grad.clone() for p in params]
+
+    full = grads(0, N)
+    parts = [grads(lo, lo + N // 4) for lo in range(0, N, N // 4)]
+    for i, g in enumerate(full):
+        ref = sum(p[i] for p in parts)
+        assert pu.relerr(g, ref) < 2e-3, i
