@@ -541,7 +541,7 @@ def run_ours(args):
                      # DRAM read+write bytes of that kernel per launch from the committed ncu --set
                      # full capture (profiles/r01b_ncu_full_bptt_c2_raw.csv: 157.7 MB read + 4.0 MB written), valid for the
                      # default workload only
-                     "traffic": ({"rollout_fwd": 96.8e6, "bptt": 161.7e6}.get(dom)
+                     "traffic": ({"rollout_fwd": 96.1e6, "bptt": 161.7e6}.get(dom)
                                  if (rows == ROWS_DEFAULT and args.precision == "fp16") else None),
                      "step_frac": step_tflops / peak, "note": note},
         "kernels": kernels,

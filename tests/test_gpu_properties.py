@@ -196,4 +196,6 @@ def test_actor_grads_add_over_row_slices_when_backward_is_chunked():
     parts = [grads(lo, lo + N // 4) for lo in range(0, N, N // 4)]
     for i, g in enumerate(full):
         ref = sum(p[i] for p in parts)
-        assert pu.relerr(g, ref) < 2e-3, i
+        err = pu.relerr(g, ref)
+        print("param", i, f"{err:.2e}")
+        assert err < 2e-3, i
