@@ -6,8 +6,9 @@
 // steps of a 64-row chunk (one cluster per chunk of rows; rows are independent):
 //   * every CTA owns a slice of each layer's output columns, for all 64 rows;
 //   * layer inputs travel between CTAs as TRANSPOSED [K][64] fp32 blocks in an L2-resident scratch
-//     (one contiguous block per layer, streamed into shared memory with 16-byte cp.async.cg in a
-//     4-stage ring of 64 k-rows), the weights as per-CTA pre-packed [K][16 slots][4] images
+//     (one contiguous block per layer, streamed into shared memory with 16-byte cp.async.cg through a
+//     double-buffered ring of 104 k-rows per stage -- K = 200 layers take two hand-offs; four stages of
+//     64 rows measured 6 % slower per step), the weights as per-CTA pre-packed [K][16 slots][4] images
 //     (pack_ops_kernel; constant over the steps, so their first ring stages are requested BEFORE
 //     the cluster barrier that waits for the other CTAs' activations);
 //   * phases are separated by the hardware cluster barrier (arrive.release / wait.acquire).
@@ -45,8 +46,8 @@ namespace obs {
 
 constexpr int kC = 16;          // CTAs per cluster (non-portable size; every B200 GPC has >= 16 SMs)
 constexpr int kR = 64;          // rows per cluster
-constexpr int kKC = 64;         // k rows per ring stage
-constexpr int kNS = 4;          // ring stages
+constexpr int kKC = 104;        // k rows per ring stage
+constexpr int kNS = 2;          // ring stages
 constexpr int kThreads = 256;
 constexpr int kRowFloats = 64;  // floats per k row of an A block (64 rows) and of a W image (16 x 4)
 constexpr int kLds = 72;        // floats between k rows in SHARED memory: 64 + 8 keeps the mma.sync fragment loads
