@@ -238,7 +238,11 @@ _ws_cache = {}
 
 
 def workspace(nbytes: int, device) -> torch.Tensor:
-    """Per-device scratch tensor (grown on demand; owned by PyTorch's allocator)."""
+    """Per-(device, stream) scratch tensor (grown on demand; owned by PyTorch's allocator).
+    During a CUDA-graph capture the scratch comes from the graph's private pool and is NOT cached:
+    a cached entry would outlive its graph and leak into later captures on the same capture stream."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
     key = (torch.device(device).index, torch.cuda.current_stream().cuda_stream)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:

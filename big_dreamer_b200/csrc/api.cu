@@ -1,6 +1,8 @@
 // extern "C" surface of libbd_b200.so (include/bd_b200.h): argument checks that are common to
 // all arithmetic modes and dispatch on bd_precision.  No CPU fallback anywhere: a precision
 // that this build does not implement returns BD_ERR_UNSUPPORTED.
+#include <atomic>
+#include <map>
 #include <mutex>
 #include <unordered_map>
 #include <stdlib.h>
@@ -8,15 +10,18 @@
 
 namespace bd {
 static thread_local char g_err[1024] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
+// function attributes are per DEVICE: the cache is keyed by (device, kernel)
 void grow_smem_attr(const void* kernel, int bytes) {
   static std::mutex mu;
-  static std::unordered_map<const void*, int> cur;
+  static std::map<std::pair<int, const void*>, int> cur;
   static const bool always_max = [] { const char* e = getenv("BD_SMEM_ATTR"); return e && e[0] == 'm'; }();
   if (always_max) bytes = kMaxOptinSmem;
+  int dev = 0;
+  cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  int& c = cur[kernel];
+  int& c = cur[{dev, kernel}];
   if (bytes > c) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     c = bytes;
@@ -34,6 +39,7 @@ void set_error(const char* fmt, ...) {
 namespace bd {
 namespace {
 struct ProfState {
+  std::mutex mu;                 // autograd runs backward on another host thread
   bool on = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[BD_PROF_COUNT];
   std::vector<cudaEvent_t> pool;
@@ -49,12 +55,15 @@ cudaEvent_t prof_event() {
 bool prof_enabled() { return g_prof.on; }
 void prof_begin(int k, cudaStream_t s) {
   if (!g_prof.on || k < 0 || k >= BD_PROF_COUNT) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, s);
   g_prof.open_start[k] = e;
 }
 void prof_end(int k, cudaStream_t s) {
-  if (!g_prof.on || k < 0 || k >= BD_PROF_COUNT || !g_prof.open_start[k]) return;
+  if (!g_prof.on || k < 0 || k >= BD_PROF_COUNT) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (!g_prof.open_start[k]) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, s);
   g_prof.ev[k].push_back({g_prof.open_start[k], e});
@@ -83,12 +92,13 @@ extern "C" {
 
 int bd_version(void) { return BD_ABI_VERSION; }
 const char* bd_last_error(void) { return bd::g_err; }
-unsigned long long bd_launch_count(void) { return bd::g_launch_count; }
+unsigned long long bd_launch_count(void) { return bd::g_launch_count.load(); }
 void bd_prof_enable(int on) { bd::g_prof.on = on != 0; }
 int bd_prof_read(int kernel, float* ms_total, int* launches) {
   if (kernel < 0 || kernel >= BD_PROF_COUNT) BD_FAIL(BD_ERR_BAD_ARG, "bd_prof_read: bad kernel id");
   float tot = 0.f;
   int n = 0;
+  std::lock_guard<std::mutex> lock(bd::g_prof.mu);
   for (auto& pr : bd::g_prof.ev[kernel]) {
     float ms = 0.f;
     cudaEventSynchronize(pr.second);
@@ -122,6 +132,7 @@ int bd_mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, in
   BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
   BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
+  BD_TRY(f32::check_mlp(*m, k1 + k2));
   if (tc::mlp_supported(*m, k1, k2, precision))
     return tc::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, precision, stream);
   return f32::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, stream);
@@ -138,6 +149,7 @@ int bd_mlp_forward_save(const bd_mlp* m, const float* x1, int k1, const float* x
   BD_NEED(x1, "x1"); BD_NEED(y, "y"); BD_NEED(ws, "workspace");
   BD_CHECK_ARG(k1 > 0 && k2 >= 0 && (k2 == 0 || x2), "bd_mlp_forward_save: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
+  BD_TRY(f32::check_mlp(*m, k1 + k2));
   if (tc::mlp_supported(*m, k1, k2, precision))
     return tc::mlp_forward(m, x1, k1, x2, k2, rows, y, ws, ws_bytes, precision, stream,
                            tc::mlp_backward_supported(*m, k1, k2, precision) ? saved : nullptr);
@@ -150,6 +162,7 @@ int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t 
   BD_NEED(ws, "workspace"); BD_NEED(a->x1, "x1"); BD_NEED(a->dy, "dy");
   BD_CHECK_ARG(a->k1 > 0 && a->k2 >= 0 && (a->k2 == 0 || a->x2), "bd_mlp_backward: bad k1/k2/x2");
   BD_ONLY_FP32(precision);
+  BD_TRY(f32::check_mlp(*m, a->k1 + a->k2));
   if (tc::mlp_backward_supported(*m, a->k1, a->k2, precision))
     return tc::mlp_backward(m, a, ws, ws_bytes, precision, stream);
   return f32::mlp_backward(m, a, ws, ws_bytes, stream);
@@ -196,7 +209,10 @@ int bd_transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes
                           bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
-  if (a->B > 0 && tc::transition_supported(*a, precision) && a->init_state && a->init_belief &&
+  BD_TRY(f32::check_rssm(a->rssm, a->embeddings != nullptr));
+  BD_CHECK_ARG(a->L >= 1 && a->B >= 0, "bd_transition_forward: bad L/B");
+  if (a->B == 0) return BD_OK;
+  if (tc::transition_supported(*a, precision) && a->init_state && a->init_belief &&
       a->actions && a->eps_prior && a->beliefs && a->prior_states && a->prior_means && a->prior_stds)
     return tc::transition_forward(a, ws, ws_bytes, precision, stream);
   return f32::transition_forward(a, ws, ws_bytes, stream, precision);
@@ -229,6 +245,9 @@ size_t bd_imagine_saved_bytes(const bd_rssm* r, int T, int64_t N, int precision)
 int bd_imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                        bd_stream_t stream) {
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  BD_TRY(f32::check_imagine(*a));
+  if (a->N == 0) return BD_OK;
   // 16-bit modes: the tensor-core rollout when the configuration fits it, else the fp32 kernels
   // (higher precision, same device path; the backward makes the same decision)
   if ((precision == BD_PREC_FP16 || precision == BD_PREC_BF16) &&
@@ -242,6 +261,8 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
   BD_NEED(a, "args"); BD_NEED(ws, "workspace");
   BD_ONLY_FP32(precision);
   const bd_imagine_args& f = a->fwd;
+  BD_TRY(f32::check_imagine(f));
+  if (f.N == 0) return BD_OK;
   bool want_actor = false;
   for (int l = 0; l < f.actor.n_layers; ++l) want_actor |= (a->actor_dw[l] || a->actor_db[l]);
   if (precision != BD_PREC_FP32 && want_actor && f.T >= 1 && f.N > 0 &&

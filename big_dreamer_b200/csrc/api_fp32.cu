@@ -1,6 +1,8 @@
 // fp32 check-mode implementations behind the C ABI (include/bd_b200.h): host-side
 // orchestration of the FFMA kernels in fp32_kernels.cuh.  Rows are processed in chunks
 // sized to the caller's workspace; all rows are independent.
+#include <map>
+#include <mutex>
 #include "api_internal.h"
 #include "fp32_kernels.cuh"
 #include "observe_persist.cuh"
@@ -94,7 +96,7 @@ size_t mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward) {
   return (size_t)(r > 0 ? r : 1) * mlp_row_floats(*m, backward != 0) * sizeof(float) + kSlackBytes;
 }
 
-static int check_mlp(const bd_mlp& m, int in_features) {
+int check_mlp(const bd_mlp& m, int in_features) {
   BD_CHECK_ARG(m.n_layers >= 1 && m.n_layers <= BD_MAX_LAYERS, "mlp: n_layers=%d out of range", m.n_layers);
   BD_CHECK_ARG(valid_act(m.activation), "mlp: unsupported activation %d", m.activation);
   int in = in_features;
@@ -225,7 +227,7 @@ int kl_loss_backward(const float* post_mean, const float* post_std, const float*
 // -------------------------------------------------------------------------------------
 // One RSSM transition step, forward and backward-with-recompute
 // -------------------------------------------------------------------------------------
-static int check_rssm(const bd_rssm& r, bool need_post) {
+int check_rssm(const bd_rssm& r, bool need_post) {
   BD_CHECK_ARG(r.belief_size > 0 && r.state_size > 0 && r.action_size > 0 && r.hidden_size > 0,
                "rssm: non-positive size");
   BD_CHECK_ARG(valid_act(r.activation), "rssm: unsupported activation %d", r.activation);
@@ -511,7 +513,13 @@ static size_t persist_ws_bytes(const bd_rssm& r, int L, int64_t B, bool backward
 // Can a cluster of 16 CTAs with this much shared memory be scheduled?  (asked once per kernel)
 template <typename Kern>
 static bool persist_launchable(Kern kern) {
-  static int cached = -1;
+  // asked once per (device, kernel): function attributes and cluster occupancy are per device
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& cached = cache.emplace(std::make_pair(dev, reinterpret_cast<const void*>(kern)), -1).first->second;
   if (cached >= 0) return cached != 0;
   const char* env = getenv("BD_OBS_PERSIST");
   if (env && env[0] == '0') { cached = 0; return false; }
@@ -844,7 +852,7 @@ size_t imagine_workspace_bytes(const bd_rssm* r, const bd_mlp* actor, int T, int
   return (size_t)(rows > 0 ? rows : 1) * imagine_row_floats(*r, *actor, backward != 0) * sizeof(float) + kSlackBytes;
 }
 
-static int check_imagine(const bd_imagine_args& a) {
+int check_imagine(const bd_imagine_args& a) {
   BD_TRY(check_rssm(a.rssm, false));
   BD_TRY(check_mlp(a.actor, a.rssm.belief_size + a.rssm.state_size));
   BD_CHECK_ARG(a.actor.layer[a.actor.n_layers - 1].out_features == 2 * a.rssm.action_size,
@@ -1066,11 +1074,7 @@ int cem_refit(const float* returns, const float* actions, int B, int C, int K, i
   while (P < (size_t)C) P <<= 1;
   size_t smem = P * sizeof(unsigned long long) + (size_t)C * sizeof(int) + (size_t)K * sizeof(int);
   BD_CHECK_ARG(smem <= 200 * 1024, "cem_refit: candidates=%d too large for one CTA", C);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(cem_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  set_smem_attr(cem_refit_kernel, 200 * 1024);     // per (device, kernel), grows only
   cem_refit_kernel<<<B, CEM_REFIT_THREADS, smem, S(stream)>>>(
       returns, actions, B, C, K, H, A, reinterpret_cast<long long*>(topk_idx), action_mean, action_std);
   BD_CUDA_LAUNCH_CHECK();

@@ -8,6 +8,10 @@ constexpr int64_t kMaxChunkRows = 65536;   // rows processed per pass of the che
 constexpr size_t kSlackBytes = 65536;      // alignment slack for workspace carving
 
 namespace f32 {
+// argument validation shared by every arithmetic mode (run in api.cu BEFORE the precision dispatch)
+int check_mlp(const bd_mlp& m, int in_features);
+int check_rssm(const bd_rssm& r, bool need_post);
+int check_imagine(const bd_imagine_args& a);
 size_t mlp_workspace_bytes(const bd_mlp* m, int64_t rows, int backward);
 int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
                 float* y, void* ws, size_t ws_bytes, bd_stream_t stream);

@@ -1,6 +1,7 @@
 // Shared helpers for libbd_b200: error reporting, activation math, workspace carving.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -10,7 +11,7 @@
 namespace bd {
 
 void set_error(const char* fmt, ...);
-extern unsigned long long g_launch_count;   // kernels launched by this library (bd_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library (bd_launch_count)
 
 #define BD_FAIL(code, ...)        \
   do {                            \

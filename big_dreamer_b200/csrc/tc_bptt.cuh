@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
   const BpttArgs& a = A_;
   uint8_t* smem = smem_raw;
   __shared__ EngineShared sh;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = a.prog;

@@ -69,6 +69,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Whole-warp wait with a warp-UNIFORM exit: every lane polls (one broadcast shared-memory access) and
+// the loop leaves on a vote, so the branch is provably uniform and ptxas keeps everything that
+// follows -- barrier addresses, UMMA descriptors, the tcgen05.mma / cp.async.bulk operands -- on the
+// uniform datapath.  With a per-lane exit condition the code after the loop counts as divergent and
+// every tcgen05.mma pays ~5 R2UR + VOTEU (measured: ~100 issue cycles per MMA instead of a handful).
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) break;
+    ++spins;
+    if (__any_sync(0xffffffffu, spins > (1u << 28))) {
+      if ((threadIdx.x & 31) == 0)
+        printf("bd_b200: mbarrier wait timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_u(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) break;
+    ++spins;
+    if (__any_sync(0xffffffffu, spins > (1u << 28))) {
+      if ((threadIdx.x & 31) == 0)
+        printf("bd_b200: cluster mbarrier wait timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ thread-block clusters
 // Used by the column-split mode of the row-tile engine (tc_engine.cuh): the CTAs of a cluster
 // share one 128-row tile, each computing a slice of every layer's output columns and writing
@@ -225,6 +271,28 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint32_t a_lo, u
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 64-bit descriptor form (descriptors kept loop-carried in uniform registers by the caller)
+__device__ __forceinline__ void umma_f16_u(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.u32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// bulk copy + its expect_tx, both predicated on the elected lane (producer warp, converged)
+__device__ __forceinline__ void tma_bulk_g2s_elect(uint32_t smem_dst, const void* gmem_src, uint32_t bytes,
+                                                   uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+      ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar_addr)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {

@@ -196,13 +196,15 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
   return sh.tmem_holder;
 }
 
-// The whole warp walks the program so every address stays in uniform registers; one elected
-// lane issues the copies.
+// The whole warp walks the program converged with warp-uniform waits (mbar_wait_u), so every
+// address stays in uniform registers; the copy and its expect_tx are single instructions predicated
+// on the elected lane.
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
                                               const uint16_t* wpack, long long ntiles, int T,
                                               uint8_t* smem, EngineShared& sh,
                                               const PrefetchPlan* pf = nullptr, uint32_t R = 1) {
-  uint8_t* ring = smem + sm.off_ring;
+  const uint32_t ring = smem_u32(smem) + sm.off_ring;
+  const uint32_t bar_full = smem_u32(&sh.w_full[0]), bar_empty = smem_u32(&sh.w_empty[0]);
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, ph = 0;
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
@@ -219,12 +221,8 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
         for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
           const int kc = min((int)g.kc, g.Kp - k0);
           const uint32_t bytes = (uint32_t)g.Np * kc * 2;
-          mbar_wait(&sh.w_empty[st], ph ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(&sh.w_full[st], bytes);
-            tma_bulk_g2s(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, &sh.w_full[st]);
-          }
-          __syncwarp();
+          mbar_wait_u(bar_empty + st * 8, ph ^ 1);
+          tma_bulk_g2s_elect(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
           if (++st == nstage) { st = 0; ph ^= 1; }
         }
       }
@@ -242,22 +240,21 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
 template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
-                                            uint32_t tmem_base_, long long* prof, uint32_t R = 1) {
+                                            uint32_t tmem_base, long long* prof, uint32_t R = 1) {
   const int lane = threadIdx.x & 31;
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
   uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
-  // provably warp-uniform copies (lane 0's value) of everything that feeds an MMA operand
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_, 0);
-  const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+  const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring_addr = smem_base + sm.off_ring;
-  const uint32_t bar_w_empty = __shfl_sync(0xffffffffu, smem_u32(&sh.w_empty[0]), 0);
-  const uint32_t bar_acc_full = __shfl_sync(0xffffffffu, smem_u32(&sh.acc_full[0]), 0);
-  const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, 0, 128) >> 32);   // SBO = 128, version, no swizzle
+  const uint32_t bar_w_full = smem_u32(&sh.w_full[0]), bar_w_empty = smem_u32(&sh.w_empty[0]);
+  const uint32_t bar_acc_full = smem_u32(&sh.acc_full[0]), bar_epi_done = smem_u32(&sh.epi_done[0]);
+  // descriptor high word: SBO = 128 B, version 1, no swizzle; low word: start >> 4 | LBO >> 4 << 16
+  const uint64_t desc_hi = make_smem_desc(0, 0, 128);
   for (long long tile = blockIdx.x / R; tile < ntiles; tile += gridDim.x / R) {
     ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
     for (int t = 0; t < T; ++t) {
-      const int par = t & 1;
+      const uint32_t par = (uint32_t)t & 1u;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
         long long c1 = 0, wsum = 0, dsum = 0;
@@ -270,12 +267,11 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               long long d0 = 0;
               if (PROF) d0 = clock64();
               if (R > 1) {     // peers wrote their column slices of the operand tiles (generic proxy)
-                mbar_wait_cluster(&sh.epi_done[D & 7], (D >> 3) & 1);
+                mbar_wait_cluster_u(bar_epi_done + (D & 7) * 8, (D >> 3) & 1);
                 fence_proxy_async_all();
               } else {
-                mbar_wait(&sh.epi_done[D & 7], (D >> 3) & 1);
+                mbar_wait_u(bar_epi_done + (D & 7) * 8, (D >> 3) & 1);
               }
-              __syncwarp();      // lanes leave the spin loop at different times: reconverge before elect.sync
               tc_fence_after_sync();
               waited = D;
               if (PROF) dsum += clock64() - d0;
@@ -283,11 +279,11 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           }
           uint32_t tile_id = g.a_tile;
           if (tile_id < 2) tile_id ^= par;
-          // descriptor low words: start address >> 4 in [0,14), LBO >> 4 in [16,30)
           // (in a cluster launch the shared-window address carries the CTA rank in its upper bits:
           // the descriptor takes only the 18-bit offset)
-          uint32_t a_lo = ((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) + (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4)) |
-                          ((kLboA >> 4) << 16);
+          uint64_t a_desc = desc_hi | ((uint64_t)(kLboA >> 4) << 16) |
+                            (uint64_t)((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) +
+                                       (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4));
           const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
           const uint32_t lbo_b = (uint32_t)g.Np * 16;
           const uint32_t d_tmem = tmem_base + g.d_col;
@@ -296,17 +292,19 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             const int kc = min((int)g.kc, g.Kp - k0);
             long long w0 = 0;
             if (PROF) w0 = clock64();
-            mbar_wait(&sh.w_full[st], wph);
-            __syncwarp();
-            tc_fence_after_sync();
+            // (no tcgen05.fence here: the weights arrive through the async proxy and their mbarrier
+            // completion orders them before the MMAs; a fence::after_thread_sync per ring stage measured
+            // ~220 cycles of issue stall each -- it is only needed after the epilogue hand-offs above)
+            mbar_wait_u(bar_w_full + st * 8, wph);
             if (PROF) wsum += clock64() - w0;
-            uint32_t b_lo = (((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu) | ((lbo_b >> 4) << 16);
+            uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
+                              (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu);
             for (int ks = 0; ks < kc; ks += 16) {
               // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
-              umma_f16_elect(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc, acc);
+              umma_f16_u(d_tmem, a_desc, b_desc, idesc, acc);
               acc = 1;
-              a_lo += 2 * (kLboA >> 4);
-              b_lo += 2 * (lbo_b >> 4);
+              a_desc += 2 * (kLboA >> 4);
+              b_desc += 2 * (lbo_b >> 4);
             }
             umma_commit_elect(bar_w_empty + st * 8);
             if (++st == nstage) { st = 0; wph ^= 1; }
@@ -363,9 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   const RolloutArgs& a = A_;
   uint8_t* smem = smem_raw;
   __shared__ EngineShared sh;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   const uint32_t R = CLUSTER ? (uint32_t)a.nranks : 1u;   // compile-time 1 keeps the single-CTA path lean
-  const uint32_t rank = R > 1 ? cluster_ctarank() : 0u;
+  const uint32_t rank = R > 1 ? (uint32_t)blockIdx.x % R : 0u;   // = %cluster_ctarank for (R,1,1) clusters; provably uniform
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;

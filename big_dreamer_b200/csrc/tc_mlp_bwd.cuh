@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   const MlpBwdArgs& a = A_;
   uint8_t* smem = smem_raw;
   __shared__ EngineShared sh;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = a.prog;
@@ -409,7 +410,8 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ W
   const WgradJob j = a.job[blockIdx.y];
   __shared__ uint64_t full[2], empty[2], done;
   __shared__ uint32_t tmem_holder;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&done, 1);

@@ -19,7 +19,8 @@ _precision = "fp32"
 
 
 def set_precision(name: str) -> None:
-    """'fp32' (check mode, FFMA), 'bf16' or 'tf32' (tcgen05 tensor cores)."""
+    """'fp32' (check mode, FFMA kernels; the module default), 'fp16' (the fast mode: tcgen05 tensor
+    cores, fp16 operands, fp32 accumulation and state) or 'bf16' (same kernels, bf16 operands)."""
     global _precision
     if name not in _lib.PRECISIONS:
         raise ValueError(f"unknown precision {name!r}")
@@ -77,6 +78,10 @@ class MlpFunction(torch.autograd.Function):
         a2 = _f32c(x2).reshape(-1, x2.shape[-1]) if x2 is not None else None
         if a2 is not None and a2.shape[0] != a1.shape[0]:
             raise BdError("DenseModel: belief/state leading dims differ")
+        k_in = a1.shape[1] + (a2.shape[1] if a2 is not None else 0)
+        if k_in != ws_[0].shape[1]:
+            raise BdError(f"DenseModel: input has {k_in} features, the first layer expects "
+                          f"{ws_[0].shape[1]}")
         rows, out = a1.shape[0], ws_[-1].shape[0]
         mlp = _lib.make_mlp(ws_, bs_, act_id)
         y = torch.empty(rows, out, device=a1.device, dtype=torch.float32)
@@ -238,6 +243,7 @@ class TransitionFunction(torch.autograd.Function):
         _lib.check(lib.bd_transition_forward(C.byref(a), ws.data_ptr(), ws.numel(), _prec(),
                                              _lib.stream_ptr()), "bd_transition_forward")
         ctx.dims, ctx.observe, ctx.has_nt = dims, observe, nt is not None
+        ctx.prec = _prec()
         ctx.n_params = len(P)
         keep = [s0, b0, act, ep] + ([emb, eq] if observe else []) + ([nt] if nt is not None else [])
         ctx.save_for_backward(*keep, *outs, *[p for p in P if p is not None])
@@ -292,7 +298,7 @@ class TransitionFunction(torch.autograd.Function):
             setattr(a.grads, name, _lib.ptr(gp))
         nbytes = lib.bd_transition_workspace_bytes(C.byref(f.rssm), L, B, int(ctx.observe), 1)
         ws = _lib.workspace(nbytes, s0.device)
-        _lib.check(lib.bd_transition_backward(C.byref(a), ws.data_ptr(), ws.numel(), _prec(),
+        _lib.check(lib.bd_transition_backward(C.byref(a), ws.data_ptr(), ws.numel(), ctx.prec,
                                               _lib.stream_ptr()), "bd_transition_backward")
         return (None, d_s0, d_act, d_b0, d_emb, None, None, None, *dP)
 
@@ -324,7 +330,7 @@ class ImagineFunction(torch.autograd.Function):
         actor_raw, dent = new(T, N, 2 * A), new(T, N, 2 * A)
         a = _lib.ImagineArgs()
         a.rssm = make_rssm(RP, dims)
-        a.actor = _lib.make_mlp(AP[0::2], AP[1::2], dims["act_id"])
+        a.actor = _lib.make_mlp(AP[0::2], AP[1::2], actor_cfg.get("act_id", dims["act_id"]))
         a.actor_cfg = _lib.ActorCfg(actor_cfg["mean_scale"], actor_cfg["raw_init_std"],
                                     actor_cfg["min_std"], J)
         a.T, a.N = T, N
@@ -365,7 +371,7 @@ class ImagineFunction(torch.autograd.Function):
         a = _lib.ImagineBwdArgs()
         f = a.fwd
         f.rssm = make_rssm(RP, dims)
-        f.actor = _lib.make_mlp(AP[0::2], AP[1::2], dims["act_id"])
+        f.actor = _lib.make_mlp(AP[0::2], AP[1::2], cfg.get("act_id", dims["act_id"]))
         f.actor_cfg = _lib.ActorCfg(cfg["mean_scale"], cfg["raw_init_std"], cfg["min_std"],
                                     cfg["entropy_samples"])
         f.T, f.N = T, N

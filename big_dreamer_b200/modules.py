@@ -186,12 +186,22 @@ class TransitionModel(nn.Module):
 # =============================================================================
 # Dreamer.imagine_ahead / lambda_return
 # =============================================================================
+def _mlp_act_id(seq: nn.Sequential) -> int:
+    """Activation id of a build_mlp chain: its first non-Linear module (Identity if none)."""
+    for m in seq:
+        if not isinstance(m, nn.Linear):
+            return _lib.activation_id(type(m).__name__)
+    return _lib.activation_id("Identity")
+
+
 def actor_config(actor) -> Dict:
-    """Squashing constants read from the reference's ActorModel (src/models.py:499-503)."""
+    """Squashing constants read from the reference's ActorModel (src/models.py:499-503) and the
+    actor's OWN hidden activation (an independent constructor argument, src/models.py:469-481)."""
     raw = actor.raw_init_std
     raw = float(raw.item()) if isinstance(raw, torch.Tensor) else float(raw)
     return dict(mean_scale=float(actor._mean_scale), raw_init_std=raw,
-                min_std=float(actor._min_std), entropy_samples=ENTROPY_SAMPLES)
+                min_std=float(actor._min_std), entropy_samples=ENTROPY_SAMPLES,
+                act_id=_mlp_act_id(actor.model))
 
 
 def draw_imagine_noise(T: int, N: int, S: int, A: int, device, generator=None):

@@ -38,15 +38,40 @@ def patch(fused: bool = False) -> None:
             _saved[(mod.__name__, attr)] = (mod, getattr(mod, attr))
             setattr(mod, attr, new)
 
+    # Categorical (DreamerV2) latents are not on the B200 path: the swapped-in name is a factory that
+    # hands those configurations to the reference's own class (config.yaml:56, src/models.py:166-181)
+    ref_tm = models.TransitionModel
+
+    class TransitionModel(M.TransitionModel):
+        def __new__(cls, *args, **kwargs):
+            names = ("belief_size", "state_size", "action_size", "hidden_size", "embedding_size",
+                     "activation", "min_std_dev", "latent_distribution")
+            bound = dict(zip(names, args))
+            bound.update(kwargs)
+            if bound.get("latent_distribution", "Gaussian") != "Gaussian":
+                return ref_tm(*args, **kwargs)       # not an instance of cls: __init__ is not re-run
+            return super().__new__(cls)
+    TransitionModel.__name__ = TransitionModel.__qualname__ = "TransitionModel"
+
     for mod in (models, planet, dreamer):
-        swap(mod, "TransitionModel", M.TransitionModel)
+        swap(mod, "TransitionModel", TransitionModel)
         swap(mod, "DenseModel", M.DenseModel)
     for mod in (planner, planet, dreamer):
         swap(mod, "MPCPlanner", M.MPCPlanner)
     swap(dreamer, "lambda_return", M.lambda_return)
     cls = dreamer.Dreamer
-    _saved[("dreamer.Dreamer", "imagine_ahead")] = (cls, cls.imagine_ahead)
-    cls.imagine_ahead = M.imagine_ahead
+    ref_imagine = cls.imagine_ahead
+    _saved[("dreamer.Dreamer", "imagine_ahead")] = (cls, ref_imagine)
+
+    def imagine_ahead(self, prev_state, prev_belief, *args, **kwargs):
+        # Categorical latents / a Categorical actor / a reference (non-B200) transition model keep
+        # the reference's own Python loop
+        if (getattr(self, "latent_distribution", "Gaussian") != "Gaussian"
+                or getattr(self.actor, "action_distribution", "Gaussian") != "Gaussian"
+                or not isinstance(self.transition_model, M.TransitionModel)):
+            return ref_imagine(self, prev_state, prev_belief)
+        return M.imagine_ahead(self, prev_state, prev_belief, *args, **kwargs)
+    cls.imagine_ahead = imagine_ahead
     # dynamics-update KL (Gaussian latents; the Categorical path keeps the reference's method)
     for owner in (planet.Planet, cls):
         if "_kl_loss" in vars(owner):

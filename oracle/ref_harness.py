@@ -1,8 +1,9 @@
 """Runs the UNMODIFIED reference (jgsimard/big-dreamer at /root/reference) with
 injected noise.  TEST INFRASTRUCTURE ONLY -- used in this container to (a) pin
 oracle/rssm_oracle.py against the real code and (b) generate tests/golden/*.
-/root/reference does not exist on the GPU box, so nothing that runs there may
-import this module (``available()`` is False there and the tests skip).
+/root/reference does not exist on the GPU box; there the harness finds the unmodified
+copy installed under baseline/_ref (see ``_find_reference_root``) or reports
+``available() == False`` and the tests that need it skip.
 
 The reference draws its Gaussians internally: ``torch.randn_like``
 (src/models.py:72), ``torch.randn`` (src/planner.py:53) and
@@ -20,7 +21,18 @@ from typing import List
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("BD_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """BD_REFERENCE_ROOT, else the read-only tree of the build container, else the unmodified copy
+    `pip install --target baseline/_ref` made of it (git-ignored; it travels to the GPU box)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("BD_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "models.py")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 _mods = None
 
@@ -214,3 +226,98 @@ def ref_kl_loss(agent: str, posterior_params, prior_params, free_nats: float, kl
         return sys.modules["planet"].Planet._kl_loss(ns, posterior_params, prior_params)
     ns._get_dist = types.MethodType(m.dreamer.Dreamer._get_dist, ns)
     return m.dreamer.Dreamer._kl_loss(ns, posterior_params, prior_params)
+
+
+# ----------------------------------------------------------------------------
+# whole-agent harness (SURVEY 8c "whole-agent oracle"): the reference's own Dreamer(params, env)
+# ----------------------------------------------------------------------------
+def default_params() -> dict:
+    """The reference's hydra config as the plain dict `my_app` hands to the agents
+    (src/main.py:27-29).  Read from src/conf/config.yaml when the tree has it (PyYAML reads
+    `2e-4` as a string where omegaconf gave a float: coerced here); the pip-installed copy under
+    baseline/_ref carries no yaml, so the same defaults are restated below (src/conf/config.yaml:1-81)."""
+    path = os.path.join(REFERENCE_ROOT, "src", "conf", "config.yaml")
+    if os.path.isfile(path):
+        import yaml
+
+        def coerce(d):
+            for k, v in list(d.items()):
+                if isinstance(v, dict):
+                    coerce(v)
+                elif isinstance(v, str):
+                    try:
+                        d[k] = float(v)
+                    except ValueError:
+                        pass
+            return d
+        return coerce(yaml.safe_load(open(path)))
+    return dict(
+        algorithm="dreamer", exp_name="default", seed=0, disable_cuda=False, env="Pendulum-v0",
+        max_episode_length=1000, experience_size=1000000, cnn_activation_function="ELU",
+        dense_activation_function="ELU", embedding_size=1024, hidden_size=200, n_layers=4,
+        belief_size=200, state_size=30, action_repeat=2, action_noise=0.3, episodes=1000,
+        seed_episodes=1, seed_steps=5000, train_steps=1000000, collect_interval=5, batch_size=50,
+        seq_len=50, free_nats=3.0, bit_depth=5, model_learning_rate=2e-4, adam_epsilon=1e-5,
+        weight_decay=1e-6, grad_clip_norm=100.0, planning_horizon=15, discount=0.995, disclam=0.95,
+        test=False, test_interval=25, test_episodes=10, checkpoint_interval=5,
+        checkpoint_experience=False, models="", experience_replay="", render=False, log_freq=100,
+        log_video_freq=-1, wandb_project=None, fps=10, kl_balance=0.8, kl_loss_weight=0.1,
+        latent_distribution="Gaussian", discrete_latent_dimensions=32, discrete_latent_classes=32,
+        action_distribution="Gaussian", jit=False,
+        MPC=dict(optimisation_iters=10, candidates=1000, top_candidates=100),
+        ActorCritic=dict(actor_learning_rate=4e-5, value_learning_rate=1e-4, entropy_weight=1e-5,
+                         slow_critic_update_interval=100, polyak_avg=1.0, gradient_mixing=-1),
+        use_discount=False, discount_weight=5.0, pixel_observation=True,
+        environment_steps_per_update=10)
+
+
+class FakeEnv:
+    """What Planet.__init__ / the replay buffer read off an env (src/planet.py:33-77)."""
+
+    def __init__(self, action_size=2, observation_size=(3, 64, 64)):
+        self.action_size, self.observation_size = action_size, observation_size
+
+    def reset(self):
+        return torch.zeros(1, *self.observation_size)
+
+    def step(self, action):
+        return torch.zeros(1, *self.observation_size), 0.0, False
+
+    def sample_random_action(self):
+        return torch.zeros(self.action_size)
+
+    def close(self):
+        pass
+
+
+@contextlib.contextmanager
+def agent_modules():
+    """sys.path / sys.modules set up so `import planet, dreamer, models, planner` gives the
+    reference's modules (with the import shims); restored on exit."""
+    load()
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.pop(k, None) for k in ("typeguard", "torchtyping", "plotly", "gym")}
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, "src"))
+    sys.path.insert(0, _SHIMS)
+    try:
+        import dreamer
+        import models
+        import planet
+        import planner
+        yield types.SimpleNamespace(planet=planet, dreamer=dreamer, models=models, planner=planner)
+    finally:
+        sys.path[:] = saved_path
+        for k, v in saved_mods.items():
+            if v is not None:
+                sys.modules[k] = v
+
+
+def fill_buffer(agent, steps: int, seed: int = 0):
+    """Synthetic experience through the reference's own buffer.append (src/memory.py:33-49)."""
+    g = torch.Generator().manual_seed(seed)
+    A = agent.env.action_size if hasattr(agent, "env") else agent.buffer.actions.shape[1]
+    obs_shape = agent.buffer.observations.shape[1:]
+    for i in range(steps):
+        obs = torch.rand(1, *obs_shape, generator=g) - 0.5
+        act = torch.rand(A, generator=g) * 2 - 1
+        agent.buffer.append(obs, act, float(torch.randn((), generator=g)), (i + 1) % 37 == 0)

@@ -77,7 +77,9 @@ def test_patch_rebinds_and_reference_agent_constructs(ref_agent_modules):
     assert planet.Planet._kl_loss is not ref_kl_p and dreamer.Dreamer._kl_loss is not ref_kl_d
     # the classes themselves and every copy the agents took with `from models import ...`
     # (src/planet.py:15,17, src/dreamer.py:13)
-    assert models.TransitionModel is bd.TransitionModel and planet.TransitionModel is bd.TransitionModel
+    # (a thin factory subclass: Gaussian latents build the B200 module, Categorical the reference's)
+    assert issubclass(models.TransitionModel, bd.TransitionModel)
+    assert planet.TransitionModel is models.TransitionModel
     for mod in (models, planet, dreamer):
         assert mod.DenseModel is bd.DenseModel
     assert planner.MPCPlanner is bd.MPCPlanner and planet.MPCPlanner is bd.MPCPlanner
@@ -111,3 +113,36 @@ def test_patch_rebinds_and_reference_agent_constructs(ref_agent_modules):
     assert planner.MPCPlanner is ref_planner and dreamer.lambda_return is ref_lambda
     assert dreamer.Dreamer.imagine_ahead is ref_imagine
     assert planet.Planet._kl_loss is ref_kl_p and dreamer.Dreamer._kl_loss is ref_kl_d
+
+
+def test_patch_keeps_categorical_on_the_reference(ref_agent_modules):
+    """after bd.patch() a Categorical (DreamerV2) agent must still construct and its
+    imagine_ahead / _kl_loss must run the reference's own code (config.yaml:56, src/models.py:166-181)."""
+    planet, dreamer, models, planner, params = ref_agent_modules
+    ref_tm = models.TransitionModel
+    bd.patch()
+    p = dict(params, latent_distribution="Categorical")
+    agent = dreamer.Dreamer(p, FakeEnv())
+    assert type(agent.transition_model) is ref_tm                   # the reference class, untouched
+    assert not isinstance(agent.transition_model, bd.TransitionModel)
+    # imagine_ahead delegates to the reference's own method: same result -- or the same failure, the
+    # reference's Categorical imagine loop raises a TypeError at HEAD (src/dreamer.py:226-231 appends a
+    # tuple where stack() wants a tensor) -- as the unpatched method gives on the same CPU inputs
+    L, B = 2, 3
+    state_size = p["discrete_latent_dimensions"] * p["discrete_latent_classes"]
+    s0, b0 = torch.zeros(L, B, state_size), torch.zeros(L, B, p["belief_size"])
+    ref_imagine = bd.patch.__globals__["_saved"][("dreamer.Dreamer", "imagine_ahead")][1]
+
+    def outcome(fn):
+        torch.manual_seed(0)
+        try:
+            with torch.no_grad():
+                return ("ok", fn(agent, s0, b0)[0].shape)
+        except bd.BdError:
+            raise
+        except Exception as e:      # noqa: BLE001 - the reference's own failure mode is the datum
+            return ("raised", type(e).__name__)
+    assert outcome(type(agent).imagine_ahead) == outcome(ref_imagine)
+    # Gaussian agents built in the same process still get the B200 module
+    agent2 = dreamer.Dreamer(params, FakeEnv())
+    assert isinstance(agent2.transition_model, bd.TransitionModel)
