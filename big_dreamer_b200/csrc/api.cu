@@ -198,6 +198,11 @@ int bd_kl_loss_backward(const float* post_mean, const float* post_std, const flo
                                loss, g_loss, d_post_mean, d_post_std, d_prior_mean, d_prior_std, stream);
 }
 
+int bd_value_loss(const float* value, const float* target, const float* weight, int64_t n, float* loss,
+                  float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream) {
+  return f32::value_loss(value, target, weight, n, loss, d_value, ws, ws_bytes, stream);
+}
+
 size_t bd_transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
   if (!r) return 0;
   size_t f = f32::transition_workspace_bytes(r, L, B, observe, backward);

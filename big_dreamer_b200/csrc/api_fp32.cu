@@ -683,6 +683,21 @@ static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, s
   // ---- parameter gradients and d embeddings, batched over time
   return time_batched_param_grads(r, f, *a, tb, s);
 }
+int value_loss(const float* value, const float* target, const float* weight, int64_t n, float* loss,
+               float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream) {
+  BD_CHECK_ARG(value && target && loss, "value_loss: null pointer");
+  BD_CHECK_ARG(n >= 1, "value_loss: n must be >= 1");
+  BD_CHECK_ARG(ws && ws_bytes >= kValueLossBlocks * sizeof(float), "value_loss: workspace too small");
+  long long g = (n + 255) / 256;
+  if (g > kValueLossBlocks) g = kValueLossBlocks;
+  float* partial = static_cast<float*>(ws);
+  value_loss_kernel<<<(unsigned)g, 256, 0, S(stream)>>>(value, target, weight, n, d_value, partial);
+  BD_CUDA_LAUNCH_CHECK();
+  value_loss_finish_kernel<<<1, 1024, 0, S(stream)>>>(partial, (int)g, n, loss);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
+
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
   int64_t rows = B < kMaxChunkRows ? B : kMaxChunkRows;
   size_t step = (size_t)(rows > 0 ? rows : 1) * step_row_floats(*r, observe != 0, backward != 0) * sizeof(float);

@@ -44,7 +44,7 @@ extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by 
 // breaks any tool or graph path that re-issues an earlier, larger launch of the same kernel (seen
 // with ncu's per-node profiling of a replayed CUDA graph: LaunchFailed on the heads'
 // mlp_bwd_kernel after the smaller actor launch).  It only ever grows here.
-constexpr int kMaxOptinSmem = 227 * 1024 - 2048;     // device opt-in maximum less static barriers
+constexpr int kMaxOptinSmem = 227 * 1024 - 4096;     // device opt-in maximum less static barriers
 void grow_smem_attr(const void* kernel, int bytes);  // api.cu
 template <typename K>
 inline void set_smem_attr(K kernel, size_t bytes) { grow_smem_attr(reinterpret_cast<const void*>(kernel), (int)bytes); }

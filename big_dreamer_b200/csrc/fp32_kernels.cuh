@@ -517,6 +517,45 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mq, const float* __restr
 }
 
 // =====================================================================================
+// Critic regression loss of Dreamer's value update (src/dreamer.py:380-385):
+//   loss = -mean( w * Normal(v, 1).log_prob(target) ) = mean( w * (0.5 (v - target)^2 + 0.5 ln 2 pi) )
+// (w = the cumulated discount when use_discount, else 1) and its gradient d loss / d v, fused.
+//   value_loss_kernel         grid-stride: dv[i] = w (v - t) / n ; per-block partial sums
+//   value_loss_finish_kernel  one block, fixed-order tree over the partials (deterministic)
+// =====================================================================================
+constexpr int kValueLossBlocks = 1024;
+__global__ void __launch_bounds__(256) value_loss_kernel(const float* __restrict__ v, const float* __restrict__ t,
+                                                         const float* __restrict__ w, long long n,
+                                                         float* __restrict__ dv, float* __restrict__ partial) {
+  __shared__ float red[256];
+  const float inv_n = 1.f / (float)n;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float d = v[i] - t[i], wi = w ? w[i] : 1.f;
+    acc += wi * (0.5f * d * d + 0.9189385332046727f);
+    if (dv) dv[i] = wi * d * inv_n;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(1024) value_loss_finish_kernel(const float* __restrict__ partial, int nblocks,
+                                                                 long long n, float* __restrict__ loss) {
+  __shared__ float red[1024];
+  red[threadIdx.x] = (int)threadIdx.x < nblocks ? partial[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] / (float)n;
+}
+
+// =====================================================================================
 // Actor head: ActorModel squash (src/models.py:513-516), tanh-Normal rsample
 // (src/dreamer.py:435-443) and the J-sample Monte-Carlo entropy (src/models.py:725-733,
 // 656-673).  One thread per row.  Also emits d entropy / d(mean,std) for backward.

@@ -361,13 +361,18 @@ __host__ __device__ __forceinline__ uint32_t km8_offset(uint32_t rows, uint32_t 
 template <int FMT> struct Half16;
 template <> struct Half16<0> {
   using T = __half;
+  // fp16 operands SATURATE at +-65504 (F2FP.SATFINITE: same single instruction as the plain convert):
+  // a value beyond fp16's range becomes a clipped activation instead of an inf that turns the
+  // fp32 accumulators into NaN (inf - inf).  bf16 mode has fp32's range and needs no guard.
   __device__ static __forceinline__ uint32_t pack2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
   __device__ static __forceinline__ uint16_t cvt(float a) {
-    __half h = __float2half_rn(a);
-    return *reinterpret_cast<uint16_t*>(&h);
+    uint16_t r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(a));
+    return r;
   }
 };
 template <> struct Half16<1> {

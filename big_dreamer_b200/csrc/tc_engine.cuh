@@ -180,6 +180,17 @@ struct EngineShared {
   uint32_t tmem_holder;
 };
 
+// The program tables travel as kernel parameters (constant bank), but every role indexes them
+// dynamically once per GEMM / phase; an indexed constant load that misses the small constant cache
+// costs an L2 round trip (measured: ~570 cycles per GEMM on the issuer's critical path).  Each CTA
+// therefore keeps its own copy in shared memory and all roles read that.
+__device__ __forceinline__ void stage_program(Program& dst, const Program& src) {
+  static_assert(sizeof(Program) % 4 == 0, "Program must be a whole number of words");
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  for (uint32_t i = threadIdx.x; i < sizeof(Program) / 4; i += blockDim.x) d[i] = s[i];
+}
+
 __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -365,6 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   const uint32_t R = CLUSTER ? (uint32_t)a.nranks : 1u;   // compile-time 1 keeps the single-CTA path lean
   const uint32_t rank = R > 1 ? (uint32_t)blockIdx.x % R : 0u;   // = %cluster_ctarank for (R,1,1) clusters; provably uniform
+  __shared__ Program sprog;
+  stage_program(sprog, CLUSTER ? a.prog[rank] : a.prog[0]);
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   }
 
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
-  const Program& P = CLUSTER ? a.prog[rank] : a.prog[0];
+  const Program& P = sprog;
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
 
   if (warp == 0) {

@@ -31,7 +31,7 @@ static bool rollout_tiles_fit(const bd_rssm& r, int extra_hidden) {
   const size_t tiles = (size_t)kTileRows * 2 * (2 * Kp_b + Kp_sa + Kp_h);
   const int widest = max(max(r16(r.hidden_size), r16(r.belief_size)), max(192, r16(extra_hidden)));
   const size_t stage = ((size_t)widest * 64 + 1023) & ~size_t(1023);
-  return tiles + 2 * stage <= (size_t)227 * 1024 - 2048;
+  return tiles + 2 * stage <= (size_t)227 * 1024 - 4096;
 }
 
 bool imagine_supported(const bd_rssm& r, const bd_mlp& actor, int precision) {
@@ -71,7 +71,7 @@ static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& s
   sm.off_tile[4] = sm.off_tile[3];
   sm.stage_bytes = (stage + 1023) & ~1023u;
   sm.off_ring = off;
-  const uint32_t budget = 227 * 1024 - 2048;   // static barriers + alignment slack
+  const uint32_t budget = 227 * 1024 - 4096;   // static barriers + program tables + alignment slack
   if (off + 2 * sm.stage_bytes > budget) return false;
   sm.nstage = min(8u, (budget - off) / sm.stage_bytes);
   sm.total = off + sm.nstage * sm.stage_bytes + 1024;
@@ -588,7 +588,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     sm.off_tile[TILE_SLAB1] = tk(kTileRows * 192 * 2);
     sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
     sm.off_ring = o;
-    const uint32_t budget = 227 * 1024 - 2048;
+    const uint32_t budget = 227 * 1024 - 4096;
     if (o + 2 * sm.stage_bytes > budget) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core BPTT: tiles do not fit shared memory");
     sm.nstage = min(8u, (budget - o) / sm.stage_bytes);
     sm.total = o + sm.nstage * sm.stage_bytes + 1024;

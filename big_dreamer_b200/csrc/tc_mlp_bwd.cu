@@ -196,7 +196,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);
     sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
     sm.off_ring = o;
-    const uint32_t budget = 227 * 1024 - 2048;
+    const uint32_t budget = 227 * 1024 - 4096;
     if (o + 2 * sm.stage_bytes > budget)
       BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: tiles do not fit shared memory");
     sm.nstage = min(8u, (budget - o) / sm.stage_bytes);

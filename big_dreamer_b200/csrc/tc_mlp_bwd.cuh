@@ -119,9 +119,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   __shared__ EngineShared sh;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
+  __shared__ Program sprog;
+  stage_program(sprog, a.prog);
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
-  const Program& P = a.prog;
+  const Program& P = sprog;
 
   if (warp == 0) {
     producer_role(P, a.sm, a.wpack, ntiles, 1, smem, sh, &a.pf);

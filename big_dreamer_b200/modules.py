@@ -273,6 +273,72 @@ def _kl_loss_method(self, posterior_params, prior_params):
     return kl_loss(posterior_params, prior_params, self.free_nats, getattr(self, "kl_balance", -1))
 
 
+def value_update(critic, beliefs: Tensor, states: Optional[Tensor], target: Tensor,
+                 weight: Optional[Tensor] = None) -> Tensor:
+    """The critic regression update of ``Dreamer.train_step`` (src/dreamer.py:369-391) behind one call:
+
+        value_loss = -(weight * Normal(critic(beliefs, states), 1).log_prob(target)).mean()
+        value_loss.backward()                 # gradients land in critic.parameters()[i].grad
+
+    beliefs (..., Be), states (..., S) or None, target / weight (..., 1); inputs are treated as
+    detached (the reference detaches them, :370-375).  Returns the loss (0-dim tensor); the caller runs
+    ``clip_grad_norm_`` and the optimizer exactly as the reference does.  Parameter gradients of one
+    call live in ONE flat buffer (``dist.allreduce_grads`` reduces it with a single collective)."""
+    lib = _lib.load()
+    lin = _linears(critic.model)
+    ws_ = [F_._f32c(l.weight.detach()) for l in lin]
+    bs_ = [F_._f32c(l.bias.detach()) for l in lin]
+    if ws_[-1].shape[0] != 1:
+        raise BdError("value_update: the critic must have one output")
+    a1 = F_._f32c(beliefs.detach()).reshape(-1, beliefs.shape[-1])
+    a2 = F_._f32c(states.detach()).reshape(-1, states.shape[-1]) if states is not None else None
+    rows = a1.shape[0]
+    k2 = a2.shape[1] if a2 is not None else 0
+    if a1.shape[1] + k2 != ws_[0].shape[1] or (a2 is not None and a2.shape[0] != rows):
+        raise BdError("value_update: input widths do not match the critic's first layer")
+    tgt = F_._f32c(target.detach()).reshape(-1)
+    wgt = F_._f32c(weight.detach()).reshape(-1) if weight is not None else None
+    if tgt.numel() != rows or (wgt is not None and wgt.numel() != rows):
+        raise BdError("value_update: target / weight must hold one value per row")
+    prec = F_._prec()
+    mlp = _lib.make_mlp(ws_, bs_, _mlp_act_id(critic.model))
+    dev = a1.device
+    v = torch.empty(rows, 1, device=dev, dtype=torch.float32)
+    loss = torch.empty(1, device=dev, dtype=torch.float32)
+    if rows == 0:
+        return loss.zero_()[0]
+    ws = _lib.workspace(max(lib.bd_mlp_workspace_bytes(C.byref(mlp), rows, 1), 1 << 16), dev)
+    nsaved = lib.bd_mlp_saved_bytes(C.byref(mlp), a1.shape[1], k2, rows, prec)
+    saved = torch.empty(nsaved, dtype=torch.uint8, device=dev) if nsaved else None
+    _lib.check(lib.bd_mlp_forward_save(C.byref(mlp), _lib.ptr(a1), a1.shape[1], _lib.ptr(a2), k2, rows,
+                                       _lib.ptr(v), saved.data_ptr() if nsaved else None, ws.data_ptr(),
+                                       ws.numel(), prec, _lib.stream_ptr()), "bd_mlp_forward_save")
+    dv = torch.empty(rows, 1, device=dev, dtype=torch.float32)
+    _lib.check(lib.bd_value_loss(_lib.ptr(v), _lib.ptr(tgt), _lib.ptr(wgt), rows, _lib.ptr(loss),
+                                 _lib.ptr(dv), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "bd_value_loss")
+    params = [l.weight for l in lin] + [l.bias for l in lin]
+    need = [p.requires_grad for p in params]
+    g = F_._zero_grads(need, params)
+    n = len(lin)
+    args = _lib.MlpBwdArgs()
+    args.x1, args.k1, args.x2, args.k2 = _lib.ptr(a1), a1.shape[1], _lib.ptr(a2), k2
+    args.rows, args.dy = rows, _lib.ptr(dv)
+    for i in range(n):
+        args.dw[i], args.db[i] = _lib.ptr(g[i]), _lib.ptr(g[n + i])
+    if saved is not None:
+        args.saved = saved.data_ptr()
+    _lib.check(lib.bd_mlp_backward(C.byref(mlp), C.byref(args), ws.data_ptr(), ws.numel(), prec,
+                                   _lib.stream_ptr()), "bd_mlp_backward")
+    for p, gp in zip(params, g):
+        if gp is None:
+            continue
+        if p.grad is None:
+            p.grad = gp
+        else:
+            p.grad.add_(gp)
+    return loss[0]
+
+
 def imagine_and_returns(self, prev_state: Tensor, prev_belief: Tensor, reward_model, value_model,
                         discount: float, lambda_: float,
                         noise: Optional[Dict[str, Tensor]] = None):

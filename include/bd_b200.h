@@ -184,6 +184,16 @@ int bd_kl_loss_backward(const float* post_mean, const float* post_std, const flo
                         float* d_post_mean, float* d_post_std, float* d_prior_mean,
                         float* d_prior_std, bd_stream_t stream);
 
+/* ------------------------------------- critic regression loss (value update) ---- */
+/* Dreamer.train_step's value loss, src/dreamer.py:380-385:
+ *   loss = -mean( weight * Normal(value, 1).log_prob(target) ),  weight = cumulated discount
+ *   (use_discount) or NULL for 1.  value / target / weight / d_value hold n elements;
+ *   loss is one float; d_value (optional) receives d loss / d value.  ws: >= 4 KB.
+ * bd.value_update (the critic forward bd_mlp_forward_save, this loss and bd_mlp_backward with
+ * weight gradients) is the whole update block behind one host call. */
+int bd_value_loss(const float* value, const float* target, const float* weight, int64_t n,
+                  float* loss, float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream);
+
 /* ----------------------------------------------- TransitionModel.forward ---- */
 typedef struct {
   bd_rssm rssm;

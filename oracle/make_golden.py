@@ -138,10 +138,32 @@ def kl_case(name="kl_loss", L=7, B=9, S=30, seed=4):
     print(name, [float(c["loss"].sum()) for c in fx["cases"]])
 
 
+def value_update_case(name="value_update", Be=200, Hi=200, S=30, T=5, N=77, seed=6):
+    """Reference critic regression block (src/dreamer.py:369-391): loss + critic gradients, without
+    and with the use_discount weighting."""
+    mods = rh.build_modules(seed, Be, S, 1, Hi, 8, "ELU")
+    g = torch.Generator().manual_seed(seed)
+    b = torch.tanh(torch.randn(T, N, Be, generator=g))
+    st = 0.5 * torch.randn(T, N, S, generator=g)
+    target = torch.randn(T, N, 1, generator=g)
+    disc = torch.cumprod(0.995 * torch.round(torch.rand(T, N, 1, generator=g) * 0.6 + 0.45), 0)
+    fx = dict(dims=dict(Be=Be, Hi=Hi, S=S, T=T, N=N), critic=_sd(mods.critic), beliefs=b, states=st,
+              target=target, discount=disc, cases=[])
+    for w in (None, disc):
+        loss, grads = rh.ref_value_update(mods, b, st, target, w)
+        fx["cases"].append(dict(weighted=w is not None, loss=loss, grads=grads))
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, [float(c["loss"]) for c in fx["cases"]])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if os.environ.get("BD_GOLDEN_ONLY") == "kl":
+    only = os.environ.get("BD_GOLDEN_ONLY")
+    if only == "kl":
         return kl_case()
+    if only == "value":
+        return value_update_case()
+    value_update_case()
     kl_case()
     # c1 (README Pendulum sizes), well-conditioned entropy + default-init entropy
     imagine_case("imagine_c1", 32, 32, 30, 1, 64, 48, "ELU", 15, small_std=True)

@@ -188,6 +188,27 @@ def ref_actor_loss(mods, planning_horizon, prev_state, prev_belief, eps_a, eps_e
     return loss.detach(), {k: v.detach() for k, v in inter.items()}, grads
 
 
+def ref_actor_step(mods, planning_horizon, prev_state, prev_belief, discount=0.995, lambda_=0.95,
+                   entropy_weight=1e-5):
+    """The same block as ref_actor_loss through the reference's STOCK code path (it draws its own
+    noise): what `bench.py --impl reference` times.  Returns the loss as a float."""
+    r = load()
+    d, u = r.dreamer, r.utils
+    agent = fake_agent(mods, planning_horizon)
+    model_modules = mods.transition.modules + [mods.reward]
+    for p in mods.actor.parameters():
+        p.grad = None
+    with u.FreezeParameters(model_modules):
+        beliefs, states, _, entropy = d.Dreamer.imagine_ahead(agent, prev_state.detach(), prev_belief.detach())
+    with u.FreezeParameters(model_modules + [mods.critic]):
+        reward = mods.reward(beliefs, states)
+        value = mods.critic(beliefs, states)
+    returns = d.lambda_return(reward, value, bootstrap=value[-1], discount=discount, lambda_=lambda_)
+    loss = -(returns + entropy_weight * entropy.unsqueeze(-1)).mean()
+    loss.backward()
+    return float(loss.detach())
+
+
 def ref_transition(mods, init_state, actions, init_belief, eps_prior, embeddings=None,
                    nonterminals=None, eps_post=None):
     draws = []
@@ -210,6 +231,22 @@ def ref_cem(mods, action_size, planning_horizon, iters, candidates, top, belief,
         draws += [eps_s[it, h] for h in range(planning_horizon)]
     with NoiseTape(draws).playing(), torch.no_grad():
         return planner(belief, state)
+
+
+def ref_value_update(mods, beliefs, states, target, discount=None):
+    """The critic regression block exactly as src/dreamer.py:369-391 runs it (value_dist =
+    Normal(critic(b, s), 1); -log_prob(target).mean(), optionally weighted by the cumulated discount);
+    returns the loss and the critic's parameter gradients."""
+    from torch.distributions import Normal
+    for p in mods.critic.parameters():
+        p.grad = None
+    value_dist = Normal(mods.critic(beliefs.detach(), states.detach()), 1)
+    if discount is not None:
+        value_loss = -(discount.detach() * value_dist.log_prob(target.detach())).mean()
+    else:
+        value_loss = -value_dist.log_prob(target.detach()).mean()
+    value_loss.backward()
+    return value_loss.detach(), {k: p.grad.detach().clone() for k, p in mods.critic.named_parameters()}
 
 
 def ref_lambda_return(*a, **k):
