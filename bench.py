@@ -72,7 +72,8 @@ def kernel_macs_per_row_step(d):
     rec = m["embed"] + m["gru"] + m["prior"]
     return {"rollout_fwd": rec + m["actor"], "mlp_fwd": 2 * m["head"], "bptt": rec,
             "mlp_bwd": 2 * m["head"] + m["actor_dgrad"], "wgrad": m["actor"], "entropy": 0,
-            "rollout_fused_fwd": rec + m["actor"] + 2 * m["head"], "bptt_fused": rec + 2 * m["head"]}
+            "rollout_fused_fwd": rec + m["actor"] + 2 * m["head"], "bptt_fused": rec + 2 * m["head"],
+            "actor_dgrad": m["actor_dgrad"]}
 
 
 PROF_IDS = {"rollout_fwd": 0, "mlp_fwd": 1, "bptt": 2, "mlp_bwd": 3, "wgrad": 4, "entropy": 5}

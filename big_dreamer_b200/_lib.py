@@ -91,6 +91,20 @@ class ImagineBwdArgs(C.Structure):
                [("actor_dw", C.c_void_p * BD_MAX_LAYERS), ("actor_db", C.c_void_p * BD_MAX_LAYERS)]
 
 
+class ImagineReturnsArgs(C.Structure):
+    _fields_ = [("img", ImagineArgs), ("reward", Mlp), ("value", Mlp), ("discount", C.c_double),
+                ("lambda_", C.c_double)] + \
+               [(n, C.c_void_p) for n in ("reward_out", "value_out", "returns", "heads_saved")]
+
+
+class ImagineReturnsBwdArgs(C.Structure):
+    _fields_ = [("fwd", ImagineReturnsArgs)] + \
+               [(n, C.c_void_p) for n in
+                ("g_beliefs", "g_states", "g_means", "g_stds", "g_entropy", "g_reward", "g_value",
+                 "g_returns", "d_prev_state", "d_prev_belief")] + \
+               [("actor_dw", C.c_void_p * BD_MAX_LAYERS), ("actor_db", C.c_void_p * BD_MAX_LAYERS)]
+
+
 class CemEvalArgs(C.Structure):
     _fields_ = [("rssm", Rssm), ("reward", Mlp), ("B", C.c_int), ("C", C.c_int), ("H", C.c_int),
                 ("c_begin", C.c_int), ("c_end", C.c_int)] + \
@@ -149,6 +163,14 @@ SIGNATURES = {
                                      C.c_void_p]),
     "bd_imagine_backward": (C.c_int, [C.POINTER(ImagineBwdArgs), C.c_void_p, C.c_size_t, C.c_int,
                                       C.c_void_p]),
+    "bd_imagine_returns_supported": (C.c_int, [C.POINTER(Rssm), C.POINTER(Mlp), C.POINTER(Mlp),
+                                               C.POINTER(Mlp), C.c_int]),
+    "bd_imagine_returns_workspace_bytes": (C.c_size_t, [C.POINTER(ImagineReturnsArgs), C.c_int]),
+    "bd_imagine_returns_saved_bytes": (C.c_size_t, [C.POINTER(ImagineReturnsArgs)]),
+    "bd_imagine_returns_forward": (C.c_int, [C.POINTER(ImagineReturnsArgs), C.c_void_p, C.c_size_t,
+                                             C.c_int, C.c_void_p]),
+    "bd_imagine_returns_backward": (C.c_int, [C.POINTER(ImagineReturnsBwdArgs), C.c_void_p, C.c_size_t,
+                                              C.c_int, C.c_void_p]),
     "bd_cem_workspace_bytes": (C.c_size_t, [C.POINTER(Rssm), C.POINTER(Mlp), C.c_int, C.c_int,
                                             C.c_int]),
     "bd_cem_evaluate": (C.c_int, [C.POINTER(CemEvalArgs), C.c_void_p, C.c_size_t, C.c_int,

@@ -296,6 +296,61 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
   return f32::imagine_backward(a, ws, ws_bytes, stream);
 }
 
+int bd_imagine_returns_supported(const bd_rssm* r, const bd_mlp* actor, const bd_mlp* reward,
+                                 const bd_mlp* value, int precision) {
+  if (!(r && actor && reward && value)) return 0;
+  return (tc::imagine_supported(*r, *actor, precision) && tc::heads_supported(*r, *reward, *value)) ? 1 : 0;
+}
+size_t bd_imagine_returns_workspace_bytes(const bd_imagine_returns_args* a, int backward) {
+  if (!a) return 0;
+  return bd_imagine_workspace_bytes(&a->img.rssm, &a->img.actor, a->img.T, a->img.N, backward) +
+         tc::heads_pack_bytes(a->reward, a->value) + (backward ? tc::heads_bwd_workspace_bytes(a->img.rssm, a->reward, a->img.T, a->img.N) : 0) + 65536;
+}
+size_t bd_imagine_returns_saved_bytes(const bd_imagine_returns_args* a) {
+  return a ? tc::heads_saved_bytes(a->reward, a->img.T, a->img.N) : 0;
+}
+int bd_imagine_returns_forward(const bd_imagine_returns_args* a, void* ws, size_t ws_bytes, int precision,
+                               bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  BD_TRY(f32::check_imagine(a->img));
+  const int kin = a->img.rssm.belief_size + a->img.rssm.state_size;
+  BD_TRY(f32::check_mlp(a->reward, kin));
+  BD_TRY(f32::check_mlp(a->value, kin));
+  BD_CHECK_ARG(a->reward_out && a->value_out && a->returns, "bd_imagine_returns_forward: null output");
+  if (a->img.N == 0) return BD_OK;
+  return tc::imagine_returns_forward(&a->img, &a->reward, &a->value, a->discount, a->lambda_, a->reward_out,
+                                     a->value_out, a->returns, a->heads_saved, ws, ws_bytes, precision, stream);
+}
+int bd_imagine_returns_backward(const bd_imagine_returns_bwd_args* a, void* ws, size_t ws_bytes,
+                                int precision, bd_stream_t stream) {
+  BD_NEED(a, "args"); BD_NEED(ws, "workspace");
+  BD_ONLY_FP32(precision);
+  const bd_imagine_args& f = a->fwd.img;
+  BD_TRY(f32::check_imagine(f));
+  if (f.N == 0) return BD_OK;
+  BD_CHECK_ARG(f.tc_saved && a->fwd.heads_saved, "bd_imagine_returns_backward: the forward did not save its state");
+  if (!bd_imagine_returns_supported(&f.rssm, &f.actor, &a->fwd.reward, &a->fwd.value, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "bd_imagine_returns_backward: configuration not supported");
+  // d_raw (T,N,2A) | rest: fused BPTT (lambda-return adjoint + heads dgrad + recurrence), then the actor's
+  // batched backward with weight gradients
+  const int A = f.rssm.action_size, Be = f.rssm.belief_size, S = f.rssm.state_size;
+  const size_t draw_bytes = ((size_t)f.T * f.N * 2 * A * sizeof(float) + 255) & ~size_t(255);
+  BD_CHECK_ARG(ws_bytes > draw_bytes + 65536, "bd_imagine_returns_backward: workspace too small");
+  float* d_raw = static_cast<float*>(ws);
+  void* rest = static_cast<char*>(ws) + draw_bytes;
+  const size_t rest_bytes = ws_bytes - draw_bytes;
+  BD_TRY(tc::imagine_returns_bptt(a, d_raw, rest, rest_bytes, precision, stream));
+  bool want_actor = false;
+  for (int l = 0; l < f.actor.n_layers; ++l) want_actor |= (a->actor_dw[l] || a->actor_db[l]);
+  if (!want_actor) return BD_OK;
+  bd_mlp_bwd_args m{};
+  m.k1 = Be; m.k2 = S;
+  for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }
+  m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
+  return tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N);
+}
+
 size_t bd_cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H) {
   return (r && reward) ? f32::cem_workspace_bytes(r, reward, B, C_local, H) : 0;
 }

@@ -58,6 +58,17 @@ size_t imagine_pack_bytes(const bd_rssm& r, const bd_mlp& actor);
 int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
                     bd_stream_t stream);
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
+// fused imagine + reward/value heads + lambda_return (SURVEY 8b level L2)
+bool heads_supported(const bd_rssm& r, const bd_mlp& reward, const bd_mlp& value);
+size_t heads_pack_bytes(const bd_mlp& reward, const bd_mlp& value);
+size_t heads_saved_bytes(const bd_mlp& reward, int T, long long N);
+size_t heads_bwd_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, int T, long long N);
+int imagine_returns_bptt(const bd_imagine_returns_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes,
+                         int precision, bd_stream_t stream);
+int imagine_returns_forward(const bd_imagine_args* a, const bd_mlp* reward, const bd_mlp* value,
+                            double discount, double lambda_, float* reward_out, float* value_out,
+                            float* returns, void* heads_saved, void* ws, size_t ws_bytes, int precision,
+                            bd_stream_t stream);
 size_t bptt_workspace_bytes(const bd_rssm& r, int T, long long N);
 int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
                  bd_stream_t stream);

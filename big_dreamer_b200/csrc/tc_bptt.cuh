@@ -29,7 +29,8 @@ enum BpttEpi : uint8_t {
   EPI_P_DPRE2 = 1,
   EPI_P_MULSAVED = 2,   // D . saved act' image -> H tile   (aux0: 2 = prior hidden, 1 = embed x)
   EPI_P_GATE = 3,       // gate stage (aux1 = 0: pass A, 1: pass B); aux0 = first column of the slice
-  EPI_P_DSA = 4
+  EPI_P_DSA = 4,
+  EPI_P_HEAD_DY = 5     // fused heads: d h_last = d out . w_out . act'(h_last) -> H tile (no MMA); aux0 = head
 };
 
 struct BpttArgs {
@@ -51,6 +52,16 @@ struct BpttArgs {
   float *scr_carry, *scr_gtot;   // per-CTA scratch, [gridDim.x][128][Kb] fp32
   const unsigned int* amax_bits;
   PrefetchPlan pf;
+  // fused heads (imagine_and_returns): the lambda-return adjoint runs as a per-tile prologue, the heads'
+  // dgrad chains as extra phases at the start of every step (their dX accumulates straight into ACC_B
+  // and the carried d s in TMEM).  n_heads = 0: plain imagine BPTT.
+  int n_heads, kh_hd;
+  const uint16_t* sv_hd[2 * BD_MAX_LAYERS];   // act' images of the heads' hidden layers (forward-saved)
+  const float* w_out[2];                      // last layer of each head: (1, hidden)
+  int hd_last;                                // index of the last hidden layer (n_layers - 2)
+  const float *g_returns, *g_reward, *g_value;   // upstream (T,N), each optional
+  float lr_disc, lr_lam;
+  float* scr_drv;                             // per-CTA [T][2][128]: d reward, d value of the tile's rows
 };
 
 // Upstream belief gradients (T,N,Be) row-major -> per (t, tile) images [col/4][row][4] (zero padded),
@@ -116,12 +127,30 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
     float* gtot = a.scr_gtot + (size_t)blockIdx.x * kTileRows * Kb + row * 4;
 #define SIDX(col) ((size_t)((col) >> 2) * (kTileRows * 4))
     float inv_scale;
-    const float scale = grad_scale(a.amax_bits, &inv_scale);
+    const float scale = grad_scale(a.amax_bits, &inv_scale, a.n_heads ? 5 : 0);
     uint32_t Ge = 0, Gm = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
-      mbar_arrive(&sh.epi_done[Ge & 7]);   // nothing to initialise per tile
+      if (a.n_heads && half == 0) {
+        // adjoint of lambda_return with bootstrap = value[-1] (f32::lambda_return_bwd_kernel), forward in
+        // time: G[t] = g_ret[t] + disc lam G[t-1]; d r[t] = G[t]; d v[t+1] += disc (1-lam) G[t];
+        // d v[T-1] += disc G[T-1] (the bootstrap enters as next value and as the initial return)
+        float* drv = a.scr_drv + (size_t)blockIdx.x * a.T * 2 * kTileRows + row;
+        const long long lrow = rvalid ? grow : 0;
+        float G = 0.f, dv_next = 0.f;
+        for (int t = 0; t < a.T; ++t) {
+          const long long o = (long long)t * a.N + lrow;
+          G = (a.g_returns ? a.g_returns[o] : 0.f) + a.lr_disc * a.lr_lam * G;
+          float dv = dv_next + (a.g_value ? a.g_value[o] : 0.f);
+          if (t == a.T - 1) dv += a.lr_disc * G;
+          drv[(size_t)(t * 2 + 0) * kTileRows] = rvalid ? G + (a.g_reward ? a.g_reward[o] : 0.f) : 0.f;
+          drv[(size_t)(t * 2 + 1) * kTileRows] = rvalid ? dv : 0.f;
+          dv_next = a.lr_disc * (1.f - a.lr_lam) * G;
+        }
+      }
+      if (a.n_heads) asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves read the row's d r / d v
+      mbar_arrive(&sh.epi_done[Ge & 7]);   // nothing else to initialise per tile
       ++Ge;
       for (int i = 0; i < a.T; ++i) {
         const int t = a.T - 1 - i;
@@ -182,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               for (int c = half * 16; c < Sp; c += 32) {
                 if (c != half * 16) load_chunk(c);
                 float cs[16], m_[16], s_[16];
-                if (i > 0) {
-                  tmem_ld16(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA
+                if (i > 0 || a.n_heads) {
+                  tmem_ld16(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA (+ the heads' d s_t)
                   tmem_ld_wait();
                 } else {
 #pragma unroll
@@ -208,8 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
             } break;
             case EPI_P_MULSAVED: {
-              const int kp = ph.aux0 == 1 ? Kb : a.Kh;
-              const uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) + tl * kTileRows * kp + row * 8;
+              const int kp = ph.aux0 == 1 ? Kb : (ph.aux0 == 2 ? a.Kh : a.kh_hd);
+              const uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : (ph.aux0 == 2 ? a.sv_ha : a.sv_hd[ph.aux0 - 16])) +
+                                    tl * kTileRows * kp + row * 8;
               const uint32_t tacc = trow + ph.d_col;
               for (int c = half * 32; c < kp; c += 64) {
                 float v[32];
@@ -374,6 +404,38 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                       *reinterpret_cast<float4*>(carry + SIDX(col0 + g8 * 8 + 4)) =
                           make_float4(G[g8 * 8 + 4] * zf[4], G[g8 * 8 + 5] * zf[5], G[g8 * 8 + 6] * zf[6], G[g8 * 8 + 7] * zf[7]);
                     }
+                  }
+                }
+              }
+            } break;
+            case EPI_P_HEAD_DY: {
+              // d h_last[row, c] = d out[t, row] . w_out[c] . act'(h_last)[row, c]   (the scalar output layer's
+              // dgrad is a rank-1 product: no MMA); operands carry the gradient scale
+              const int k = ph.aux0, kp = a.kh_hd;
+              const uint16_t* img = a.sv_hd[k * BD_MAX_LAYERS + a.hd_last] + tl * kTileRows * kp + row * 8;
+              const float* wo = a.w_out[k];
+              const float dout = a.scr_drv[((size_t)blockIdx.x * a.T + t) * 2 * kTileRows + (size_t)k * kTileRows + row] * scale;
+              uint4 hu[4];
+              float wv[32];
+              auto load_chunk = [&](int c) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8)
+                  if (c + g8 * 8 < kp) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) wv[j] = (c + j < ph.n_valid) ? wo[c + j] : 0.f;
+              };
+              if (half * 32 < kp) load_chunk(half * 32);
+              BD_WAIT_ACC();             // the previous phase's MMAs (which read the H tile) are done
+              for (int c = half * 32; c < kp; c += 64) {
+                if (c != half * 32) load_chunk(c);
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  if (c + g8 * 8 < kp) {
+                    float h[8], o[8];
+                    unpack8<FMT>(hu[g8], h);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = dout * wv[g8 * 8 + j] * h[j];
+                    store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, o);
                   }
                 }
               }

@@ -135,6 +135,13 @@ struct RolloutArgs {
   uint16_t *sv_gate, *sv_xa, *sv_ha;
   int kb_sv, kh_sv;
   uint16_t* sv_mlp[BD_MAX_LAYERS];   // MLP forward: image of hidden layer l (cols = its Kp_out)
+  // fused Dreamer rollout (imagine_and_returns): act'(h) images of the two heads' hidden layers per
+  // (t, tile) for the fused backward (index head * BD_MAX_LAYERS + layer; null = do not save), and the
+  // lambda-return tail (src/dreamer.py:447-471 with bootstrap = value[-1], :329-335) over head_out[0/1]
+  uint16_t* sv_hd[2 * BD_MAX_LAYERS];
+  int kh_hd;                         // columns of those images
+  float* returns;                    // (T,N); null = no tail
+  float lr_disc, lr_lam, lr_oml;     // discount, lambda, 1 - lambda as fp32 (rounded like the standalone kernel)
   int has_b1;                 // 0: single belief tile (MLP forward), 1: ping-pong
   // CEM: rows are (batch row, local candidate); start latents are per batch row and the state
   // noise is indexed by the GLOBAL candidate (src/planner.py:37-39, 53-65)
@@ -268,7 +275,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
       const uint32_t par = (uint32_t)t & 1u;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
-        long long c1 = 0, wsum = 0, dsum = 0;
+        long long c1 = 0, wsum = 0, dsum = 0, msum = 0;
         if (PROF) c1 = clock64();
         for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
           const Gemm g = P.g[gi];
@@ -310,6 +317,8 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             if (PROF) wsum += clock64() - w0;
             uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
                               (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu);
+            long long m0 = 0;
+            if (PROF) m0 = clock64();
             for (int ks = 0; ks < kc; ks += 16) {
               // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
               umma_f16_u(d_tmem, a_desc, b_desc, idesc, acc);
@@ -317,6 +326,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               a_desc += 2 * (kLboA >> 4);
               b_desc += 2 * (lbo_b >> 4);
             }
+            if (PROF) msum += clock64() - m0;
             umma_commit_elect(bar_w_empty + st * 8);
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
@@ -327,6 +337,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           prof[pi * 8 + 0] += dsum;                          // issuer: wait for the dependency epilogue(s)
           prof[pi * 8 + 1] += wsum;                          // issuer: wait for weight stages
           prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum;  // issuer: issue time
+          prof[pi * 8 + 7] += msum;                          // of which: inside the tcgen05.mma loops
         }
         ++Gm;
         Ge += ph.n_sub;
@@ -494,7 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
-              uint8_t* out = smem + a.sm.off_tile[ph.out_tile] + (row >> 3) * 128 + (row & 7) * 16;
+              // (a belief tile as output = the ping-pong half that is free at this point: the fused
+              // heads' second hidden tile)
+              const int otile = ph.out_tile < 2 ? (ph.out_tile ^ par) : ph.out_tile;
+              uint8_t* out = smem + a.sm.off_tile[otile] + (row >> 3) * 128 + (row & 7) * 16;
               const int nv = ph.n_valid;
               for (int sub = 0; sub < ph.n_sub; ++sub) {
               // this rank's columns are [col0, Kp_out) (col0 = 0 unless column-split); the
@@ -533,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                   put8(p + 2 * kLboA, v + 16);
                   put8(p + 3 * kLboA, v + 24);
                 }
-                if (ph.aux0 >= 3 && a.sv_mlp[ph.aux0 - 3]) {   // MLP forward: keep the hidden image itself
+                if (ph.aux0 >= 3 && ph.aux0 < 3 + BD_MAX_LAYERS && a.sv_mlp[ph.aux0 - 3]) {   // MLP forward: keep the hidden image itself
                   uint16_t* img = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * ph.Kp_out + row * 8;
 #pragma unroll
                   for (int g8 = 0; g8 < 4; ++g8) {
@@ -547,9 +561,12 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                                      Half16<FMT>::pack2(hv[4], hv[5]), Half16<FMT>::pack2(hv[6], hv[7]));
                     }
                   }
-                } else if (ph.aux0 && ph.aux0 < 3 && a.sv_xa) {   // act'(output) for BPTT (1: embed x, 2: prior h)
-                  const int kp = ph.aux0 == 1 ? a.kb_sv : a.kh_sv;
-                  uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) +
+                } else if ((ph.aux0 == 1 || ph.aux0 == 2) ? a.sv_xa != nullptr
+                                                          : (ph.aux0 >= 16 && a.sv_hd[ph.aux0 - 16] != nullptr)) {
+                  // act'(output) images for the backward: 1 = embed x, 2 = prior h, 16 + head * BD_MAX_LAYERS + l =
+                  // hidden layer l of a fused head
+                  const int kp = ph.aux0 == 1 ? a.kb_sv : (ph.aux0 == 2 ? a.kh_sv : a.kh_hd);
+                  uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : (ph.aux0 == 2 ? a.sv_ha : a.sv_hd[ph.aux0 - 16])) +
                                   ((size_t)t * ntiles + tile) * kTileRows * kp + row * 8;
 #pragma unroll
                   for (int g8 = 0; g8 < 4; ++g8) {
@@ -808,6 +825,23 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           }
           ++Ge;
           ++Gm;
+        }
+      }
+      // lambda-return tail of the fused Dreamer rollout: this thread wrote reward / value of its row
+      // for every step (EPI_HEAD_OUT, half 0), so program order makes them visible to it.  Same
+      // arithmetic (separate fp32 roundings, no FMA contraction) as f32::lambda_return_fwd_kernel.
+      if (a.returns != nullptr && half == 0 && rvalid && wr0) {
+        const float* rw = a.head_out[0];
+        const float* vl = a.head_out[1];
+        float last = vl[(long long)(a.T - 1) * a.N + grow];      // bootstrap = value[-1]
+        float nextv = last;
+        const float dl = __fmul_rn(a.lr_disc, a.lr_lam);
+        for (int t = a.T - 1; t >= 0; --t) {
+          const long long o = (long long)t * a.N + grow;
+          const float inp = __fadd_rn(rw[o], __fmul_rn(__fmul_rn(a.lr_disc, nextv), a.lr_oml));
+          last = __fadd_rn(inp, __fmul_rn(dl, last));
+          a.returns[o] = last;
+          nextv = vl[o];
         }
       }
     }

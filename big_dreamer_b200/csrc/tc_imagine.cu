@@ -124,7 +124,7 @@ struct ActSrc { const float* w; int ld, src_c0, len, Kp, a_tile; const float* bi
 // its first GEMM chained on the previous phase's early publication when chain_split > 0 (returns
 // this phase's own split).  R > 1: this rank's column slice of the layer (weight rows [c0, c1)).
 static int add_act_phase(Builder& b, int rank, int R, const ActSrc* src, int nsrc, int n, int Kp_out,
-                         int aux0, int out_tile, int chain_split) {
+                         int aux0, int out_tile, int chain_split, int dep_back = 1, bool allow_split = true) {
   const int Np = r16(n);
   int c0 = 0, c1 = Kp_out;
   if (R > 1) split_cols(Kp_out / 16, rank, R, c0, c1);
@@ -137,9 +137,9 @@ static int add_act_phase(Builder& b, int rank, int R, const ActSrc* src, int nsr
     if (i == 0 && R == 1 && chain_split > 0) b.chain_gemm(off, Nr, x.Kp, x.a_tile, d, chain_split);
     else b.add_gemm(off, Nr, x.Kp, x.a_tile, 0, d, i > 0 ? 1 : 0);
   }
-  b.end_phase(EPI_ACT_H, 1, n, Nr, c1, d, aux0, out_tile);
+  b.end_phase(EPI_ACT_H, dep_back, n, Nr, c1, d, aux0, out_tile);
   if (b.ok) b.prog.p[b.prog.n_phases - 1].col0 = (uint16_t)c0;
-  return R == 1 ? b.split_last_phase() : 0;
+  return (R == 1 && allow_split) ? b.split_last_phase() : 0;
 }
 // GRUCell in N-slices of <= 64 belief columns: accumulators IN | R | Z | HN per slice.  Stacked
 // gate images: 3 GEMMs per slice instead of 6, so the A tiles (x, h) are fetched from shared
@@ -220,8 +220,91 @@ static int launch_rollout(int fmt, int act, bool with_actor, bool prof, unsigned
   return with_actor ? launch_rollout_f1a(act, prof, grid, ra, s) : launch_rollout_f1n(act, prof, grid, ra, s);
 }
 
-int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
-                    bd_stream_t stream) {
+// ---------------------------------------------------------------------------------------------
+// Fused Dreamer rollout (imagine_and_returns, SURVEY 8b level L2): the reward and value heads
+// (src/dreamer.py:321-322) ride in the per-step program and lambda_return (:329-335) is the kernel's
+// tail.  The two heads are independent chains: their layers alternate (reward L_k, value L_k,
+// reward L_k+1, ...), each depending on the epilogue TWO phases back, so the MMAs of one head run
+// under the epilogue of the other (the reward chain lives in the H tile, the value chain in the
+// belief ping-pong half that is free between the GRU of this step and the GRU of the next).
+// ---------------------------------------------------------------------------------------------
+struct HeadsFwd {
+  const bd_mlp* head[2];        // reward, value
+  float* out[2];                // (T,N) each
+  float* returns;               // (T,N)
+  double discount, lambda_;
+  void* saved;                  // act' images for the fused backward (heads_saved_bytes), or null
+};
+static int head_hidden(const bd_mlp& m) { return m.layer[0].out_features; }
+bool heads_supported(const bd_rssm& r, const bd_mlp& reward, const bd_mlp& value) {
+  const bd_mlp* hs[2] = {&reward, &value};
+  if (reward.n_layers != value.n_layers) return false;
+  for (const bd_mlp* m : hs) {
+    if (m->n_layers < 2 || m->n_layers > BD_MAX_LAYERS || m->activation != r.activation) return false;
+    if (m->layer[0].in_features != r.belief_size + r.state_size) return false;
+    if (m->layer[m->n_layers - 1].out_features != 1) return false;
+    const int hh = head_hidden(*m);
+    for (int l = 0; l + 1 < m->n_layers; ++l)
+      if (m->layer[l].out_features != hh || (l > 0 && m->layer[l].in_features != hh)) return false;
+    // hidden tile = a belief tile; backward: one 208-column accumulator region beside ACC_B / d_s
+    if (r16(hh + 1) > r16(r.belief_size + 1) || r16(hh) > 208) return false;
+  }
+  if (r16(r.belief_size) > 208 || r16(r.state_size + r.action_size) > 48) return false;
+  // program tables: imagine (<= 12 phases / ~31 GEMMs at 4 GRU slices) + 2 n_layers phases
+  const int slices = (r.belief_size + 63) / 64;
+  if (8 + slices + 2 * reward.n_layers > kMaxPhases) return false;
+  if (16 + 4 * slices + 2 * (reward.n_layers + 1) > kMaxGemms) return false;
+  return 13 + 3 * slices + 2 * (reward.n_layers + 1) <= kMaxPackJobs;
+}
+size_t heads_pack_bytes(const bd_mlp& reward, const bd_mlp& value) {
+  return 2 * mlp_pack_bytes(reward) + 2 * mlp_pack_bytes(value) + (size_t)kMaxRanks * 2 * 16 * 272 * 2;
+}
+struct HeadsSaved { size_t off[2][BD_MAX_LAYERS], total; int Kh; };
+static HeadsSaved heads_saved_layout(const bd_mlp& reward, int T, long long N) {
+  HeadsSaved h{};
+  h.Kh = r16(head_hidden(reward));
+  const size_t per = (size_t)((N + kTileRows - 1) / kTileRows) * T * kTileRows * h.Kh * 2;
+  size_t o = 0;
+  for (int k = 0; k < 2; ++k)
+    for (int l = 0; l + 1 < reward.n_layers; ++l) { h.off[k][l] = o; o += per; }
+  h.total = o;
+  return h;
+}
+size_t heads_saved_bytes(const bd_mlp& reward, int T, long long N) { return heads_saved_layout(reward, T, N).total + 256; }
+
+static void add_head_phases(Builder& b, const bd_rssm& r, const HeadsFwd& hd, int rank, int R, int Kp_b, int Ks) {
+  const int Be = r.belief_size, S = r.state_size;
+  const int L = hd.head[0]->n_layers;
+  for (int l = 0; l < L; ++l)
+    for (int k = 0; k < 2; ++k) {
+      const bd_mlp& m = *hd.head[k];
+      const bd_linear& Lr = m.layer[l];
+      const int tile = k == 0 ? TILE_H : TILE_BCUR;        // this head's hidden tile
+      const int dep = (l == 0 && k == 0) ? 1 : 2;           // the same head's previous layer is two phases back
+      const int n = Lr.out_features;
+      if (l + 1 < L) {
+        const int aux = hd.saved ? 16 + k * BD_MAX_LAYERS + l : 0;
+        if (l == 0) {
+          ActSrc s0[2] = {{Lr.w, Be + S, 0, Be, Kp_b, TILE_BNXT, Lr.b, Be},
+                          {Lr.w, Be + S, Be, S, Ks, TILE_SA, nullptr, -1}};
+          add_act_phase(b, rank, R, s0, 2, n, r16(n + 1), aux, tile, 0, dep, false);
+        } else {
+          const int kin = Lr.in_features;
+          ActSrc sl{Lr.w, kin, 0, kin, r16(kin + 1), tile, Lr.b, kin};
+          add_act_phase(b, rank, R, &sl, 1, n, r16(n + 1), aux, tile, 0, dep, false);
+        }
+      } else {   // scalar output: replicated on every rank
+        const int kin = Lr.in_features, Kp = r16(kin + 1);
+        const int d = b.dcol();
+        uint32_t w = b.add_pack(Lr.w, kin, 0, 1, 16, Kp, 0, kin, Lr.b, kin);
+        b.add_gemm(w, 16, Kp, tile, 0, d, 0);
+        b.end_phase(EPI_HEAD_OUT, dep, 1, 16, 0, d, k, tile);
+      }
+    }
+}
+
+static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, void* ws, size_t ws_bytes,
+                                int precision, bd_stream_t stream) {
   const bd_rssm& r = a->rssm;
   const bd_mlp& ac = a->actor;
   if (!imagine_supported(r, ac, precision))
@@ -229,7 +312,9 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
                                 "(Be,Hi <= 255, S <= 128, A <= 16, ELU/ReLU/Tanh/Identity)");
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
   const int Kp_b = r16(Be + 1), Kp_sa = r16(S + A + 1), Kp_hid = r16(Hi + 1), Kp_x = r16(Be + 1);
-  const int Kp_h = max(Kp_hid, Kp_x), Ks = r16(S);
+  const int Ks = r16(S);
+  int Kp_h = max(Kp_hid, Kp_x);
+  if (hd) Kp_h = max(Kp_h, r16(head_hidden(*hd->head[0]) + 1));
   const int Nh = r16(Hi), Nb = r16(Be), Ap = 16, Sp = r16(S);
   const long long ntiles = (a->N + kTileRows - 1) / kTileRows;
   const int act_n[2] = {Hi, Be}, act_kp[2] = {Kp_hid, Kp_x};
@@ -257,6 +342,7 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
       b.end_phase(EPI_ACTOR_OUT, 1, 2 * A, Ap, 0, d, 0, TILE_SA);
     }
     add_transition_phases(b, r, rank, R, Kp_b, Kp_sa, Kp_hid, Kp_x, true);
+    if (hd) add_head_phases(b, r, *hd, rank, R, Kp_b, Ks);
     if (R > 1) b.end_rank(rank);
   }
   if (b.ok || R == 1) break;
@@ -279,6 +365,17 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   ra.beliefs = a->beliefs; ra.states = a->states; ra.means = a->means; ra.stds = a->stds;
   ra.entropy = a->entropy; ra.actions = a->actions; ra.actor_raw = a->actor_raw; ra.dent = a->dent;
   ra.has_b1 = 1;
+  if (hd) {
+    ra.head_out[0] = hd->out[0]; ra.head_out[1] = hd->out[1]; ra.returns = hd->returns;
+    ra.lr_disc = (float)hd->discount; ra.lr_lam = (float)hd->lambda_; ra.lr_oml = (float)(1.0 - hd->lambda_);
+    if (hd->saved) {
+      const HeadsSaved hs = heads_saved_layout(*hd->head[0], a->T, a->N);
+      ra.kh_hd = hs.Kh;
+      for (int k = 0; k < 2; ++k)
+        for (int l = 0; l + 1 < hd->head[0]->n_layers; ++l)
+          ra.sv_hd[k * BD_MAX_LAYERS + l] = reinterpret_cast<uint16_t*>(static_cast<char*>(hd->saved) + hs.off[k][l]);
+    }
+  }
   if (a->tc_saved) {
     SavedLayout sl = saved_layout(r, a->T, a->N);
     char* sb = static_cast<char*>(a->tc_saved);
@@ -324,6 +421,23 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
   }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
+}
+
+int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int precision,
+                    bd_stream_t stream) {
+  return imagine_forward_impl(a, nullptr, ws, ws_bytes, precision, stream);
+}
+int imagine_returns_forward(const bd_imagine_args* a, const bd_mlp* reward, const bd_mlp* value,
+                            double discount, double lambda_, float* reward_out, float* value_out,
+                            float* returns, void* heads_saved, void* ws, size_t ws_bytes, int precision,
+                            bd_stream_t stream) {
+  if (!imagine_supported(a->rssm, a->actor, precision) || !heads_supported(a->rssm, *reward, *value))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "fused imagine + heads + lambda_return: configuration not supported by the "
+                                "tensor-core rollout (use the piecewise entries)");
+  HeadsFwd hd{};
+  hd.head[0] = reward; hd.head[1] = value; hd.out[0] = reward_out; hd.out[1] = value_out;
+  hd.returns = returns; hd.discount = discount; hd.lambda_ = lambda_; hd.saved = heads_saved;
+  return imagine_forward_impl(a, &hd, ws, ws_bytes, precision, stream);
 }
 
 bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision) {
@@ -498,12 +612,13 @@ int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, i
 // BPTT of the imagination rollout on the tensor-core engine (tc_bptt.cuh)
 // ---------------------------------------------------------------------------------------------
 static uint32_t add_pack_T(Builder& b, const float* w, int ld, int n_valid, int Np, int Kp, int nseg,
-                           const PackSeg* segs) {
+                           const PackSeg* segs, int col0 = 0) {
   // packed(n, k) = w[src_row(k), n]: the dgrad (transposed) image of an nn.Linear weight
   if (b.pack.njobs >= kMaxPackJobs) { b.ok = false; return 0; }
   PackJob& j = b.pack.job[b.pack.njobs++];
   j = PackJob{};
-  j.w = w; j.bias = nullptr; j.dst_off = b.w_elems; j.ld = ld; j.row0 = 0; j.N = n_valid; j.Np = Np;
+  // (transposed jobs: image row n <- source COLUMN col0 + n)
+  j.w = w; j.bias = nullptr; j.dst_off = b.w_elems; j.ld = ld; j.row0 = col0; j.N = n_valid; j.Np = Np;
   j.Kp = Kp; j.bias_k = -1; j.nseg = nseg; j.transpose = 1;
   for (int i = 0; i < nseg; ++i) j.seg[i] = segs[i];
   const uint32_t off = (uint32_t)b.w_elems;
@@ -519,8 +634,21 @@ size_t bptt_workspace_bytes(const bd_rssm& r, int T, long long N) {
   return pack * 2 + 4096 + (size_t)2 * 160 * kTileRows * Kb * 4 + 65536 + gbt;
 }
 
-int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
-                 bd_stream_t stream) {
+struct HeadsBwd {
+  const bd_mlp* head[2];
+  const void* saved;
+  const float *g_returns, *g_reward, *g_value;
+  double discount, lambda_;
+};
+size_t heads_bwd_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, int T, long long N) {
+  (void)r; (void)N;
+  const size_t kh = r16(head_hidden(reward));
+  size_t pack = 2 * ((size_t)(reward.n_layers - 2) * kh * kh + kh * 256 + kh * 48);   // W^T images of both heads
+  return pack * 2 + (size_t)160 * T * 2 * kTileRows * sizeof(float) + 8192;
+}
+
+static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, float* d_raw, void* ws,
+                             size_t ws_bytes, int precision, bd_stream_t stream) {
   const bd_imagine_args& f = a->fwd;
   const bd_rssm& r = f.rssm;
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
@@ -528,7 +656,31 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   if (!f.tc_saved) BD_FAIL(BD_ERR_BAD_ARG, "imagine_bptt: forward did not save tensor-core state");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Builder b;
-  // p0: d_pre2 (no MMA)
+  const int hL = hb ? hb->head[0]->n_layers : 0;
+  const int Khd = hb ? r16(head_hidden(*hb->head[0])) : 0;
+  if (hb) {
+    // fused heads: for head k, d h_last (rank-1, no MMA) -> dgrad through the hidden layers (D . act'(h) from the
+    // forward's images) -> dX = d h_0 W_0, whose belief part accumulates into ACC_B and whose state part into the
+    // carried d s (TMEM columns [256, 256 + Sp)); the chain's own accumulator sits at column 304.  The dX GEMMs of
+    // head k ride in the phase whose epilogue starts the next chain (its accumulator wait keeps the H tile safe).
+    for (int k = 0; k < 2; ++k) {
+      const bd_mlp& m = *hb->head[k];
+      b.end_phase(EPI_P_HEAD_DY, 1, head_hidden(m), 0, 0, 0, k, TILE_H);
+      for (int l = hL - 2; l >= 1; --l) {       // d h_{l-1} = (d h_l W_l) . act'(h_{l-1})
+        PackSeg sg[1] = {{0, 0, m.layer[l].out_features}};
+        uint32_t w = add_pack_T(b, m.layer[l].w, m.layer[l].in_features, m.layer[l].in_features, Khd, Khd, 1, sg);
+        b.add_gemm(w, Khd, Khd, TILE_H, 0, 304, 0);
+        b.end_phase(EPI_P_MULSAVED, 1, m.layer[l].in_features, Khd, 0, 304, 16 + k * BD_MAX_LAYERS + (l - 1), TILE_H);
+      }
+      PackSeg sg[1] = {{0, 0, m.layer[0].out_features}};
+      uint32_t wb = add_pack_T(b, m.layer[0].w, Be + S, Be, Kb, Khd, 1, sg, 0);
+      uint32_t wsx = add_pack_T(b, m.layer[0].w, Be + S, S, Sp, Khd, 1, sg, Be);
+      b.add_gemm(wb, Kb, Khd, TILE_H, 0, 0, k == 0 ? 2 : 1);        // ACC_B (+)= d h_0 W_0[:, :Be]
+      b.add_gemm(wsx, Sp, Khd, TILE_H, 0, 256, k == 0 ? 2 : 1);     // d s   (+)= d h_0 W_0[:, Be:]
+      // (closed by the next end_phase: head 1's HEAD_DY, or p0 below)
+    }
+  }
+  // p0: d_pre2 (no MMA of its own)
   b.end_phase(EPI_P_DPRE2, 1, 2 * S, 0, 0, 0, 0, TILE_D2);
   // p1: DH = d_pre2 * W_p2  (K = [mean rows | std rows], N = Hi)
   {
@@ -542,7 +694,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   {
     PackSeg sg[1] = {{0, 0, Hi}};
     uint32_t w = add_pack_T(b, r.prior1.w, Be, Be, Kb, Kh, 1, sg);
-    b.add_gemm(w, Kb, Kh, TILE_H, 0, 0, 2);
+    b.add_gemm(w, Kb, Kh, TILE_H, 0, 0, hb ? 1 : 2);     // (with fused heads ACC_B already holds their d b_t)
   }
   int nsl = 0, n0s[8], nss[8], nvs[8];
   for (int n0 = 0; n0 < Be; n0 += 64) { n0s[nsl] = n0; nvs[nsl] = min(64, Be - n0); nss[nsl] = r16(nvs[nsl]); ++nsl; }
@@ -614,12 +766,14 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   // HBM round trip of T*N*Be*4 bytes costs more than the coalescing saves beyond that)
   const bool tile_gb = a->g_beliefs && (size_t)f.T * f.N * Be * 4 <= ((size_t)48 << 20);
   float* gbt = tile_gb ? reinterpret_cast<float*>(take((size_t)f.T * ntiles * kTileRows * Kb * 4)) : nullptr;
+  float* scr_drv = hb ? reinterpret_cast<float*>(take((size_t)grid * f.T * 2 * kTileRows * 4)) : nullptr;
   if (off > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core BPTT: workspace %zu < %zu", ws_bytes, off);
   cudaMemsetAsync(amax, 0, 256, s);
   {
-    const float* gs[5] = {a->g_beliefs, a->g_states, a->g_means, a->g_stds, a->g_entropy};
-    const long long ns[5] = {(long long)f.T * f.N * Be, (long long)f.T * f.N * S, (long long)f.T * f.N * S,
-                             (long long)f.T * f.N * S, (long long)f.T * f.N};
+    const float* gs[8] = {a->g_beliefs, a->g_states, a->g_means, a->g_stds, a->g_entropy,
+                          hb ? hb->g_returns : nullptr, hb ? hb->g_reward : nullptr, hb ? hb->g_value : nullptr};
+    const long long tn = (long long)f.T * f.N;
+    const long long ns[8] = {tn * Be, tn * S, tn * S, tn * S, tn, tn, tn, tn};
     if (gbt) {     // upstream belief gradients in the kernel's tile layout (coalesced gate-stage reads)
       gb_tile_kernel<<<dim3((unsigned)ntiles, (unsigned)f.T, (unsigned)((Kb + 63) / 64)), 256, 0, s>>>(
           a->g_beliefs, f.N, Be, Kb, ntiles, gbt, amax);
@@ -628,7 +782,7 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
     AbsmaxJobs jobs{};
     int nj = 0;
     long long nmax = 0;
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 8; ++i) {
       if (!gs[i] || (i == 0 && gbt)) continue;      // g_beliefs: folded into gb_tile_kernel
       jobs.x[nj] = gs[i]; jobs.n[nj] = ns[i]; ++nj;
       nmax = max(nmax, ns[i]);
@@ -667,6 +821,19 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   ba.d_raw = d_raw; ba.d_prev_state = a->d_prev_state; ba.d_prev_belief = a->d_prev_belief;
   ba.scr_carry = scr_carry; ba.scr_gtot = scr_gtot; ba.amax_bits = amax;
   ba.gbt = gbt;
+  if (hb) {
+    // the lambda-return adjoint sums up to T upstream terms per row: leave headroom in the fp16 operands
+    ba.n_heads = 2; ba.kh_hd = Khd; ba.hd_last = hL - 2;
+    const HeadsSaved hs = heads_saved_layout(*hb->head[0], f.T, f.N);
+    for (int k = 0; k < 2; ++k) {
+      ba.w_out[k] = hb->head[k]->layer[hL - 1].w;
+      for (int l = 0; l + 1 < hL; ++l)
+        ba.sv_hd[k * BD_MAX_LAYERS + l] = reinterpret_cast<const uint16_t*>(static_cast<const char*>(hb->saved) + hs.off[k][l]);
+    }
+    ba.g_returns = hb->g_returns; ba.g_reward = hb->g_reward; ba.g_value = hb->g_value;
+    ba.lr_disc = (float)hb->discount; ba.lr_lam = (float)hb->lambda_;
+    ba.scr_drv = scr_drv;
+  }
   {
     // next-step inputs the producer warp prefetches into L2 (per tile and time step)
     PrefetchPlan& pf = ba.pf;
@@ -717,6 +884,24 @@ int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws
   }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
+}
+
+int imagine_bptt(const bd_imagine_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes, int precision,
+                 bd_stream_t stream) {
+  return imagine_bptt_impl(a, nullptr, d_raw, ws, ws_bytes, precision, stream);
+}
+int imagine_returns_bptt(const bd_imagine_returns_bwd_args* a, float* d_raw, void* ws, size_t ws_bytes,
+                         int precision, bd_stream_t stream) {
+  bd_imagine_bwd_args ia{};
+  ia.fwd = a->fwd.img;
+  ia.g_beliefs = a->g_beliefs; ia.g_states = a->g_states; ia.g_means = a->g_means; ia.g_stds = a->g_stds;
+  ia.g_entropy = a->g_entropy; ia.d_prev_state = a->d_prev_state; ia.d_prev_belief = a->d_prev_belief;
+  for (int l = 0; l < BD_MAX_LAYERS; ++l) { ia.actor_dw[l] = a->actor_dw[l]; ia.actor_db[l] = a->actor_db[l]; }
+  HeadsBwd hb{};
+  hb.head[0] = &a->fwd.reward; hb.head[1] = &a->fwd.value; hb.saved = a->fwd.heads_saved;
+  hb.g_returns = a->g_returns; hb.g_reward = a->g_reward; hb.g_value = a->g_value;
+  hb.discount = a->fwd.discount; hb.lambda_ = a->fwd.lambda_;
+  return imagine_bptt_impl(&ia, &hb, d_raw, ws, ws_bytes, precision, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

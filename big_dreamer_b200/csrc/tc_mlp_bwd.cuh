@@ -48,13 +48,15 @@ struct MlpBwdArgs {
 // 16-bit operands carry dy * 2^k with k chosen (on the device, from max|dy|) so that the largest
 // magnitude lands in [128, 256); results are multiplied by 2^-k on the way out.  Powers of two
 // make the scaling exact.
-__device__ __forceinline__ float grad_scale(const unsigned int* amax_bits, float* inv) {
+// `shift` lowers the target by 2^shift (headroom when the kernel itself amplifies the upstream
+// gradients, e.g. the fused heads: a lambda-return adjoint sums up to 1 / (1 - disc lam) terms).
+__device__ __forceinline__ float grad_scale(const unsigned int* amax_bits, float* inv, int shift = 0) {
   const float amax = __uint_as_float(*amax_bits);
   int e = 0;
   float sc = 1.f;
   if (amax > 0.f && amax < 3.0e38f) {
     frexpf(amax, &e);
-    int k = 8 - e;
+    int k = 8 - shift - e;
     k = max(-100, min(100, k));
     sc = ldexpf(1.f, k);
   }
@@ -74,7 +76,7 @@ static __global__ void absmax_kernel(const float* __restrict__ x, long long n, u
 }
 
 // several tensors in one launch (blockIdx.y selects the tensor): the BPTT's upstream gradients
-struct AbsmaxJobs { const float* x[6]; long long n[6]; };
+struct AbsmaxJobs { const float* x[8]; long long n[8]; };
 static __global__ void absmax_multi_kernel(const AbsmaxJobs jobs, unsigned int* out) {
   const float* __restrict__ x = jobs.x[blockIdx.y];
   const long long n = jobs.n[blockIdx.y];

@@ -401,6 +401,113 @@ class ImagineFunction(torch.autograd.Function):
 
 
 # =============================================================================
+# imagine_ahead + reward / value heads + lambda_return, fused (src/dreamer.py:313-335)
+# =============================================================================
+def _fill_imagine_args(a, dims, actor_cfg, T, N, s0, b0, ea, ee, es, AP, RP, outs):
+    a.rssm = make_rssm(RP, dims)
+    a.actor = _lib.make_mlp(AP[0::2], AP[1::2], actor_cfg.get("act_id", dims["act_id"]))
+    a.actor_cfg = _lib.ActorCfg(actor_cfg["mean_scale"], actor_cfg["raw_init_std"],
+                                actor_cfg["min_std"], actor_cfg["entropy_samples"])
+    a.T, a.N = T, N
+    a.prev_state, a.prev_belief = _lib.ptr(s0), _lib.ptr(b0)
+    a.eps_a, a.eps_e, a.eps_s = _lib.ptr(ea), _lib.ptr(ee), _lib.ptr(es)
+    (a.beliefs, a.states, a.means, a.stds, a.entropy, a.actions, a.actor_raw,
+     a.dent) = (_lib.ptr(t) for t in outs)
+
+
+class ImagineReturnsFunction(torch.autograd.Function):
+    """inputs: dims, actor_cfg, head_act_id, T, discount, lambda_, prev_state (N,S), prev_belief (N,Be),
+    eps_a, eps_e, eps_s, n_actor, n_head, *actor params, *10 prior-path rssm params, *reward params,
+    *value params.  One forward call (bd_imagine_returns_forward) and one backward call
+    (bd_imagine_returns_backward).  Only the actor receives parameter gradients: transition and head
+    weights are constants, as under the reference's FreezeParameters blocks (src/dreamer.py:313,320)."""
+
+    @staticmethod
+    def forward(ctx, dims, actor_cfg, head_act, T, discount, lambda_, prev_state, prev_belief, eps_a,
+                eps_e, eps_s, n_actor, n_head, *params):
+        lib = _lib.load()
+        AP = [_f32c(p) for p in params[:2 * n_actor]]
+        RP = [_f32c(p) for p in params[2 * n_actor:2 * n_actor + 10]] + [None] * 4
+        HP = [_f32c(p) for p in params[2 * n_actor + 10:]]
+        RW, VW = HP[:2 * n_head], HP[2 * n_head:]
+        s0, b0 = _f32c(prev_state), _f32c(prev_belief)
+        N = s0.shape[0]
+        Be, S, A, J = dims["Be"], dims["S"], dims["A"], actor_cfg["entropy_samples"]
+        ea, ee, es = _f32c(eps_a), _f32c(eps_e), _f32c(eps_s)
+        if ea.shape != (T, N, A) or ee.shape != (T, J, N, A) or es.shape != (T, N, S):
+            raise BdError("imagine_and_returns: noise shapes do not match T, N, A, S, J")
+        dev = s0.device
+        new = lambda *d: torch.empty(*d, device=dev, dtype=torch.float32)
+        beliefs, states, means, stds = new(T, N, Be), new(T, N, S), new(T, N, S), new(T, N, S)
+        entropy, actions = new(T, N), new(T, N, A)
+        actor_raw, dent = new(T, N, 2 * A), new(T, N, 2 * A)
+        reward, value, returns = new(T, N, 1), new(T, N, 1), new(T, N, 1)
+        a = _lib.ImagineReturnsArgs()
+        outs = (beliefs, states, means, stds, entropy, actions, actor_raw, dent)
+        _fill_imagine_args(a.img, dims, actor_cfg, T, N, s0, b0, ea, ee, es, AP, RP, outs)
+        a.reward = _lib.make_mlp(RW[0::2], RW[1::2], head_act)
+        a.value = _lib.make_mlp(VW[0::2], VW[1::2], head_act)
+        a.discount, a.lambda_ = float(discount), float(lambda_)
+        a.reward_out, a.value_out, a.returns = _lib.ptr(reward), _lib.ptr(value), _lib.ptr(returns)
+        need_bwd = any(ctx.needs_input_grad)
+        prec = _prec()
+        saved = hsaved = None
+        if need_bwd:
+            saved = torch.empty(lib.bd_imagine_saved_bytes(C.byref(a.img.rssm), T, N, prec), dtype=torch.uint8,
+                                device=dev)
+            a.img.tc_saved = saved.data_ptr()
+            hsaved = torch.empty(lib.bd_imagine_returns_saved_bytes(C.byref(a)), dtype=torch.uint8, device=dev)
+            a.heads_saved = hsaved.data_ptr()
+        ws = _lib.workspace(lib.bd_imagine_returns_workspace_bytes(C.byref(a), 0), dev)
+        _lib.check(lib.bd_imagine_returns_forward(C.byref(a), ws.data_ptr(), ws.numel(), prec,
+                                                  _lib.stream_ptr()), "bd_imagine_returns_forward")
+        ctx.cfg = (dims, actor_cfg, head_act, T, float(discount), float(lambda_), n_actor, n_head, prec)
+        ctx.bufs = (saved, hsaved)
+        ctx.save_for_backward(s0, b0, ea, ee, es, beliefs, states, means, stds, entropy, actions, actor_raw,
+                              dent, reward, value, returns, *AP, *RP[:10], *RW, *VW)
+        ctx.mark_non_differentiable(actions)
+        return beliefs, states, means, stds, entropy, actions, reward, value, returns
+
+    @staticmethod
+    def backward(ctx, g_b, g_s, g_m, g_sd, g_ent, _g_act, g_rew, g_val, g_ret):
+        lib = _lib.load()
+        dims, actor_cfg, head_act, T, discount, lambda_, n_actor, n_head, prec = ctx.cfg
+        sv = list(ctx.saved_tensors)
+        (s0, b0, ea, ee, es, beliefs, states, means, stds, entropy, actions, actor_raw, dent, reward, value,
+         returns) = sv[:16]
+        AP = sv[16:16 + 2 * n_actor]
+        RP = sv[16 + 2 * n_actor:26 + 2 * n_actor] + [None] * 4
+        HP = sv[26 + 2 * n_actor:]
+        RW, VW = HP[:2 * n_head], HP[2 * n_head:]
+        N = s0.shape[0]
+        a = _lib.ImagineReturnsBwdArgs()
+        f = a.fwd
+        outs = (beliefs, states, means, stds, entropy, actions, actor_raw, dent)
+        _fill_imagine_args(f.img, dims, actor_cfg, T, N, s0, b0, ea, ee, es, AP, RP, outs)
+        f.reward = _lib.make_mlp(RW[0::2], RW[1::2], head_act)
+        f.value = _lib.make_mlp(VW[0::2], VW[1::2], head_act)
+        f.discount, f.lambda_ = discount, lambda_
+        f.reward_out, f.value_out, f.returns = _lib.ptr(reward), _lib.ptr(value), _lib.ptr(returns)
+        saved, hsaved = ctx.bufs
+        f.img.tc_saved, f.heads_saved = saved.data_ptr(), hsaved.data_ptr()
+        gc = lambda t: _f32c(t) if t is not None else None
+        (a.g_beliefs, a.g_states, a.g_means, a.g_stds, a.g_entropy, a.g_reward, a.g_value,
+         a.g_returns) = (_lib.ptr(gc(t)) for t in (g_b, g_s, g_m, g_sd, g_ent, g_rew, g_val, g_ret))
+        need = ctx.needs_input_grad   # dims, cfg, head_act, T, disc, lam, s0, b0, ea, ee, es, n_actor, n_head, *params
+        d_s0 = torch.empty_like(s0) if need[6] else None
+        d_b0 = torch.empty_like(b0) if need[7] else None
+        a.d_prev_state, a.d_prev_belief = _lib.ptr(d_s0), _lib.ptr(d_b0)
+        dA = _zero_grads([need[13 + j] for j in range(2 * n_actor)], list(AP))
+        for i in range(n_actor):
+            a.actor_dw[i], a.actor_db[i] = _lib.ptr(dA[2 * i]), _lib.ptr(dA[2 * i + 1])
+        ws = _lib.workspace(lib.bd_imagine_returns_workspace_bytes(C.byref(f), 1), s0.device)
+        _lib.check(lib.bd_imagine_returns_backward(C.byref(a), ws.data_ptr(), ws.numel(), prec,
+                                                   _lib.stream_ptr()), "bd_imagine_returns_backward")
+        n_rest = 10 + 4 * n_head
+        return (None,) * 6 + (d_s0, d_b0, None, None, None, None, None, *dA, *([None] * n_rest))
+
+
+# =============================================================================
 # KL loss (Planet._kl_loss src/planet.py:288-308, Dreamer._kl_loss src/dreamer.py:111-146)
 # =============================================================================
 class KlLossFunction(torch.autograd.Function):

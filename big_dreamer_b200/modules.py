@@ -30,6 +30,11 @@ from ._lib import BdError
 
 ENTROPY_SAMPLES = 100  # SampleDist(samples=100), src/models.py:684
 
+# patch(fused=True): the last fused imagine_and_returns call made on behalf of an UNMODIFIED
+# Dreamer.train_step (see imagine_ahead_fused): the heads / lambda_return calls that follow it in
+# src/dreamer.py:321-335 recognise their inputs by identity and hand back the fused results.
+_fused_record = None
+
 
 def build_mlp(input_size: int, hidden_size: int, output_size: int, n_layers: int,
               activation="ELU", output_activation="Identity") -> nn.Sequential:
@@ -73,6 +78,13 @@ class DenseModel(nn.Module):
     def forward(self, *args: Tensor) -> Tensor:
         if len(args) == 2:
             x1, x2 = args
+            rec = _fused_record
+            if rec is not None and x1 is rec["beliefs"] and x2 is rec["states"]:
+                # patch(fused=True): this head already ran inside the fused rollout on exactly these tensors
+                if self is rec["reward_model"]:
+                    return rec["reward"]
+                if self is rec["value_model"]:
+                    return rec["value"]
         else:
             (x1,), x2 = args, None
         lin = _linears(self.model)
@@ -252,6 +264,11 @@ def imagine_ahead(self, prev_state: Tensor, prev_belief: Tensor,
 def lambda_return(imged_reward: Tensor, value_pred: Tensor, bootstrap: Tensor,
                   discount: float = 0.99, lambda_: float = 0.95) -> Tensor:
     """Drop-in for src/dreamer.py:447-471.  (T,N,1),(T,N,1),(N,1) -> (T,N,1)."""
+    rec = _fused_record
+    if (rec is not None and imged_reward is rec["reward"] and value_pred is rec["value"]
+            and float(discount) == rec["discount"] and float(lambda_) == rec["lambda_"]
+            and bootstrap.shape == value_pred.shape[1:] and bootstrap.data_ptr() == value_pred[-1].data_ptr()):
+        return rec["returns"]        # computed by the fused rollout's tail (bootstrap = value[-1])
     return F_.LambdaReturnFunction.apply(imged_reward, value_pred, bootstrap, discount, lambda_)
 
 
@@ -271,6 +288,26 @@ def kl_loss(posterior_params, prior_params, free_nats, kl_balance: float = -1) -
 def _kl_loss_method(self, posterior_params, prior_params):
     """Bound by patch() as Planet._kl_loss / Dreamer._kl_loss (Gaussian latents)."""
     return kl_loss(posterior_params, prior_params, self.free_nats, getattr(self, "kl_balance", -1))
+
+
+def imagine_ahead_fused(self, prev_state: Tensor, prev_belief: Tensor,
+                        noise: Optional[Dict[str, Tensor]] = None):
+    """``Dreamer.imagine_ahead`` for ``patch(fused=True)``: runs the fused imagine + heads + lambda_return
+    kernels with the agent's own ``reward_model`` / ``critic_target`` / ``discount`` / ``disclam`` -- what the
+    unmodified ``train_step`` computes next (src/dreamer.py:320-335, heads under FreezeParameters) -- and
+    remembers the results; the ``reward_model(b, s)``, ``critic_target(b, s)`` and ``lambda_return(...)`` calls
+    that follow return them when handed exactly these tensors.  Agents without those attributes (or with
+    heads the fused kernels do not cover) get the plain imagine_ahead."""
+    global _fused_record
+    _fused_record = None
+    rm, vm = getattr(self, "reward_model", None), getattr(self, "critic_target", None)
+    if rm is None or vm is None or not hasattr(self, "discount") or not hasattr(self, "disclam"):
+        return imagine_ahead(self, prev_state, prev_belief, noise)
+    beliefs, states, (means, stds), entropy, reward, value, returns = imagine_and_returns(
+        self, prev_state, prev_belief, rm, vm, self.discount, self.disclam, noise, assume_frozen_heads=True)
+    _fused_record = dict(beliefs=beliefs, states=states, reward_model=rm, value_model=vm, reward=reward,
+                         value=value, returns=returns, discount=float(self.discount), lambda_=float(self.disclam))
+    return beliefs, states, (means, stds), entropy
 
 
 def value_update(critic, beliefs: Tensor, states: Optional[Tensor], target: Tensor,
@@ -339,12 +376,64 @@ def value_update(critic, beliefs: Tensor, states: Optional[Tensor], target: Tens
     return loss[0]
 
 
+def _fused_heads_ok(tm, actor, reward_model, value_model) -> bool:
+    """Can bd_imagine_returns_* run this configuration in the current precision mode?"""
+    if F_.get_precision() == "fp32":
+        return False                      # check mode stays piecewise (the fp32 kernels)
+    for m in (reward_model, value_model):
+        if not isinstance(m, DenseModel):
+            return False
+    lib = _lib.load()
+    dims = rssm_dims(tm)
+    rp = rssm_params(tm, with_posterior=False)
+    det = lambda ps: [F_._f32c(p.detach()) for p in ps]
+    r = F_.make_rssm(det(rp[:10]) + [None] * 4, dims)
+    la, lr, lv = _linears(actor.model), _linears(reward_model.model), _linears(value_model.model)
+    mk = lambda lin, act: _lib.make_mlp(det([l.weight for l in lin]), det([l.bias for l in lin]), act)
+    if _mlp_act_id(reward_model.model) != _mlp_act_id(value_model.model):
+        return False
+    ma, mr, mv = mk(la, _mlp_act_id(actor.model)), mk(lr, _mlp_act_id(reward_model.model)), mk(lv, _mlp_act_id(value_model.model))
+    return bool(lib.bd_imagine_returns_supported(C.byref(r), C.byref(ma), C.byref(mr), C.byref(mv), F_._prec()))
+
+
 def imagine_and_returns(self, prev_state: Tensor, prev_belief: Tensor, reward_model, value_model,
                         discount: float, lambda_: float,
-                        noise: Optional[Dict[str, Tensor]] = None):
-    """Added fused entry (level L2): imagine_ahead + reward/value heads +
-    lambda_return in one call.  Returns beliefs, states, (means, stds), entropy, reward, value,
-    returns with the reference's shapes."""
+                        noise: Optional[Dict[str, Tensor]] = None, assume_frozen_heads: bool = False):
+    """Fused entry (level L2): ``imagine_ahead`` + ``reward_model(b, s)`` +
+    ``value_model(b, s)`` + ``lambda_return(reward, value, value[-1], discount, lambda_)`` of
+    ``Dreamer.train_step`` (src/dreamer.py:313-335) as ONE forward call and ONE backward call.  Returns
+    beliefs, states, (means, stds), entropy, reward, value, returns with the reference's shapes.
+
+    In the tensor-core modes the heads ride inside the persistent rollout kernel and lambda_return is its
+    tail (bd_imagine_returns_forward / _backward).  Head and transition weights are treated as constants,
+    which is what the reference's FreezeParameters blocks make them (:313, :320).  Configurations the
+    fused kernels do not cover (fp32 check mode, non-DenseModel heads, sizes beyond the tile limits,
+    head parameters that require grad) run the same arithmetic through the piecewise entry points."""
+    tm, actor = self.transition_model, self.actor
+    heads_frozen = assume_frozen_heads or not (torch.is_grad_enabled() and any(
+        p.requires_grad for m in (reward_model, value_model) for p in m.parameters()))
+    if (getattr(self, "latent_distribution", "Gaussian") == "Gaussian"
+            and getattr(actor, "action_distribution", "Gaussian") == "Gaussian"
+            and heads_frozen and prev_state.is_cuda and _fused_heads_ok(tm, actor, reward_model, value_model)):
+        T = self.planning_horizon - 1
+        b0 = prev_belief.reshape(-1, prev_belief.shape[-1])
+        s0 = prev_state.reshape(-1, prev_state.shape[-1])
+        dims = rssm_dims(tm)
+        rp = rssm_params(tm, with_posterior=False)[:10]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in rp):
+            raise NotImplementedError(
+                "imagine_and_returns: transition-model parameters require grad; call it under "
+                "FreezeParameters(model_modules) as Dreamer.train_step does (src/dreamer.py:313)")
+        if noise is None:
+            noise = draw_imagine_noise(T, s0.shape[0], dims["S"], dims["A"], s0.device)
+        la, lr, lv = _linears(actor.model), _linears(reward_model.model), _linears(value_model.model)
+        flat = lambda lin: [t for l in lin for t in (l.weight, l.bias)]
+        (beliefs, states, means, stds, entropy, _actions, reward, value,
+         returns) = F_.ImagineReturnsFunction.apply(
+            dims, actor_config(actor), _mlp_act_id(reward_model.model), T, float(discount), float(lambda_),
+            s0, b0, noise["eps_a"], noise["eps_e"], noise["eps_s"], len(la), len(lr),
+            *flat(la), *rp, *[t.detach() for t in flat(lr)], *[t.detach() for t in flat(lv)])
+        return beliefs, states, (means, stds), entropy, reward, value, returns
     beliefs, states, (means, stds), entropy = imagine_ahead(self, prev_state, prev_belief, noise)
     reward = reward_model(beliefs, states)
     value = value_model(beliefs, states)

@@ -27,7 +27,13 @@ def _get(name):
 def patch(fused: bool = False) -> None:
     """Rebind models.TransitionModel / DenseModel, planner.MPCPlanner (and the copies
     ``planet`` / ``dreamer`` took with ``from ... import``), Dreamer.imagine_ahead,
-    dreamer.lambda_return and Planet/Dreamer._kl_loss."""
+    dreamer.lambda_return and Planet/Dreamer._kl_loss.
+
+    fused=True (SURVEY 8b level L2): ``Dreamer.imagine_ahead`` runs the fused imagine + reward/value
+    heads + lambda_return kernels (one forward launch chain, one backward) and the unmodified
+    ``train_step``'s following ``reward_model(b, s)`` / ``critic_target(b, s)`` / ``lambda_return(...)``
+    calls pick up those results (modules.imagine_ahead_fused); ``Dreamer.imagine_and_returns`` is
+    also added as a method."""
     if _saved:
         return
     models, planner = _get("models"), _get("planner")
@@ -70,6 +76,8 @@ def patch(fused: bool = False) -> None:
                 or getattr(self.actor, "action_distribution", "Gaussian") != "Gaussian"
                 or not isinstance(self.transition_model, M.TransitionModel)):
             return ref_imagine(self, prev_state, prev_belief)
+        if fused:
+            return M.imagine_ahead_fused(self, prev_state, prev_belief, *args, **kwargs)
         return M.imagine_ahead(self, prev_state, prev_belief, *args, **kwargs)
     cls.imagine_ahead = imagine_ahead
     # dynamics-update KL (Gaussian latents; the Categorical path keeps the reference's method)
@@ -84,10 +92,16 @@ def patch(fused: bool = False) -> None:
                 return M._kl_loss_method(self, posterior_params, prior_params)
             owner._kl_loss = _kl
     if fused:
+        _saved[("dreamer.Dreamer", "imagine_and_returns")] = (cls, getattr(cls, "imagine_and_returns", None))
         cls.imagine_and_returns = M.imagine_and_returns
 
 
 def unpatch() -> None:
     for (_, attr), (owner, old) in list(_saved.items()):
-        setattr(owner, attr, old)
+        if old is None:
+            if hasattr(owner, attr):
+                delattr(owner, attr)
+        else:
+            setattr(owner, attr, old)
     _saved.clear()
+    M._fused_record = None

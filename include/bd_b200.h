@@ -272,6 +272,46 @@ typedef struct {
 int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes, int precision,
                         bd_stream_t stream);
 
+/* ------------------------- imagine_ahead + reward/value heads + lambda_return ---- */
+/* The behaviour-learning block of Dreamer.train_step, src/dreamer.py:313-335, as ONE forward and ONE
+ * backward call ("imagine_and_returns", SURVEY.md 8b level L2):
+ *     beliefs, states, (means, stds), entropy = imagine_ahead(prev_state, prev_belief)
+ *     reward = reward_model(beliefs, states); value = value_model(beliefs, states)
+ *     returns = lambda_return(reward, value, bootstrap=value[-1], discount, lambda_)
+ * In the tensor-core modes the heads ride in the per-step program of the persistent rollout kernel
+ * (their epilogues feed the next layer from shared memory: (T,N,Be+S) is never re-read from HBM) and
+ * the lambda-return recursion is the kernel's tail; the backward runs the lambda-return adjoint and
+ * the heads' dgrad chain inside the BPTT kernel.  Head weights are constants here (the reference
+ * evaluates them under FreezeParameters, src/dreamer.py:320): no head weight gradients.
+ * bd_imagine_returns_supported() == 0 -> use the piecewise entry points (same results). */
+typedef struct {
+  bd_imagine_args img;     /* as for bd_imagine_forward (tc_saved required when a backward follows) */
+  bd_mlp reward, value;    /* DenseModel heads on [belief ; state], one output each               */
+  double discount, lambda_;
+  float* reward_out;       /* (T,N)                                                               */
+  float* value_out;        /* (T,N)                                                               */
+  float* returns;          /* (T,N)                                                               */
+  void* heads_saved;       /* bd_imagine_returns_saved_bytes() bytes, or NULL (no backward)       */
+} bd_imagine_returns_args;
+int bd_imagine_returns_supported(const bd_rssm* r, const bd_mlp* actor, const bd_mlp* reward,
+                                 const bd_mlp* value, int precision);
+size_t bd_imagine_returns_workspace_bytes(const bd_imagine_returns_args* a, int backward);
+size_t bd_imagine_returns_saved_bytes(const bd_imagine_returns_args* a);
+int bd_imagine_returns_forward(const bd_imagine_returns_args* a, void* ws, size_t ws_bytes, int precision,
+                               bd_stream_t stream);
+typedef struct {
+  bd_imagine_returns_args fwd;   /* the forward call's arguments (outputs filled, saved buffers intact) */
+  /* upstream gradients, each optional: (T,N,Be) (T,N,S) (T,N,S) (T,N,S) (T,N) | (T,N) (T,N) (T,N) */
+  const float *g_beliefs, *g_states, *g_means, *g_stds, *g_entropy;
+  const float *g_reward, *g_value, *g_returns;
+  float* d_prev_state;           /* (N,S)  optional */
+  float* d_prev_belief;          /* (N,Be) optional */
+  float* actor_dw[BD_MAX_LAYERS];   /* optional, accumulated (+=) */
+  float* actor_db[BD_MAX_LAYERS];
+} bd_imagine_returns_bwd_args;
+int bd_imagine_returns_backward(const bd_imagine_returns_bwd_args* a, void* ws, size_t ws_bytes,
+                                int precision, bd_stream_t stream);
+
 /* ------------------------------------------------------------- CEM planner ---- */
 typedef struct {
   bd_rssm rssm;

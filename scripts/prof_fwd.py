@@ -29,15 +29,15 @@ if os.environ.get("BD_TC_PROF"):
     import struct
     for off in range(0, 4 << 20, 4096):
         v = np.frombuffer(raw[off:off + 40 * 64].tobytes(), dtype=np.int64).reshape(40, 8)
-        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[:12, 7].sum() == 0 and v[39, 0] > 0:
+        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[39, 0] > 0:
             names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed", "gru0", "gru1", "gru2", "gru3", "prior1", "priorOut"]
             nph = int((v[:20, 2] > 0).sum())
             if nph != 12:
                 names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed"] + ["gru%d" % i for i in range(nph - 8)] + ["prior1", "priorOut"]
-            print("phase      iss_dep  iss_wwait iss_issue | epi0_wait epi0_work | epi1_wait epi1_work   (cycles per step, CTA 0, last launch, 14 steps)")
+            print("phase      iss_dep  iss_wwait iss_issue | epi0_wait epi0_work | epi1_wait epi1_work | mma_loop  (cycles per step, CTA 0, last launch, 14 steps)")
             for i, n in enumerate(names):
-                print(f"{n:9s}", " ".join(f"{int(x)//14:9d}" for x in v[i, :7]))
-            tot = v[:12, :7].sum(0) // 14
+                print(f"{n:9s}", " ".join(f"{int(x)//14:9d}" for x in v[i, :8]))
+            tot = v[:20, :8].sum(0) // 14
             print("total    ", " ".join(f"{int(x):9d}" for x in tot))
             w = np.frombuffer(raw[off + 40 * 64: off + 40 * 64 + 160 * 24].tobytes(), dtype=np.int64).reshape(160, 3)
             w = w[w[:, 0] > 0]

@@ -184,13 +184,17 @@ def _oracle_imagine_mixed(trans, actor, d, s0, b0, ea, ee, es):
 # ----------------------------------------------------------------------------------------------
 # fused entries
 # ----------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+@pytest.mark.parametrize("prec,tol,cluster", [("fp32", 1e-4, None), ("fp16", 1e-2, None), ("fp16", 1e-2, "1"),
+                                              ("fp16", 1e-2, "2"), ("bf16", 5e-2, None)])
 @pytest.mark.parametrize("d", [dict(Be=200, Hi=200, S=30, A=1, E=8, N=300, H=15, act="ELU"),
                                dict(Be=32, Hi=32, S=30, A=1, E=8, N=130, H=15, act="ELU"),
                                dict(Be=48, Hi=40, S=10, A=3, E=8, N=129, H=7, act="Tanh")])
-def test_imagine_and_returns_fused_vs_oracle(d, prec, tol):
+def test_imagine_and_returns_fused_vs_oracle(d, prec, tol, cluster, monkeypatch):
     """bd.imagine_and_returns (heads + lambda_return fused with the rollout: SURVEY 8b level L2) against the
-    oracle's actor-loss block: every output and the actor gradients (src/dreamer.py:313-363)."""
+    oracle's actor-loss block: every output and the actor gradients (src/dreamer.py:313-363).  `cluster`
+    forces the column-split cluster size of the rollout engine (1 = one CTA per row tile)."""
+    if cluster:
+        monkeypatch.setenv("BD_TC_CLUSTER", cluster)
     bd.set_precision(prec)
     trans, actor, reward, value = orc.make_models(7, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
     actor["model.8.bias"][d["A"]:] -= 6.0
@@ -304,8 +308,13 @@ def test_patched_reference_train_step_on_gpu(fused):
                 import numpy as np
                 np.random.seed(1)
                 before = [p.detach().clone() for p in agent.actor.parameters()]
+                n0 = bd.load_library().bd_launch_count()
                 logs[mode] = agent.train_step()
                 assert any(not torch.equal(a, b.detach()) for a, b in zip(before, agent.actor.parameters()))
+                if mode == "patched_gpu":
+                    from big_dreamer_b200 import modules as M_
+                    assert bd.load_library().bd_launch_count() > n0          # the library's kernels ran
+                    assert (M_._fused_record is not None) == fused           # fused results were handed out
             finally:
                 bd.unpatch()
                 bd.set_precision("fp32")
