@@ -348,6 +348,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {   // 16 co
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {    // 8 columns
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -361,6 +369,7 @@ __host__ __device__ __forceinline__ uint32_t km8_offset(uint32_t rows, uint32_t 
 template <int FMT> struct Half16;
 template <> struct Half16<0> {
   using T = __half;
+  static constexpr uint32_t kOne = 0x3C00u;    // bit pattern of 1.0
   // fp16 operands SATURATE at +-65504 (F2FP.SATFINITE: same single instruction as the plain convert):
   // a value beyond fp16's range becomes a clipped activation instead of an inf that turns the
   // fp32 accumulators into NaN (inf - inf).  bf16 mode has fp32's range and needs no guard.
@@ -377,6 +386,7 @@ template <> struct Half16<0> {
 };
 template <> struct Half16<1> {
   using T = __nv_bfloat16;
+  static constexpr uint32_t kOne = 0x3F80u;
   __device__ static __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);

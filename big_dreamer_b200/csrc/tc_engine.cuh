@@ -39,6 +39,9 @@ namespace tc {
 constexpr int kTileRows = 128;
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
+// rollout kernel (round 2): 16 epilogue warps
+constexpr int kThreads2 = 576;
+constexpr int kEpiThreads2 = 512;
 constexpr int kMaxGemms = 64, kMaxPhases = 40;
 constexpr int kMaxRanks = 4;            // CTAs per cluster in column-split mode (1 = off)
 constexpr uint32_t kLboA = kTileRows * 16;   // bytes between 8-column groups of an activation tile
@@ -198,12 +201,15 @@ __device__ __forceinline__ void stage_program(Program& dst, const Program& src) 
   for (uint32_t i = threadIdx.x; i < sizeof(Program) / 4; i += blockDim.x) d[i] = s[i];
 }
 
-__device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1) {
+__device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1,
+                                                 uint32_t epi_threads = kEpiThreads) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
     for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], R);
-    for (int i = 0; i < 8; ++i) mbar_init(&sh.epi_done[i], R == 1 ? kEpiThreads : (kEpiThreads / 32) * R);
+    // epi_threads == kEpiThreads2: the 16-warp kernels arrive once per warp; the 8-warp kernels once per thread
+    for (int i = 0; i < 8; ++i)
+      mbar_init(&sh.epi_done[i], (R == 1 && epi_threads == kEpiThreads) ? epi_threads : (epi_threads / 32) * R);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&sh.tmem_holder);
@@ -269,13 +275,16 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
   const uint32_t bar_acc_full = smem_u32(&sh.acc_full[0]), bar_epi_done = smem_u32(&sh.epi_done[0]);
   // descriptor high word: SBO = 128 B, version 1, no swizzle; low word: start >> 4 | LBO >> 4 << 16
   const uint64_t desc_hi = make_smem_desc(0, 0, 128);
+  // per-stage clock reads cost ~70 cycles each on this warp's critical path: only on request
+  // (BD_TC_PROF=2); the default debug build times whole phases and dependency waits only
+  const bool fine = PROF && prof != nullptr && prof[39 * 8 + 7] != 0;
   for (long long tile = blockIdx.x / R; tile < ntiles; tile += gridDim.x / R) {
     ++Ge;  // the tile-initialisation pseudo-phase (epilogue only)
     for (int t = 0; t < T; ++t) {
       const uint32_t par = (uint32_t)t & 1u;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
-        long long c1 = 0, wsum = 0, dsum = 0, msum = 0;
+        long long c1 = 0, wsum = 0, dsum = 0, msum = 0, csum = 0;
         if (PROF) c1 = clock64();
         for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
           const Gemm g = P.g[gi];
@@ -309,16 +318,16 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
             const int kc = min((int)g.kc, g.Kp - k0);
             long long w0 = 0;
-            if (PROF) w0 = clock64();
+            if (PROF && fine) w0 = clock64();
             // (no tcgen05.fence here: the weights arrive through the async proxy and their mbarrier
             // completion orders them before the MMAs; a fence::after_thread_sync per ring stage measured
             // ~220 cycles of issue stall each -- it is only needed after the epilogue hand-offs above)
             mbar_wait_u(bar_w_full + st * 8, wph);
-            if (PROF) wsum += clock64() - w0;
+            if (PROF && fine) wsum += clock64() - w0;
             uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
                               (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu);
             long long m0 = 0;
-            if (PROF) m0 = clock64();
+            if (PROF && fine) m0 = clock64();
             for (int ks = 0; ks < kc; ks += 16) {
               // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
               umma_f16_u(d_tmem, a_desc, b_desc, idesc, acc);
@@ -326,8 +335,9 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               a_desc += 2 * (kLboA >> 4);
               b_desc += 2 * (lbo_b >> 4);
             }
-            if (PROF) msum += clock64() - m0;
+            if (PROF && fine) msum += clock64() - m0;
             umma_commit_elect(bar_w_empty + st * 8);
+            if (PROF && fine) csum += clock64() - m0;
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
         }
@@ -338,6 +348,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           prof[pi * 8 + 1] += wsum;                          // issuer: wait for weight stages
           prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum;  // issuer: issue time
           prof[pi * 8 + 7] += msum;                          // of which: inside the tcgen05.mma loops
+          prof[(20 + pi) * 8 + 0] += csum - msum;            //           the per-stage tcgen05.commit
         }
         ++Gm;
         Ge += ph.n_sub;
@@ -377,8 +388,108 @@ __device__ __forceinline__ void store8(uint8_t* p, const float* v) {
                  Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Activation of an accumulator pair -> packed 16-bit pair.  fp16 ELU: the exponential stays in fp32
+// (e^x - 1 formed on a 10-bit exponential loses the small negative outputs to cancellation: measured
+// 2e-2 instead of 7e-3 on the c3 CEM action) but the scale and the -1 run as packed fp32x2
+// instructions, so a pair costs 9 instructions instead of 11.
+// ---------------------------------------------------------------------------------------------
+template <int FMT, int ACT>
+__device__ __forceinline__ uint32_t act_pack2(float a, float b) {
+  if (ACT == BD_ACT_ELU) {
+    // max(x, 2^(min(x log2 e, 0)) - 1)
+    uint64_t xv, tv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(a), "f"(b));
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(tv) : "l"(xv), "l"(0x3FB8AA3B3FB8AA3Bull));   // log2 e
+    float t0, t1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(tv));
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(t0, 0.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(t1, 0.f)));
+    uint64_t ev;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ev) : "f"(e0), "f"(e1));
+    asm("add.f32x2 %0, %1, %2;" : "=l"(ev) : "l"(ev), "l"(0xBF800000BF800000ull));   // - 1
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(e0), "=f"(e1) : "l"(ev));
+    return Half16<FMT>::pack2(fmaxf(a, e0), fmaxf(b, e1));
+  }
+  if (FMT == 0 && ACT == BD_ACT_RELU) {
+    uint32_t x = Half16<0>::pack2(a, b), y;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(x), "r"(0u));
+    return y;
+  }
+  return Half16<FMT>::pack2(tc_act_t<ACT>(a), tc_act_t<ACT>(b));
+}
+// act'(x) from the packed activation output y
+template <int FMT, int ACT>
+__device__ __forceinline__ uint32_t dact_pack2(uint32_t y) {
+  if (FMT == 0) {
+    uint32_t d;
+    if (ACT == BD_ACT_ELU) {            // y > 0 ? 1 : y + 1  =  min(y, 0) + 1
+      asm("{\n\t.reg .b32 t;\n\tmin.f16x2 t, %1, %2;\n\tadd.f16x2 %0, t, %3;\n\t}"
+          : "=r"(d) : "r"(y), "r"(0u), "r"(0x3C003C00u));
+    } else if (ACT == BD_ACT_RELU) {
+      asm("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(y), "r"(0u));
+    } else if (ACT == BD_ACT_TANH) {    // 1 - y^2
+      asm("{\n\t.reg .b32 t;\n\tneg.f16x2 t, %1;\n\tfma.rn.f16x2 %0, t, %1, %2;\n\t}"
+          : "=r"(d) : "r"(y), "r"(0x3C003C00u));
+    } else {
+      d = 0x3C003C00u;
+    }
+    return d;
+  }
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&y);
+  const float2 f = __bfloat1622float2(h);
+  return Half16<FMT>::pack2(tc_dact_from_out<ACT>(f.x), tc_dact_from_out<ACT>(f.y));
+}
+// The five saved planes of a GRU gate column (c_r, c_z, c_n, c_nr, z; see EPI_GRU) for 8 columns.
+template <int FMT>
+__device__ __forceinline__ void gru_coeff_planes(const float* r, const float* z, const float* hn,
+                                                 const float* omn2, const float* hmn, uint4* pl) {
+  uint32_t cr[4], cz[4], cn[4], cnr[4], zz[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (FMT == 0) {
+      const uint32_t R2 = Half16<0>::pack2(r[2 * j], r[2 * j + 1]), Z2 = Half16<0>::pack2(z[2 * j], z[2 * j + 1]);
+      const uint32_t HN2 = Half16<0>::pack2(hn[2 * j], hn[2 * j + 1]);
+      const uint32_t ON2 = Half16<0>::pack2(omn2[2 * j], omn2[2 * j + 1]);
+      const uint32_t HM2 = Half16<0>::pack2(hmn[2 * j], hmn[2 * j + 1]);
+      asm("{\n\t.reg .b32 omz, omr, t;\n\t"
+          "sub.f16x2 omz, %5, %6;\n\t"          // 1 - z
+          "mul.f16x2 %2, omz, %8;\n\t"          // c_n = (1 - z)(1 - n^2)
+          "sub.f16x2 omr, %5, %7;\n\t"          // 1 - r
+          "mul.f16x2 t, %2, %9;\n\t"
+          "mul.f16x2 t, t, %7;\n\t"
+          "mul.f16x2 %0, t, omr;\n\t"           // c_r = c_n hn r (1 - r)
+          "mul.f16x2 %3, %2, %7;\n\t"           // c_nr = c_n r
+          "mul.f16x2 t, %10, %6;\n\t"
+          "mul.f16x2 %1, t, omz;\n\t"           // c_z = (h - n) z (1 - z)
+          "mov.b32 %4, %6;\n\t}"
+          : "=&r"(cr[j]), "=&r"(cz[j]), "=&r"(cn[j]), "=&r"(cnr[j]), "=&r"(zz[j])
+          : "r"(0x3C003C00u), "r"(Z2), "r"(R2), "r"(ON2), "r"(HN2), "r"(HM2));
+    } else {
+      float c_r[2], c_z[2], c_n[2], c_nr[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = 2 * j + k;
+        c_n[k] = (1.f - z[i]) * omn2[i];
+        c_r[k] = c_n[k] * hn[i] * r[i] * (1.f - r[i]);
+        c_nr[k] = c_n[k] * r[i];
+        c_z[k] = hmn[i] * z[i] * (1.f - z[i]);
+      }
+      cr[j] = Half16<FMT>::pack2(c_r[0], c_r[1]); cz[j] = Half16<FMT>::pack2(c_z[0], c_z[1]);
+      cn[j] = Half16<FMT>::pack2(c_n[0], c_n[1]); cnr[j] = Half16<FMT>::pack2(c_nr[0], c_nr[1]);
+      zz[j] = Half16<FMT>::pack2(z[2 * j], z[2 * j + 1]);
+    }
+  }
+  pl[0] = make_uint4(cr[0], cr[1], cr[2], cr[3]);
+  pl[1] = make_uint4(cz[0], cz[1], cz[2], cz[3]);
+  pl[2] = make_uint4(cn[0], cn[1], cn[2], cn[3]);
+  pl[3] = make_uint4(cnr[0], cnr[1], cnr[2], cnr[3]);
+  pl[4] = make_uint4(zz[0], zz[1], zz[2], zz[3]);
+}
+
 template <int FMT, int ACT, bool WITH_ACTOR, bool PROF, bool CLUSTER>
-__global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_constant__ RolloutArgs A_) {
+__global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_constant__ RolloutArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const RolloutArgs& a = A_;
   uint8_t* smem = smem_raw;
@@ -389,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
   const uint32_t rank = R > 1 ? (uint32_t)blockIdx.x % R : 0u;   // = %cluster_ctarank for (R,1,1) clusters; provably uniform
   __shared__ Program sprog;
   stage_program(sprog, CLUSTER ? a.prog[rank] : a.prog[0]);
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R);
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R, kEpiThreads2);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;
   long long prof_c0 = 0, prof_g0 = 0;
@@ -408,18 +519,21 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
     issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R);
   } else {
     // =========================================================== epilogue warps
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // 16 warps: TMEM quadrant q = warp % 4 (a warp reaches lanes [32 q, 32 q + 32) only), column part
+    // (warp - 2) / 4 in 0..3.  Four warps per scheduler hide the TMEM-load / MUFU latencies that two could
+    // not (the epilogues, not the MMAs, bound this engine); chunks are 16 columns (activations) or 8
+    // (GRU / prior output) so the whole kernel fits the 112 registers 576 threads leave.
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t rowoff = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);   // this row inside a KM8 column group
     const int etid = tid - 64;
     const int Be = a.Be, S = a.S, Ad = a.A;
     const bool be4 = (Be & 3) == 0;
     const bool wr0 = rank == 0;       // replicated phases: only rank 0 writes the global outputs
-    // 16 B of an operand tile (8 columns of one row): local store, mirrored into every peer's
-    // shared memory in column-split mode
-    auto put8 = [&](uint8_t* p, const float* v) {
-      const uint4 u = make_uint4(Half16<FMT>::pack2(v[0], v[1]), Half16<FMT>::pack2(v[2], v[3]),
-                                 Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
+    // 16 B of an operand tile (8 columns of one row, already packed): local store, mirrored into every
+    // peer's shared memory in column-split mode
+    auto put16 = [&](uint8_t* p, const uint4 u) {
       if (R == 1) {
         *reinterpret_cast<uint4*>(p) = u;
       } else {
@@ -427,11 +541,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         for (uint32_t k = 0; k < R; ++k) st_cluster_v4(mapa_u32(la, k), u);
       }
     };
-    // publish epilogue completion Ge: 256 local arrivals, or one arrival per warp on every rank
+    // publish epilogue completion Ge: one arrival per warp (512 thread arrivals on one mbarrier serialise in
+    // shared memory), on every rank in column-split mode
     auto epi_arrive = [&](uint32_t ge) {
       if (R == 1) {
         fence_proxy_async_smem();
-        mbar_arrive(&epi_done[ge & 7]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&epi_done[ge & 7]);
       } else {
         fence_proxy_async_all();
         __syncwarp();
@@ -451,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         // one 8-column group (16 B of the operand tile) per item; consecutive threads take
         // consecutive rows of the same group -> conflict-free 16 B shared stores
         const int gb = a.Kp_b >> 3;
-        for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
+        for (int i = etid; i < kTileRows * gb; i += kEpiThreads2) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
           const long long sr = a.cem_cl ? gr / a.cem_cl : gr;     // CEM: latents are per batch row
@@ -466,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           if (a.has_b1) store8<FMT>(B1 + kg * kLboA + r * 16, z);
         }
         const int gs = a.Kp_sa >> 3;
-        for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
+        for (int i = etid; i < kTileRows * gs; i += kEpiThreads2) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
           const long long sr = a.cem_cl ? gr / a.cem_cl : gr;
@@ -483,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           store8<FMT>(SA + kg * kLboA + r * 16, v);
         }
         const int gh = a.Kp_h >> 3;
-        for (int i = etid; i < kTileRows * gh; i += kEpiThreads) {
+        for (int i = etid; i < kTileRows * gh; i += kEpiThreads2) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           *reinterpret_cast<uint4*>(H + kg * kLboA + r * 16) = make_uint4(0, 0, 0, 0);
         }
@@ -502,113 +618,129 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
           const uint32_t tacc = trow + ph.d_col;
           switch (ph.epi) {
             case EPI_ACT_H: {
+              // What this layer also leaves in HBM for a backward pass: 1 = the hidden activation itself
+              // (MLP forward; padded rows zero: the image doubles as the wgrad operand), 2 = act'(output)
+              // (embed x, prior h, fused heads; padding needs no mask: every consumer multiplies it into an
+              // accumulator whose padded rows / columns are exactly zero)
+              int smode = 0, skp = 0;
+              uint16_t* simg = nullptr;
+              if (ph.aux0 >= 3 && ph.aux0 < 3 + BD_MAX_LAYERS) {
+                if (a.sv_mlp[ph.aux0 - 3]) {
+                  smode = 1; skp = ph.Kp_out;
+                  simg = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * skp + row * 8;
+                }
+              } else if (ph.aux0 == 1 || ph.aux0 == 2) {
+                if (a.sv_xa) {
+                  smode = 2; skp = ph.aux0 == 1 ? a.kb_sv : a.kh_sv;
+                  simg = (ph.aux0 == 1 ? a.sv_xa : a.sv_ha) + ((size_t)t * ntiles + tile) * kTileRows * skp + row * 8;
+                }
+              } else if (ph.aux0 >= 16) {
+                if (a.sv_hd[ph.aux0 - 16]) {
+                  smode = 2; skp = a.kh_hd;
+                  simg = a.sv_hd[ph.aux0 - 16] + ((size_t)t * ntiles + tile) * kTileRows * skp + row * 8;
+                }
+              }
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
               // (a belief tile as output = the ping-pong half that is free at this point: the fused
               // heads' second hidden tile)
               const int otile = ph.out_tile < 2 ? (ph.out_tile ^ par) : ph.out_tile;
-              uint8_t* out = smem + a.sm.off_tile[otile] + (row >> 3) * 128 + (row & 7) * 16;
+              uint8_t* out = smem + a.sm.off_tile[otile] + rowoff;
               const int nv = ph.n_valid;
               for (int sub = 0; sub < ph.n_sub; ++sub) {
-              // this rank's columns are [col0, Kp_out) (col0 = 0 unless column-split); the
-              // accumulator holds them at TMEM columns [0, Np)
-              const int c_lo = sub == 0 ? ph.col0 : ph.split;
-              const int c_hi = (sub == ph.n_sub - 1) ? ph.Kp_out : ph.split;
-              if (sub > 0) {   // publish the first column range: the next layer's K-slab 0 may start
-                tc_fence_before_sync();
-                epi_arrive(Ge);
-                ++Ge;
-              }
-              for (int c = c_lo + half * 32; c < c_hi; c += 64) {
-                float v[32];
-                const bool two = (c + 16) < ph.Kp_out;
-                const int ca = c - ph.col0;           // accumulator column
-                if (ca + 32 <= ph.Np) {
-                  tmem_ld32(tacc + ca, v);
-                } else {
-                  if (ca < ph.Np) tmem_ld16(tacc + ca, v);
-                  if (ca + 16 < ph.Np) tmem_ld16(tacc + ca + 16, v + 16);
+                // this rank's columns are [col0, Kp_out) (col0 = 0 unless column-split); the
+                // accumulator holds them at TMEM columns [0, Np)
+                const int c_lo = sub == 0 ? ph.col0 : ph.split;
+                const int c_hi = (sub == ph.n_sub - 1) ? ph.Kp_out : ph.split;
+                if (sub > 0) {   // publish the first column range: the next layer's K-slab 0 may start
+                  tc_fence_before_sync();
+                  epi_arrive(Ge);
+                  ++Ge;
                 }
-                tmem_ld_wait();
+                // 16-column chunks, the next chunk's TMEM load in flight while this one is processed
+                float v[2][16];
+                const int c0 = c_lo + part * 16;
+                auto load = [&](int c, float* dst) {
+                  const int ca = c - ph.col0;           // accumulator column
+                  if (ca < ph.Np) {
+                    tmem_ld16(tacc + ca, dst);
+                  } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tc_act_t<ACT>(v[j]);
-                if (c + 32 > nv) {   // the chunk holding the constant-1 (bias) column and zero padding
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    const int col = c + j;
-                    if (col >= nv) v[j] = (col == nv) ? 1.f : 0.f;
+                    for (int j = 0; j < 16; ++j) dst[j] = 0.f;
                   }
-                }
-                uint8_t* p = out + (c >> 3) * kLboA;
-                put8(p, v);
-                put8(p + kLboA, v + 8);
-                if (two) {
-                  put8(p + 2 * kLboA, v + 16);
-                  put8(p + 3 * kLboA, v + 24);
-                }
-                if (ph.aux0 >= 3 && ph.aux0 < 3 + BD_MAX_LAYERS && a.sv_mlp[ph.aux0 - 3]) {   // MLP forward: keep the hidden image itself
-                  uint16_t* img = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * ph.Kp_out + row * 8;
+                };
+                if (c0 < c_hi) load(c0, v[0]);
 #pragma unroll
-                  for (int g8 = 0; g8 < 4; ++g8) {
-                    const int cg = c + g8 * 8;
-                    if (cg < ph.Kp_out) {
-                      float hv[8];
+                for (int it = 0; it < 4; ++it) {
+                  const int c = c0 + it * 64;
+                  if (c < c_hi) {
+                    tmem_ld_wait();
+                    if (c + 64 < c_hi) load(c + 64, v[(it + 1) & 1]);
+                    uint32_t y[8];
 #pragma unroll
-                      for (int j = 0; j < 8; ++j) hv[j] = rvalid ? v[g8 * 8 + j] : 0.f;
-                      *reinterpret_cast<uint4*>(img + (size_t)(cg >> 3) * kTileRows * 8) =
-                          make_uint4(Half16<FMT>::pack2(hv[0], hv[1]), Half16<FMT>::pack2(hv[2], hv[3]),
-                                     Half16<FMT>::pack2(hv[4], hv[5]), Half16<FMT>::pack2(hv[6], hv[7]));
+                    for (int j = 0; j < 8; ++j) y[j] = act_pack2<FMT, ACT>(v[it & 1][2 * j], v[it & 1][2 * j + 1]);
+                    if (c + 16 > nv) {   // the chunk holding the constant-1 (bias) column and zero padding
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) {
+                        const int col = c + 2 * j;
+                        if (col >= nv) y[j] = (y[j] & 0xFFFF0000u) | (col == nv ? Half16<FMT>::kOne : 0u);
+                        if (col + 1 >= nv) y[j] = (y[j] & 0x0000FFFFu) | ((col + 1 == nv ? Half16<FMT>::kOne : 0u) << 16);
+                      }
                     }
-                  }
-                } else if ((ph.aux0 == 1 || ph.aux0 == 2) ? a.sv_xa != nullptr
-                                                          : (ph.aux0 >= 16 && a.sv_hd[ph.aux0 - 16] != nullptr)) {
-                  // act'(output) images for the backward: 1 = embed x, 2 = prior h, 16 + head * BD_MAX_LAYERS + l =
-                  // hidden layer l of a fused head
-                  const int kp = ph.aux0 == 1 ? a.kb_sv : (ph.aux0 == 2 ? a.kh_sv : a.kh_hd);
-                  uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : (ph.aux0 == 2 ? a.sv_ha : a.sv_hd[ph.aux0 - 16])) +
-                                  ((size_t)t * ntiles + tile) * kTileRows * kp + row * 8;
+                    uint8_t* p = out + (c >> 3) * kLboA;
+                    put16(p, make_uint4(y[0], y[1], y[2], y[3]));
+                    put16(p + kLboA, make_uint4(y[4], y[5], y[6], y[7]));
+                    if (smode == 1) {          // the hidden image itself (rows past N: zeros)
+                      uint16_t* gi = simg + (size_t)(c >> 3) * kTileRows * 8;
+                      const uint32_t m = rvalid ? 0xFFFFFFFFu : 0u;
+                      *reinterpret_cast<uint4*>(gi) = make_uint4(y[0] & m, y[1] & m, y[2] & m, y[3] & m);
+                      *reinterpret_cast<uint4*>(gi + (size_t)kTileRows * 8) = make_uint4(y[4] & m, y[5] & m, y[6] & m, y[7] & m);
+                    } else if (smode == 2 && c < skp) {
+                      uint32_t dy[8];
 #pragma unroll
-                  for (int g8 = 0; g8 < 4; ++g8) {
-                    const int cg = c + g8 * 8;
-                    if (cg < kp && cg < ph.Kp_out) {
-                      float dv[8];
-#pragma unroll
-                      for (int j = 0; j < 8; ++j)
-                        dv[j] = (cg + j < nv && rvalid) ? tc_dact_from_out<ACT>(v[g8 * 8 + j]) : 0.f;
-                      *reinterpret_cast<uint4*>(img + (size_t)(cg >> 3) * kTileRows * 8) =
-                          make_uint4(Half16<FMT>::pack2(dv[0], dv[1]), Half16<FMT>::pack2(dv[2], dv[3]),
-                                     Half16<FMT>::pack2(dv[4], dv[5]), Half16<FMT>::pack2(dv[6], dv[7]));
+                      for (int j = 0; j < 8; ++j) dy[j] = dact_pack2<FMT, ACT>(y[j]);
+                      uint16_t* gi = simg + (size_t)(c >> 3) * kTileRows * 8;
+                      *reinterpret_cast<uint4*>(gi) = make_uint4(dy[0], dy[1], dy[2], dy[3]);
+                      if (c + 8 < skp)
+                        *reinterpret_cast<uint4*>(gi + (size_t)kTileRows * 8) = make_uint4(dy[4], dy[5], dy[6], dy[7]);
                     }
                   }
                 }
-              }
               }
             } break;
             case EPI_GRU: {
+              // 8-column chunks: c = 8 part + 32 it (a slice is at most 64 columns wide)
               const int n0 = ph.aux0, Ns = ph.Np;
               const float* bold = (t == 0) ? a.prev_belief + (a.cem_cl ? grow / a.cem_cl : grow) * Be
                                            : a.beliefs + ((long long)(t - 1) * a.N + grow) * Be;
               float* bnew = a.beliefs + orow * Be;
-              // previous belief (fp32 master copy) for this thread's columns: issued before the wait
-              float hb[2][16];
+              // previous belief h_t for this thread's columns.  fp16 mode: the 16-bit copy in the operand tile
+              // (one 16-byte shared-memory load per chunk, no L2 round trip on the recurrence's critical path;
+              // the carried state is thereby rounded to fp16 once per step -- 2^-12 relative, below the
+              // operand rounding the GEMMs see anyway).  bf16 mode (7-bit mantissa): the fp32 master copy
+              // from the previous step's output, requested before the accumulator wait.
+              const uint8_t* Bcur = smem + a.sm.off_tile[par] + rowoff;
+              float hb[2][8];
+              if (FMT != 0) {
 #pragma unroll
-              for (int it = 0; it < 2; ++it) {
-                const int c = half * 16 + it * 32;
+                for (int it = 0; it < 2; ++it) {
+                  const int col = n0 + part * 8 + it * 32;
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  const int col = n0 + c + j4 * 4;
-                  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (rvalid && c < Ns) {
-                    if (be4 && col + 3 < Be) x = *reinterpret_cast<const float4*>(bold + col);
-                    else {
-                      if (col < Be) x.x = bold[col];
-                      if (col + 1 < Be) x.y = bold[col + 1];
-                      if (col + 2 < Be) x.z = bold[col + 2];
-                      if (col + 3 < Be) x.w = bold[col + 3];
+                  for (int j4 = 0; j4 < 2; ++j4) {
+                    const int cc = col + j4 * 4;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rvalid && part * 8 + it * 32 < Ns) {
+                      if (be4 && cc + 3 < Be) x = *reinterpret_cast<const float4*>(bold + cc);
+                      else {
+                        if (cc < Be) x.x = bold[cc];
+                        if (cc + 1 < Be) x.y = bold[cc + 1];
+                        if (cc + 2 < Be) x.z = bold[cc + 2];
+                        if (cc + 3 < Be) x.w = bold[cc + 3];
+                      }
                     }
+                    hb[it][j4 * 4] = x.x; hb[it][j4 * 4 + 1] = x.y; hb[it][j4 * 4 + 2] = x.z; hb[it][j4 * 4 + 3] = x.w;
                   }
-                  hb[it][j4 * 4] = x.x; hb[it][j4 * 4 + 1] = x.y; hb[it][j4 * 4 + 2] = x.z; hb[it][j4 * 4 + 3] = x.w;
                 }
               }
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
@@ -616,53 +748,51 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               if (PROF) e1 = clock64();
 #pragma unroll
               for (int it = 0; it < 2; ++it) {
-                const int c = half * 16 + it * 32;
+                const int c = part * 8 + it * 32;
                 if (c < Ns) {
-                  float r_[16], z_[16], in_[16], hn_[16], o[16];
-                  tmem_ld16(tacc + c, in_);              // accumulator columns: IN | R | Z | HN
-                  tmem_ld16(tacc + Ns + c, r_);
-                  tmem_ld16(tacc + 2 * Ns + c, z_);
-                  tmem_ld16(tacc + 3 * Ns + c, hn_);
-                  tmem_ld_wait();
+                  float r_[8], z_[8], in_[8], hn_[8], o[8];
+                  tmem_ld8(tacc + c, in_);              // accumulator columns: IN | R | Z | HN
+                  tmem_ld8(tacc + Ns + c, r_);
+                  tmem_ld8(tacc + 2 * Ns + c, z_);
+                  tmem_ld8(tacc + 3 * Ns + c, hn_);
                   const int col0 = n0 + c;
+                  if (FMT == 0) {
+                    const uint4 hu = *reinterpret_cast<const uint4*>(Bcur + (col0 >> 3) * kLboA);
+                    const uint32_t hw[4] = {hu.x, hu.y, hu.z, hu.w};
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+                      hb[it][2 * j] = f.x; hb[it][2 * j + 1] = f.y;
+                    }
+                  }
+                  tmem_ld_wait();
+                  float hmn[8], omn2[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
                     const float r = sigmoid_via_tanh(r_[j]);
                     const float z = sigmoid_via_tanh(z_[j]);
                     const float n = fast_tanh(fmaf(r, hn_[j], in_[j]));
-                    o[j] = fmaf(z, hb[it][j] - n, n);          // (1-z) n + z h
-                    if (a.sv_gate) {
-                      // backward coefficients of this gate column: d(pre_r), d(pre_z), d(pre_n),
-                      // d(pre_n)*r per unit of dL/db', and z for the carry (SURVEY A.1 / tc_bptt.cuh)
-                      const bool ok = rvalid && (col0 + j < Be);
-                      const float cn = ok ? (1.f - z) * (1.f - n * n) : 0.f;
-                      r_[j] = cn * hn_[j] * r * (1.f - r);           // c_r
-                      in_[j] = cn;                                   // c_n
-                      hn_[j] = cn * r;                               // c_nr
-                      const float cz = ok ? (hb[it][j] - n) * z * (1.f - z) : 0.f;
-                      z_[j] = ok ? z : 0.f;                          // z (plane 4)
-                      hb[it][j] = cz;                                // c_z (plane 1); hb no longer needed
-                    }
+                    hmn[j] = hb[it][j] - n;
+                    o[j] = fmaf(z, hmn[j], n);                 // (1-z) n + z h
+                    omn2[j] = fmaf(-n, n, 1.f);                // 1 - n^2
+                    r_[j] = r; z_[j] = z;
                   }
                   if (a.sv_gate && col0 < a.kb_sv) {
+                    // backward coefficients of this gate column per unit of dL/db' (SURVEY A.1 / tc_bptt.cuh):
+                    //   c_n = (1-z)(1-n^2), c_r = c_n hn r (1-r), c_nr = c_n r, c_z = (h-n) z (1-z), and z for the
+                    // carry.  The cancellation-prone factors (h - n, 1 - n^2) are formed in fp32 above; the
+                    // products run on packed 16-bit pairs (their results are stored at that precision anyway).
+                    uint4 pl[5];
+                    gru_coeff_planes<FMT>(r_, z_, hn_, omn2, hmn, pl);
                     uint16_t* img = a.sv_gate + ((size_t)t * ntiles + tile) * 5 * kTileRows * a.kb_sv +
                                     (size_t)(col0 >> 3) * kTileRows * 8 + row * 8;
                     const size_t plane = (size_t)kTileRows * a.kb_sv;
-                    const float* src[5] = {r_, hb[it], in_, hn_, z_};
 #pragma unroll
-                    for (int pl = 0; pl < 5; ++pl) {
-#pragma unroll
-                      for (int g8 = 0; g8 < 2; ++g8) {
-                        const float* q8 = src[pl] + g8 * 8;
-                        *reinterpret_cast<uint4*>(img + pl * plane + (size_t)g8 * kTileRows * 8) =
-                            make_uint4(Half16<FMT>::pack2(q8[0], q8[1]), Half16<FMT>::pack2(q8[2], q8[3]),
-                                       Half16<FMT>::pack2(q8[4], q8[5]), Half16<FMT>::pack2(q8[6], q8[7]));
-                      }
-                    }
+                    for (int k = 0; k < 5; ++k) *reinterpret_cast<uint4*>(img + k * plane) = pl[k];
                   }
                   if (rvalid) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
+                    for (int j4 = 0; j4 < 2; ++j4) {
                       const int col = col0 + j4 * 4;
                       if (be4 && col + 3 < Be)
                         *reinterpret_cast<float4*>(bnew + col) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
@@ -672,108 +802,105 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
                       }
                     }
                   }
-                  if (col0 + 16 > Be) {
+                  if (col0 + 8 > Be) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (col0 + j >= Be) o[j] = (col0 + j == Be) ? 1.f : 0.f;
+                    for (int j = 0; j < 8; ++j) if (col0 + j >= Be) o[j] = (col0 + j == Be) ? 1.f : 0.f;
                   }
-                  if (col0 < a.Kp_b) {
-                    uint8_t* p = Bnxt + (col0 >> 3) * kLboA + (row >> 3) * 128 + (row & 7) * 16;
-                    put8(p, o);
-                    put8(p + kLboA, o + 8);
-                  }
+                  if (col0 < a.Kp_b)
+                    put16(Bnxt + (col0 >> 3) * kLboA + rowoff,
+                          make_uint4(Half16<FMT>::pack2(o[0], o[1]), Half16<FMT>::pack2(o[2], o[3]),
+                                     Half16<FMT>::pack2(o[4], o[5]), Half16<FMT>::pack2(o[6], o[7])));
                 }
               }
             } break;
             case EPI_PRIOR_OUT: {
               const int Sp = ph.Np;    // mean at [0,Sp), raw std at [Sp, 2Sp)
-              const int c = half * 16;
               // row of this thread in the state-noise tensor
               const long long erow = a.cem_cl
                   ? (long long)t * ((a.N / a.cem_cl) * a.cem_c) + (grow / a.cem_cl) * a.cem_c + a.cem_c0 + grow % a.cem_cl
                   : orow;
-              float eps[16];
+              // 8-column chunks cc = 8 part + 32 it; the first chunk's noise is requested before the wait
+              float eps[8];
+              const int cc0 = part * 8;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) eps[j] = (rvalid && c + j < S) ? a.eps_s[erow * S + c + j] : 0.f;
+              for (int j = 0; j < 8; ++j) eps[j] = (rvalid && cc0 + j < S) ? a.eps_s[erow * S + cc0 + j] : 0.f;
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
-              // The (mean, std, state) rows of a tile are one contiguous block of each fp32 output:
-              // stage them row-major in the H tile (dead during this epilogue: its last reader was
-              // this phase's MMA) and write them out coalesced, instead of 3*S strided scalar stores
-              // per thread.  Falls back to direct stores when the tile is too small.
-              const bool want_out = a.means != nullptr && wr0;
-              const bool staged = want_out && (3 * S * 4 <= a.Kp_h * 2);
-              float* stage = reinterpret_cast<float*>(smem + a.sm.off_tile[TILE_H]);
-              for (int cc = c, it = 0; cc < Sp; cc += 32, ++it) {
-                if (it > 0) {
+              // each thread owns 8 consecutive columns of its row: 32-byte pieces of the fp32 outputs go out
+              // as 8-byte stores (a full sector per thread: no staging through shared memory, no barrier)
+              const bool want_out = a.means != nullptr && wr0 && rvalid;
+              const bool s2 = (S & 1) == 0;      // rows are 8-byte aligned
+              for (int cc = cc0; cc < Sp; cc += 32) {
+                if (cc != cc0) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[erow * S + cc + j] : 0.f;
+                  for (int j = 0; j < 8; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[erow * S + cc + j] : 0.f;
                 }
-                float m_[16], s_[16];
-                tmem_ld16(tacc + cc, m_);
-                tmem_ld16(tacc + Sp + cc, s_);
+                float m_[8], s_[8], st[8];
+                tmem_ld8(tacc + cc, m_);
+                tmem_ld8(tacc + Sp + cc, s_);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int col = cc + j;
-                  if (col < S) {
-                    // softplus(x) = max(x,0) + log(1 + exp(-|x|)) with single-MUFU exp / log
-                    const float sd = fmaxf(s_[j], 0.f) + __logf(1.f + fast_exp(-fabsf(s_[j]))) + a.min_std;
-                    const float st = fmaf(sd, eps[j], m_[j]);
-                    if (staged) {
-                      stage[row * S + col] = m_[j];
-                      stage[(kTileRows + row) * S + col] = sd;
-                      stage[(2 * kTileRows + row) * S + col] = st;
-                    } else if (rvalid && want_out) {
-                      a.means[orow * S + col] = m_[j];
-                      a.stds[orow * S + col] = sd;
-                      a.states[orow * S + col] = st;
-                    }
-                    store1<FMT>(SAt, row, col, st);
-                  }
+                for (int j = 0; j < 8; ++j) {
+                  // softplus(x) = max(x,0) + log(1 + exp(-|x|)) with single-MUFU exp / log
+                  s_[j] = fmaxf(s_[j], 0.f) + __logf(1.f + fast_exp(-fabsf(s_[j]))) + a.min_std;
+                  st[j] = fmaf(s_[j], eps[j], m_[j]);
                 }
-              }
-              if (staged) {      // uniform per CTA: all 256 epilogue threads take part
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const long long row0 = tile * kTileRows;
-                const int nrows = (int)((a.N - row0) < kTileRows ? (a.N - row0) : kTileRows);
-                const int nfl = nrows * S;                                  // floats per output
-                const long long g0 = ((long long)t * a.N + row0) * S;
-                float* outs[3] = {a.means, a.stds, a.states};
+                if (cc + 8 <= S) {
+                  *reinterpret_cast<uint4*>(SAt + (cc >> 3) * kLboA + rowoff) =
+                      make_uint4(Half16<FMT>::pack2(st[0], st[1]), Half16<FMT>::pack2(st[2], st[3]),
+                                 Half16<FMT>::pack2(st[4], st[5]), Half16<FMT>::pack2(st[6], st[7]));
+                } else {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                  float* dst = outs[k] + g0;
-                  const float* src = stage + k * kTileRows * S;
-                  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nfl & 3) == 0) {
-                    for (int i = etid * 4; i < nfl; i += 256 * 4)
-                      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
-                  } else {
-                    for (int i = etid; i < nfl; i += 256) dst[i] = src[i];
+                  for (int j = 0; j < 8; ++j) if (cc + j < S) store1<FMT>(SAt, row, cc + j, st[j]);
+                }
+                if (want_out) {
+                  float* om = a.means + orow * S + cc;
+                  float* od = a.stds + orow * S + cc;
+                  float* os = a.states + orow * S + cc;
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    if (s2 && cc + j + 1 < S) {
+                      *reinterpret_cast<float2*>(om + j) = make_float2(m_[j], m_[j + 1]);
+                      *reinterpret_cast<float2*>(od + j) = make_float2(s_[j], s_[j + 1]);
+                      *reinterpret_cast<float2*>(os + j) = make_float2(st[j], st[j + 1]);
+                    } else {
+                      if (cc + j < S) { om[j] = m_[j]; od[j] = s_[j]; os[j] = st[j]; }
+                      if (cc + j + 1 < S) { om[j + 1] = m_[j + 1]; od[j + 1] = s_[j + 1]; os[j + 1] = st[j + 1]; }
+                    }
                   }
                 }
               }
-              if (!WITH_ACTOR && half == 0 && t + 1 < a.T && a.ext_actions) {   // next step's given action -> [s ; a] tile
+              if (!WITH_ACTOR && part == 0 && t + 1 < a.T && a.ext_actions) {   // next step's given action -> [s ; a] tile
                 for (int j = 0; j < Ad; ++j)
                   store1<FMT>(SAt, row, S + j, rvalid ? a.ext_actions[((long long)(t + 1) * a.N + grow) * Ad + j] : 0.f);
               }
             } break;
             case EPI_ACTOR_OUT: {
+              // (src/models.py:513-516, src/dreamer.py:435-443) the action noise is requested before the wait;
+              // single-MUFU tanh / exp / log: the 16-bit modes round the action to 10 / 7 mantissa bits anyway
+              float ea[16];
+              if (WITH_ACTOR && part == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ea[j] = (j < Ad && rvalid) ? a.eps_a[orow * Ad + j] : 0.f;
+              }
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
-              if (WITH_ACTOR && half == 0) {
+              if (WITH_ACTOR && part == 0) {
                 const int Ap = ph.Np;
                 float m_[16], s_[16];
                 tmem_ld16(tacc, m_);
                 tmem_ld16(tacc + Ap, s_);
                 tmem_ld_wait();
+                const float inv_ms = 1.f / a.cfg.mean_scale;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   if (j < Ad) {
-                    const float mean = a.cfg.mean_scale * tanhf(m_[j] / a.cfg.mean_scale);
-                    const float sd = softplusf_(s_[j] + a.cfg.raw_init_std) + a.cfg.min_std;
-                    const float ea = rvalid ? a.eps_a[orow * Ad + j] : 0.f;
-                    const float act = tanhf(mean + ea * sd);
+                    const float mean = a.cfg.mean_scale * fast_tanh(m_[j] * inv_ms);
+                    const float xs = s_[j] + a.cfg.raw_init_std;
+                    const float sd = (xs > 20.f ? xs : fmaxf(xs, 0.f) + __logf(1.f + fast_exp(-fabsf(xs)))) + a.cfg.min_std;
+                    const float act = fast_tanh(fmaf(ea[j], sd, mean));
                     store1<FMT>(SAt, row, S + j, act);
                     if (rvalid && wr0) {
                       a.actions[orow * Ad + j] = act;
@@ -788,9 +915,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
-              if (half == 0) {
-                float v[16];
-                tmem_ld16(tacc, v);
+              if (part == 0) {
+                float v[8];
+                tmem_ld8(tacc, v);
                 tmem_ld_wait();
                 if (rvalid && wr0 && a.head_out[ph.aux0]) a.head_out[ph.aux0][orow] = v[0];
               }
@@ -800,7 +927,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
               const int nv = ph.n_valid;
-              for (int c = half * 16; c < ph.Np; c += 32) {
+              for (int c = part * 16; c < ph.Np; c += 64) {
                 float v[16];
                 tmem_ld16(tacc + c, v);
                 tmem_ld_wait();
@@ -828,9 +955,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_fwd_kernel(const __grid_c
         }
       }
       // lambda-return tail of the fused Dreamer rollout: this thread wrote reward / value of its row
-      // for every step (EPI_HEAD_OUT, half 0), so program order makes them visible to it.  Same
+      // for every step (EPI_HEAD_OUT, part 0), so program order makes them visible to it.  Same
       // arithmetic (separate fp32 roundings, no FMA contraction) as f32::lambda_return_fwd_kernel.
-      if (a.returns != nullptr && half == 0 && rvalid && wr0) {
+      if (a.returns != nullptr && part == 0 && rvalid && wr0) {
         const float* rw = a.head_out[0];
         const float* vl = a.head_out[1];
         float last = vl[(long long)(a.T - 1) * a.N + grow];      // bootstrap = value[-1]

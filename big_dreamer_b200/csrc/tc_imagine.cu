@@ -391,6 +391,10 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
   if (prof) {
     ra.prof = reinterpret_cast<long long*>(static_cast<char*>(ws) + ((pack_bytes + 4095) & ~size_t(4095)));
     cudaMemsetAsync(ra.prof, 0, kMaxPhases * 64 + 160 * 24, s);
+    if (getenv("BD_TC_PROF")[0] == '2') {     // per-stage counters as well (they perturb the issuer)
+      const long long one = 1;
+      cudaMemcpyAsync(ra.prof + 39 * 8 + 7, &one, sizeof(one), cudaMemcpyHostToDevice, s);
+    }
   }
   long long max_img = 0;
   for (int i = 0; i < b.pack.njobs; ++i)

@@ -14,7 +14,7 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cud
   auto go = [&](auto kernel) -> int {
     set_smem_attr(kernel, ra.sm.total);
     cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreads2);
     cfg.dynamicSmemBytes = ra.sm.total;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -43,12 +43,14 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra, cud
     if (e != cudaSuccess) BD_FAIL(BD_ERR_CUDA, "tensor-core rollout launch: %s", cudaGetErrorString(e));
     return BD_OK;
   };
-  const bool p = prof && FMT == 0 && ACT == BD_ACT_ELU;
+  // (debug counters are compiled for fp16 ELU / ReLU only)
+  constexpr bool kProfBuilt = FMT == 0 && (ACT == BD_ACT_ELU || ACT == BD_ACT_RELU);
+  const bool p = prof && kProfBuilt;
   if (R > 1) {
-    if (p) BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, (FMT == 0 && ACT == BD_ACT_ELU), true>));
+    if (p) BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, kProfBuilt, true>));
     else BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false, true>));
   } else {
-    if (p) BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, (FMT == 0 && ACT == BD_ACT_ELU), false>));
+    if (p) BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, kProfBuilt, false>));
     else BD_TRY(go(rollout_fwd_kernel<FMT, ACT, WITH_ACTOR, false, false>));
   }
   BD_CUDA_LAUNCH_CHECK();

@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import big_dreamer_b200 as bd
 from tests import parity_utils as pu
 from oracle import rssm_oracle as orc
-d = dict(Be=200, Hi=200, S=30, A=1, E=8, H=15, act="ELU")
+d = dict(Be=200, Hi=200, S=30, A=1, E=8, H=15, act=os.environ.get("ACT", "ELU"))
 trans, actor, reward, value = orc.make_models(0, 200, 30, 1, 200, 8)
 mods = pu.build_gpu_models(d, trans, actor, reward, value)
 pu.freeze(mods.transition, mods.reward, mods.critic)
@@ -17,7 +17,14 @@ with torch.no_grad():
     for _ in range(2):
         bd.imagine_ahead(agent, s0[None], b0[None], noise)
 torch.cuda.synchronize()
-print("ok")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.no_grad():
+    e0.record()
+    for _ in range(5):
+        bd.imagine_ahead(agent, s0[None], b0[None], noise)
+    e1.record()
+torch.cuda.synchronize()
+print("ok: imagine_ahead forward %.1f us per call (N=%d, CUDA events, 5 calls incl. packing + entropy)" % (e0.elapsed_time(e1) * 200, N))
 
 if os.environ.get("BD_TC_PROF"):
     from big_dreamer_b200 import _lib
@@ -29,7 +36,7 @@ if os.environ.get("BD_TC_PROF"):
     import struct
     for off in range(0, 4 << 20, 4096):
         v = np.frombuffer(raw[off:off + 40 * 64].tobytes(), dtype=np.int64).reshape(40, 8)
-        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[20:39].sum() == 0 and v[39, 0] > 0:
+        if 0 < v[0, 2] < 10**9 and 0 < v[0, 4] < 10**9 and v[39, 0] > 0 and v[13:20].sum() == 0 and 0 < v[39, 1] < 10**10:
             names = ["actorL0", "actorL1", "actorL2", "actorL3", "actorOut", "embed", "gru0", "gru1", "gru2", "gru3", "prior1", "priorOut"]
             nph = int((v[:20, 2] > 0).sum())
             if nph != 12:
@@ -39,6 +46,7 @@ if os.environ.get("BD_TC_PROF"):
                 print(f"{n:9s}", " ".join(f"{int(x)//14:9d}" for x in v[i, :8]))
             tot = v[:20, :8].sum(0) // 14
             print("total    ", " ".join(f"{int(x):9d}" for x in tot))
+            print("per-stage commit cycles per phase:", [int(x) // 14 for x in v[20:20 + len(names), 0]])
             w = np.frombuffer(raw[off + 40 * 64: off + 40 * 64 + 160 * 24].tobytes(), dtype=np.int64).reshape(160, 3)
             w = w[w[:, 0] > 0]
             t0 = w[:, 0].min()
