@@ -19,6 +19,7 @@ scaling).  Secondary blocks in the same JSON line (every N unless noted):
               the ranks (one all-gather per iteration)
     observe   BASELINE configs[3] (N = 1: the path does not shard -- "replicas only")
     value_update   critic regression update (N = 1)
+    act       acting path (N = 1): us per environment step, actor and CEM policies
 
 Prints ONE JSON line (see README / DESIGN.md for the keys).
 """
@@ -600,6 +601,53 @@ def value_update_block(cx: Ctx, precision, rows, T):
                          "frac": tf / cx.pk["bf16_sustained"]}}
 
 
+def act_block(cx: Ctx, precision, with_cpu):
+    """SURVEY 8f-3, the acting path (src/planet.py:370-403 between the encoder and env.step), B = 1: one
+    posterior step + policy + exploration noise per environment step, replayed as one CUDA graph
+    (bd.ActPath).  Policies: Dreamer's actor (get_action) and PlaNet's CEM planner (BASELINE configs[2])."""
+    bd, orc, pu = cx.bd, cx.orc, cx.pu
+    d = dict(CFG, E=1024, **CEM_CFG)
+    trans, actor, reward, _ = orc.make_models(0, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    mods = pu.build_gpu_models(d, trans, actor, reward_sd=reward, device=cx.dev)
+    pl = bd.MPCPlanner(d["A"], d["H"], d["iters"], d["C"], d["K"], mods.transition, mods.reward)
+    pl.shard_candidates = False
+    z = lambda n: torch.zeros(1, n, device=cx.dev)
+    emb = torch.randn(1, d["E"], device=cx.dev)
+    out = {"metric": "env_steps_per_sec", "unit": "steps/s", "batch": 1, "precision": precision,
+           "path": "posterior step (TransitionModel.forward, L = 1, observe) + policy + exploration noise; "
+                   "encoder and env.step excluded (out of scope)", "launch": "one CUDA graph replay per step"}
+    for name, policy in (("actor", mods.actor), ("cem", pl)):
+        act = bd.ActPath(mods.transition, policy, batch=1, action_noise=0.3)
+        state = [z(d["Be"]), z(d["S"]), z(d["A"])]
+
+        def step():
+            b, s, a = act(state[0], state[1], state[2], emb, explore=True)
+            state[0], state[1], state[2] = b, s, a
+        reps = 50 if name == "actor" else 10
+        ms_list, _ = cx.timed(step, reps, 3)
+        ms = sum(ms_list) / reps
+        out[name] = {"us_per_env_step": ms * 1e3, "value": 1e3 / ms}
+    out["value"] = out["actor"]["value"]
+    if with_cpu and cx.rank == 0:
+        cores = host_threads()
+        g = torch.Generator().manual_seed(0)
+        b0, s0, a0 = torch.zeros(1, d["Be"]), torch.zeros(1, d["S"]), torch.zeros(1, d["A"])
+        embc = torch.randn(1, d["E"], generator=g)
+        ep, eq, ea = (torch.randn(1, d["S"], generator=g), torch.randn(1, d["S"], generator=g),
+                      torch.randn(1, d["A"], generator=g))
+        with torch.no_grad():
+            for _ in range(3):
+                orc.act_step(trans, actor, d["act"], 0.1, b0, s0, a0, embc, ep, eq, ea)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                orc.act_step(trans, actor, d["act"], 0.1, b0, s0, a0, embc, ep, eq, ea)
+            cpu_s = (time.perf_counter() - t0) / 200
+        out["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "steps/s", "cores": cores, "kind": "port",
+                               "us_per_env_step": cpu_s * 1e6,
+                               "sample": "oracle port of the posterior step + get_action (actor policy), 200 steps"}
+    return out
+
+
 def run_ours(args):
     cx = Ctx(args)
     bd, D_ = cx.bd, cx.D
@@ -696,6 +744,7 @@ def run_ours(args):
         if world == 1:
             blocks["observe"] = lambda: observe_block(cx, args.precision, not args.no_cpu_baseline)
             blocks["value_update"] = lambda: value_update_block(cx, args.precision, min(rows, 131072), T)
+            blocks["act"] = lambda: act_block(cx, args.precision, not args.no_cpu_baseline)
         for name, fn in blocks.items():
             try:
                 out[name] = fn()

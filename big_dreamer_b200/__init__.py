@@ -13,8 +13,10 @@ from .modules import (DenseModel, MPCPlanner, TransitionModel, build_mlp, draw_i
                       imagine_ahead, imagine_and_returns, kl_loss, lambda_return, value_update)
 from .patch import patch, unpatch
 from .graph import CapturedStep
+from .act import ActPath, get_action
 
 __all__ = ["BdError", "LIB_PATH", "load_library", "get_precision", "set_precision", "DenseModel",
            "MPCPlanner", "TransitionModel", "build_mlp", "draw_imagine_noise", "imagine_ahead",
-           "imagine_and_returns", "kl_loss", "lambda_return", "value_update", "patch", "unpatch", "CapturedStep"]
+           "imagine_and_returns", "kl_loss", "lambda_return", "value_update", "patch", "unpatch", "CapturedStep",
+           "ActPath", "get_action"]
 __version__ = "0.1.0"

@@ -146,6 +146,8 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bd_value_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "bd_actor_act": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ActorCfg), C.c_int64, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p]),
     "bd_lambda_return_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                            C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "bd_lambda_return_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_double,

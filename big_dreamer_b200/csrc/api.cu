@@ -203,6 +203,11 @@ int bd_value_loss(const float* value, const float* target, const float* weight, 
   return f32::value_loss(value, target, weight, n, loss, d_value, ws, ws_bytes, stream);
 }
 
+int bd_actor_act(const float* raw, const float* eps, const bd_actor_cfg* cfg, int64_t rows, int action_size,
+                 int deterministic, float* action, bd_stream_t stream) {
+  return f32::actor_act(raw, eps, cfg, rows, action_size, deterministic, action, stream);
+}
+
 size_t bd_transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward) {
   if (!r) return 0;
   size_t f = f32::transition_workspace_bytes(r, L, B, observe, backward);

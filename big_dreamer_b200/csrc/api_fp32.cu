@@ -683,6 +683,18 @@ static int observe_backward_persist(const bd_transition_bwd_args* a, void* ws, s
   // ---- parameter gradients and d embeddings, batched over time
   return time_batched_param_grads(r, f, *a, tb, s);
 }
+int actor_act(const float* raw, const float* eps, const bd_actor_cfg* cfg, int64_t rows, int A,
+              int deterministic, float* action, bd_stream_t stream) {
+  BD_CHECK_ARG(raw && eps && cfg && action, "actor_act: null pointer");
+  BD_CHECK_ARG(rows >= 0 && A >= 1, "actor_act: bad rows / action size");
+  BD_CHECK_ARG(!deterministic || cfg->entropy_samples >= 1, "actor_act: SampleDist.mode needs >= 1 sample");
+  if (rows == 0) return BD_OK;
+  const int wpb = 4;
+  actor_act_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, S(stream)>>>(raw, eps, *cfg, rows, A,
+                                                                                 deterministic, action);
+  BD_CUDA_LAUNCH_CHECK();
+  return BD_OK;
+}
 int value_loss(const float* value, const float* target, const float* weight, int64_t n, float* loss,
                float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream) {
   BD_CHECK_ARG(value && target && loss, "value_loss: null pointer");

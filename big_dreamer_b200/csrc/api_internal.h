@@ -32,6 +32,8 @@ int kl_loss_backward(const float* post_mean, const float* post_std, const float*
                      float* d_post_std, float* d_prior_mean, float* d_prior_std, bd_stream_t stream);
 int value_loss(const float* value, const float* target, const float* weight, int64_t n, float* loss,
                float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream);
+int actor_act(const float* raw, const float* eps, const bd_actor_cfg* cfg, int64_t rows, int A,
+              int deterministic, float* action, bd_stream_t stream);
 size_t transition_workspace_bytes(const bd_rssm* r, int L, int64_t B, int observe, int backward);
 int transition_forward(const bd_transition_args* a, void* ws, size_t ws_bytes, bd_stream_t stream,
                        int precision = BD_PREC_FP32);

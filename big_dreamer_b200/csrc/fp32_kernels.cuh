@@ -607,6 +607,54 @@ __global__ void actor_head_fwd_kernel(const float* __restrict__ raw, const float
   entropy[r] = -ent_acc / (float)J;
 }
 
+// Acting (src/dreamer.py:429-444 called from Planet.update_belief_and_act, src/planet.py:370-403): the action
+// alone, no entropy.  One warp per row.
+//   deterministic == 0: action = tanh(mean + eps sd), eps (rows, A)            (dist.rsample, :443)
+//   deterministic == 1: SampleDist.mode (src/models.py:707-723): J samples y_j = tanh(mean + eps_j sd), eps
+//     (J, rows, A); the one with the largest log-probability (summed over A; first maximum) is the action.
+//     The log-probability is that of actor_head_fwd_kernel (tanh-Normal with the clamped inverse).
+__global__ void actor_act_kernel(const float* __restrict__ raw, const float* __restrict__ eps, bd_actor_cfg cfg,
+                                 long long rows, int A, int deterministic, float* __restrict__ action) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  if (!deterministic) {
+    for (int a = lane; a < A; a += 32) {
+      float mean, sd;
+      actor_squash(raw[r * 2 * A + a], raw[r * 2 * A + A + a], cfg, mean, sd);
+      action[r * A + a] = tanhf(mean + eps[r * A + a] * sd);
+    }
+    return;
+  }
+  const float kClamp = 0.99999997f, kLogSqrt2Pi = 0.9189385332046727f, kLog2 = 0.6931471805599453f;
+  const int J = cfg.entropy_samples;
+  float best = -INFINITY;
+  int best_j = 0x7fffffff;
+  for (int j = lane; j < J; j += 32) {
+    float lp = 0.f;
+    for (int a = 0; a < A; ++a) {
+      float mean, sd;
+      actor_squash(raw[r * 2 * A + a], raw[r * 2 * A + A + a], cfg, mean, sd);
+      const float y = tanhf(mean + eps[((long long)j * rows + r) * A + a] * sd);
+      const float yc = fminf(fmaxf(y, -kClamp), kClamp);
+      const float xh = 0.5f * logf((1.f + yc) / (1.f - yc));
+      const float d = xh - mean;
+      lp += -(d * d) / (2.f * sd * sd) - logf(sd) - kLogSqrt2Pi - 2.f * (kLog2 - xh - softplusf_(-2.f * xh));
+    }
+    if (lp > best) { best = lp; best_j = j; }       // (ascending j per lane: keeps the first maximum)
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (ob > best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+  }
+  for (int a = lane; a < A; a += 32) {
+    float mean, sd;
+    actor_squash(raw[r * 2 * A + a], raw[r * 2 * A + A + a], cfg, mean, sd);
+    action[r * A + a] = tanhf(mean + eps[((long long)best_j * rows + r) * A + a] * sd);
+  }
+}
+
 // d_raw (rows,2A) from d_action (rows, lda: strided view into d[s;a]) and g_entropy (rows)
 __global__ void actor_head_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ eps_a,
                                       const float* __restrict__ action,

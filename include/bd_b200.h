@@ -194,6 +194,17 @@ int bd_kl_loss_backward(const float* post_mean, const float* post_std, const flo
 int bd_value_loss(const float* value, const float* target, const float* weight, int64_t n,
                   float* loss, float* d_value, void* ws, size_t ws_bytes, bd_stream_t stream);
 
+/* ------------------------------------------------- acting: Dreamer.get_action ---- */
+/* The action of Dreamer.get_action (src/dreamer.py:429-444) as Planet.update_belief_and_act uses it
+ * (src/planet.py:388-390: the entropy is discarded): raw (rows, 2A) = the actor MLP's output
+ * (bd_mlp_forward on ActorModel.model), squashed as ActorModel.forward does (src/models.py:513-516).
+ *   deterministic == 0: action = tanh(mean + eps * std), eps (rows, A)                 (dist.rsample)
+ *   deterministic == 1: SampleDist.mode (src/models.py:707-723): eps (cfg->entropy_samples, rows, A);
+ *     the sample with the largest tanh-Normal log-probability is the action.
+ * action (rows, A). */
+int bd_actor_act(const float* raw, const float* eps, const bd_actor_cfg* cfg, int64_t rows, int action_size,
+                 int deterministic, float* action, bd_stream_t stream);
+
 /* ----------------------------------------------- TransitionModel.forward ---- */
 typedef struct {
   bd_rssm rssm;

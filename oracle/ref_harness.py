@@ -158,6 +158,28 @@ def ref_imagine(mods, planning_horizon, prev_state, prev_belief, eps_a, eps_e, e
         return d.Dreamer.imagine_ahead(agent, prev_state, prev_belief)
 
 
+def ref_get_action(mods, belief, state, eps_first, eps_entropy, deterministic=False):
+    """Dreamer.get_action (src/dreamer.py:429-444) of the unmodified reference.  Draw order: the sample
+    (``rsample``: (B,A); ``mode``: (100,B,A)) and then the entropy's (100,B,A)."""
+    d = load().dreamer
+    agent = fake_agent(mods, 2)
+    with NoiseTape([eps_first, eps_entropy]).playing():
+        return d.Dreamer.get_action(agent, belief, state, deterministic)
+
+
+def ref_act_step(mods, belief, state, action, embedding, eps_prior, eps_post, eps_first, eps_entropy,
+                 deterministic=False):
+    """The transition / get_action part of Planet.update_belief_and_act (src/planet.py:379-390) run on the
+    reference's own modules: posterior step with a time dimension of 1, then get_action."""
+    d = load().dreamer
+    agent = fake_agent(mods, 2)
+    with NoiseTape([eps_prior, eps_post, eps_first, eps_entropy]).playing():
+        b, _, _, post, _ = mods.transition(state, action.unsqueeze(dim=0), belief, embedding.unsqueeze(dim=0))
+        b, post = b.squeeze(dim=0), post.squeeze(dim=0)
+        a, _ = d.Dreamer.get_action(agent, b, post, deterministic)
+    return b, post, a
+
+
 def ref_actor_loss(mods, planning_horizon, prev_state, prev_belief, eps_a, eps_e, eps_s,
                    discount=0.995, lambda_=0.95, entropy_weight=1e-5):
     """The behaviour-learning block exactly as src/dreamer.py:313-353 runs it

@@ -208,6 +208,36 @@ def get_action(actor_sd: SD, act: str, belief: Tensor, state: Tensor, eps_a: Ten
     return action, entropy
 
 
+def get_action_mode(actor_sd: SD, act: str, belief: Tensor, state: Tensor, eps_m: Tensor, **actor_kw):
+    """Dreamer.get_action, deterministic=True (src/dreamer.py:440-441): SampleDist.mode
+    (src/models.py:707-723) -- of 100 samples the one with the largest log-probability.
+    eps_m: (100,N,A), the draw of ``dist.rsample()`` on the expanded distribution."""
+    mean, std = actor_mean_std(actor_sd, act, belief, state, **actor_kw)
+    y = torch.tanh(mean.unsqueeze(0) + eps_m * std.unsqueeze(0))
+    logprob = tanh_normal_logprob(y, mean.unsqueeze(0), std.unsqueeze(0))        # (100, N)
+    idx = torch.argmax(logprob, dim=0).reshape(1, -1, 1).expand(1, y.size(1), y.size(2))
+    return torch.gather(y, 0, idx).squeeze(0)
+
+
+def act_step(trans_sd: SD, actor_sd: SD, act: str, min_std: float, belief: Tensor, state: Tensor,
+             action: Tensor, embedding: Tensor, eps_prior: Tensor, eps_post: Tensor, eps_act: Tensor,
+             deterministic: bool = False, **actor_kw):
+    """Planet.update_belief_and_act (src/planet.py:370-403) for an actor policy, without the encoder,
+    the exploration noise and env.step: one posterior step of the transition model (no nonterminals),
+    then Dreamer.get_action on the new (belief, posterior state).
+    belief (B,Be), state (B,S), action (B,A), embedding (B,E), eps_prior / eps_post (B,S),
+    eps_act (B,A) or, deterministic, (100,B,A).  -> belief, posterior_state, action."""
+    b, _, _, post, _ = transition_forward(trans_sd, act, min_std, state, action[None], belief, eps_prior[None],
+                                          embedding[None], None, eps_post[None])
+    b, post = b[0], post[0]
+    if deterministic:
+        a = get_action_mode(actor_sd, act, b, post, eps_act, **actor_kw)
+    else:
+        mean, std = actor_mean_std(actor_sd, act, b, post, **actor_kw)
+        a = torch.tanh(mean + eps_act * std)
+    return b, post, a
+
+
 # ----------------------------------------------------------------------------
 # Dreamer.imagine_ahead (src/dreamer.py:178-237)
 # ----------------------------------------------------------------------------

@@ -329,3 +329,80 @@ def test_patched_reference_train_step_on_gpu(fused):
     for k in ("observation_loss", "reward_loss", "kl_loss", "model_loss", "actor_loss", "policy_entropy", "value_loss"):
         assert k in got and got[k] == got[k], k                  # present and not NaN
         assert abs(got[k] - ref[k]) <= 0.08 * abs(ref[k]) + 0.05, (k, got[k], ref[k])
+
+
+# ----------------------------------------------------------------------------------------------
+# acting path
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("d", [dict(Be=200, Hi=200, S=30, A=1, E=1024, B=1, act="ELU"),
+                               dict(Be=48, Hi=40, S=10, A=3, E=32, B=5, act="Tanh")])
+def test_act_path_vs_oracle(d, deterministic, prec, tol):
+    """bd.ActPath (posterior step + Dreamer.get_action + exploration noise, src/planet.py:370-403) with
+    explicit noise against oracle.act_step; SampleDist.mode picks the oracle's sample."""
+    bd.set_precision(prec)
+    trans, actor, _, _ = orc.make_models(5, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    actor["model.8.bias"][d["A"]:] -= 3.0
+    mods = pu.build_gpu_models(d, trans, actor)
+    g = torch.Generator().manual_seed(3)
+    B = d["B"]
+    s0, b0 = orc.make_latents(5, B, d["Be"], d["S"])
+    a0 = torch.rand(B, d["A"], generator=g) * 2 - 1
+    emb = torch.randn(B, d["E"], generator=g)
+    ep, eq = torch.randn(B, d["S"], generator=g), torch.randn(B, d["S"], generator=g)
+    ea = torch.randn(*((100, B, d["A"]) if deterministic else (B, d["A"])), generator=g)
+    ex = torch.randn(B, d["A"], generator=g)
+    with torch.no_grad():
+        bo, po, ao = orc.act_step(trans, actor, d["act"], 0.1, b0, s0, a0, emb, ep, eq, ea, deterministic)
+    ao_x = torch.clamp(ao + 0.3 * ex, -1, 1)
+    act = bd.ActPath(mods.transition, mods.actor, batch=B, action_noise=0.3, deterministic=deterministic)
+    noise = dict(eps_prior=ep.cuda(), eps_post=eq.cuda(), eps_act=ea.cuda(), eps_explore=ex.cuda())
+    bg, pg, ag = act(b0.cuda(), s0.cuda(), a0.cuda(), emb.cuda(), explore=True, noise=noise)
+    assert pu.relerr(bg, bo) < tol and pu.relerr(pg, po) < tol
+    if deterministic and prec != "fp32":
+        # 16-bit contractions may pick another of the 100 samples when two log-probabilities are closer than
+        # the rounding error: the action must then be ANOTHER sample of the oracle's set
+        mean, std = orc.actor_mean_std(actor, d["act"], bo, po)
+        cand = torch.clamp(torch.tanh(mean[None] + ea * std[None]) + 0.3 * ex[None], -1, 1)      # (100,B,A)
+        assert float((cand - ag.cpu()[None]).abs().amax(dim=2).amin(dim=0).max()) < tol
+    else:
+        assert float((ag.cpu() - ao_x).abs().max()) < tol
+    # the replayed graph (noise drawn inside): same belief (no noise enters it), actions in range
+    bg2, pg2, ag2 = act(b0.cuda(), s0.cuda(), a0.cuda(), emb.cuda(), explore=True)
+    torch.cuda.synchronize()
+    assert pu.relerr(bg2, bo) < tol
+    assert bool(torch.isfinite(pg2).all()) and float(ag2.abs().max()) <= 1.0
+    bg3, _, _ = act(bg2, pg2, ag2, emb.cuda(), explore=True)          # outputs fed back as the next inputs
+    assert bool(torch.isfinite(bg3).all())
+
+
+def test_act_path_planner_policy():
+    """ActPath with the CEM planner as policy (PlaNet): explicit noise reproduces MPCPlanner on the
+    posterior latents; the captured graph replays."""
+    bd.set_precision("fp32")
+    d = dict(Be=32, Hi=32, S=30, A=2, E=16, B=2, C=64, K=8, H=4, iters=2, act="ELU")
+    trans, _, reward, _ = orc.make_models(2, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    mods = pu.build_gpu_models(d, trans, reward_sd=reward)
+    pl = bd.MPCPlanner(d["A"], d["H"], d["iters"], d["C"], d["K"], mods.transition, mods.reward)
+    g = torch.Generator().manual_seed(4)
+    B = d["B"]
+    s0, b0 = orc.make_latents(2, B, d["Be"], d["S"])
+    a0 = torch.rand(B, d["A"], generator=g) * 2 - 1
+    emb = torch.randn(B, d["E"], generator=g)
+    ep, eq = torch.randn(B, d["S"], generator=g), torch.randn(B, d["S"], generator=g)
+    ea = torch.randn(d["iters"], d["H"], B, d["C"], d["A"], generator=g)
+    es = torch.randn(d["iters"], d["H"], B * d["C"], d["S"], generator=g)
+    with torch.no_grad():
+        bo, _, _, po, _ = orc.transition_forward(trans, d["act"], 0.1, s0, a0[None], b0, ep[None], emb[None], None,
+                                                 eq[None])
+        ref = orc.cem_plan(trans, reward, d["act"], 0.1, d["A"], d["H"], d["iters"], d["C"], d["K"], bo[0], po[0],
+                           ea, es)
+    act = bd.ActPath(mods.transition, pl, batch=B)
+    noise = dict(eps_prior=ep.cuda(), eps_post=eq.cuda(), planner=dict(eps_act=ea.cuda(), eps_s=es.cuda()))
+    bg, pg, ag = act(b0.cuda(), s0.cuda(), a0.cuda(), emb.cuda(), noise=noise)
+    assert pu.relerr(bg, bo[0]) < 1e-4 and pu.relerr(pg, po[0]) < 1e-4
+    assert pu.relerr(ag, ref) < 1e-4
+    bg2, _, ag2 = act(b0.cuda(), s0.cuda(), a0.cuda(), emb.cuda())
+    torch.cuda.synchronize()
+    assert pu.relerr(bg2, bo[0]) < 1e-4 and bool(torch.isfinite(ag2).all())

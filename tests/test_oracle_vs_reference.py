@@ -132,3 +132,28 @@ def test_kl_loss(agent, free_nats, bal):
         gx = x.grad if x.grad is not None else torch.zeros_like(x)
         gy = y.grad if y.grad is not None else torch.zeros_like(y)
         assert float((gx - gy).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("shape", SHAPES[:3])
+def test_act_step_matches_reference(shape, deterministic):
+    """oracle.act_step (posterior step + get_action) against the reference's own
+    TransitionModel.forward + Dreamer.get_action driven as Planet.update_belief_and_act drives them."""
+    Be, Hi, S, A, E, N, act = shape
+    dt = torch.float64
+    mods = rh.build_modules(3, Be, S, A, Hi, E, act, dt)
+    with torch.no_grad():
+        mods.actor.model[8].bias[A:] -= 3.0
+    g = torch.Generator().manual_seed(11)
+    s0, b0 = orc.make_latents(3, N, Be, S, dt)
+    a0 = torch.rand(N, A, generator=g, dtype=dt) * 2 - 1
+    emb = torch.randn(N, E, generator=g, dtype=dt)
+    ep, eq = torch.randn(N, S, generator=g, dtype=dt), torch.randn(N, S, generator=g, dtype=dt)
+    e1 = torch.randn(*((100, N, A) if deterministic else (N, A)), generator=g, dtype=dt)
+    e2 = torch.randn(100, N, A, generator=g, dtype=dt)
+    with torch.no_grad():
+        br, pr, ar = rh.ref_act_step(mods, b0, s0, a0, emb, ep, eq, e1, e2, deterministic)
+        bo, po, ao = orc.act_step(mods.transition.state_dict(), mods.actor.state_dict(), act, 0.1, b0, s0, a0,
+                                  emb, ep, eq, e1, deterministic)
+    assert relerr(bo, br) < 1e-10 and relerr(po, pr) < 1e-10
+    assert relerr(ao, ar) < 1e-9
