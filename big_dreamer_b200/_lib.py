@@ -14,6 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbd_b200.so")
+TEST_LIB_PATH = os.path.join(_HERE, "libbd_b200_test.so")
 
 BD_MAX_LAYERS = 8
 ACTIVATIONS = {"Identity": 0, "ELU": 1, "ReLU": 2, "Tanh": 3, "Sigmoid": 4}
@@ -183,6 +184,13 @@ SIGNATURES = {
                                                  C.c_int, C.c_int]),
     "bd_cem_plan": (C.c_int, [C.POINTER(CemPlanArgs), C.c_void_p, C.c_size_t, C.c_int,
                               C.c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+# libbd_b200_test.so (include/bd_b200_test.h): self-test + micro-benchmarks, tests/ and scripts/ only
+TEST_SIGNATURES = {
     "bd_tc_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     # debug micro-benchmarks (scripts/mmabench*.py, scripts/dsmembench.py)
@@ -190,9 +198,8 @@ SIGNATURES = {
     "bd_tc_mmabench2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
     "bd_tc_dsmembench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bd_test_last_error": (C.c_char_p, []),
 }
-
-_lib: Optional[C.CDLL] = None
 
 
 class BdError(RuntimeError):
@@ -213,6 +220,29 @@ def load() -> C.CDLL:
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+_test_lib = None
+
+
+def load_test() -> C.CDLL:
+    """The separate debug library (never loaded by the product path)."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.isfile(TEST_LIB_PATH):
+            raise BdError(f"{TEST_LIB_PATH} not found: build it with `make -C big_dreamer_b200/csrc`")
+        lib = C.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in TEST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _test_lib = lib
+    return _test_lib
+
+
+def check_test(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_test().bd_test_last_error()
+        raise BdError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
 
 
 def check(rc: int, what: str) -> None:

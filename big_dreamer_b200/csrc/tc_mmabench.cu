@@ -2,6 +2,7 @@
 // MMAs accumulating into one TMEM tile, for the no-swizzle KM8 operand layout and for SWIZZLE_128B.
 // Operand contents are irrelevant (smem is zero-filled); only fetch/issue rates are measured.
 #include "api_internal.h"
+#include "../../include/bd_b200_test.h"
 #include "tc_common.cuh"
 
 namespace bd {

@@ -3,6 +3,7 @@
 // of the packed image, accumulator in TMEM, read back with tcgen05.ld).  Exposed through the C ABI
 // as bd_tc_selftest so the GPU test-suite can validate descriptors/layouts in isolation.
 #include "api_internal.h"
+#include "../../include/bd_b200_test.h"
 #include "tc_common.cuh"
 #include "tc_pack.cuh"
 

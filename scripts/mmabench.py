@@ -1,7 +1,8 @@
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import big_dreamer_b200 as bd
-lib = bd.load_library()
+from big_dreamer_b200 import _lib
+lib = _lib.load_test()      # libbd_b200_test.so
 lib.bd_tc_mmabench.restype = C.c_int
 lib.bd_tc_mmabench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 out = torch.zeros(1, dtype=torch.int64, device="cuda")

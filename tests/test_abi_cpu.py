@@ -41,6 +41,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.bd_precision_supported(0) == 1
 
 
+def test_debug_entry_points_live_in_the_test_library_only():
+    """bd_tc_selftest / bd_tc_mmabench* / bd_tc_dsmembench (include/bd_b200_test.h) are built into
+    libbd_b200_test.so; the product library and its public header do not carry them."""
+    lib = bd.load_library()
+    tsrc = open(os.path.join(ROOT, "include", "bd_b200_test.h")).read()
+    tsyms = sorted(set(re.findall(r"\b(bd_[a-z0-9_]+)\s*\(", tsrc)))
+    assert "bd_tc_selftest" in tsyms and len(tsyms) >= 5
+    tlib = _lib.load_test()
+    for s in tsyms:
+        assert hasattr(tlib, s), f"{s} declared in bd_b200_test.h but not exported by the test library"
+        assert s in _lib.TEST_SIGNATURES
+        assert not hasattr(lib, s), f"{s} leaked into the product library"
+        assert s not in header_symbols()
+
+
 def test_ctypes_struct_sizes_match_header():
     """Compile a tiny C program against the header and compare sizeof() of every struct."""
     names = {"bd_linear": _lib.Linear, "bd_mlp": _lib.Mlp, "bd_rssm": _lib.Rssm,

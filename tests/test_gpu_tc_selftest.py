@@ -10,14 +10,14 @@ pytestmark = pytest.mark.gpu
 
 
 def run(K, N, fmt, swap=0, seed=0):
-    lib = bd.load_library()
+    lib = _lib.load_test()          # libbd_b200_test.so: the debug entry points are not in the product library
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(128, K, generator=g).cuda()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     b = torch.randn(N, generator=g).cuda()
     y = torch.full((128, N), float("nan"), device="cuda")
     ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
-    _lib.check(lib.bd_tc_selftest(x.data_ptr(), w.data_ptr(), b.data_ptr(), K, N, fmt, swap,
+    _lib.check_test(lib.bd_tc_selftest(x.data_ptr(), w.data_ptr(), b.data_ptr(), K, N, fmt, swap,
                                   ws.data_ptr(), ws.numel(), y.data_ptr(), _lib.stream_ptr()),
                "bd_tc_selftest")
     torch.cuda.synchronize()
