@@ -12,7 +12,9 @@
 //     p0  d_pre2 = [d mu ; d raw_sigma] from (carry d s_{t+1}, upstream g_*)          -> D2 tile
 //     p1  DH  = d_pre2 W_p2 ;            d_h = DH . act'(h)                            -> H tile
 //     p2  ACC_B (+)= d_h W_p1            (ACC_B already holds  d_gh(t+1) W_hh )
-//         gate stage A, slice 0:  G = ACC_B + g_beliefs[t] + z(t+1) G(t+1)  -> scratch; slab <- d_gi
+//         gate stage A, slice 0:  G = ACC_B + g_beliefs[t]  -> scratch; slab <- d_gi; ACC_B[slice] <- z(t) G
+//         (the carry z.G of the GRU's direct path is written back into ACC_B with tcgen05.st, so the W_hh
+//          GEMMs of stage B accumulate onto it and the next step's ACC_B already contains it)
 //     p3..  DX (+)= slab W_ih[slice]  |  next gate stage A / B (B re-reads G, slab <- d_gh)
 //     ..    ACC_B' (+)= slab W_hh[slice]
 //     p10 d_pre_x = DX . act'(x)                                                       -> H tile
@@ -123,7 +125,6 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
     uint8_t* D2 = smem + a.sm.off_tile[TILE_D2];
     // per-CTA fp32 scratch, stored as [col/4][row][4] so a warp's float4 accesses are contiguous;
     // SIDX(col) (col a multiple of 4) is this thread's float4 slot
-    float* carry = a.scr_carry + (size_t)blockIdx.x * kTileRows * Kb + row * 4;
     float* gtot = a.scr_gtot + (size_t)blockIdx.x * kTileRows * Kb + row * 4;
 #define SIDX(col) ((size_t)((col) >> 2) * (kTileRows * 4))
     float inv_scale;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                 // per load pair), then combine
                 const float* gbrow = (a.g_beliefs && !a.gbt) ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
                 const float* gbt = a.gbt ? a.gbt + tl * kTileRows * Kb + row * 4 : nullptr;
-                float4 cin4[2][4], gb4[2][4];
+                float4 gb4[2][4];
                 const bool vec = ((Be & 3) == 0);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
@@ -290,9 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
 #pragma unroll
                   for (int j4 = 0; j4 < 4; ++j4) {
                     const int cb = col0 + j4 * 4;
-                    cin4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     gb4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i > 0) cin4[it][j4] = *reinterpret_cast<const float4*>(carry + SIDX(cb));
                     if (gbt) {
                       gb4[it][j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
                     } else if (gbrow) {
@@ -317,8 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                     if (cb + 1 >= Be) gb.y = 0.f;
                     if (cb + 2 >= Be) gb.z = 0.f;
                     if (cb + 3 >= Be) gb.w = 0.f;
-                    pre[it][j4 * 4] = cin4[it][j4].x + gb.x * sc; pre[it][j4 * 4 + 1] = cin4[it][j4].y + gb.y * sc;
-                    pre[it][j4 * 4 + 2] = cin4[it][j4].z + gb.z * sc; pre[it][j4 * 4 + 3] = cin4[it][j4].w + gb.w * sc;
+                    pre[it][j4 * 4] = gb.x * sc; pre[it][j4 * 4 + 1] = gb.y * sc;
+                    pre[it][j4 * 4 + 2] = gb.z * sc; pre[it][j4 * 4 + 3] = gb.w * sc;
                   }
                 }
               }
@@ -394,19 +393,22 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                     store8<FMT>(p, o);
                     store8<FMT>(p + kLboA, o + 8);
                   }
-                  if (!passB) {   // carry for the next (earlier) step: z . G
+                  if (!passB) {
+                    // carry of the GRU's direct path for the next (earlier) step, z . G, back into this slice's
+                    // ACC_B columns: the W_hh GEMMs of stage B accumulate onto it
+                    float cz[16];
 #pragma unroll
                     for (int g8 = 0; g8 < 2; ++g8) {
                       float zf[8];
                       unpack8<FMT>(cf[3][g8], zf);
-                      *reinterpret_cast<float4*>(carry + SIDX(col0 + g8 * 8)) =
-                          make_float4(G[g8 * 8] * zf[0], G[g8 * 8 + 1] * zf[1], G[g8 * 8 + 2] * zf[2], G[g8 * 8 + 3] * zf[3]);
-                      *reinterpret_cast<float4*>(carry + SIDX(col0 + g8 * 8 + 4)) =
-                          make_float4(G[g8 * 8 + 4] * zf[4], G[g8 * 8 + 5] * zf[5], G[g8 * 8 + 6] * zf[6], G[g8 * 8 + 7] * zf[7]);
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) cz[g8 * 8 + j] = G[g8 * 8 + j] * zf[j];
                     }
+                    tmem_st16(trow + col0, cz);
                   }
                 }
               }
+              if (!passB) tmem_st_wait();
             } break;
             case EPI_P_HEAD_DY: {
               // d h_last[row, c] = d out[t, row] . w_out[c] . act'(h_last)[row, c]   (the scalar output layer's
@@ -498,12 +500,12 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                 if (a.d_prev_belief) {
                   for (int c = half * 16; c < Kb; c += 32) {
                     float v[16];
-                    tmem_ld16(trow + c, v);            // ACC_B = d_gh(0) W_hh
+                    tmem_ld16(trow + c, v);            // ACC_B = d_gh(0) W_hh + z(0) G(0)
                     tmem_ld_wait();
                     if (rvalid) {
 #pragma unroll
                       for (int j = 0; j < 16; ++j)
-                        if (c + j < Be) a.d_prev_belief[grow * Be + c + j] = (v[j] + carry[SIDX((c + j) & ~3) + ((c + j) & 3)]) * inv_scale;
+                        if (c + j < Be) a.d_prev_belief[grow * Be + c + j] = v[j] * inv_scale;
                     }
                   }
                 }

@@ -248,6 +248,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {   // 16 columns of fp32
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -293,6 +301,19 @@ __device__ __forceinline__ void tma_bulk_g2s_elect(uint32_t smem_dst, const void
       "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
       "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
       ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar_addr)
+      : "memory");
+}
+// Weight-share clusters (tc_engine.cuh): this CTA's slice of a ring stage, delivered to the same
+// shared-memory offset of every CTA in `mask` and completing on the barrier at this offset in each
+// of them; the full-stage expect_tx is posted on the local barrier only.
+__device__ __forceinline__ void tma_bulk_g2s_mc_elect(uint32_t smem_dst, const void* gmem_src, uint32_t bytes,
+                                                      uint32_t bar_addr, uint32_t expect_bytes, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %4;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %5;\n\t}"
+      ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar_addr), "r"(expect_bytes), "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar_addr) {

@@ -119,6 +119,7 @@ __device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long 
 struct RolloutArgs {
   Program prog[kMaxRanks];   // one program per cluster rank (column-split mode); [0] when nranks == 1
   int nranks;
+  int ws;                    // weight-share cluster size (1, 2 or 4; nranks == 1 only), set by the launcher
   SmemPlan sm;
   const uint16_t* wpack;
   long long N;            // rows
@@ -201,11 +202,13 @@ __device__ __forceinline__ void stage_program(Program& dst, const Program& src) 
   for (uint32_t i = threadIdx.x; i < sizeof(Program) / 4; i += blockDim.x) d[i] = s[i];
 }
 
+// ws > 1 (weight-share cluster, see producer_role): a ring stage is refilled by all ws producers of the
+// cluster, so it is free only when the issuers of all ws CTAs have consumed it.
 __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1,
-                                                 uint32_t epi_threads = kEpiThreads) {
+                                                 uint32_t epi_threads = kEpiThreads, uint32_t ws = 1) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
+    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], ws); }
     for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], R);
     // epi_threads == kEpiThreads2: the 16-warp kernels arrive once per warp; the 8-warp kernels once per thread
     for (int i = 0; i < 8; ++i)
@@ -216,17 +219,26 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (R > 1) cluster_sync_all();   // peers' barriers are initialised before anyone arrives remotely
+  if (R > 1 || ws > 1) cluster_sync_all();   // peers' barriers are initialised before anyone arrives remotely
   return sh.tmem_holder;
 }
 
 // The whole warp walks the program converged with warp-uniform waits (mbar_wait_u), so every
 // address stays in uniform registers; the copy and its expect_tx are single instructions predicated
 // on the elected lane.
+//
+// Weight-share clusters (ws = 2 or 4 CTAs, each with its OWN row tile, all walking the same program in
+// lockstep): every weight stage is read from L2 once per cluster -- producer k copies the k-th 1/ws of the
+// stage with .multicast::cluster into the ring of every CTA of the cluster.  With one CTA per SM streaming
+// all ~1 MB of weights per time step for a single 128-row tile, the L2 -> SM weight stream (148 x 1 MB per
+// step) and the latency it queues up at the ring's depth were what the issuer waited for (measured: ~20 B/clk
+// per SM = 4.1 K cycles per 208 x 208 layer against 1.35 K of MMA).
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
                                               const uint16_t* wpack, long long ntiles, int T,
                                               uint8_t* smem, EngineShared& sh,
-                                              const PrefetchPlan* pf = nullptr, uint32_t R = 1) {
+                                              const PrefetchPlan* pf = nullptr, uint32_t R = 1, uint32_t ws = 1) {
+  const uint32_t wrank = ws > 1 ? (uint32_t)blockIdx.x % ws : 0u;
+  const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t ring = smem_u32(smem) + sm.off_ring;
   const uint32_t bar_full = smem_u32(&sh.w_full[0]), bar_empty = smem_u32(&sh.w_empty[0]);
   const uint32_t nstage = sm.nstage;
@@ -246,7 +258,14 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
           const int kc = min((int)g.kc, g.Kp - k0);
           const uint32_t bytes = (uint32_t)g.Np * kc * 2;
           mbar_wait_u(bar_empty + st * 8, ph ^ 1);
-          tma_bulk_g2s_elect(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
+          if (ws == 1) {
+            tma_bulk_g2s_elect(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
+          } else {      // (bytes is a multiple of 512: Np and kc are multiples of 16)
+            const uint32_t slice = bytes / ws;
+            tma_bulk_g2s_mc_elect(ring + st * sm.stage_bytes + wrank * slice,
+                                  reinterpret_cast<const char*>(src + (size_t)k0 * g.Np) + wrank * slice, slice,
+                                  bar_full + st * 8, bytes, wmask);
+          }
           if (++st == nstage) { st = 0; ph ^= 1; }
         }
       }
@@ -264,8 +283,10 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
 template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
-                                            uint32_t tmem_base, long long* prof, uint32_t R = 1) {
+                                            uint32_t tmem_base, long long* prof, uint32_t R = 1,
+                                            uint32_t ws = 1) {
   const int lane = threadIdx.x & 31;
+  const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t nstage = sm.nstage;
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
   uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
@@ -336,7 +357,8 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               b_desc += 2 * (lbo_b >> 4);
             }
             if (PROF && fine) msum += clock64() - m0;
-            umma_commit_elect(bar_w_empty + st * 8);
+            if (ws == 1) umma_commit_elect(bar_w_empty + st * 8);
+            else umma_commit_mc_elect(bar_w_empty + st * 8, wmask);     // the stage is free in every CTA of the cluster
             if (PROF && fine) csum += clock64() - m0;
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
@@ -500,7 +522,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
   const uint32_t rank = R > 1 ? (uint32_t)blockIdx.x % R : 0u;   // = %cluster_ctarank for (R,1,1) clusters; provably uniform
   __shared__ Program sprog;
   stage_program(sprog, CLUSTER ? a.prog[rank] : a.prog[0]);
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R, kEpiThreads2);
+  const uint32_t WS = CLUSTER ? 1u : (uint32_t)a.ws;       // weight-share cluster (independent row tiles)
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R, kEpiThreads2, WS);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;
   long long prof_c0 = 0, prof_g0 = 0;
@@ -514,9 +537,9 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R);
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R, WS);
   } else if (warp == 1) {
-    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R);
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R, WS);
   } else {
     // =========================================================== epilogue warps
     // 16 warps: TMEM quadrant q = warp % 4 (a warp reaches lanes [32 q, 32 q + 32) only), column part
@@ -990,7 +1013,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
       a.prof[40 * 8 + blockIdx.x * 3 + 2] = smid;
     }
   }
-  if (R > 1) cluster_sync_all();   // no rank leaves while peers may still write to / arrive on it
+  if (R > 1 || WS > 1) cluster_sync_all();   // no rank leaves while peers may still write to / arrive on it
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 

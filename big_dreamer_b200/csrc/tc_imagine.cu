@@ -376,7 +376,7 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
           ra.sv_hd[k * BD_MAX_LAYERS + l] = reinterpret_cast<uint16_t*>(static_cast<char*>(hd->saved) + hs.off[k][l]);
     }
   }
-  if (a->tc_saved) {
+  if (a->tc_saved && !getenv("BD_DBG_NOSAVE")) {
     SavedLayout sl = saved_layout(r, a->T, a->N);
     char* sb = static_cast<char*>(a->tc_saved);
     ra.sv_gate = reinterpret_cast<uint16_t*>(sb + sl.off_gate);
@@ -716,7 +716,8 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
       const int Ns = nss[sl], nv = nvs[sl], n0 = n0s[sl];
       PackSeg sg[3] = {{0, n0, nv}, {Ns, Be + n0, nv}, {2 * Ns, 2 * Be + n0, nv}};
       uint32_t w = add_pack_T(b, wsrc, Be, Be, Kb, 3 * Ns, 3, sg);
-      b.add_gemm(w, Kb, 3 * Ns, slab ? TILE_SLAB1 : TILE_SLAB0, 0, dcol, sl > 0 ? 1 : 0);
+      // (stage B accumulates from its first slice on: ACC_B holds the carry z . G written by stage A)
+      b.add_gemm(w, Kb, 3 * Ns, slab ? TILE_SLAB1 : TILE_SLAB0, 0, dcol, (pass == 1 || sl > 0) ? 1 : 0);
       slab ^= 1;
       if (pass == 0 && sl + 1 < nsl) gate_phase(sl + 1, false);
       else if (pass == 0) gate_phase(0, true);
