@@ -61,6 +61,7 @@ struct BpttArgs {
   const uint16_t* sv_hd[2 * BD_MAX_LAYERS];   // act' images of the heads' hidden layers (forward-saved)
   const float* w_out[2];                      // last layer of each head: (1, hidden)
   int hd_last;                                // index of the last hidden layer (n_layers - 2)
+  int hd_nvalid;                              // its width (columns of w_out)
   const float *g_returns, *g_reward, *g_value;   // upstream (T,N), each optional
   float lr_disc, lr_lam;
   float* scr_drv;                             // per-CTA [T][2][128]: d reward, d value of the tile's rows
@@ -107,7 +108,16 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   __shared__ Program sprog;
   stage_program(sprog, a.prog);
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
+  // fused heads: the output layers' weight rows (every thread multiplies its row by all of them in
+  // EPI_P_HEAD_DY) staged once per CTA; read back as broadcast 16-byte shared loads
+  __shared__ __align__(16) float s_wout[2][256];
+  if (a.n_heads) {
+    for (int i = tid; i < 2 * 256; i += blockDim.x) {
+      const int k = i >> 8, c = i & 255;
+      s_wout[k][c] = (k < a.n_heads && a.w_out[k] && c < a.hd_nvalid) ? a.w_out[k][c] : 0.f;
+    }
+  }
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);     // (its __syncthreads also publishes s_wout)
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = sprog;
 
@@ -415,16 +425,13 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               // dgrad is a rank-1 product: no MMA); operands carry the gradient scale
               const int k = ph.aux0, kp = a.kh_hd;
               const uint16_t* img = a.sv_hd[k * BD_MAX_LAYERS + a.hd_last] + tl * kTileRows * kp + row * 8;
-              const float* wo = a.w_out[k];
+              const float* wo = s_wout[k];
               const float dout = a.scr_drv[((size_t)blockIdx.x * a.T + t) * 2 * kTileRows + (size_t)k * kTileRows + row] * scale;
               uint4 hu[4];
-              float wv[32];
               auto load_chunk = [&](int c) {
 #pragma unroll
                 for (int g8 = 0; g8 < 4; ++g8)
                   if (c + g8 * 8 < kp) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) wv[j] = (c + j < ph.n_valid) ? wo[c + j] : 0.f;
               };
               if (half * 32 < kp) load_chunk(half * 32);
               BD_WAIT_ACC();             // the previous phase's MMAs (which read the H tile) are done
@@ -435,8 +442,11 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   if (c + g8 * 8 < kp) {
                     float h[8], o[8];
                     unpack8<FMT>(hu[g8], h);
+                    const float4 w0 = *reinterpret_cast<const float4*>(wo + c + g8 * 8);      // (zero past n_valid)
+                    const float4 w1 = *reinterpret_cast<const float4*>(wo + c + g8 * 8 + 4);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = dout * wv[g8 * 8 + j] * h[j];
+                    for (int j = 0; j < 8; ++j) o[j] = dout * wv[j] * h[j];
                     store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, o);
                   }
                 }

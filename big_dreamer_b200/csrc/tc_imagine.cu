@@ -828,7 +828,7 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
   ba.gbt = gbt;
   if (hb) {
     // the lambda-return adjoint sums up to T upstream terms per row: leave headroom in the fp16 operands
-    ba.n_heads = 2; ba.kh_hd = Khd; ba.hd_last = hL - 2;
+    ba.n_heads = 2; ba.kh_hd = Khd; ba.hd_last = hL - 2; ba.hd_nvalid = head_hidden(*hb->head[0]);
     const HeadsSaved hs = heads_saved_layout(*hb->head[0], f.T, f.N);
     for (int k = 0; k < 2; ++k) {
       ba.w_out[k] = hb->head[k]->layer[hL - 1].w;

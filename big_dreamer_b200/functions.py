@@ -213,6 +213,7 @@ class TransitionFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dims, init_state, actions, init_belief, embeddings, nonterminals, eps_prior,
                 eps_post, *params):
+        ctx.set_materialize_grads(False)     # outputs the loss does not use arrive as None, not as zero tensors
         lib = _lib.load()
         observe = embeddings is not None
         P = [(_f32c(p) if p is not None else None) for p in params]
@@ -313,6 +314,7 @@ class ImagineFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dims, actor_cfg, T, prev_state, prev_belief, eps_a, eps_e, eps_s, n_actor,
                 *params):
+        ctx.set_materialize_grads(False)     # outputs the loss does not use arrive as None, not as zero tensors
         lib = _lib.load()
         AP = [_f32c(p) for p in params[:2 * n_actor]]
         RP = [_f32c(p) for p in params[2 * n_actor:]] + [None] * 4
@@ -425,6 +427,7 @@ class ImagineReturnsFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dims, actor_cfg, head_act, T, discount, lambda_, prev_state, prev_belief, eps_a,
                 eps_e, eps_s, n_actor, n_head, *params):
+        ctx.set_materialize_grads(False)     # outputs the loss does not use arrive as None, not as zero tensors
         lib = _lib.load()
         AP = [_f32c(p) for p in params[:2 * n_actor]]
         RP = [_f32c(p) for p in params[2 * n_actor:2 * n_actor + 10]] + [None] * 4
