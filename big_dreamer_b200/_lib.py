@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbd_b200.so")
+# BD_B200_LIB: another build of the same library (A/B timing of kernel changes); default = the in-tree build
+LIB_PATH = os.environ.get("BD_B200_LIB") or os.path.join(_HERE, "libbd_b200.so")
 TEST_LIB_PATH = os.path.join(_HERE, "libbd_b200_test.so")
 
 BD_MAX_LAYERS = 8

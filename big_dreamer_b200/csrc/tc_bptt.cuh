@@ -282,17 +282,16 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               uint8_t* slab = smem + a.sm.off_tile[ph.out_tile];
               const uint16_t* gimg = a.sv_gate + tl * 5 * kTileRows * Kb + row * 8;
               const size_t plane = (size_t)kTileRows * Kb;
-              // pass A: upstream belief gradient and the carried z.G of the later step, fetched
-              // (branch-free, clamped) before the accumulator wait
-              float pre[2][16];
+              // pass A: the upstream belief gradient of this thread's columns (both 16-column chunks), requested
+              // raw before the accumulator wait; masked / scaled where it is added.  Nothing to fetch when the
+              // loss reaches the beliefs only through this kernel's own heads (fused step: g_beliefs == null).
+              const bool have_gb = !passB && (a.g_beliefs != nullptr);
+              float4 gb4[2][4];
               long long q0 = 0, q1 = 0, q2 = 0;
               if (PROF) q0 = clock64();
-              if (!passB) {
-                // issue every load first (in-order issue would otherwise serialise one round trip
-                // per load pair), then combine
-                const float* gbrow = (a.g_beliefs && !a.gbt) ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
+              if (have_gb) {
+                const float* gbrow = !a.gbt ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
                 const float* gbt = a.gbt ? a.gbt + tl * kTileRows * Kb + row * 4 : nullptr;
-                float4 gb4[2][4];
                 const bool vec = ((Be & 3) == 0);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
@@ -301,33 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
 #pragma unroll
                   for (int j4 = 0; j4 < 4; ++j4) {
                     const int cb = col0 + j4 * 4;
-                    gb4[it][j4] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (gbt) {
                       gb4[it][j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
-                    } else if (gbrow) {
-                      if (vec) gb4[it][j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
-                      else {
-                        gb4[it][j4].x = gbrow[min(cb, Be - 1)]; gb4[it][j4].y = gbrow[min(cb + 1, Be - 1)];
-                        gb4[it][j4].z = gbrow[min(cb + 2, Be - 1)]; gb4[it][j4].w = gbrow[min(cb + 3, Be - 1)];
-                      }
+                    } else if (vec) {
+                      gb4[it][j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
+                    } else {
+                      gb4[it][j4].x = gbrow[min(cb, Be - 1)]; gb4[it][j4].y = gbrow[min(cb + 1, Be - 1)];
+                      gb4[it][j4].z = gbrow[min(cb + 2, Be - 1)]; gb4[it][j4].w = gbrow[min(cb + 3, Be - 1)];
                     }
-                  }
-                }
-                const float sc = rvalid ? scale : 0.f;
-#pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                  const int c = half * 16 + it * 32;
-                  const int col0 = n0 + min(c, Ns - 16);
-#pragma unroll
-                  for (int j4 = 0; j4 < 4; ++j4) {
-                    const int cb = col0 + j4 * 4;
-                    float4 gb = gb4[it][j4];
-                    if (cb >= Be) gb.x = 0.f;          // columns past Be (padding of the last slice)
-                    if (cb + 1 >= Be) gb.y = 0.f;
-                    if (cb + 2 >= Be) gb.z = 0.f;
-                    if (cb + 3 >= Be) gb.w = 0.f;
-                    pre[it][j4 * 4] = gb.x * sc; pre[it][j4 * 4 + 1] = gb.y * sc;
-                    pre[it][j4 * 4 + 2] = gb.z * sc; pre[it][j4 * 4 + 3] = gb.w * sc;
                   }
                 }
               }
@@ -372,10 +352,18 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   if (!passB) {
                     tmem_ld16(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
                     tmem_ld_wait();
+                    if (have_gb) {
+                      const float sc = rvalid ? scale : 0.f;
+#pragma unroll
+                      for (int j4 = 0; j4 < 4; ++j4) {
+                        const int cb = col0 + j4 * 4;       // (columns past Be: padding of the last slice)
+                        const float4 gb = gb4[it][j4];
+                        G[j4 * 4] += cb < Be ? gb.x * sc : 0.f; G[j4 * 4 + 1] += cb + 1 < Be ? gb.y * sc : 0.f;
+                        G[j4 * 4 + 2] += cb + 2 < Be ? gb.z * sc : 0.f; G[j4 * 4 + 3] += cb + 3 < Be ? gb.w * sc : 0.f;
+                      }
+                    }
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                      G[j4 * 4] += pre[it][j4 * 4]; G[j4 * 4 + 1] += pre[it][j4 * 4 + 1];
-                      G[j4 * 4 + 2] += pre[it][j4 * 4 + 2]; G[j4 * 4 + 3] += pre[it][j4 * 4 + 3];
                       *reinterpret_cast<float4*>(gtot + SIDX(col0 + j4 * 4)) =
                           make_float4(G[j4 * 4], G[j4 * 4 + 1], G[j4 * 4 + 2], G[j4 * 4 + 3]);
                     }
