@@ -99,7 +99,7 @@ static __global__ void gb_tile_kernel(const float* __restrict__ g, long long N, 
 }
 
 template <int FMT, bool PROF>
-__global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
+__global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const BpttArgs& a = A_;
   uint8_t* smem = smem_raw;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
       s_wout[k][c] = (k < a.n_heads && a.w_out[k] && c < a.hd_nvalid) ? a.w_out[k][c] : 0.f;
     }
   }
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);     // (its __syncthreads also publishes s_wout)
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, kEpiThreads2);     // (its __syncthreads also publishes s_wout)
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = sprog;
 
@@ -126,8 +126,16 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
   } else if (warp == 1) {
     issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof);
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // 16 epilogue warps: TMEM quadrant q = warp % 4, column part (warp - 2) / 4 in 0..3; chunks of 16 columns
+    // (image products) or 8 (gate stages, d_pre2) keep the kernel inside the 112 registers 576 threads leave
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int row = q * 32 + lane;
+    // one arrival per warp on the epilogue-completion barrier
+    auto epi_arrive = [&](uint32_t ge) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.epi_done[ge & 7]);
+    };
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t rowoff = (row >> 3) * 128 + (row & 7) * 16;
     const int Be = a.Be, S = a.S, Ad = a.A, Kb = a.Kb;
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long grow = tile * kTileRows + row;
       const bool rvalid = grow < a.N;
-      if (a.n_heads && half == 0) {
+      if (a.n_heads && part == 0) {
         // adjoint of lambda_return with bootstrap = value[-1] (f32::lambda_return_bwd_kernel), forward in
         // time: G[t] = g_ret[t] + disc lam G[t-1]; d r[t] = G[t]; d v[t+1] += disc (1-lam) G[t];
         // d v[T-1] += disc G[T-1] (the bootstrap enters as next value and as the initial return)
@@ -160,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
           dv_next = a.lr_disc * (1.f - a.lr_lam) * G;
         }
       }
-      if (a.n_heads) asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves read the row's d r / d v
-      mbar_arrive(&sh.epi_done[Ge & 7]);   // nothing else to initialise per tile
+      if (a.n_heads) asm volatile("bar.sync 1, 512;" ::: "memory");   // every column part reads the row's d r / d v
+      epi_arrive(Ge);   // nothing else to initialise per tile
       ++Ge;
       for (int i = 0; i < a.T; ++i) {
         const int t = a.T - 1 - i;
@@ -186,11 +194,11 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               // branch-free clamped loads of everything that does not depend on TMEM; the first
               // chunk's loads are issued before the accumulator wait
               const long long lrow = rvalid ? orow : (long long)t * a.N;       // any valid row
-              float sd_[16], ep_[16], gs_[16], gm_[16], gd_[16];
+              float sd_[8], ep_[8], gs_[8], gm_[8], gd_[8];
               auto load_chunk = [&](int c) {
                 if ((S & 1) == 0) {     // rows are 8-byte aligned: 64-bit loads, clamped inside the row
 #pragma unroll
-                  for (int j = 0; j < 16; j += 2) {
+                  for (int j = 0; j < 8; j += 2) {
                     const long long o = lrow * S + min(c + j, S - 2);
                     const float2 x0 = *reinterpret_cast<const float2*>(a.stds + o);
                     const float2 x1 = *reinterpret_cast<const float2*>(a.eps_s + o);
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   }
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
+                  for (int j = 0; j < 8; ++j) {
                     const long long o = lrow * S + min(c + j, S - 1);
                     sd_[j] = a.stds[o];
                     ep_[j] = a.eps_s[o];
@@ -217,20 +225,20 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   }
                 }
               };
-              if (half * 16 < Sp) load_chunk(half * 16);
+              if (part * 8 < Sp) load_chunk(part * 8);
               BD_WAIT_ACC();
-              for (int c = half * 16; c < Sp; c += 32) {
-                if (c != half * 16) load_chunk(c);
-                float cs[16], m_[16], s_[16];
+              for (int c = part * 8; c < Sp; c += 32) {
+                if (c != part * 8) load_chunk(c);
+                float cs[8], m_[8], s_[8];
                 if (i > 0 || a.n_heads) {
-                  tmem_ld16(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA (+ the heads' d s_t)
+                  tmem_ld8(trow + 256 + c, cs);     // d s_{t+1} left by the previous step's DSA (+ the heads' d s_t)
                   tmem_ld_wait();
                 } else {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) cs[j] = 0.f;
+                  for (int j = 0; j < 8; ++j) cs[j] = 0.f;
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                   const bool ok = (c + j < S) && rvalid;
                   const float gs = cs[j] + gs_[j] * scale;
                   const float dmu = gs + gm_[j] * scale;
@@ -239,12 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   m_[j] = ok ? dmu : 0.f;
                   s_[j] = ok ? draw : 0.f;
                 }
-                uint8_t* p = D2 + (c >> 3) * kLboA + rowoff;
-                store8<FMT>(p, m_);
-                store8<FMT>(p + kLboA, m_ + 8);
-                uint8_t* p2 = D2 + ((Sp + c) >> 3) * kLboA + rowoff;
-                store8<FMT>(p2, s_);
-                store8<FMT>(p2 + kLboA, s_ + 8);
+                store8<FMT>(D2 + (c >> 3) * kLboA + rowoff, m_);
+                store8<FMT>(D2 + ((Sp + c) >> 3) * kLboA + rowoff, s_);
               }
             } break;
             case EPI_P_MULSAVED: {
@@ -252,41 +256,43 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               const uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : (ph.aux0 == 2 ? a.sv_ha : a.sv_hd[ph.aux0 - 16])) +
                                     tl * kTileRows * kp + row * 8;
               const uint32_t tacc = trow + ph.d_col;
-              for (int c = half * 32; c < kp; c += 64) {
-                float v[32];
-                const bool two = (c + 16) < kp;
-                const int ngroups = two ? 4 : 2;
-                uint4 hu[4];
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8)
-                  if (g8 < ngroups) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
-                if (c == half * 32) BD_WAIT_ACC();
-                if (two) tmem_ld32(tacc + c, v);
-                else tmem_ld16(tacc + c, v);
+              // 16-column chunks (kp is a multiple of 16); the next chunk's image is requested while this one
+              // is processed, the first one before the accumulator wait
+              uint4 hn[2];
+              auto load_img = [&](int c) {
+                hn[0] = *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8);
+                hn[1] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8);
+              };
+              if (part * 16 < kp) load_img(part * 16);
+              BD_WAIT_ACC();
+              for (int c = part * 16; c < kp; c += 64) {
+                float v[16];
+                const uint4 hu[2] = {hn[0], hn[1]};
+                tmem_ld16(tacc + c, v);
+                if (c + 64 < kp) load_img(c + 64);
                 tmem_ld_wait();
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                  if (g8 < ngroups) {
-                    float h[8];
-                    unpack8<FMT>(hu[g8], h);
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  float h[8];
+                  unpack8<FMT>(hu[g8], h);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= h[j];
-                    store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, v + g8 * 8);
-                  }
+                  for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= h[j];
+                  store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, v + g8 * 8);
                 }
               }
             } break;
             case EPI_P_GATE: {
+              // 8-column chunks: c = 8 part + 32 it (a slice is at most 64 columns wide)
               const int n0 = ph.aux0, Ns = ph.Np;
               const bool passB = ph.pad != 0;
               uint8_t* slab = smem + a.sm.off_tile[ph.out_tile];
               const uint16_t* gimg = a.sv_gate + tl * 5 * kTileRows * Kb + row * 8;
               const size_t plane = (size_t)kTileRows * Kb;
-              // pass A: the upstream belief gradient of this thread's columns (both 16-column chunks), requested
+              // pass A: the upstream belief gradient of this thread's columns (both chunks), requested
               // raw before the accumulator wait; masked / scaled where it is added.  Nothing to fetch when the
               // loss reaches the beliefs only through this kernel's own heads (fused step: g_beliefs == null).
               const bool have_gb = !passB && (a.g_beliefs != nullptr);
-              float4 gb4[2][4];
+              float4 gb4[2][2];
               long long q0 = 0, q1 = 0, q2 = 0;
               if (PROF) q0 = clock64();
               if (have_gb) {
@@ -295,10 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                 const bool vec = ((Be & 3) == 0);
 #pragma unroll
                 for (int it = 0; it < 2; ++it) {
-                  const int c = half * 16 + it * 32;
-                  const int col0 = n0 + min(c, Ns - 16);
+                  const int c = part * 8 + it * 32;
+                  const int col0 = n0 + min(c, Ns - 8);
 #pragma unroll
-                  for (int j4 = 0; j4 < 4; ++j4) {
+                  for (int j4 = 0; j4 < 2; ++j4) {
                     const int cb = col0 + j4 * 4;
                     if (gbt) {
                       gb4[it][j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
@@ -313,24 +319,21 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
               if (PROF) q1 = clock64();
               const int pl3 = passB ? 3 : 2;
-              uint4 cf[4][2];
+              uint4 cf[4];
               auto load_planes = [&](int c) {
                 const uint16_t* gp = gimg + (size_t)((n0 + c) >> 3) * kTileRows * 8;
-#pragma unroll
-                for (int g8 = 0; g8 < 2; ++g8) {
-                  cf[0][g8] = *reinterpret_cast<const uint4*>(gp + 0 * plane + (size_t)g8 * kTileRows * 8);
-                  cf[1][g8] = *reinterpret_cast<const uint4*>(gp + 1 * plane + (size_t)g8 * kTileRows * 8);
-                  cf[2][g8] = *reinterpret_cast<const uint4*>(gp + pl3 * plane + (size_t)g8 * kTileRows * 8);
-                  if (!passB) cf[3][g8] = *reinterpret_cast<const uint4*>(gp + 4 * plane + (size_t)g8 * kTileRows * 8);
-                }
+                cf[0] = *reinterpret_cast<const uint4*>(gp + 0 * plane);
+                cf[1] = *reinterpret_cast<const uint4*>(gp + 1 * plane);
+                cf[2] = *reinterpret_cast<const uint4*>(gp + pl3 * plane);
+                if (!passB) cf[3] = *reinterpret_cast<const uint4*>(gp + 4 * plane);
               };
-              float Gb[16];
-              if (half * 16 < Ns) {
-                load_planes(half * 16);
+              float Gb[8];
+              if (part * 8 < Ns) {
+                load_planes(part * 8);
                 if (passB) {
 #pragma unroll
-                  for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 g4 = *reinterpret_cast<const float4*>(gtot + SIDX(n0 + half * 16 + j4 * 4));
+                  for (int j4 = 0; j4 < 2; ++j4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(gtot + SIDX(n0 + part * 8 + j4 * 4));
                     Gb[j4 * 4] = g4.x; Gb[j4 * 4 + 1] = g4.y; Gb[j4 * 4 + 2] = g4.z; Gb[j4 * 4 + 3] = g4.w;
                   }
                 }
@@ -344,18 +347,18 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
 #pragma unroll
               for (int it = 0; it < 2; ++it) {
-                const int c = half * 16 + it * 32;
+                const int c = part * 8 + it * 32;
                 if (c < Ns) {
                   const int col0 = n0 + c;
-                  float G[16];
+                  float G[8];
                   if (it > 0) load_planes(c);
                   if (!passB) {
-                    tmem_ld16(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
+                    tmem_ld8(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
                     tmem_ld_wait();
                     if (have_gb) {
                       const float sc = rvalid ? scale : 0.f;
 #pragma unroll
-                      for (int j4 = 0; j4 < 4; ++j4) {
+                      for (int j4 = 0; j4 < 2; ++j4) {
                         const int cb = col0 + j4 * 4;       // (columns past Be: padding of the last slice)
                         const float4 gb = gb4[it][j4];
                         G[j4 * 4] += cb < Be ? gb.x * sc : 0.f; G[j4 * 4 + 1] += cb + 1 < Be ? gb.y * sc : 0.f;
@@ -363,46 +366,37 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                       }
                     }
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
+                    for (int j4 = 0; j4 < 2; ++j4) {
                       *reinterpret_cast<float4*>(gtot + SIDX(col0 + j4 * 4)) =
                           make_float4(G[j4 * 4], G[j4 * 4 + 1], G[j4 * 4 + 2], G[j4 * 4 + 3]);
                     }
                   } else if (it == 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) G[j] = Gb[j];
+                    for (int j = 0; j < 8; ++j) G[j] = Gb[j];
                   } else {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
+                    for (int j4 = 0; j4 < 2; ++j4) {
                       const float4 g4 = *reinterpret_cast<const float4*>(gtot + SIDX(col0 + j4 * 4));
                       G[j4 * 4] = g4.x; G[j4 * 4 + 1] = g4.y; G[j4 * 4 + 2] = g4.z; G[j4 * 4 + 3] = g4.w;
                     }
                   }
 #pragma unroll
-                  for (int part = 0; part < 3; ++part) {
-                    float o[16];
+                  for (int gt = 0; gt < 3; ++gt) {
+                    float o[8], c8[8];
+                    unpack8<FMT>(cf[gt], c8);
 #pragma unroll
-                    for (int g8 = 0; g8 < 2; ++g8) {
-                      float c8[8];
-                      unpack8<FMT>(cf[part][g8], c8);
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) o[g8 * 8 + j] = G[g8 * 8 + j] * c8[j];
-                    }
-                    uint8_t* p = slab + ((part * Ns + c) >> 3) * kLboA + rowoff;
-                    store8<FMT>(p, o);
-                    store8<FMT>(p + kLboA, o + 8);
+                    for (int j = 0; j < 8; ++j) o[j] = G[j] * c8[j];
+                    store8<FMT>(slab + ((gt * Ns + c) >> 3) * kLboA + rowoff, o);
                   }
                   if (!passB) {
                     // carry of the GRU's direct path for the next (earlier) step, z . G, back into this slice's
                     // ACC_B columns: the W_hh GEMMs of stage B accumulate onto it
-                    float cz[16];
+                    float zf[8];
+                    uint32_t cz[8];
+                    unpack8<FMT>(cf[3], zf);
 #pragma unroll
-                    for (int g8 = 0; g8 < 2; ++g8) {
-                      float zf[8];
-                      unpack8<FMT>(cf[3][g8], zf);
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) cz[g8 * 8 + j] = G[g8 * 8 + j] * zf[j];
-                    }
-                    tmem_st16(trow + col0, cz);
+                    for (int j = 0; j < 8; ++j) cz[j] = __float_as_uint(G[j] * zf[j]);
+                    tmem_st8(trow + col0, cz);
                   }
                 }
               }
@@ -415,28 +409,25 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               const uint16_t* img = a.sv_hd[k * BD_MAX_LAYERS + a.hd_last] + tl * kTileRows * kp + row * 8;
               const float* wo = s_wout[k];
               const float dout = a.scr_drv[((size_t)blockIdx.x * a.T + t) * 2 * kTileRows + (size_t)k * kTileRows + row] * scale;
-              uint4 hu[4];
+              uint4 hu[2];
               auto load_chunk = [&](int c) {
-#pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8)
-                  if (c + g8 * 8 < kp) hu[g8] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8);
+                hu[0] = *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8);
+                hu[1] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8);
               };
-              if (half * 32 < kp) load_chunk(half * 32);
+              if (part * 16 < kp) load_chunk(part * 16);
               BD_WAIT_ACC();             // the previous phase's MMAs (which read the H tile) are done
-              for (int c = half * 32; c < kp; c += 64) {
-                if (c != half * 32) load_chunk(c);
+              for (int c = part * 16; c < kp; c += 64) {
+                if (c != part * 16) load_chunk(c);
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                  if (c + g8 * 8 < kp) {
-                    float h[8], o[8];
-                    unpack8<FMT>(hu[g8], h);
-                    const float4 w0 = *reinterpret_cast<const float4*>(wo + c + g8 * 8);      // (zero past n_valid)
-                    const float4 w1 = *reinterpret_cast<const float4*>(wo + c + g8 * 8 + 4);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  float h[8], o[8];
+                  unpack8<FMT>(hu[g8], h);
+                  const float4 w0 = *reinterpret_cast<const float4*>(wo + c + g8 * 8);      // (zero past n_valid)
+                  const float4 w1 = *reinterpret_cast<const float4*>(wo + c + g8 * 8 + 4);
+                  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = dout * wv[j] * h[j];
-                    store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, o);
-                  }
+                  for (int j = 0; j < 8; ++j) o[j] = dout * wv[j] * h[j];
+                  store8<FMT>(Ht + ((c >> 3) + g8) * kLboA + rowoff, o);
                 }
               }
             } break;
@@ -444,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               // A = 1 (the common case): the per-row inputs of the action gradient are loaded before
               // the accumulator wait; larger action spaces load them in the loop below
               float pm = 0.f, ps = 0.f, pa = 0.f, pdm = 0.f, pds = 0.f, pe = 0.f, pge = 0.f;
-              const bool pre = half == 0 && rvalid && Ad == 1;
+              const bool pre = part == 0 && rvalid && Ad == 1;
               if (pre) {
                 pge = a.g_entropy ? a.g_entropy[orow] : 0.f;
                 pm = a.actor_raw[orow * 2]; ps = a.actor_raw[orow * 2 + 1];
@@ -453,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
               BD_WAIT_ACC();
               const uint32_t tacc = trow + 256;
-              if (half == 0) {
+              if (part == 0) {
                 const int c0 = (S >> 4) << 4;
                 float vv[32];
                 tmem_ld16(tacc + c0, vv);
@@ -485,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
               }
               if (t == 0) {   // gradients wrt the start latents
                 if (a.d_prev_state) {
-                  for (int c = half * 16; c < a.Sp; c += 32) {
+                  for (int c = part * 16; c < a.Sp; c += 64) {
                     float v[16];
                     tmem_ld16(tacc + c, v);            // warp-collective: never under a per-lane branch
                     tmem_ld_wait();
@@ -496,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
                   }
                 }
                 if (a.d_prev_belief) {
-                  for (int c = half * 16; c < Kb; c += 32) {
+                  for (int c = part * 16; c < Kb; c += 64) {
                     float v[16];
                     tmem_ld16(trow + c, v);            // ACC_B = d_gh(0) W_hh + z(0) G(0)
                     tmem_ld_wait();
@@ -513,8 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) bptt_kernel(const __grid_constant
           }
 #undef BD_WAIT_ACC
           tc_fence_before_sync();
-          fence_proxy_async_smem();
-          mbar_arrive(&sh.epi_done[Ge & 7]);
+          epi_arrive(Ge);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
             a.prof[o] += e1 - e0;

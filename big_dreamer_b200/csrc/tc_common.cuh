@@ -61,6 +61,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef BD_WAIT_SLEEP
+    __nanosleep(BD_WAIT_SLEEP);
+#endif
     if (++spins > (1u << 28)) {
       printf("bd_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
              (int)threadIdx.x);

@@ -134,6 +134,7 @@ struct RolloutArgs {
   float *head_out[2];     // optional fused heads: (T,N) reward / value
   const float* ext_actions;   // CEM / TransitionModel.forward: actions given, no actor
   long long* prof;            // optional (debug): per-phase cycle counters of CTA 0, see tc_imagine.cu
+  int dbg;                    // debug experiments of the PROF build (BD_TC_DBG): 1 = epilogues skip their work, 2 = no weight copies
   float* mlp_out;             // EPI_STORE_OUT target (rows, n_valid)
   // saved for the tensor-core BPTT (16-bit tile images, see tc_bptt.cuh); null = do not save
   uint16_t *sv_gate, *sv_xa, *sv_ha;
@@ -236,7 +237,8 @@ __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nsta
 __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& sm,
                                               const uint16_t* wpack, long long ntiles, int T,
                                               uint8_t* smem, EngineShared& sh,
-                                              const PrefetchPlan* pf = nullptr, uint32_t R = 1, uint32_t ws = 1) {
+                                              const PrefetchPlan* pf = nullptr, uint32_t R = 1, uint32_t ws = 1,
+                                              bool dbg_no_copy = false) {
   const uint32_t wrank = ws > 1 ? (uint32_t)blockIdx.x % ws : 0u;
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t ring = smem_u32(smem) + sm.off_ring;
@@ -258,7 +260,10 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
           const int kc = min((int)g.kc, g.Kp - k0);
           const uint32_t bytes = (uint32_t)g.Np * kc * 2;
           mbar_wait_u(bar_empty + st * 8, ph ^ 1);
-          if (ws == 1) {
+          if (dbg_no_copy) {
+            if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + st * 8) : "memory");
+            __syncwarp();
+          } else if (ws == 1) {
             tma_bulk_g2s_elect(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
           } else {      // (bytes is a multiple of 512: Np and kc are multiples of 16)
             const uint32_t slice = bytes / ws;
@@ -284,7 +289,7 @@ template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
                                             uint32_t tmem_base, long long* prof, uint32_t R = 1,
-                                            uint32_t ws = 1) {
+                                            uint32_t ws = 1, bool dbg_no_ring = false) {
   const int lane = threadIdx.x & 31;
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t nstage = sm.nstage;
@@ -343,7 +348,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             // (no tcgen05.fence here: the weights arrive through the async proxy and their mbarrier
             // completion orders them before the MMAs; a fence::after_thread_sync per ring stage measured
             // ~220 cycles of issue stall each -- it is only needed after the epilogue hand-offs above)
-            mbar_wait_u(bar_w_full + st * 8, wph);
+            if (!(PROF && dbg_no_ring)) mbar_wait_u(bar_w_full + st * 8, wph);
             if (PROF && fine) wsum += clock64() - w0;
             uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
                               (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu);
@@ -357,7 +362,8 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
               b_desc += 2 * (lbo_b >> 4);
             }
             if (PROF && fine) msum += clock64() - m0;
-            if (ws == 1) umma_commit_elect(bar_w_empty + st * 8);
+            if (PROF && dbg_no_ring) {}
+            else if (ws == 1) umma_commit_elect(bar_w_empty + st * 8);
             else umma_commit_mc_elect(bar_w_empty + st * 8, wmask);     // the stage is free in every CTA of the cluster
             if (PROF && fine) csum += clock64() - m0;
             if (++st == nstage) { st = 0; wph ^= 1; }
@@ -537,9 +543,10 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R, WS);
+    if (!(PROF && (a.dbg & 4)))
+    producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R, WS, PROF && (a.dbg & 2));
   } else if (warp == 1) {
-    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R, WS);
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R, WS, (a.dbg & 4) != 0);
   } else {
     // =========================================================== epilogue warps
     // 16 warps: TMEM quadrant q = warp % 4 (a warp reaches lanes [32 q, 32 q + 32) only), column part
@@ -639,7 +646,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
           long long e0 = 0, e1 = 0;
           if (PROF) e0 = clock64();
           const uint32_t tacc = trow + ph.d_col;
-          switch (ph.epi) {
+          switch ((PROF && (a.dbg & 1)) ? 0 : ph.epi) {
             case EPI_ACT_H: {
               // What this layer also leaves in HBM for a backward pass: 1 = the hidden activation itself
               // (MLP forward; padded rows zero: the image doubles as the wgrad operand), 2 = act'(output)
@@ -964,6 +971,12 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
             default: {
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
+              if (PROF) e1 = clock64();
+              for (int sub = 1; sub < ph.n_sub; ++sub) {   // (debug skip of an ACT epilogue: keep the completion count)
+                tc_fence_before_sync();
+                epi_arrive(Ge);
+                ++Ge;
+              }
             } break;
           }
           tc_fence_before_sync();

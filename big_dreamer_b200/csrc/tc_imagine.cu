@@ -65,7 +65,7 @@ static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& s
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 1023) & ~1023u; return o; };
   sm.off_tile[0] = take(kTileRows * Kp_b * 2);
-  sm.off_tile[1] = has_b1 ? take(kTileRows * Kp_b * 2) : sm.off_tile[0];
+  sm.off_tile[1] = (has_b1 && !getenv("BD_DBG_ALIAS")) ? take(kTileRows * Kp_b * 2) : sm.off_tile[0];
   sm.off_tile[2] = take(kTileRows * Kp_sa * 2);
   sm.off_tile[3] = take(kTileRows * Kp_h * 2);
   sm.off_tile[4] = sm.off_tile[3];
@@ -395,6 +395,7 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
       const long long one = 1;
       cudaMemcpyAsync(ra.prof + 39 * 8 + 7, &one, sizeof(one), cudaMemcpyHostToDevice, s);
     }
+    if (const char* e = getenv("BD_TC_DBG")) ra.dbg = atoi(e);
   }
   long long max_img = 0;
   for (int i = 0; i < b.pack.njobs; ++i)
@@ -863,7 +864,7 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     ba.prof = reinterpret_cast<long long*>(base + ((off + 4095) & ~size_t(4095)));
     cudaMemsetAsync(ba.prof, 0, kMaxPhases * 64, s);
     set_smem_attr(bptt_kernel<0, true>, ba.sm.total);
-    bptt_kernel<0, true><<<grid, kThreads, ba.sm.total, s>>>(ba);
+    bptt_kernel<0, true><<<grid, kThreads2, ba.sm.total, s>>>(ba);
     static long long* host_prof = nullptr;
     if (!host_prof) cudaMallocHost(&host_prof, kMaxPhases * 64);
     cudaMemcpyAsync(host_prof, ba.prof, kMaxPhases * 64, cudaMemcpyDeviceToHost, s);
@@ -882,10 +883,10 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     fprintf(stderr, "\n");
   } else if (fmt == 0) {
     set_smem_attr(bptt_kernel<0, false>, ba.sm.total);
-    bptt_kernel<0, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
+    bptt_kernel<0, false><<<grid, kThreads2, ba.sm.total, s>>>(ba);
   } else {
     set_smem_attr(bptt_kernel<1, false>, ba.sm.total);
-    bptt_kernel<1, false><<<grid, kThreads, ba.sm.total, s>>>(ba);
+    bptt_kernel<1, false><<<grid, kThreads2, ba.sm.total, s>>>(ba);
   }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;

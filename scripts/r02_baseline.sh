@@ -1,0 +1,14 @@
+#!/bin/bash
+# usage: scripts/r02_baseline.sh TAG -- full GPU pass: tests, bench line, ncu launch list, full captures
+TAG=$1
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_tests.log 2>&1
+tail -3 gpurun_out/${TAG}_tests.log
+timeout 900 python bench.py > gpurun_out/${TAG}_bench_fp16_c2.json 2> gpurun_out/${TAG}_bench.err
+echo bench rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_bench_fp16_c2.csv python bench.py --no-extra --no-cpu-baseline --steps 2 --warmup 1 --no-graph > gpurun_out/${TAG}_ncu_launch.log 2>&1
+echo launches rc=$?
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bptt_kernel|rollout_fwd_kernel' -s 4 -c 4 -o gpurun_out/${TAG}_ncu_full_c2 python bench.py --no-extra --no-cpu-baseline --steps 2 --warmup 1 --no-graph > gpurun_out/${TAG}_ncu_full_c2.log 2>&1
+echo full c2 rc=$?
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bptt_kernel|rollout_fwd_kernel' -s 4 -c 2 -o gpurun_out/${TAG}_ncu_full_131k python bench.py --no-extra --no-cpu-baseline --steps 1 --warmup 1 --no-graph --rows 131072 > gpurun_out/${TAG}_ncu_full_131k.log 2>&1
+echo full 131k rc=$?
