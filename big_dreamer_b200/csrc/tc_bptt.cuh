@@ -194,34 +194,39 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               // branch-free clamped loads of everything that does not depend on TMEM; the first
               // chunk's loads are issued before the accumulator wait
               const long long lrow = rvalid ? orow : (long long)t * a.N;       // any valid row
-              float sd_[8], ep_[8], gs_[8], gm_[8], gd_[8];
+              // With cs = carried d s_{t+1}:  d mu = cs + A,  d raw_sigma = cs C + D, where
+              //   A = (g_s + g_mu) k,  C = eps f,  D = (g_s k eps + g_sigma k) f,  f = softplus'(raw) = 1 - e^-(sigma - min_std)
+              // (k = gradient scale) -- three values per element instead of five live across the accumulator wait
+              float A_[8], C_[8], D_[8];
               auto load_chunk = [&](int c) {
-                if ((S & 1) == 0) {     // rows are 8-byte aligned: 64-bit loads, clamped inside the row
 #pragma unroll
-                  for (int j = 0; j < 8; j += 2) {
+                for (int j = 0; j < 8; j += 2) {
+                  float sd[2], ep[2], gs[2] = {0.f, 0.f}, gm[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f};
+                  if ((S & 1) == 0) {     // rows are 8-byte aligned: 64-bit loads, clamped inside the row
                     const long long o = lrow * S + min(c + j, S - 2);
                     const float2 x0 = *reinterpret_cast<const float2*>(a.stds + o);
                     const float2 x1 = *reinterpret_cast<const float2*>(a.eps_s + o);
-                    sd_[j] = x0.x; sd_[j + 1] = x0.y; ep_[j] = x1.x; ep_[j + 1] = x1.y;
-                    float2 y = make_float2(0.f, 0.f);
-                    if (a.g_states) y = *reinterpret_cast<const float2*>(a.g_states + o);
-                    gs_[j] = y.x; gs_[j + 1] = y.y;
-                    y = make_float2(0.f, 0.f);
-                    if (a.g_means) y = *reinterpret_cast<const float2*>(a.g_means + o);
-                    gm_[j] = y.x; gm_[j + 1] = y.y;
-                    y = make_float2(0.f, 0.f);
-                    if (a.g_stds) y = *reinterpret_cast<const float2*>(a.g_stds + o);
-                    gd_[j] = y.x; gd_[j + 1] = y.y;
-                  }
-                } else {
+                    sd[0] = x0.x; sd[1] = x0.y; ep[0] = x1.x; ep[1] = x1.y;
+                    if (a.g_states) { const float2 y = *reinterpret_cast<const float2*>(a.g_states + o); gs[0] = y.x; gs[1] = y.y; }
+                    if (a.g_means) { const float2 y = *reinterpret_cast<const float2*>(a.g_means + o); gm[0] = y.x; gm[1] = y.y; }
+                    if (a.g_stds) { const float2 y = *reinterpret_cast<const float2*>(a.g_stds + o); gd[0] = y.x; gd[1] = y.y; }
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const long long o = lrow * S + min(c + j, S - 1);
-                    sd_[j] = a.stds[o];
-                    ep_[j] = a.eps_s[o];
-                    gs_[j] = a.g_states ? a.g_states[o] : 0.f;
-                    gm_[j] = a.g_means ? a.g_means[o] : 0.f;
-                    gd_[j] = a.g_stds ? a.g_stds[o] : 0.f;
+                    for (int k = 0; k < 2; ++k) {
+                      const long long o = lrow * S + min(c + j + k, S - 1);
+                      sd[k] = a.stds[o]; ep[k] = a.eps_s[o];
+                      if (a.g_states) gs[k] = a.g_states[o];
+                      if (a.g_means) gm[k] = a.g_means[o];
+                      if (a.g_stds) gd[k] = a.g_stds[o];
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) {
+                    const float f = 1.f - fast_exp(-(sd[k] - a.min_std));
+                    const float gss = gs[k] * scale;
+                    A_[j + k] = gss + gm[k] * scale;
+                    C_[j + k] = ep[k] * f;
+                    D_[j + k] = (gss * ep[k] + gd[k] * scale) * f;
                   }
                 }
               };
@@ -240,12 +245,8 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const bool ok = (c + j < S) && rvalid;
-                  const float gs = cs[j] + gs_[j] * scale;
-                  const float dmu = gs + gm_[j] * scale;
-                  const float dsd = gs * ep_[j] + gd_[j] * scale;
-                  const float draw = dsd * (1.f - fast_exp(-(sd_[j] - a.min_std)));   // softplus'
-                  m_[j] = ok ? dmu : 0.f;
-                  s_[j] = ok ? draw : 0.f;
+                  m_[j] = ok ? cs[j] + A_[j] : 0.f;
+                  s_[j] = ok ? fmaf(cs[j], C_[j], D_[j]) : 0.f;
                 }
                 store8<FMT>(D2 + (c >> 3) * kLboA + rowoff, m_);
                 store8<FMT>(D2 + ((Sp + c) >> 3) * kLboA + rowoff, s_);
@@ -292,31 +293,29 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               // raw before the accumulator wait; masked / scaled where it is added.  Nothing to fetch when the
               // loss reaches the beliefs only through this kernel's own heads (fused step: g_beliefs == null).
               const bool have_gb = !passB && (a.g_beliefs != nullptr);
-              float4 gb4[2][2];
-              long long q0 = 0, q1 = 0, q2 = 0;
-              if (PROF) q0 = clock64();
-              if (have_gb) {
+              float4 gb4[2];
+              auto load_gb = [&](int it) {
                 const float* gbrow = !a.gbt ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
                 const float* gbt = a.gbt ? a.gbt + tl * kTileRows * Kb + row * 4 : nullptr;
                 const bool vec = ((Be & 3) == 0);
+                const int c = part * 8 + it * 32;
+                const int col0 = n0 + min(c, Ns - 8);
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                  const int c = part * 8 + it * 32;
-                  const int col0 = n0 + min(c, Ns - 8);
-#pragma unroll
-                  for (int j4 = 0; j4 < 2; ++j4) {
-                    const int cb = col0 + j4 * 4;
-                    if (gbt) {
-                      gb4[it][j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
-                    } else if (vec) {
-                      gb4[it][j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
-                    } else {
-                      gb4[it][j4].x = gbrow[min(cb, Be - 1)]; gb4[it][j4].y = gbrow[min(cb + 1, Be - 1)];
-                      gb4[it][j4].z = gbrow[min(cb + 2, Be - 1)]; gb4[it][j4].w = gbrow[min(cb + 3, Be - 1)];
-                    }
+                for (int j4 = 0; j4 < 2; ++j4) {
+                  const int cb = col0 + j4 * 4;
+                  if (gbt) {
+                    gb4[j4] = *reinterpret_cast<const float4*>(gbt + SIDX(cb));     // zero padded
+                  } else if (vec) {
+                    gb4[j4] = *reinterpret_cast<const float4*>(gbrow + min(cb, Be - 4));
+                  } else {
+                    gb4[j4].x = gbrow[min(cb, Be - 1)]; gb4[j4].y = gbrow[min(cb + 1, Be - 1)];
+                    gb4[j4].z = gbrow[min(cb + 2, Be - 1)]; gb4[j4].w = gbrow[min(cb + 3, Be - 1)];
                   }
                 }
-              }
+              };
+              long long q0 = 0, q1 = 0, q2 = 0;
+              if (PROF) q0 = clock64();
+              if (have_gb) load_gb(0);
               if (PROF) q1 = clock64();
               const int pl3 = passB ? 3 : 2;
               uint4 cf[4];
@@ -351,7 +350,10 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
                 if (c < Ns) {
                   const int col0 = n0 + c;
                   float G[8];
-                  if (it > 0) load_planes(c);
+                  if (it > 0) {
+                    load_planes(c);
+                    if (have_gb) load_gb(1);
+                  }
                   if (!passB) {
                     tmem_ld8(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
                     tmem_ld_wait();
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
 #pragma unroll
                       for (int j4 = 0; j4 < 2; ++j4) {
                         const int cb = col0 + j4 * 4;       // (columns past Be: padding of the last slice)
-                        const float4 gb = gb4[it][j4];
+                        const float4 gb = gb4[j4];
                         G[j4 * 4] += cb < Be ? gb.x * sc : 0.f; G[j4 * 4 + 1] += cb + 1 < Be ? gb.y * sc : 0.f;
                         G[j4 * 4 + 2] += cb + 2 < Be ? gb.z * sc : 0.f; G[j4 * 4 + 3] += cb + 3 < Be ? gb.w * sc : 0.f;
                       }
@@ -445,14 +447,12 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               BD_WAIT_ACC();
               const uint32_t tacc = trow + 256;
               if (part == 0) {
+                // d a_t sits at accumulator columns [S, S + A): at most two 16-column pieces (A <= 16)
                 const int c0 = (S >> 4) << 4;
-                float vv[32];
+                float vv[16], vw[16];
                 tmem_ld16(tacc + c0, vv);
-                if (c0 + 16 < a.Ksa) tmem_ld16(tacc + c0 + 16, vv + 16);
-                else {
-#pragma unroll
-                  for (int j = 16; j < 32; ++j) vv[j] = 0.f;
-                }
+                const bool two = (S + Ad > c0 + 16) && (c0 + 16 < a.Ksa);      // warp-uniform
+                if (two) tmem_ld16(tacc + c0 + 16, vw);
                 tmem_ld_wait();
                 if (rvalid) {
                   const float ge = (pre ? pge : (a.g_entropy ? a.g_entropy[orow] : 0.f)) * scale;
@@ -460,7 +460,11 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
                     const int idx = S - c0 + j;
                     float da = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) if (k == idx) da = vv[k];
+                    for (int k = 0; k < 16; ++k) if (k == idx) da = vv[k];
+                    if (two) {
+#pragma unroll
+                      for (int k = 0; k < 16; ++k) if (k + 16 == idx) da = vw[k];
+                    }
                     const long long oa = orow * Ad + j;
                     const float m_raw = pre ? pm : a.actor_raw[orow * 2 * Ad + j];
                     const float s_raw = pre ? ps : a.actor_raw[orow * 2 * Ad + Ad + j];
