@@ -98,8 +98,11 @@ static __global__ void gb_tile_kernel(const float* __restrict__ g, long long N, 
   }
 }
 
-template <int FMT, bool PROF>
-__global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
+// NPARTS = column parts of the epilogue (4 warps each, one per TMEM quadrant): 4 -> 18 warps, 5 on two of the
+// SM's sub-partitions, i.e. 96 registers per thread; 3 -> 14 warps at 128 registers.
+template <int FMT, bool PROF, int NPARTS>
+__global__ void __launch_bounds__(64 + NPARTS * 128, 1) bptt_kernel(const __grid_constant__ BpttArgs A_) {
+  static_assert(NPARTS == 3 || NPARTS == 4, "per-warp epilogue arrivals: engine_setup counts threads at 256");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const BpttArgs& a = A_;
   uint8_t* smem = smem_raw;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
       s_wout[k][c] = (k < a.n_heads && a.w_out[k] && c < a.hd_nvalid) ? a.w_out[k][c] : 0.f;
     }
   }
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, kEpiThreads2);     // (its __syncthreads also publishes s_wout)
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, NPARTS * 128);     // (per-warp arrivals; its __syncthreads also publishes s_wout)
   const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
   const Program& P = sprog;
 
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
           dv_next = a.lr_disc * (1.f - a.lr_lam) * G;
         }
       }
-      if (a.n_heads) asm volatile("bar.sync 1, 512;" ::: "memory");   // every column part reads the row's d r / d v
+      if (a.n_heads) asm volatile("bar.sync 1, %0;" ::"n"(NPARTS * 128) : "memory");   // every column part reads the row's d r / d v
       epi_arrive(Ge);   // nothing else to initialise per tile
       ++Ge;
       for (int i = 0; i < a.T; ++i) {
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               };
               if (part * 8 < Sp) load_chunk(part * 8);
               BD_WAIT_ACC();
-              for (int c = part * 8; c < Sp; c += 32) {
+              for (int c = part * 8; c < Sp; c += NPARTS * 8) {
                 if (c != part * 8) load_chunk(c);
                 float cs[8], m_[8], s_[8];
                 if (i > 0 || a.n_heads) {
@@ -266,11 +269,11 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               };
               if (part * 16 < kp) load_img(part * 16);
               BD_WAIT_ACC();
-              for (int c = part * 16; c < kp; c += 64) {
+              for (int c = part * 16; c < kp; c += NPARTS * 16) {
                 float v[16];
                 const uint4 hu[2] = {hn[0], hn[1]};
                 tmem_ld16(tacc + c, v);
-                if (c + 64 < kp) load_img(c + 64);
+                if (c + NPARTS * 16 < kp) load_img(c + NPARTS * 16);
                 tmem_ld_wait();
 #pragma unroll
                 for (int g8 = 0; g8 < 2; ++g8) {
@@ -283,7 +286,8 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               }
             } break;
             case EPI_P_GATE: {
-              // 8-column chunks: c = 8 part + 32 it (a slice is at most 64 columns wide)
+              // 8-column chunks: c = 8 (part + NPARTS it) (a slice is at most 64 columns wide)
+              constexpr int kIts = (8 + NPARTS - 1) / NPARTS;
               const int n0 = ph.aux0, Ns = ph.Np;
               const bool passB = ph.pad != 0;
               uint8_t* slab = smem + a.sm.off_tile[ph.out_tile];
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
                 const float* gbrow = !a.gbt ? a.g_beliefs + (rvalid ? orow : (long long)t * a.N) * Be : nullptr;
                 const float* gbt = a.gbt ? a.gbt + tl * kTileRows * Kb + row * 4 : nullptr;
                 const bool vec = ((Be & 3) == 0);
-                const int c = part * 8 + it * 32;
+                const int c = (part + NPARTS * it) * 8;
                 const int col0 = n0 + min(c, Ns - 8);
 #pragma unroll
                 for (int j4 = 0; j4 < 2; ++j4) {
@@ -345,14 +349,14 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
                 a.prof[(20 + pi) * 8 + 2] += e1 - q2;    // accumulator wait proper
               }
 #pragma unroll
-              for (int it = 0; it < 2; ++it) {
-                const int c = part * 8 + it * 32;
+              for (int it = 0; it < kIts; ++it) {
+                const int c = (part + NPARTS * it) * 8;
                 if (c < Ns) {
                   const int col0 = n0 + c;
                   float G[8];
                   if (it > 0) {
                     load_planes(c);
-                    if (have_gb) load_gb(1);
+                    if (have_gb) load_gb(it);
                   }
                   if (!passB) {
                     tmem_ld8(trow + col0, G);           // ACC_B = d_gh(t+1) W_hh + d_h W_p1
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               };
               if (part * 16 < kp) load_chunk(part * 16);
               BD_WAIT_ACC();             // the previous phase's MMAs (which read the H tile) are done
-              for (int c = part * 16; c < kp; c += 64) {
+              for (int c = part * 16; c < kp; c += NPARTS * 16) {
                 if (c != part * 16) load_chunk(c);
 #pragma unroll
                 for (int g8 = 0; g8 < 2; ++g8) {
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
               }
               if (t == 0) {   // gradients wrt the start latents
                 if (a.d_prev_state) {
-                  for (int c = part * 16; c < a.Sp; c += 64) {
+                  for (int c = part * 16; c < a.Sp; c += NPARTS * 16) {
                     float v[16];
                     tmem_ld16(tacc + c, v);            // warp-collective: never under a per-lane branch
                     tmem_ld_wait();
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(kThreads2, 1) bptt_kernel(const __grid_constan
                   }
                 }
                 if (a.d_prev_belief) {
-                  for (int c = part * 16; c < Kb; c += 64) {
+                  for (int c = part * 16; c < Kb; c += NPARTS * 16) {
                     float v[16];
                     tmem_ld16(trow + c, v);            // ACC_B = d_gh(0) W_hh + z(0) G(0)
                     tmem_ld_wait();

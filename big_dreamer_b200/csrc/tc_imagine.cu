@@ -863,8 +863,8 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     // debug: per-phase cycle counters of CTA 0 (printed by scripts/prof_bptt.py)
     ba.prof = reinterpret_cast<long long*>(base + ((off + 4095) & ~size_t(4095)));
     cudaMemsetAsync(ba.prof, 0, kMaxPhases * 64, s);
-    set_smem_attr(bptt_kernel<0, true>, ba.sm.total);
-    bptt_kernel<0, true><<<grid, kThreads2, ba.sm.total, s>>>(ba);
+    set_smem_attr(bptt_kernel<0, true, 4>, ba.sm.total);
+    bptt_kernel<0, true, 4><<<grid, kThreads2, ba.sm.total, s>>>(ba);
     static long long* host_prof = nullptr;
     if (!host_prof) cudaMallocHost(&host_prof, kMaxPhases * 64);
     cudaMemcpyAsync(host_prof, ba.prof, kMaxPhases * 64, cudaMemcpyDeviceToHost, s);
@@ -881,12 +881,16 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     fprintf(stderr, "total     ");
     for (int k = 0; k < 7; ++k) fprintf(stderr, "%9lld", tot[k]);
     fprintf(stderr, "\n");
-  } else if (fmt == 0) {
-    set_smem_attr(bptt_kernel<0, false>, ba.sm.total);
-    bptt_kernel<0, false><<<grid, kThreads2, ba.sm.total, s>>>(ba);
   } else {
-    set_smem_attr(bptt_kernel<1, false>, ba.sm.total);
-    bptt_kernel<1, false><<<grid, kThreads2, ba.sm.total, s>>>(ba);
+    static const int nparts = getenv("BD_BPTT_PARTS") ? atoi(getenv("BD_BPTT_PARTS")) : 4;   // (A/B timing)
+#define BD_LAUNCH_BPTT(F, NP)                                                      \
+  do {                                                                             \
+    set_smem_attr(bptt_kernel<F, false, NP>, ba.sm.total);                         \
+    bptt_kernel<F, false, NP><<<grid, 64 + NP * 128, ba.sm.total, s>>>(ba);        \
+  } while (0)
+    if (fmt == 0) { if (nparts == 3) BD_LAUNCH_BPTT(0, 3); else BD_LAUNCH_BPTT(0, 4); }
+    else { if (nparts == 3) BD_LAUNCH_BPTT(1, 3); else BD_LAUNCH_BPTT(1, 4); }
+#undef BD_LAUNCH_BPTT
   }
   BD_CUDA_LAUNCH_CHECK();
   return BD_OK;
