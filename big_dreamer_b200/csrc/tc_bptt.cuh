@@ -260,20 +260,30 @@ __global__ void __launch_bounds__(64 + NPARTS * 128, 1) bptt_kernel(const __grid
               const uint16_t* img = (ph.aux0 == 1 ? a.sv_xa : (ph.aux0 == 2 ? a.sv_ha : a.sv_hd[ph.aux0 - 16])) +
                                     tl * kTileRows * kp + row * 8;
               const uint32_t tacc = trow + ph.d_col;
-              // 16-column chunks (kp is a multiple of 16); the next chunk's image is requested while this one
-              // is processed, the first one before the accumulator wait
-              uint4 hn[2];
-              auto load_img = [&](int c) {
-                hn[0] = *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8);
-                hn[1] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8);
-              };
-              if (part * 16 < kp) load_img(part * 16);
+              // 16-column chunks c = 16 (part + NPARTS k) (kp is a multiple of 16); the image pieces of two or three
+              // chunks are in flight at any time, the first ones requested before the accumulator wait (one chunk
+              // ahead left a full L2 / HBM round trip exposed per chunk: ~5 K cycles per phase)
+              // (a rotating set of named registers: an array indexed by the chunk number ends up in local memory)
+              const int cstep = NPARTS * 16;
+              auto ld0 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+              auto ld1 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+              const int cfirst = part * 16;
+              uint4 a0 = ld0(cfirst), a1 = ld1(cfirst);
+              uint4 b0 = ld0(cfirst + cstep), b1 = ld1(cfirst + cstep);
+              uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+              if (NPARTS == 3) { d0 = ld0(cfirst + 2 * cstep); d1 = ld1(cfirst + 2 * cstep); }
               BD_WAIT_ACC();
-              for (int c = part * 16; c < kp; c += NPARTS * 16) {
+              for (int c = cfirst; c < kp; c += cstep) {
                 float v[16];
-                const uint4 hu[2] = {hn[0], hn[1]};
                 tmem_ld16(tacc + c, v);
-                if (c + NPARTS * 16 < kp) load_img(c + NPARTS * 16);
+                const uint4 hu[2] = {a0, a1};
+                a0 = b0; a1 = b1;
+                if (NPARTS == 3) {
+                  b0 = d0; b1 = d1;
+                  d0 = ld0(c + 3 * cstep); d1 = ld1(c + 3 * cstep);
+                } else {
+                  b0 = ld0(c + 2 * cstep); b1 = ld1(c + 2 * cstep);
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int g8 = 0; g8 < 2; ++g8) {
@@ -415,15 +425,24 @@ __global__ void __launch_bounds__(64 + NPARTS * 128, 1) bptt_kernel(const __grid
               const uint16_t* img = a.sv_hd[k * BD_MAX_LAYERS + a.hd_last] + tl * kTileRows * kp + row * 8;
               const float* wo = s_wout[k];
               const float dout = a.scr_drv[((size_t)blockIdx.x * a.T + t) * 2 * kTileRows + (size_t)k * kTileRows + row] * scale;
-              uint4 hu[2];
-              auto load_chunk = [&](int c) {
-                hu[0] = *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8);
-                hu[1] = *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8);
-              };
-              if (part * 16 < kp) load_chunk(part * 16);
+              const int cstep = NPARTS * 16;
+              auto ld0 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(img + (size_t)(c >> 3) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+              auto ld1 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(img + (size_t)((c >> 3) + 1) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+              const int cfirst = part * 16;
+              uint4 a0 = ld0(cfirst), a1 = ld1(cfirst);
+              uint4 b0 = ld0(cfirst + cstep), b1 = ld1(cfirst + cstep);
+              uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+              if (NPARTS == 3) { d0 = ld0(cfirst + 2 * cstep); d1 = ld1(cfirst + 2 * cstep); }
               BD_WAIT_ACC();             // the previous phase's MMAs (which read the H tile) are done
-              for (int c = part * 16; c < kp; c += NPARTS * 16) {
-                if (c != part * 16) load_chunk(c);
+              for (int c = cfirst; c < kp; c += cstep) {
+                const uint4 hu[2] = {a0, a1};
+                a0 = b0; a1 = b1;
+                if (NPARTS == 3) {
+                  b0 = d0; b1 = d1;
+                  d0 = ld0(c + 3 * cstep); d1 = ld1(c + 3 * cstep);
+                } else {
+                  b0 = ld0(c + 2 * cstep); b1 = ld1(c + 2 * cstep);
+                }
 #pragma unroll
                 for (int g8 = 0; g8 < 2; ++g8) {
                   float h[8], o[8];

@@ -39,9 +39,14 @@ namespace tc {
 constexpr int kTileRows = 128;
 constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
-// rollout kernel (round 2): 16 epilogue warps
-constexpr int kThreads2 = 576;
-constexpr int kEpiThreads2 = 512;
+// rollout kernel (round 2): kParts2 column parts of 4 epilogue warps (one per TMEM quadrant).  4 parts = 18 warps:
+// five on two of the SM's sub-partitions, hence 96 registers per thread; 3 parts = 14 warps at 128 registers.
+#ifndef BD_ROLLOUT_PARTS
+#define BD_ROLLOUT_PARTS 3
+#endif
+constexpr int kParts2 = BD_ROLLOUT_PARTS;
+constexpr int kEpiThreads2 = 128 * kParts2;
+constexpr int kThreads2 = 64 + kEpiThreads2;
 constexpr int kMaxGemms = 64, kMaxPhases = 40;
 constexpr int kMaxRanks = 4;            // CTAs per cluster in column-split mode (1 = off)
 constexpr uint32_t kLboA = kTileRows * 16;   // bytes between 8-column groups of an activation tile
@@ -702,11 +707,11 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
                 };
                 if (c0 < c_hi) load(c0, v[0]);
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                  const int c = c0 + it * 64;
+                for (int it = 0; it < (16 + kParts2 - 1) / kParts2; ++it) {
+                  const int c = c0 + it * (16 * kParts2);
                   if (c < c_hi) {
                     tmem_ld_wait();
-                    if (c + 64 < c_hi) load(c + 64, v[(it + 1) & 1]);
+                    if (c + 16 * kParts2 < c_hi) load(c + 16 * kParts2, v[(it + 1) & 1]);
                     uint32_t y[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) y[j] = act_pack2<FMT, ACT>(v[it & 1][2 * j], v[it & 1][2 * j + 1]);
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               }
             } break;
             case EPI_GRU: {
-              // 8-column chunks: c = 8 part + 32 it (a slice is at most 64 columns wide)
+              // 8-column chunks: c = 8 (part + kParts2 it) (a slice is at most 64 columns wide)
               const int n0 = ph.aux0, Ns = ph.Np;
               const float* bold = (t == 0) ? a.prev_belief + (a.cem_cl ? grow / a.cem_cl : grow) * Be
                                            : a.beliefs + ((long long)(t - 1) * a.N + grow) * Be;
@@ -751,16 +756,17 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               // operand rounding the GEMMs see anyway).  bf16 mode (7-bit mantissa): the fp32 master copy
               // from the previous step's output, requested before the accumulator wait.
               const uint8_t* Bcur = smem + a.sm.off_tile[par] + rowoff;
-              float hb[2][8];
+              constexpr int kGruIts = (8 + kParts2 - 1) / kParts2;
+              float hb[kGruIts][8];
               if (FMT != 0) {
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                  const int col = n0 + part * 8 + it * 32;
+                for (int it = 0; it < kGruIts; ++it) {
+                  const int col = n0 + (part + kParts2 * it) * 8;
 #pragma unroll
                   for (int j4 = 0; j4 < 2; ++j4) {
                     const int cc = col + j4 * 4;
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rvalid && part * 8 + it * 32 < Ns) {
+                    if (rvalid && (part + kParts2 * it) * 8 < Ns) {
                       if (be4 && cc + 3 < Be) x = *reinterpret_cast<const float4*>(bold + cc);
                       else {
                         if (cc < Be) x.x = bold[cc];
@@ -777,8 +783,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
 #pragma unroll
-              for (int it = 0; it < 2; ++it) {
-                const int c = part * 8 + it * 32;
+              for (int it = 0; it < kGruIts; ++it) {
+                const int c = (part + kParts2 * it) * 8;
                 if (c < Ns) {
                   float r_[8], z_[8], in_[8], hn_[8], o[8];
                   tmem_ld8(tacc + c, in_);              // accumulator columns: IN | R | Z | HN
@@ -861,7 +867,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               // as 8-byte stores (a full sector per thread: no staging through shared memory, no barrier)
               const bool want_out = a.means != nullptr && wr0 && rvalid;
               const bool s2 = (S & 1) == 0;      // rows are 8-byte aligned
-              for (int cc = cc0; cc < Sp; cc += 32) {
+              for (int cc = cc0; cc < Sp; cc += 8 * kParts2) {
                 if (cc != cc0) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) eps[j] = (rvalid && cc + j < S) ? a.eps_s[erow * S + cc + j] : 0.f;
@@ -957,7 +963,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
               const int nv = ph.n_valid;
-              for (int c = part * 16; c < ph.Np; c += 64) {
+              for (int c = part * 16; c < ph.Np; c += 16 * kParts2) {
                 float v[16];
                 tmem_ld16(tacc + c, v);
                 tmem_ld_wait();

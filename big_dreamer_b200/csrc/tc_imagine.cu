@@ -882,7 +882,7 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     for (int k = 0; k < 7; ++k) fprintf(stderr, "%9lld", tot[k]);
     fprintf(stderr, "\n");
   } else {
-    static const int nparts = getenv("BD_BPTT_PARTS") ? atoi(getenv("BD_BPTT_PARTS")) : 4;   // (A/B timing)
+    static const int nparts = getenv("BD_BPTT_PARTS") ? atoi(getenv("BD_BPTT_PARTS")) : 3;   // (4: A/B timing)
 #define BD_LAUNCH_BPTT(F, NP)                                                      \
   do {                                                                             \
     set_smem_attr(bptt_kernel<F, false, NP>, ba.sm.total);                         \
