@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(64 + NPARTS * 128, 1) bptt_kernel(const __grid
               if (PROF) q2 = clock64();
               BD_WAIT_ACC();
               if (PROF && blockIdx.x == 0 && lane == 0 && warp == 2) {
-                a.prof[(20 + pi) * 8 + 0] += q1 - q0;    // upstream-gradient / carry fetch + combine
-                a.prof[(20 + pi) * 8 + 1] += q2 - q1;    // coefficient-plane loads issued
-                a.prof[(20 + pi) * 8 + 2] += e1 - q2;    // accumulator wait proper
+                prof_add(&a.prof[(20 + pi) * 8 + 0], q1 - q0);    // upstream-gradient / carry fetch + combine
+                prof_add(&a.prof[(20 + pi) * 8 + 1], q2 - q1);    // coefficient-plane loads issued
+                prof_add(&a.prof[(20 + pi) * 8 + 2], e1 - q2);    // accumulator wait proper
               }
 #pragma unroll
               for (int it = 0; it < kIts; ++it) {
@@ -534,8 +534,8 @@ __global__ void __launch_bounds__(64 + NPARTS * 128, 1) bptt_kernel(const __grid
           epi_arrive(Ge);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
-            a.prof[o] += e1 - e0;
-            a.prof[o + 1] += clock64() - e1;
+            prof_add(&a.prof[o], e1 - e0);
+            prof_add(&a.prof[o + 1], clock64() - e1);
           }
           ++Ge;
           ++Gm;

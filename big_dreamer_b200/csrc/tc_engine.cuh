@@ -121,6 +121,11 @@ __device__ __forceinline__ void prefetch_step(const PrefetchPlan& pf, long long 
   }
 }
 
+// debug counters: fire-and-forget reductions (a load-add-store would stall the in-order issuer on the load)
+__device__ __forceinline__ void prof_add(long long* p, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+
 struct RolloutArgs {
   Program prog[kMaxRanks];   // one program per cluster rank (column-split mode); [0] when nranks == 1
   int nranks;
@@ -377,11 +382,11 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
         if (R > 1) umma_commit_mc_elect(bar_acc_full + (Gm & 3) * 8, (uint16_t)((1u << R) - 1));
         else umma_commit_elect(bar_acc_full + (Gm & 3) * 8);
         if (PROF && blockIdx.x == 0 && lane == 0) {
-          prof[pi * 8 + 0] += dsum;                          // issuer: wait for the dependency epilogue(s)
-          prof[pi * 8 + 1] += wsum;                          // issuer: wait for weight stages
-          prof[pi * 8 + 2] += clock64() - c1 - wsum - dsum;  // issuer: issue time
-          prof[pi * 8 + 7] += msum;                          // of which: inside the tcgen05.mma loops
-          prof[(20 + pi) * 8 + 0] += csum - msum;            //           the per-stage tcgen05.commit
+          prof_add(&prof[pi * 8 + 0], dsum);                          // issuer: wait for the dependency epilogue(s)
+          prof_add(&prof[pi * 8 + 1], wsum);                          // issuer: wait for weight stages
+          prof_add(&prof[pi * 8 + 2], clock64() - c1 - wsum - dsum);  // issuer: issue time
+          prof_add(&prof[pi * 8 + 7], msum);                          // of which: inside the tcgen05.mma loops
+          prof_add(&prof[(20 + pi) * 8 + 0], csum - msum);            //           the per-stage tcgen05.commit
         }
         ++Gm;
         Ge += ph.n_sub;
@@ -989,8 +994,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
           epi_arrive(Ge);
           if (PROF && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
             const int o = pi * 8 + (warp == 2 ? 3 : 5);
-            a.prof[o] += e1 - e0;                          // epilogue: wait for the accumulator
-            a.prof[o + 1] += clock64() - e1;               // epilogue: work
+            prof_add(&a.prof[o], e1 - e0);                          // epilogue: wait for the accumulator
+            prof_add(&a.prof[o + 1], clock64() - e1);               // epilogue: work
           }
           ++Ge;
           ++Gm;
@@ -1021,8 +1026,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
     long long g1;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
     if (blockIdx.x == 0) {
-      a.prof[39 * 8 + 0] += clock64() - prof_c0;   // whole-kernel SM cycles of CTA 0
-      a.prof[39 * 8 + 1] += g1 - prof_g0;          // same interval in ns
+      prof_add(&a.prof[39 * 8 + 0], clock64() - prof_c0);   // whole-kernel SM cycles of CTA 0
+      prof_add(&a.prof[39 * 8 + 1], g1 - prof_g0);          // same interval in ns
     }
     if (blockIdx.x < 160) {                        // per-CTA start / end timestamps
       uint32_t smid;

@@ -863,8 +863,8 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     // debug: per-phase cycle counters of CTA 0 (printed by scripts/prof_bptt.py)
     ba.prof = reinterpret_cast<long long*>(base + ((off + 4095) & ~size_t(4095)));
     cudaMemsetAsync(ba.prof, 0, kMaxPhases * 64, s);
-    set_smem_attr(bptt_kernel<0, true, 4>, ba.sm.total);
-    bptt_kernel<0, true, 4><<<grid, kThreads2, ba.sm.total, s>>>(ba);
+    set_smem_attr(bptt_kernel<0, true, 3>, ba.sm.total);
+    bptt_kernel<0, true, 3><<<grid, 64 + 3 * 128, ba.sm.total, s>>>(ba);
     static long long* host_prof = nullptr;
     if (!host_prof) cudaMallocHost(&host_prof, kMaxPhases * 64);
     cudaMemcpyAsync(host_prof, ba.prof, kMaxPhases * 64, cudaMemcpyDeviceToHost, s);
