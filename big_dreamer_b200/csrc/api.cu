@@ -295,7 +295,10 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
     // ONE batched backward over all T*N rows: step 0 reads (prev_belief, prev_state), steps 1.. read
     // (beliefs, states)[t-1] -- a two-segment input (two passes cost a second, 20-CTA launch chain)
     m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
-    BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N));
+    // (hidden activations saved per (t, tile) by the tensor-core forward: no recompute, step-wise tiling)
+    m.saved = tc::imagine_saved_actor(f.rssm, f.actor, f.T, f.N, f.tc_saved);
+    BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N,
+                            m.saved ? f.N : 0));
     return BD_OK;
   }
   return f32::imagine_backward(a, ws, ws_bytes, stream);
@@ -353,7 +356,9 @@ int bd_imagine_returns_backward(const bd_imagine_returns_bwd_args* a, void* ws, 
   m.k1 = Be; m.k2 = S;
   for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }
   m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
-  return tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N);
+  m.saved = tc::imagine_saved_actor(f.rssm, f.actor, f.T, f.N, f.tc_saved);
+  return tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N,
+                          m.saved ? f.N : 0);
 }
 
 size_t bd_cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H) {

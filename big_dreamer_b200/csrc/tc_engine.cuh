@@ -149,7 +149,8 @@ struct RolloutArgs {
   // saved for the tensor-core BPTT (16-bit tile images, see tc_bptt.cuh); null = do not save
   uint16_t *sv_gate, *sv_xa, *sv_ha;
   int kb_sv, kh_sv;
-  uint16_t* sv_mlp[BD_MAX_LAYERS];   // MLP forward: image of hidden layer l (cols = its Kp_out)
+  uint16_t* sv_mlp[BD_MAX_LAYERS];   // MLP forward / the rollout's actor: image of hidden layer l
+  int kact_sv;                       // its columns (0: the phase's own Kp_out -- not in column-split mode, where Kp_out is the rank's slice end)
   // fused Dreamer rollout (imagine_and_returns): act'(h) images of the two heads' hidden layers per
   // (t, tile) for the fused backward (index head * BD_MAX_LAYERS + layer; null = do not save), and the
   // lambda-return tail (src/dreamer.py:447-471 with bootstrap = value[-1], :329-335) over head_out[0/1]
@@ -666,8 +667,9 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               uint16_t* simg = nullptr;
               if (ph.aux0 >= 3 && ph.aux0 < 3 + BD_MAX_LAYERS) {
                 if (a.sv_mlp[ph.aux0 - 3]) {
-                  smode = 1; skp = ph.Kp_out;
-                  simg = a.sv_mlp[ph.aux0 - 3] + (size_t)tile * kTileRows * skp + row * 8;
+                  smode = 1; skp = a.kact_sv ? a.kact_sv : ph.Kp_out;
+                  // (per (t, tile): the MLP forward has T = 1; the rollout saves the actor's hidden layers per step)
+                  simg = a.sv_mlp[ph.aux0 - 3] + ((size_t)t * ntiles + tile) * kTileRows * skp + row * 8;
                 }
               } else if (ph.aux0 == 1 || ph.aux0 == 2) {
                 if (a.sv_xa) {

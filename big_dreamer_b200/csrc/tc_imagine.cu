@@ -10,7 +10,10 @@
 namespace bd {
 namespace tc {
 
-struct SavedLayout { size_t off_gate, off_xa, off_ha, total; int Kb, Kh; };
+// (+ the actor's hidden activations, up to kSavedActorLayers images of (T x tiles) x 128 x Kact: the batched actor
+// backward reads them instead of recomputing the actor's forward pass)
+constexpr int kSavedActorLayers = 4;
+struct SavedLayout { size_t off_gate, off_xa, off_ha, off_act, act_bytes, total; int Kb, Kh, Kact; };
 static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
   SavedLayout s;
   s.Kb = r16(r.belief_size); s.Kh = r16(r.hidden_size);
@@ -18,10 +21,23 @@ static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
   s.off_gate = 0;
   s.off_xa = s.off_gate + tiles * 5 * kTileRows * s.Kb * 2;
   s.off_ha = s.off_xa + tiles * kTileRows * s.Kb * 2;
-  s.total = s.off_ha + tiles * kTileRows * s.Kh * 2;
+  s.off_act = s.off_ha + tiles * kTileRows * s.Kh * 2;
+  s.Kact = r16(r.hidden_size + 1);
+  s.act_bytes = tiles * kTileRows * s.Kact * 2;          // one hidden layer
+  s.total = s.off_act + kSavedActorLayers * s.act_bytes;
   return s;
 }
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N) { return saved_layout(r, T, N).total + 256; }
+// the actor's saved hidden images inside tc_saved (layout of mlp_backward's `saved`: layer after layer), or null
+// when the actor has more hidden layers than the buffer holds / the debug switch BD_NO_ACTOR_SAVE is set
+const void* imagine_saved_actor(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved) {
+  // (small row counts run latency-bound in column-split clusters: there the extra stores cost the rollout what
+  // the backward saves -- measured at 2 500 rows: rollout +0.03 ms, actor backward -0.02 ms)
+  const char* e = getenv("BD_ACTOR_SAVE_MIN_ROWS");      // (read per call: the tests switch it)
+  const long long min_rows = e ? atoll(e) : 8192;
+  if (!tc_saved || actor.n_layers - 1 > kSavedActorLayers || N < min_rows || getenv("BD_NO_ACTOR_SAVE")) return nullptr;
+  return static_cast<const char*>(tc_saved) + saved_layout(r, T, N).off_act;
+}
 
 // Do the operand tiles of the rollout engine (two belief tiles, [s;a], one hidden tile) plus at
 // least two weight-ring stages fit the 227 KB of shared memory?  (Same arithmetic as plan_smem.)
@@ -326,11 +342,12 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
     const bd_linear& L0 = ac.layer[0];
     ActSrc s0[2] = {{L0.w, Be + S, 0, Be, Kp_b, TILE_BCUR, L0.b, Be},
                     {L0.w, Be + S, Be, S, Ks, TILE_SA, nullptr, -1}};
-    int sp = add_act_phase(b, rank, R, s0, 2, Hi, Kp_hid, 0, TILE_H, 0);
+    // (aux0 = 3 + l: the hidden activation image goes to sv_mlp[l] when the backward will want it)
+    int sp = add_act_phase(b, rank, R, s0, 2, Hi, Kp_hid, 3, TILE_H, 0);
     for (int l = 1; l + 1 < ac.n_layers; ++l) {
       const bd_linear& L = ac.layer[l];
       ActSrc sl{L.w, Hi, 0, Hi, Kp_hid, TILE_H, L.b, Hi};
-      sp = add_act_phase(b, rank, R, &sl, 1, Hi, Kp_hid, 0, TILE_H, sp);
+      sp = add_act_phase(b, rank, R, &sl, 1, Hi, Kp_hid, 3 + l, TILE_H, sp);
     }
     {   // output layer: narrow, replicated on every rank in column-split mode
       const bd_linear& Lo = ac.layer[ac.n_layers - 1];
@@ -383,6 +400,11 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
     ra.sv_xa = reinterpret_cast<uint16_t*>(sb + sl.off_xa);
     ra.sv_ha = reinterpret_cast<uint16_t*>(sb + sl.off_ha);
     ra.kb_sv = sl.Kb; ra.kh_sv = sl.Kh;
+    if (imagine_saved_actor(r, ac, a->T, a->N, a->tc_saved)) {
+      ra.kact_sv = sl.Kact;
+      for (int l = 0; l + 1 < ac.n_layers; ++l)
+        ra.sv_mlp[l] = reinterpret_cast<uint16_t*>(sb + sl.off_act + (size_t)l * sl.act_bytes);
+    }
   }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -62,7 +62,7 @@ static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStre
 #define BD_LAUNCH_BWD(ACTV)                                                                          \
   do {                                                                                               \
     set_smem_attr(mlp_bwd_kernel<FMT, ACTV>, ba.sm.total);                                           \
-    mlp_bwd_kernel<FMT, ACTV><<<grid, kThreads, ba.sm.total, s>>>(ba);                               \
+    mlp_bwd_kernel<FMT, ACTV><<<grid, kBwdThreads, ba.sm.total, s>>>(ba);                               \
   } while (0)
   switch (act) {
     case BD_ACT_ELU: BD_LAUNCH_BWD(BD_ACT_ELU); break;
@@ -76,7 +76,7 @@ static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStre
 }
 
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
-                 bd_stream_t stream, const float* x1b, const float* x2b, int64_t split) {
+                 bd_stream_t stream, const float* x1b, const float* x2b, int64_t split, int64_t seg_rows) {
   const int k1 = a->k1, k2 = a->k2, L = m->n_layers;
   if (!mlp_backward_supported(*m, k1, k2, precision))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: sizes/activation not supported");
@@ -165,7 +165,10 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   if (off + p.per_tile_bytes + 4096 > ws_bytes)
     BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_backward: workspace %zu too small", ws_bytes);
   long long chunk_tiles = (long long)((ws_bytes - off - 4096) / (p.per_tile_bytes ? p.per_tile_bytes : 1));
-  const long long total_tiles = (a->rows + 127) / 128;
+  // segmented tiling (see MlpBwdArgs): rows = T steps of seg_rows rows, each step tiled on its own
+  const bool seg = seg_rows > 0 && a->rows % seg_rows == 0;
+  const long long seg_tiles = seg ? (seg_rows + 127) / 128 : 0;
+  const long long total_tiles = seg ? (a->rows / seg_rows) * seg_tiles : (a->rows + 127) / 128;
   if (chunk_tiles > total_tiles) chunk_tiles = total_tiles;
   if (chunk_tiles < 1) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_backward: workspace too small");
   char* scratch = base + off;
@@ -237,17 +240,30 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     if (!want_w) ba.ds[L - 1] = nullptr;
     ba.x0b = want_w ? st((size_t)nt * 128 * p.Kp_b * 2) : nullptr;
     ba.x0s = want_w ? st((size_t)nt * 128 * p.Ks * 2) : nullptr;
-    ba.N = nrows;
+    ba.N = nrows; ba.ntiles = nt;
+    ba.seg_tiles = (int)seg_tiles; ba.seg_rows = seg ? seg_rows : 0; ba.tile_base = seg ? t0 : 0;
+    if (seg) {      // row pointers stay those of row 0: the kernel maps (tile_base + tile) to its rows
+      ba.N = a->rows;
+      ba.x1 = a->x1; ba.x2 = a->x2;
+    } else {
     ba.x1 = a->x1 + r0 * k1;
     ba.x2 = a->x2 ? a->x2 + r0 * k2 : nullptr;
+    }
     // two-segment input: rows [0, split) from x1 / x2, the rest from x1b / x2b (chunk-relative here)
     const bool two_seg = x1b != nullptr && split >= 0 && split < a->rows;
+    if (seg) {
+      ba.split = two_seg ? split : a->rows;
+      ba.x1b = two_seg ? x1b : ba.x1;
+      ba.x2b = (two_seg && x2b) ? x2b : ba.x2;
+      ba.dy = a->dy; ba.dx1 = a->dx1; ba.dx2 = a->dx2;
+    } else {
     ba.split = two_seg ? (split > r0 ? split - r0 : 0) : nrows;
     ba.x1b = two_seg ? x1b + (r0 > split ? (r0 - split) * k1 : 0) : ba.x1;
     ba.x2b = (two_seg && x2b) ? x2b + (r0 > split ? (r0 - split) * k2 : 0) : ba.x2;
     ba.dy = a->dy + r0 * out;
     ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
+    }
     const unsigned grid = (unsigned)(nt < sms ? nt : sms);
     {
       // the producer warp pulls the NEXT tile's inputs (rows of x1 / x2 / dy, saved hidden images) into L2
@@ -258,11 +274,11 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
         pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
         pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
       };
-      if (ba.need_x && !two_seg) {     // (the L2 prefetch assumes one contiguous input per tile index)
+      if (ba.need_x && !two_seg && !seg) {     // (the L2 prefetch assumes one contiguous input per tile index)
         add(ba.x1, (size_t)128 * k1 * 4);
         add(ba.x2, (size_t)128 * k2 * 4);
       }
-      add(ba.dy, (size_t)128 * out * 4);
+      if (!seg) add(ba.dy, (size_t)128 * out * 4);
       if (have_saved)
         for (int l = 0; l + 1 < L && pf.n < 6; ++l) add(ba.xs[l], (size_t)128 * p.kp_xs[l] * 2);
     }

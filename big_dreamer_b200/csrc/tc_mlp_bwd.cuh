@@ -35,6 +35,11 @@ struct MlpBwdArgs {
   // inputs of imagine_ahead are (prev_belief, prev_state) for step 0 and (beliefs, states)[t-1] after.
   const float *x1b, *x2b;
   long long split;              // >= N when unused
+  // Segmented tiling (the actor's backward over the T steps of a rollout whose forward saved its hidden images per
+  // (t, tile)): tile g = tile_base + tile covers rows [t N' + 128 j, ...) of step t = g / seg_tiles, j = g % seg_tiles,
+  // with N' = seg_rows rows per step; all row pointers are then those of row 0.  seg_tiles = 0: plain tiling of N rows.
+  long long seg_rows, tile_base, ntiles;
+  int seg_tiles;
   float *dx1, *dx2;
   uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
   uint16_t* ds[BD_MAX_LAYERS];  // ds[l]: images of dY_l (cols kp_ds[l]), l = 0..L-1
@@ -113,8 +118,12 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
                     Half16<FMT>::pack2(v[4], v[5]), Half16<FMT>::pack2(v[6], v[7]));
 }
 
+// 12 epilogue warps (3 column parts x 4 TMEM quadrants, 14 warps = 128 registers per thread), 16-column chunks
+constexpr int kBwdParts = 3;
+constexpr int kBwdEpiThreads = kBwdParts * 128;
+constexpr int kBwdThreads = 64 + kBwdEpiThreads;
 template <int FMT, int ACT>
-__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_constant__ MlpBwdArgs A_) {
+__global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_constant__ MlpBwdArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const MlpBwdArgs& a = A_;
   uint8_t* smem = smem_raw;
@@ -123,8 +132,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   __shared__ Program sprog;
   stage_program(sprog, a.prog);
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage);
-  const long long ntiles = (a.N + kTileRows - 1) / kTileRows;
+  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, kBwdEpiThreads);
+  const long long ntiles = a.ntiles;
   const Program& P = sprog;
 
   if (warp == 0) {
@@ -132,7 +141,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
   } else if (warp == 1) {
     issuer_role<FMT, false>(P, a.sm, ntiles, 1, smem, sh, tmem_base, nullptr);
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, part = (warp - 2) >> 2;
+    auto epi_arrive = [&](uint32_t ge) {     // one arrival per warp
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.epi_done[ge & 7]);
+    };
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int etid = tid - 64;
@@ -145,20 +159,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
     float inv_scale;
     const float scale = grad_scale(a.amax_bits, &inv_scale);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long grow = tile * kTileRows + row;
-      const bool rvalid = grow < a.N;
+      long long trow0 = tile * kTileRows;
+      int tvalid;
+      if (a.seg_tiles > 0) {
+        const long long g = a.tile_base + tile, tt = g / a.seg_tiles;
+        const long long j0 = (g - tt * a.seg_tiles) * kTileRows;
+        trow0 = tt * a.seg_rows + j0;
+        tvalid = (int)(a.seg_rows - j0 < kTileRows ? a.seg_rows - j0 : kTileRows);
+      } else {
+        tvalid = (int)(a.N - trow0 < kTileRows ? a.N - trow0 : kTileRows);
+      }
+      const long long grow = trow0 + row;
+      const bool rvalid = row < tvalid;
       // ---------------- init: B0 <- [x1 | 1], SA <- x2 (and their images for wgrad)
       if (a.need_x) {
         const int gb = a.Kp_b >> 3;
-        for (int i = etid; i < kTileRows * gb; i += kEpiThreads) {
+        for (int i = etid; i < kTileRows * gb; i += kBwdEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
-          const long long gr = tile * kTileRows + r;
+          const long long gr = trow0 + r;
+          const bool rv = r < tvalid;
           const float* x1r = gr < a.split ? a.x1 + gr * a.k1 : a.x1b + (gr - a.split) * a.k1;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = (k < a.k1) ? ((gr < a.N) ? x1r[k] : 0.f) : ((k == a.k1 && gr < a.N) ? 1.f : 0.f);
+            v[j] = (k < a.k1) ? (rv ? x1r[k] : 0.f) : ((k == a.k1 && rv) ? 1.f : 0.f);
           }
           const uint4 u = pack8<FMT>(v);
           *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
@@ -166,24 +191,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             *reinterpret_cast<uint4*>(a.x0b + (size_t)tile * kTileRows * a.Kp_b + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
         const int gs = a.Ks >> 3;
-        for (int i = etid; i < kTileRows * gs; i += kEpiThreads) {
+        for (int i = etid; i < kTileRows * gs; i += kBwdEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
-          const long long gr = tile * kTileRows + r;
+          const long long gr = trow0 + r;
+          const bool rv = r < tvalid;
           const float* x2r = gr < a.split ? a.x2 + gr * a.k2 : a.x2b + (gr - a.split) * a.k2;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = kg * 8 + j;
-            v[j] = (k < a.k2 && gr < a.N) ? x2r[k] : 0.f;
+            v[j] = (k < a.k2 && rv) ? x2r[k] : 0.f;
           }
           const uint4 u = pack8<FMT>(v);
           *reinterpret_cast<uint4*>(SA + kg * kLboA + r * 16) = u;
           if (a.want_images)
             *reinterpret_cast<uint4*>(a.x0s + (size_t)tile * kTileRows * a.Ks + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
-        fence_proxy_async_smem();
       }
-      mbar_arrive(&sh.epi_done[Ge & 7]);
+      epi_arrive(Ge);
       ++Ge;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
@@ -198,38 +223,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             BD_WAIT_ACC();
             const int l = ph.aux0, nv = ph.n_valid;
             uint16_t* img = a.xs[l] + (size_t)tile * kTileRows * ph.Kp_out;
-            for (int c = half * 32; c < ph.Kp_out; c += 64) {
-              float v[32];
-              const bool two = (c + 16) < ph.Kp_out;
-              if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
+            for (int c = part * 16; c < ph.Kp_out; c += kBwdParts * 16) {
+              float v[16];
+              if (c < ph.Np) tmem_ld16(tacc + c, v);
               else {
-                if (c < ph.Np) tmem_ld16(tacc + c, v);
-                if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
               }
               tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = tc_act_t<ACT>(v[j]);
-              if (c + 32 > nv) {
+              for (int j = 0; j < 16; ++j) v[j] = tc_act_t<ACT>(v[j]);
+              if (c + 16 > nv) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                   const int col = c + j;
                   if (col >= nv) v[j] = (col == nv && rvalid) ? 1.f : 0.f;
                 }
               }
               if (!rvalid) {   // padded rows carry exact zeros so they add nothing to dW / db
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
               }
               uint8_t* p = H + (c >> 3) * kLboA + rowoff;
               uint16_t* gi = img + (size_t)(c >> 3) * kTileRows * 8 + row * 8;
-              const int ngroups = two ? 4 : 2;
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
-                if (g8 < ngroups) {
-                  const uint4 u = pack8<FMT>(v + 8 * g8);
-                  *reinterpret_cast<uint4*>(p + g8 * kLboA) = u;
-                  *reinterpret_cast<uint4*>(gi + (size_t)g8 * kTileRows * 8) = u;
-                }
+              for (int g8 = 0; g8 < 2; ++g8) {
+                const uint4 u = pack8<FMT>(v + 8 * g8);
+                *reinterpret_cast<uint4*>(p + g8 * kLboA) = u;
+                *reinterpret_cast<uint4*>(gi + (size_t)g8 * kTileRows * 8) = u;
               }
             }
           } break;
@@ -237,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             BD_WAIT_ACC();
             const int l = a.n_layers - 1, kp = a.kp_ds[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
-            for (int c = half * 8; c < kp; c += 16) {
+            for (int c = part * 8; c < kp; c += kBwdParts * 8) {
               float v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -252,44 +273,41 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             const int nv = ph.n_valid, kp = a.kp_ds[l];
             const uint16_t* himg = a.xs[l] + (size_t)tile * kTileRows * a.kp_xs[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
-            uint4 hu[4], hn[4];
-            auto load_h = [&](int c, uint4* dst) {
-              const int ngroups = ((c + 16) < kp) ? 4 : 2;
-#pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8)
-                if (g8 < ngroups)
-                  dst[g8] = *reinterpret_cast<const uint4*>(himg + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8);
-            };
-            if (half * 32 < kp) load_h(half * 32, hn);      // issued before the accumulator wait
+            // 16-column chunks c = 16 (part + kBwdParts k); the hidden-image pieces of three chunks are in flight
+            // (rotating registers), the first ones requested before the accumulator wait
+            const uint16_t* hrow = himg + row * 8;
+            const int cstep = kBwdParts * 16;
+            auto ld0 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(hrow + (size_t)(c >> 3) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+            auto ld1 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(hrow + (size_t)((c >> 3) + 1) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+            const int cfirst = part * 16;
+            uint4 a0 = ld0(cfirst), a1 = ld1(cfirst);
+            uint4 b0 = ld0(cfirst + cstep), b1 = ld1(cfirst + cstep);
+            uint4 d0 = ld0(cfirst + 2 * cstep), d1 = ld1(cfirst + 2 * cstep);
             BD_WAIT_ACC();
-            for (int c = half * 32; c < kp; c += 64) {
-              float v[32];
-              const bool two = (c + 16) < kp;
-              const int ngroups = two ? 4 : 2;
-#pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) hu[g8] = hn[g8];
-              if (c + 64 < kp) load_h(c + 64, hn);          // next chunk's image while this one is processed
-              if (c + 32 <= ph.Np) tmem_ld32(tacc + c, v);
+            for (int c = cfirst; c < kp; c += cstep) {
+              float v[16];
+              if (c < ph.Np) tmem_ld16(tacc + c, v);
               else {
-                if (c < ph.Np) tmem_ld16(tacc + c, v);
-                if (c + 16 < ph.Np) tmem_ld16(tacc + c + 16, v + 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
               }
+              const uint4 hu[2] = {a0, a1};
+              a0 = b0; a1 = b1; b0 = d0; b1 = d1;
+              d0 = ld0(c + 3 * cstep); d1 = ld1(c + 3 * cstep);
               tmem_ld_wait();
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
-                if (g8 < ngroups) {
-                  float h[8];
-                  unpack8<FMT>(hu[g8], h);
+              for (int g8 = 0; g8 < 2; ++g8) {
+                float h[8];
+                unpack8<FMT>(hu[g8], h);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const int col = c + g8 * 8 + j;
-                    v[g8 * 8 + j] = (col < nv && rvalid) ? v[g8 * 8 + j] * tc_dact_from_out<ACT>(h[j]) : 0.f;
-                  }
-                  const uint4 u = pack8<FMT>(v + 8 * g8);
-                  *reinterpret_cast<uint4*>(Gt + ((c >> 3) + g8) * kLboA + rowoff) = u;
-                  if (a.want_images)
-                    *reinterpret_cast<uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8) = u;
+                for (int j = 0; j < 8; ++j) {
+                  const int col = c + g8 * 8 + j;
+                  v[g8 * 8 + j] = (col < nv && rvalid) ? v[g8 * 8 + j] * tc_dact_from_out<ACT>(h[j]) : 0.f;
                 }
+                const uint4 u = pack8<FMT>(v + 8 * g8);
+                *reinterpret_cast<uint4*>(Gt + ((c >> 3) + g8) * kLboA + rowoff) = u;
+                if (a.want_images)
+                  *reinterpret_cast<uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8) = u;
               }
             }
           } break;
@@ -305,16 +323,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
             float* stage2 = stage1 + (size_t)kTileRows * st1;
             const bool staged = (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);
             const bool v4 = ((a.k1 & 3) == 0);
-            for (int c = half * 32; c < ph.Np; c += 64) {
-              float v[32];
-              const bool two = c + 16 < ph.Np;
-              if (two) tmem_ld32(tacc + c, v);
-              else tmem_ld16(tacc + c, v);
+            for (int c = part * 16; c < ph.Np; c += kBwdParts * 16) {
+              float v[16];
+              tmem_ld16(tacc + c, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
+              for (int j4 = 0; j4 < 4; ++j4) {
                 const int col = c + j4 * 4;
-                if (j4 >= 4 && !two) break;
                 const float4 o = make_float4(v[j4 * 4] * inv_scale, v[j4 * 4 + 1] * inv_scale,
                                              v[j4 * 4 + 2] * inv_scale, v[j4 * 4 + 3] * inv_scale);
                 const float ov[4] = {o.x, o.y, o.z, o.w};
@@ -344,27 +359,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
               }
             }
             if (staged) {      // uniform per CTA
-              asm volatile("bar.sync 1, 256;" ::: "memory");
-              const long long row0 = tile * kTileRows;
-              const int nrows = (int)((a.N - row0) < kTileRows ? (a.N - row0) : kTileRows);
+              asm volatile("bar.sync 1, %0;" ::"n"(kBwdEpiThreads) : "memory");
+              const long long row0 = trow0;
+              const int nrows = tvalid;
               const int et = tid - 64;
               if (a.dx1) {
                 float* dst = a.dx1 + row0 * a.k1;
                 if (v4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                   const int q4 = a.k1 >> 2, n4 = nrows * q4;
-                  for (int i = et; i < n4; i += 256) {
+                  for (int i = et; i < n4; i += kBwdEpiThreads) {
                     const int r = i / q4, c4 = i - r * q4;
                     reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(stage1 + (size_t)r * st1 + c4 * 4);
                   }
                 } else {
                   const int n = nrows * a.k1;
-                  for (int i = et; i < n; i += 256) { const int r = i / a.k1; dst[i] = stage1[(size_t)r * st1 + (i - r * a.k1)]; }
+                  for (int i = et; i < n; i += kBwdEpiThreads) { const int r = i / a.k1; dst[i] = stage1[(size_t)r * st1 + (i - r * a.k1)]; }
                 }
               }
               if (a.dx2 && a.k2 > 0) {
                 float* dst = a.dx2 + row0 * a.k2;
                 const int n = nrows * a.k2;
-                for (int i = et; i < n; i += 256) { const int r = i / a.k2; dst[i] = stage2[(size_t)r * st2 + (i - r * a.k2)]; }
+                for (int i = et; i < n; i += kBwdEpiThreads) { const int r = i / a.k2; dst[i] = stage2[(size_t)r * st2 + (i - r * a.k2)]; }
               }
             }
           } break;
@@ -372,8 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_kernel(const __grid_const
         }
 #undef BD_WAIT_ACC
         tc_fence_before_sync();
-        fence_proxy_async_smem();
-        mbar_arrive(&sh.epi_done[Ge & 7]);
+        epi_arrive(Ge);
         ++Ge;
         ++Gm;
       }

@@ -224,6 +224,24 @@ def test_imagine_and_returns_fused_vs_oracle(d, prec, tol, cluster, monkeypatch)
         assert e < tol, (k, errs)
 
 
+@pytest.mark.parametrize("save_rows", ["0", "1000000"])
+@pytest.mark.parametrize("cluster", ["1", "4"])
+@pytest.mark.parametrize("prec,tol", [("fp16", 1e-2), ("bf16", 5e-2)])
+@pytest.mark.parametrize("d", [dict(Be=200, Hi=200, S=30, A=1, E=8, N=300, H=15, act="ELU"),
+                               dict(Be=48, Hi=40, S=10, A=3, E=8, N=129, H=7, act="Tanh")])
+def test_actor_backward_from_saved_hidden_images(d, prec, tol, cluster, save_rows, monkeypatch):
+    """The batched actor backward of imagine_ahead reads the hidden activations the rollout saved per (step, row
+    tile) (row counts >= BD_ACTOR_SAVE_MIN_ROWS, default 8192) or recomputes the actor's forward pass: both against
+    the oracle's actor gradients (src/dreamer.py:363), with and without column-split clusters, on row counts that
+    are not a multiple of the 128-row tile."""
+    monkeypatch.setenv("BD_ACTOR_SAVE_MIN_ROWS", save_rows)
+    monkeypatch.setenv("BD_TC_CLUSTER", cluster)
+    res = pu.run_imagine_case(d, seed=5, precision=prec, oracle_dtype=torch.float64)
+    print(prec, cluster, save_rows, {k: f"{v:.2e}" for k, v in res["errors"].items()})
+    for k, e in res["errors"].items():
+        assert e < tol, (k, res["errors"])
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
 def test_value_update_vs_reference_fixture(prec, tol):
     """bd.value_update against the reference's own critic regression block (src/dreamer.py:369-391;
