@@ -866,14 +866,22 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
               float eps[8];
               const int cc0 = part * 8;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) eps[j] = (rvalid && cc0 + j < S) ? a.eps_s[erow * S + cc0 + j] : 0.f;
+              for (int j = 0; j < 8; ++j) eps[j] = (rvalid && cc0 + j < S && !(PROF && (a.dbg & 32))) ? a.eps_s[erow * S + cc0 + j] : 0.f;
               mbar_wait(&acc_full[Gm & 3], (Gm >> 2) & 1);
               tc_fence_after_sync();
               if (PROF) e1 = clock64();
-              // each thread owns 8 consecutive columns of its row: 32-byte pieces of the fp32 outputs go out
-              // as 8-byte stores (a full sector per thread: no staging through shared memory, no barrier)
-              const bool want_out = a.means != nullptr && wr0 && rvalid;
+              // The (mean, std, state) rows of a tile are one contiguous block of each fp32 output tensor.  A thread
+              // owns 8 consecutive columns of its row, so direct stores are 8-byte pieces at a 4 S-byte row stride:
+              // 32 sectors per warp instruction, 12 instructions per chunk -- measured 6.5 K cycles per time step of
+              // store issue on the recurrence's critical path (the next step's actor waits for this epilogue).
+              // Instead the three tiles are staged row-major in the H tile (dead here: its last reader was this
+              // phase's MMA, its next writer is a later epilogue of these same warps) with conflict-free 8-byte
+              // shared stores and copied out by all epilogue threads as contiguous 16-byte stores.
+              const bool out_cta = a.means != nullptr && wr0 && !(PROF && (a.dbg & 16));     // uniform per CTA
               const bool s2 = (S & 1) == 0;      // rows are 8-byte aligned
+              const bool staged = out_cta && s2 && (3 * S * 4 <= a.Kp_h * 2);
+              const bool want_out = out_cta && rvalid && !staged;
+              float* stage = reinterpret_cast<float*>(smem + a.sm.off_tile[TILE_H]);
               for (int cc = cc0; cc < Sp; cc += 8 * kParts2) {
                 if (cc != cc0) {
 #pragma unroll
@@ -897,7 +905,17 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
 #pragma unroll
                   for (int j = 0; j < 8; ++j) if (cc + j < S) store1<FMT>(SAt, row, cc + j, st[j]);
                 }
-                if (want_out) {
+                if (staged) {
+                  float* sm_ = stage + row * S + cc;
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    if (cc + j + 1 < S) {
+                      *reinterpret_cast<float2*>(sm_ + j) = make_float2(m_[j], m_[j + 1]);
+                      *reinterpret_cast<float2*>(sm_ + kTileRows * S + j) = make_float2(s_[j], s_[j + 1]);
+                      *reinterpret_cast<float2*>(sm_ + 2 * kTileRows * S + j) = make_float2(st[j], st[j + 1]);
+                    }
+                  }
+                } else if (want_out) {
                   float* om = a.means + orow * S + cc;
                   float* od = a.stds + orow * S + cc;
                   float* os = a.states + orow * S + cc;
@@ -913,6 +931,28 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
                     }
                   }
                 }
+              }
+              if (staged) {      // uniform per CTA: all epilogue threads take part
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads2) : "memory");
+                const long long row0 = tile * kTileRows;
+                const int nrows = (int)((a.N - row0) < kTileRows ? (a.N - row0) : kTileRows);
+                const int nfl = nrows * S;                                  // floats per output (even)
+                const long long g0 = ((long long)t * a.N + row0) * S;
+                float* outs[3] = {a.means, a.stds, a.states};
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  float* dst = outs[k] + g0;
+                  const float* src = stage + k * kTileRows * S;
+                  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nfl & 3) == 0) {
+                    for (int i = etid * 4; i < nfl; i += kEpiThreads2 * 4)
+                      *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(src + i);
+                  } else {
+                    for (int i = etid * 2; i < nfl; i += kEpiThreads2 * 2)
+                      *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<const float2*>(src + i);
+                  }
+                }
+                // (the H tile's next writer must not overtake the copy-out of a slower warp)
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads2) : "memory");
               }
               if (!WITH_ACTOR && part == 0 && t + 1 < a.T && a.ext_actions) {   // next step's given action -> [s ; a] tile
                 for (int j = 0; j < Ad; ++j)
