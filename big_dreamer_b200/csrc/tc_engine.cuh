@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
                     omn2[j] = fmaf(-n, n, 1.f);                // 1 - n^2
                     r_[j] = r; z_[j] = z;
                   }
-                  if (a.sv_gate && col0 < a.kb_sv) {
+                  if (a.sv_gate && col0 < a.kb_sv && !(PROF && (a.dbg & 64))) {
                     // backward coefficients of this gate column per unit of dL/db' (SURVEY A.1 / tc_bptt.cuh):
                     //   c_n = (1-z)(1-n^2), c_r = c_n hn r (1-r), c_nr = c_n r, c_z = (h-n) z (1-z), and z for the
                     // carry.  The cancellation-prone factors (h - n, 1 - n^2) are formed in fp32 above; the
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
 #pragma unroll
                     for (int k = 0; k < 5; ++k) *reinterpret_cast<uint4*>(img + k * plane) = pl[k];
                   }
-                  if (rvalid) {
+                  if (rvalid && !(PROF && (a.dbg & 128))) {
 #pragma unroll
                     for (int j4 = 0; j4 < 2; ++j4) {
                       const int col = col0 + j4 * 4;
