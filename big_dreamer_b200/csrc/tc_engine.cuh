@@ -254,7 +254,8 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t ring = smem_u32(smem) + sm.off_ring;
   const uint32_t bar_full = smem_u32(&sh.w_full[0]), bar_empty = smem_u32(&sh.w_empty[0]);
-  const uint32_t nstage = sm.nstage;
+  uint32_t nstage = sm.nstage, stage_bytes = sm.stage_bytes;
+  asm volatile("" : "+r"(nstage), "+r"(stage_bytes));     // (kept in registers, see issuer_role)
   uint32_t st = 0, ph = 0;
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
   for (long long tile = tile0; tile < ntiles; tile += tstride)
@@ -275,10 +276,10 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
             if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full + st * 8) : "memory");
             __syncwarp();
           } else if (ws == 1) {
-            tma_bulk_g2s_elect(ring + st * sm.stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
+            tma_bulk_g2s_elect(ring + st * stage_bytes, src + (size_t)k0 * g.Np, bytes, bar_full + st * 8);
           } else {      // (bytes is a multiple of 512: Np and kc are multiples of 16)
             const uint32_t slice = bytes / ws;
-            tma_bulk_g2s_mc_elect(ring + st * sm.stage_bytes + wrank * slice,
+            tma_bulk_g2s_mc_elect(ring + st * stage_bytes + wrank * slice,
                                   reinterpret_cast<const char*>(src + (size_t)k0 * g.Np) + wrank * slice, slice,
                                   bar_full + st * 8, bytes, wmask);
           }
@@ -303,7 +304,9 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
                                             uint32_t ws = 1, bool dbg_no_ring = false) {
   const int lane = threadIdx.x & 31;
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
-  const uint32_t nstage = sm.nstage;
+  uint32_t nstage = sm.nstage, stage_bytes = sm.stage_bytes;
+  // (opaque to the compiler: otherwise both are re-read from the constant bank on every ring stage)
+  asm volatile("" : "+r"(nstage), "+r"(stage_bytes));
   uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
   uint32_t waited = 0xFFFFFFFFu;   // highest epilogue-completion index already waited for (-1: none)
   const uint32_t smem_base = smem_u32(smem);
@@ -362,7 +365,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             if (!(PROF && dbg_no_ring)) mbar_wait_u(bar_w_full + st * 8, wph);
             if (PROF && fine) wsum += clock64() - w0;
             uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
-                              (uint64_t)(((ring_addr + st * sm.stage_bytes) >> 4) & 0x3FFFu);
+                              (uint64_t)(((ring_addr + st * stage_bytes) >> 4) & 0x3FFFu);
             long long m0 = 0;
             if (PROF && fine) m0 = clock64();
             for (int ks = 0; ks < kc; ks += 16) {
@@ -539,7 +542,9 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
   const uint32_t rank = R > 1 ? (uint32_t)blockIdx.x % R : 0u;   // = %cluster_ctarank for (R,1,1) clusters; provably uniform
   __shared__ Program sprog;
   stage_program(sprog, CLUSTER ? a.prog[rank] : a.prog[0]);
-  const uint32_t WS = CLUSTER ? 1u : (uint32_t)a.ws;       // weight-share cluster (independent row tiles)
+  // (weight-share clusters -- multicast weight stages for CTAs with their own row tiles -- measured no gain and are
+  // compiled out: a run-time cluster size costs the issuer a constant load and a branch per ring stage)
+  constexpr uint32_t WS = 1u;
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, R, kEpiThreads2, WS);
   uint64_t* const acc_full = sh.acc_full;
   uint64_t* const epi_done = sh.epi_done;

@@ -29,7 +29,8 @@ static int launch_rollout_t(bool prof, unsigned grid, const RolloutArgs& ra_in, 
   RolloutArgs ra = ra_in;
   const unsigned R = ra.nranks > 1 ? (unsigned)ra.nranks : 1u;
   const long long ntiles = (ra.N + kTileRows - 1) / kTileRows;
-  const unsigned WS = R == 1 ? pick_weight_share(ntiles, grid) : 1u;
+  const unsigned WS = 1u;      // (pick_weight_share: compiled out of the kernels, see rollout_fwd_kernel)
+  (void)ntiles;
   const unsigned CS = R > 1 ? R : WS;             // CTAs per cluster
   ra.ws = (int)WS;
   auto go = [&](auto kernel) -> int {
