@@ -9,6 +9,17 @@ namespace bd {
 namespace tc {
 
 inline int r16(int x) { return (x + 15) / 16 * 16; }
+// K columns of the widest GEMM that one weight-ring stage holds (BD_TC_KC overrides, multiples of 16), and the
+// stage size rounding (descriptors and bulk copies need 16 bytes; 256 keeps the stages on 128-byte lines)
+inline uint32_t stage_kc() {
+  static const uint32_t v = [] {
+    const char* e = getenv("BD_TC_KC");
+    const int k = e ? atoi(e) : 32;
+    return (uint32_t)((k >= 16 && k <= 256) ? k / 16 * 16 : 32);
+  }();
+  return v;
+}
+inline uint32_t align_stage(uint32_t bytes) { return (bytes + 255u) & ~255u; }
 
 struct Builder {
   PackTable pack{};
@@ -46,7 +57,7 @@ struct Builder {
     g.w_off = w_off; g.Np = (uint16_t)Np; g.Kp = (uint16_t)Kp; g.a_k0 = (uint16_t)a_k0;
     g.d_col = (uint16_t)d_col; g.a_tile = (uint8_t)a_tile; g.accumulate = (uint8_t)accumulate;
     g.kc = 32; g.pad = 0; g.dep_back = 1;
-    max_stage = max(max_stage, (uint32_t)Np * 32 * 2);
+    max_stage = max(max_stage, (uint32_t)Np * stage_kc() * 2);
   }
   // K columns per ring stage: as many as fit (narrow GEMMs move their whole K in one or two copies)
   void finalize_blocks(uint32_t stage_bytes) { finalize_blocks_of(prog, stage_bytes); }

@@ -85,7 +85,7 @@ static bool plan_smem(int Kp_b, int Kp_sa, int Kp_h, uint32_t stage, SmemPlan& s
   sm.off_tile[2] = take(kTileRows * Kp_sa * 2);
   sm.off_tile[3] = take(kTileRows * Kp_h * 2);
   sm.off_tile[4] = sm.off_tile[3];
-  sm.stage_bytes = (stage + 1023) & ~1023u;
+  sm.stage_bytes = align_stage(stage);
   sm.off_ring = off;
   const uint32_t budget = 227 * 1024 - 4096;   // static barriers + program tables + alignment slack
   if (off + 2 * sm.stage_bytes > budget) return false;
@@ -766,7 +766,7 @@ static int imagine_bptt_impl(const bd_imagine_bwd_args* a, const HeadsBwd* hb, f
     sm.off_tile[TILE_H] = tk(kTileRows * max(Kb, Kh) * 2);
     sm.off_tile[TILE_SLAB0] = tk(kTileRows * 192 * 2);
     sm.off_tile[TILE_SLAB1] = tk(kTileRows * 192 * 2);
-    sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
+    sm.stage_bytes = align_stage(b.max_stage);
     sm.off_ring = o;
     const uint32_t budget = 227 * 1024 - 4096;
     if (o + 2 * sm.stage_bytes > budget) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core BPTT: tiles do not fit shared memory");

@@ -197,7 +197,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     sm.off_tile[2] = tk(kTileRows * p.Ks * 2);
     sm.off_tile[3] = tk(kTileRows * p.Kp_h * 2);
     sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);
-    sm.stage_bytes = (b.max_stage + 1023) & ~1023u;
+    sm.stage_bytes = align_stage(b.max_stage);
     sm.off_ring = o;
     const uint32_t budget = 227 * 1024 - 4096;
     if (o + 2 * sm.stage_bytes > budget)
@@ -291,7 +291,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     if (want_w) {
       WgradArgs wa{};
       int nj = 0;
-      uint32_t max_x = 0;
+      uint32_t max_x = 0, max_dy = 0;
       for (int l = 0; l < L; ++l) {
         if (!a->dw[l] && !a->db[l]) continue;
         for (int part = 0; part < 2; ++part) {
@@ -301,14 +301,21 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
           j.dwp = dwp[l][part]; j.kp_x = dwp_kp[l][part];
           j.ximg = (l == 0) ? (part == 0 ? ba.x0b : ba.x0s) : ba.xs[l - 1];
           max_x = max(max_x, (uint32_t)j.kp_x);
+          max_dy = max(max_dy, (uint32_t)j.kp_dy);
         }
       }
       if (nj > 0) {
         wa.ntiles = nt;
         wa.amax_bits = amax;
-        wa.stage_bytes = 128 * 256 * 2 + ((128 * max_x * 2 + 1023) & ~1023u);
+        // a stage = [dY image | X image], packed (the widest of each over the jobs); two stages so the copies of
+        // tile i + 1 run under the MMAs of tile i (a stage with a fixed 64 KB dY slot left room for one: the
+        // kernel alternated between loading and contracting and streamed at 4.1 TB/s)
+        wa.x_off = (128 * max_dy * 2 + 1023) & ~1023u;
+        wa.stage_bytes = wa.x_off + ((128 * max_x * 2 + 1023) & ~1023u);
         wa.nstage = (2 * wa.stage_bytes <= 220 * 1024) ? 2 : 1;
-        const size_t smem = (size_t)wa.nstage * wa.stage_bytes;
+        // the second M tile of a 129..256-feature dY reads 64 KB from the stage start (see wgrad_kernel)
+        const size_t smem = max((size_t)wa.nstage * wa.stage_bytes,
+                                (size_t)(wa.nstage - 1) * wa.stage_bytes + 128 * 256 * 2);
         long long per = (sms + nj - 1) / nj;
         if (per > nt) per = nt;
         if (per < 1) per = 1;

@@ -414,6 +414,7 @@ struct WgradArgs {
   WgradJob job[BD_MAX_LAYERS + 1];
   long long ntiles;
   uint32_t stage_bytes, nstage;
+  uint32_t x_off;          // byte offset of the X image inside a stage (= the widest dY image, 1024-aligned)
   const unsigned int* amax_bits;
 };
 
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ W
         uint8_t* dst = smem + st * a.stage_bytes;
         mbar_expect_tx(&full[st], bytes_dy + bytes_x);
         tma_bulk_g2s(dst, j.dyimg + (size_t)tile * 128 * j.kp_dy, bytes_dy, &full[st]);
-        tma_bulk_g2s(dst + 128 * 256 * 2, j.ximg + (size_t)tile * 128 * j.kp_x, bytes_x, &full[st]);
+        tma_bulk_g2s(dst + a.x_off, j.ximg + (size_t)tile * 128 * j.kp_x, bytes_x, &full[st]);
       }
       __syncwarp();
       if (++st == a.nstage) { st = 0; ph ^= 1; }
@@ -468,10 +469,11 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t base = smem_u32(smem + st * a.stage_bytes);
       if (elect_one()) {
         for (int mt = 0; mt < nmt; ++mt) {
-          // dY image has kp_dy columns; the second M tile may run past them into the (finite-or-not)
-          // tail of the stage: those accumulator rows (>= m_valid) are never read back.
+          // dY image has kp_dy columns; the second M tile may run past them into whatever follows in shared
+          // memory (the X image, the next stage: finite or not): those accumulator rows (>= m_valid) are
+          // never read back.  The launcher keeps 128 x 256 x 2 bytes readable behind every stage's start.
           const uint64_t ad0 = make_smem_desc(base + mt * 16 * kLboA, 128, kLboA);
-          const uint64_t bd0 = make_smem_desc(base + 128 * 256 * 2, 128, kLboA);
+          const uint64_t bd0 = make_smem_desc(base + a.x_off, 128, kLboA);
           for (int ks = 0; ks < 8; ++ks)   // K = 128 rows, 16 per MMA = two 8-row groups of 128 B
             umma_f16(tmem_base + mt * 256, ad0 + (uint64_t)(ks * 16), bd0 + (uint64_t)(ks * 16), idesc,
                      (acc | (uint32_t)ks) ? 1u : 0u);
