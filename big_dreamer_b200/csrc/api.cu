@@ -297,8 +297,11 @@ int bd_imagine_backward(const bd_imagine_bwd_args* a, void* ws, size_t ws_bytes,
     m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
     // (hidden activations saved per (t, tile) by the tensor-core forward: no recompute, step-wise tiling)
     m.saved = tc::imagine_saved_actor(f.rssm, f.actor, f.T, f.N, f.tc_saved);
+    // (and its layer-0 input images, copied out of the rollout's operand tiles)
+    const void* x0s = nullptr;
+    const void* x0b = tc::imagine_saved_actor_x0(f.rssm, f.actor, f.T, f.N, f.tc_saved, &x0s);
     BD_TRY(tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N,
-                            m.saved ? f.N : 0));
+                            m.saved ? f.N : 0, x0b, x0s));
     return BD_OK;
   }
   return f32::imagine_backward(a, ws, ws_bytes, stream);
@@ -357,8 +360,10 @@ int bd_imagine_returns_backward(const bd_imagine_returns_bwd_args* a, void* ws, 
   for (int l = 0; l < f.actor.n_layers; ++l) { m.dw[l] = a->actor_dw[l]; m.db[l] = a->actor_db[l]; }
   m.x1 = f.prev_belief; m.x2 = f.prev_state; m.rows = (int64_t)f.T * f.N; m.dy = d_raw;
   m.saved = tc::imagine_saved_actor(f.rssm, f.actor, f.T, f.N, f.tc_saved);
+  const void* x0s = nullptr;
+  const void* x0b = tc::imagine_saved_actor_x0(f.rssm, f.actor, f.T, f.N, f.tc_saved, &x0s);
   return tc::mlp_backward(&f.actor, &m, rest, rest_bytes, precision, stream, f.beliefs, f.states, f.N,
-                          m.saved ? f.N : 0);
+                          m.saved ? f.N : 0, x0b, x0s);
 }
 
 size_t bd_cem_workspace_bytes(const bd_rssm* r, const bd_mlp* reward, int B, int C_local, int H) {

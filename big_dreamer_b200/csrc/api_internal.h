@@ -61,6 +61,8 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
                     bd_stream_t stream);
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
 const void* imagine_saved_actor(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved);
+const void* imagine_saved_actor_x0(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved,
+                                   const void** x0s);
 // fused imagine + reward/value heads + lambda_return (SURVEY 8b level L2)
 bool heads_supported(const bd_rssm& r, const bd_mlp& reward, const bd_mlp& value);
 size_t heads_pack_bytes(const bd_mlp& reward, const bd_mlp& value);
@@ -92,7 +94,7 @@ bool mlp_backward_supported(const bd_mlp& m, int k1, int k2, int precision);
 size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t rows);
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
                  bd_stream_t stream, const float* x1b = nullptr, const float* x2b = nullptr, int64_t split = -1,
-                 int64_t seg_rows = 0);
+                 int64_t seg_rows = 0, const void* x0b_img = nullptr, const void* x0s_img = nullptr);
 }  // namespace tc
 
 }  // namespace bd

@@ -126,6 +126,16 @@ __device__ __forceinline__ void prof_add(long long* p, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
 }
 
+// The actor's layer-0 input of a rollout step IS the belief tile [b_t | 1] and the first columns of the [s_t ; a]
+// tile as they sit in shared memory when the step starts -- exactly the wgrad operand images (x0b / x0s) the batched
+// actor backward would otherwise rebuild from the fp32 outputs (a serial, latency-bound tile prologue: ~17 K cycles
+// of its 57 K per tile).  The issuer warp copies them out per (step, tile) with two bulk shared -> global copies.
+struct X0Save {
+  uint16_t* x0b;             // [(t * ntiles + tile)][128 x kp_b]; null = off
+  uint16_t* x0s;             // [(t * ntiles + tile)][128 x kp_s]
+  uint32_t bytes_b, bytes_s; // bytes per tile image
+};
+
 struct RolloutArgs {
   Program prog[kMaxRanks];   // one program per cluster rank (column-split mode); [0] when nranks == 1
   int nranks;
@@ -163,6 +173,7 @@ struct RolloutArgs {
   // noise is indexed by the GLOBAL candidate (src/planner.py:37-39, 53-65)
   int cem_cl, cem_c, cem_c0;  // local candidates per batch row (0 = off), global candidates, first
   PrefetchPlan pf;            // next tile's / step's epilogue inputs (producer-warp L2 prefetch)
+  X0Save x0;                  // the actor's layer-0 input images for the batched actor backward (see X0Save)
 };
 
 // fast-math activations for the 16-bit path (the result is rounded to 10 / 7 mantissa bits anyway)
@@ -301,8 +312,11 @@ template <int FMT, bool PROF>
 __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm, long long ntiles,
                                             int T, uint8_t* smem, EngineShared& sh,
                                             uint32_t tmem_base, long long* prof, uint32_t R = 1,
-                                            uint32_t ws = 1, bool dbg_no_ring = false) {
+                                            uint32_t ws = 1, bool dbg_no_ring = false,
+                                            const X0Save* x0 = nullptr) {
   const int lane = threadIdx.x & 31;
+  const bool x0_on = x0 != nullptr && x0->x0b != nullptr && (R == 1 || blockIdx.x % R == 0);
+  const long long x0_tiles = (long long)ntiles;
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   uint32_t nstage = sm.nstage, stage_bytes = sm.stage_bytes;
   // (opaque to the compiler: otherwise both are re-read from the constant bank on every ring stage)
@@ -383,6 +397,24 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             if (++st == nstage) { st = 0; wph ^= 1; }
           }
         }
+        if (x0_on && pi <= 1) {
+          // phase 0's dependency wait saw the tiles of this step complete (and published to the async proxy by the
+          // epilogues' fence); the copies read shared memory while the first phases' MMAs run, and their reads are
+          // waited for one phase later -- long before anything rewrites either tile
+          if (lane == 0) {
+            if (pi == 0) {
+              const size_t img = (size_t)t * x0_tiles + (size_t)tile;
+              tma_bulk_s2g(reinterpret_cast<char*>(x0->x0b) + img * x0->bytes_b,
+                           smem_base + sm.off_tile[TILE_BCUR ^ par], x0->bytes_b);
+              tma_bulk_s2g(reinterpret_cast<char*>(x0->x0s) + img * x0->bytes_s,
+                           smem_base + sm.off_tile[TILE_SA], x0->bytes_s);
+              bulk_commit();
+            } else {
+              bulk_wait_read();
+            }
+          }
+          __syncwarp();
+        }
         if (R > 1) umma_commit_mc_elect(bar_acc_full + (Gm & 3) * 8, (uint16_t)((1u << R) - 1));
         else umma_commit_elect(bar_acc_full + (Gm & 3) * 8);
         if (PROF && blockIdx.x == 0 && lane == 0) {
@@ -397,6 +429,7 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
       }
     }
   }
+  if (x0_on && lane == 0) bulk_wait_all();     // the images are in global memory before the CTA retires
   __syncwarp();
 }
 
@@ -415,7 +448,7 @@ __device__ __forceinline__ float tc_act_t(float x) {
 }
 template <int ACT>
 __device__ __forceinline__ float tc_dact_from_out(float y) {
-  if (ACT == BD_ACT_ELU) return y > 0.f ? 1.f : y + 1.f;
+  if (ACT == BD_ACT_ELU) return fminf(y, 0.f) + 1.f;      // y > 0 ? 1 : y + 1
   if (ACT == BD_ACT_RELU) return y > 0.f ? 1.f : 0.f;
   if (ACT == BD_ACT_TANH) return 1.f - y * y;
   return 1.f;
@@ -562,7 +595,8 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
     if (!(PROF && (a.dbg & 4)))
     producer_role(P, a.sm, a.wpack, ntiles, a.T, smem, sh, &a.pf, R, WS, PROF && (a.dbg & 2));
   } else if (warp == 1) {
-    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R, WS, (a.dbg & 4) != 0);
+    issuer_role<FMT, PROF>(P, a.sm, ntiles, a.T, smem, sh, tmem_base, a.prof, R, WS, (a.dbg & 4) != 0,
+                           WITH_ACTOR ? &a.x0 : nullptr);
   } else {
     // =========================================================== epilogue warps
     // 16 warps: TMEM quadrant q = warp % 4 (a warp reaches lanes [32 q, 32 q + 32) only), column part

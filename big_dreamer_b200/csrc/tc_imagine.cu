@@ -13,7 +13,9 @@ namespace tc {
 // (+ the actor's hidden activations, up to kSavedActorLayers images of (T x tiles) x 128 x Kact: the batched actor
 // backward reads them instead of recomputing the actor's forward pass)
 constexpr int kSavedActorLayers = 4;
-struct SavedLayout { size_t off_gate, off_xa, off_ha, off_act, act_bytes, total; int Kb, Kh, Kact; };
+// (+ the actor's layer-0 input images x0b = [b_t | 1], x0s = s_t per (t, tile), copied out of the rollout's operand
+// tiles: see X0Save)
+struct SavedLayout { size_t off_gate, off_xa, off_ha, off_act, act_bytes, off_x0b, off_x0s, total; int Kb, Kh, Kact, Kx0b, Kx0s; };
 static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
   SavedLayout s;
   s.Kb = r16(r.belief_size); s.Kh = r16(r.hidden_size);
@@ -24,7 +26,10 @@ static SavedLayout saved_layout(const bd_rssm& r, int T, long long N) {
   s.off_act = s.off_ha + tiles * kTileRows * s.Kh * 2;
   s.Kact = r16(r.hidden_size + 1);
   s.act_bytes = tiles * kTileRows * s.Kact * 2;          // one hidden layer
-  s.total = s.off_act + kSavedActorLayers * s.act_bytes;
+  s.Kx0b = r16(r.belief_size + 1); s.Kx0s = r16(r.state_size);
+  s.off_x0b = s.off_act + kSavedActorLayers * s.act_bytes;
+  s.off_x0s = s.off_x0b + tiles * kTileRows * s.Kx0b * 2;
+  s.total = s.off_x0s + tiles * kTileRows * s.Kx0s * 2;
   return s;
 }
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N) { return saved_layout(r, T, N).total + 256; }
@@ -37,6 +42,15 @@ const void* imagine_saved_actor(const bd_rssm& r, const bd_mlp& actor, int T, lo
   const long long min_rows = e ? atoll(e) : 8192;
   if (!tc_saved || actor.n_layers - 1 > kSavedActorLayers || N < min_rows || getenv("BD_NO_ACTOR_SAVE")) return nullptr;
   return static_cast<const char*>(tc_saved) + saved_layout(r, T, N).off_act;
+}
+// the actor's layer-0 input images next to them (x0b images of all (t, tile), then the x0s images), or null
+const void* imagine_saved_actor_x0(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved,
+                                   const void** x0s) {
+  if (!imagine_saved_actor(r, actor, T, N, tc_saved) || getenv("BD_NO_X0_SAVE")) return nullptr;
+  // (the rollout's [s ; a] tile must hold the state image's columns: r16(S) <= r16(S + A + 1) always)
+  const SavedLayout sl = saved_layout(r, T, N);
+  if (x0s) *x0s = static_cast<const char*>(tc_saved) + sl.off_x0s;
+  return static_cast<const char*>(tc_saved) + sl.off_x0b;
 }
 
 // Do the operand tiles of the rollout engine (two belief tiles, [s;a], one hidden tile) plus at
@@ -404,6 +418,12 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
       ra.kact_sv = sl.Kact;
       for (int l = 0; l + 1 < ac.n_layers; ++l)
         ra.sv_mlp[l] = reinterpret_cast<uint16_t*>(sb + sl.off_act + (size_t)l * sl.act_bytes);
+      if (imagine_saved_actor_x0(r, ac, a->T, a->N, a->tc_saved, nullptr)) {
+        ra.x0.x0b = reinterpret_cast<uint16_t*>(sb + sl.off_x0b);
+        ra.x0.x0s = reinterpret_cast<uint16_t*>(sb + sl.off_x0s);
+        ra.x0.bytes_b = (uint32_t)kTileRows * sl.Kx0b * 2;
+        ra.x0.bytes_s = (uint32_t)kTileRows * sl.Kx0s * 2;
+      }
     }
   }
 

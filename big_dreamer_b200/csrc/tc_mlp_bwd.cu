@@ -76,7 +76,8 @@ static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStre
 }
 
 int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes, int precision,
-                 bd_stream_t stream, const float* x1b, const float* x2b, int64_t split, int64_t seg_rows) {
+                 bd_stream_t stream, const float* x1b, const float* x2b, int64_t split, int64_t seg_rows,
+                 const void* x0b_img, const void* x0s_img) {
   const int k1 = a->k1, k2 = a->k2, L = m->n_layers;
   if (!mlp_backward_supported(*m, k1, k2, precision))
     BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: sizes/activation not supported");
@@ -88,6 +89,10 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   make_plan(*m, k1, k2, want_w, p);
   if (have_saved)
     for (int l = 0; l + 1 < L; ++l) p.per_tile_bytes -= 128 * p.kp_xs[l] * 2;
+  // layer-0 input images made by the caller (the rollout copies them out of its operand tiles): with the saved hidden
+  // images the kernel then needs no inputs at all -- its tile prologue (fp32 rows -> images) disappears
+  const bool have_x0 = have_saved && want_w && x0b_img != nullptr && (k2 == 0 || x0s_img != nullptr);
+  if (have_x0) p.per_tile_bytes -= 128 * (p.Kp_b + p.Ks) * 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
 
@@ -113,7 +118,29 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
       b.end_phase(EPI_B_ACT_SAVE, 1, n, Np, p.kp_xs[l], d, l, TILE_H);
     }
   }
-  b.end_phase(EPI_B_LOAD_DY, 1, m->layer[L - 1].out_features, 0, 0, 0, L - 1, TILE_H2);
+  // Paired tiles (see MlpBwdArgs::pair): with saved hidden images the chain needs one operand tile per row tile, so two
+  // row tiles fit a CTA and their chains are interleaved phase by phase, each phase depending on the epilogue TWO
+  // phases back (its own tile's previous layer).
+  const bool seg_ = seg_rows > 0 && a->rows % seg_rows == 0;
+  const long long total_tiles_ = seg_ ? (a->rows / seg_rows) * ((seg_rows + 127) / 128) : (a->rows + 127) / 128;
+  int sms_ = 148;
+  {
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev_);
+  }
+  // (measured at 2^17 start states: 1.78 ms paired vs 1.75 ms single -- the 12 epilogue warps, not the MMAs, bound this
+  // kernel, and the two tiles' epilogues still run one after the other; kept as an opt-in, BD_BWD_PAIR=1)
+  bool pair = false;
+  if (const char* e = getenv("BD_BWD_PAIR")) pair = have_saved && atoi(e) != 0;
+  (void)total_tiles_; (void)sms_;
+  const int nsub = pair ? 2 : 1;
+  const int sub_tile[2] = {TILE_H2, TILE_H};
+  const int dep = pair ? 2 : 1;
+  for (int sb = 0; sb < nsub; ++sb) {
+    b.end_phase(EPI_B_LOAD_DY, 1, m->layer[L - 1].out_features, 0, 0, 0, L - 1, sub_tile[sb]);
+    b.prog.p[b.prog.n_phases - 1].pad = (uint8_t)sb;
+  }
   for (int l = L - 1; l >= 0; --l) {
     const bd_linear& Lr = m->layer[l];
     const int kin = Lr.in_features, n = Lr.out_features;
@@ -127,10 +154,13 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     j.Kp = Kp; j.bias_k = -1; j.nseg = 1; j.seg[0] = {0, 0, n}; j.transpose = 1;
     const uint32_t woff = (uint32_t)b.w_elems;
     b.w_elems += (long long)Np * Kp;
-    const int d = b.dcol();
-    b.add_gemm(woff, Np, Kp, TILE_H2, 0, d, 0);
-    if (l > 0) b.end_phase(EPI_B_DACT, 1, kin, Np, p.kp_ds[l - 1], d, l - 1, TILE_H2);
-    else b.end_phase(EPI_B_DX, 1, kin, Np, 0, d, 0, TILE_H2);
+    for (int sb = 0; sb < nsub; ++sb) {
+      const int d = b.dcol();
+      b.add_gemm(woff, Np, Kp, sub_tile[sb], 0, d, 0);
+      if (l > 0) b.end_phase(EPI_B_DACT, dep, kin, Np, p.kp_ds[l - 1], d, l - 1, sub_tile[sb]);
+      else b.end_phase(EPI_B_DX, dep, kin, Np, 0, d, 0, sub_tile[sb]);
+      b.prog.p[b.prog.n_phases - 1].pad = (uint8_t)sb;
+    }
   }
   if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core mlp_backward: program too large");
 
@@ -192,11 +222,17 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     SmemPlan& sm = ba.sm;
     uint32_t o = 0;
     auto tk = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 1023) & ~1023u; return r; };
+    if (pair) {        // one G tile per sub-tile (TILE_H2, TILE_H); no forward recompute, hence no input / hidden tiles
+      sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);
+      sm.off_tile[3] = tk(kTileRows * p.Kp_g * 2);
+      sm.off_tile[0] = sm.off_tile[1] = sm.off_tile[2] = sm.off_tile[4];
+    } else {
     sm.off_tile[0] = tk(kTileRows * p.Kp_b * 2);
     sm.off_tile[1] = sm.off_tile[0];
     sm.off_tile[2] = tk(kTileRows * p.Ks * 2);
     sm.off_tile[3] = tk(kTileRows * p.Kp_h * 2);
     sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);
+    }
     sm.stage_bytes = align_stage(b.max_stage);
     sm.off_ring = o;
     const uint32_t budget = 227 * 1024 - 4096;
@@ -210,7 +246,7 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   ba.wpack = wpack; ba.T = 1; ba.prof = nullptr; ba.amax_bits = amax;
   ba.k1 = k1; ba.k2 = k2; ba.out = m->layer[L - 1].out_features; ba.n_layers = L; ba.act = m->activation;
   ba.Kp_b = p.Kp_b; ba.Ks = p.Ks; ba.Kp_h = p.Kp_h; ba.Kp_g = p.Kp_g; ba.want_images = want_w ? 1 : 0;
-  ba.need_x = (want_w || !have_saved) ? 1 : 0;
+  ba.need_x = ((want_w && !have_x0) || !have_saved) ? 1 : 0;
   for (int l = 0; l < L; ++l) { ba.kp_xs[l] = p.kp_xs[l]; ba.kp_ds[l] = p.kp_ds[l]; }
 
   int dev = 0, sms = 148;
@@ -238,9 +274,19 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     }
     for (int l = 0; l < L; ++l) ba.ds[l] = want_w ? st((size_t)nt * 128 * p.kp_ds[l] * 2) : nullptr;
     if (!want_w) ba.ds[L - 1] = nullptr;
+    if (have_x0) {
+      ba.x0b = reinterpret_cast<uint16_t*>(const_cast<char*>(static_cast<const char*>(x0b_img)) + (size_t)t0 * 128 * p.Kp_b * 2);
+      ba.x0s = k2 > 0 ? reinterpret_cast<uint16_t*>(const_cast<char*>(static_cast<const char*>(x0s_img)) + (size_t)t0 * 128 * p.Ks * 2)
+                      : nullptr;
+    } else {
     ba.x0b = want_w ? st((size_t)nt * 128 * p.Kp_b * 2) : nullptr;
     ba.x0s = want_w ? st((size_t)nt * 128 * p.Ks * 2) : nullptr;
+    }
     ba.N = nrows; ba.ntiles = nt;
+    ba.pair = pair ? 1 : 0; ba.nloop = pair ? (nt + 1) / 2 : nt;
+#ifdef BD_BWD_DBG
+    ba.dbg = getenv("BD_BWD_DBGV") ? atoi(getenv("BD_BWD_DBGV")) : 0;
+#endif
     ba.seg_tiles = (int)seg_tiles; ba.seg_rows = seg ? seg_rows : 0; ba.tile_base = seg ? t0 : 0;
     if (seg) {      // row pointers stay those of row 0: the kernel maps (tile_base + tile) to its rows
       ba.N = a->rows;
@@ -264,13 +310,14 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
     }
-    const unsigned grid = (unsigned)(nt < sms ? nt : sms);
+    const unsigned grid = (unsigned)(ba.nloop < sms ? ba.nloop : sms);
     {
       // the producer warp pulls the NEXT tile's inputs (rows of x1 / x2 / dy, saved hidden images) into L2
       PrefetchPlan& pf = ba.pf;
       pf.n = 0; pf.reverse = 0;
-      auto add = [&](const void* ptr, size_t tile_bytes) {
+      auto add = [&](const void* ptr, size_t tile_bytes) {      // (paired tiles: a loop item = two consecutive tiles)
         if (!ptr || pf.n >= 6) return;
+        tile_bytes *= (size_t)nsub;
         pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
         pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
       };

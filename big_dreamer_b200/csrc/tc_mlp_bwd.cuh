@@ -40,6 +40,13 @@ struct MlpBwdArgs {
   // with N' = seg_rows rows per step; all row pointers are then those of row 0.  seg_tiles = 0: plain tiling of N rows.
   long long seg_rows, tile_base, ntiles;
   int seg_tiles;
+  // Paired tiles (saved hidden images, more tiles than SMs): a CTA keeps TWO row tiles in flight -- the program
+  // interleaves their dgrad chains (phase.pad = sub-tile, each phase depending on the epilogue two phases back), so
+  // the MMAs of one tile run under the epilogue of the other.  Each sub-tile owns one G tile (rewritten in place:
+  // the MMAs that read it are complete when its epilogue runs) and one 256-column TMEM half.  nloop = tile pairs.
+  int pair;
+  long long nloop;
+  int dbg;                        // BD_BWD_DBG builds only (BD_BWD_DBGV): 1 no hidden-image loads, 2 no image stores, 4 no epilogue math
   float *dx1, *dx2;
   uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
   uint16_t* ds[BD_MAX_LAYERS];  // ds[l]: images of dY_l (cols kp_ds[l]), l = 0..L-1
@@ -134,12 +141,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
   stage_program(sprog, a.prog);
   const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, kBwdEpiThreads);
   const long long ntiles = a.ntiles;
+  const long long nloop = a.pair ? a.nloop : a.ntiles;     // loop items per CTA walk: tiles, or tile pairs
   const Program& P = sprog;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, ntiles, 1, smem, sh, &a.pf);
+    producer_role(P, a.sm, a.wpack, nloop, 1, smem, sh, &a.pf);
   } else if (warp == 1) {
-    issuer_role<FMT, false>(P, a.sm, ntiles, 1, smem, sh, tmem_base, nullptr);
+    issuer_role<FMT, false>(P, a.sm, nloop, 1, smem, sh, tmem_base, nullptr);
   } else {
     const int q = warp & 3, part = (warp - 2) >> 2;
     auto epi_arrive = [&](uint32_t ge) {     // one arrival per warp
@@ -154,25 +162,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
     uint8_t* B0 = smem + a.sm.off_tile[0];
     uint8_t* SA = smem + a.sm.off_tile[2];
     uint8_t* H = smem + a.sm.off_tile[3];
-    uint8_t* Gt = smem + a.sm.off_tile[4];
     uint32_t Ge = 0, Gm = 0;
     float inv_scale;
     const float scale = grad_scale(a.amax_bits, &inv_scale);
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      long long trow0 = tile * kTileRows;
-      int tvalid;
-      if (a.seg_tiles > 0) {
-        const long long g = a.tile_base + tile, tt = g / a.seg_tiles;
-        const long long j0 = (g - tt * a.seg_tiles) * kTileRows;
-        trow0 = tt * a.seg_rows + j0;
-        tvalid = (int)(a.seg_rows - j0 < kTileRows ? a.seg_rows - j0 : kTileRows);
-      } else {
-        tvalid = (int)(a.N - trow0 < kTileRows ? a.N - trow0 : kTileRows);
+    const int nsub = a.pair ? 2 : 1;
+    for (long long it = blockIdx.x; it < nloop; it += gridDim.x) {
+      // the one or two row tiles of this walk: index, first row, valid rows (0 for the missing half of an odd pair,
+      // which runs through the phases on zeros and touches no global memory)
+      long long tl[2] = {0, 0}, tr0[2] = {0, 0};
+      int tv[2] = {0, 0};
+      bool tok[2] = {false, false};
+#pragma unroll
+      for (int sb = 0; sb < 2; ++sb) {
+        const long long tile_s = a.pair ? it * 2 + sb : it;
+        if (sb >= nsub || tile_s >= ntiles) continue;
+        tok[sb] = true; tl[sb] = tile_s;
+        if (a.seg_tiles > 0) {
+          const long long g = a.tile_base + tile_s, tt = g / a.seg_tiles;
+          const long long j0 = (g - tt * a.seg_tiles) * kTileRows;
+          tr0[sb] = tt * a.seg_rows + j0;
+          tv[sb] = (int)(a.seg_rows - j0 < kTileRows ? a.seg_rows - j0 : kTileRows);
+        } else {
+          tr0[sb] = tile_s * kTileRows;
+          tv[sb] = (int)(a.N - tr0[sb] < kTileRows ? a.N - tr0[sb] : kTileRows);
+        }
       }
-      const long long grow = trow0 + row;
-      const bool rvalid = row < tvalid;
-      // ---------------- init: B0 <- [x1 | 1], SA <- x2 (and their images for wgrad)
+      // ---------------- init: B0 <- [x1 | 1], SA <- x2 (and their images for wgrad); paired tiles (no forward
+      // recompute) only leave the images
       if (a.need_x) {
+#pragma unroll
+       for (int sb = 0; sb < 2; ++sb) {
+        if (!tok[sb]) continue;
+        const long long tile = tl[sb], trow0 = tr0[sb];
+        const int tvalid = tv[sb];
         const int gb = a.Kp_b >> 3;
         for (int i = etid; i < kTileRows * gb; i += kBwdEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
@@ -186,7 +208,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             v[j] = (k < a.k1) ? (rv ? x1r[k] : 0.f) : ((k == a.k1 && rv) ? 1.f : 0.f);
           }
           const uint4 u = pack8<FMT>(v);
-          *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
+          if (!a.pair) *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
           if (a.want_images)
             *reinterpret_cast<uint4*>(a.x0b + (size_t)tile * kTileRows * a.Kp_b + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
@@ -203,16 +225,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             v[j] = (k < a.k2 && rv) ? x2r[k] : 0.f;
           }
           const uint4 u = pack8<FMT>(v);
-          *reinterpret_cast<uint4*>(SA + kg * kLboA + r * 16) = u;
+          if (!a.pair) *reinterpret_cast<uint4*>(SA + kg * kLboA + r * 16) = u;
           if (a.want_images)
             *reinterpret_cast<uint4*>(a.x0s + (size_t)tile * kTileRows * a.Ks + (size_t)kg * kTileRows * 8 + r * 8) = u;
         }
+       }
       }
       epi_arrive(Ge);
       ++Ge;
       for (int pi = 0; pi < P.n_phases; ++pi) {
         const Phase ph = P.p[pi];
         const uint32_t tacc = trow + ph.d_col;
+        const int sb = a.pair ? (int)ph.pad : 0;              // sub-tile of this phase
+        const long long tile = sb ? tl[1] : tl[0], trow0 = sb ? tr0[1] : tr0[0];
+        const int tvalid = sb ? tv[1] : tv[0];
+        const bool tile_ok = sb ? tok[1] : tok[0];
+        const long long grow = trow0 + row;
+        const bool rvalid = row < tvalid;
+        uint8_t* Gt = smem + a.sm.off_tile[ph.out_tile];
 #define BD_WAIT_ACC()                                        \
   do {                                                       \
     mbar_wait(&sh.acc_full[Gm & 3], (Gm >> 2) & 1);          \
@@ -265,7 +295,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
                 v[j] = (rvalid && c + j < a.out) ? a.dy[grow * a.out + c + j] * scale : 0.f;
               const uint4 u = pack8<FMT>(v);
               *reinterpret_cast<uint4*>(Gt + (c >> 3) * kLboA + rowoff) = u;
-              if (a.want_images) *reinterpret_cast<uint4*>(img + (size_t)(c >> 3) * kTileRows * 8 + row * 8) = u;
+              if (a.want_images && tile_ok) *reinterpret_cast<uint4*>(img + (size_t)(c >> 3) * kTileRows * 8 + row * 8) = u;
             }
           } break;
           case EPI_B_DACT: {
@@ -277,8 +307,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             // (rotating registers), the first ones requested before the accumulator wait
             const uint16_t* hrow = himg + row * 8;
             const int cstep = kBwdParts * 16;
-            auto ld0 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(hrow + (size_t)(c >> 3) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
-            auto ld1 = [&](int c) { return c < kp ? *reinterpret_cast<const uint4*>(hrow + (size_t)((c >> 3) + 1) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+#ifdef BD_BWD_DBG
+            const bool dbg_nold = a.dbg & 1, dbg_nost = a.dbg & 2;
+#else
+            constexpr bool dbg_nold = false, dbg_nost = false;
+#endif
+            auto ld0 = [&](int c) { return (c < kp && !dbg_nold) ? *reinterpret_cast<const uint4*>(hrow + (size_t)(c >> 3) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
+            auto ld1 = [&](int c) { return (c < kp && !dbg_nold) ? *reinterpret_cast<const uint4*>(hrow + (size_t)((c >> 3) + 1) * kTileRows * 8) : make_uint4(0, 0, 0, 0); };
             const int cfirst = part * 16;
             uint4 a0 = ld0(cfirst), a1 = ld1(cfirst);
             uint4 b0 = ld0(cfirst + cstep), b1 = ld1(cfirst + cstep);
@@ -295,18 +330,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
               a0 = b0; a1 = b1; b0 = d0; b1 = d1;
               d0 = ld0(c + 3 * cstep); d1 = ld1(c + 3 * cstep);
               tmem_ld_wait();
+              // (padded rows: the packed result is masked to exact zeros -- they add nothing to dW / db; padded
+              // columns, only in the chunk that crosses n_valid: zeroed before the product)
+              const uint32_t rmask = rvalid ? 0xFFFFFFFFu : 0u;
+              if (c + 16 > nv) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c + j >= nv) v[j] = 0.f;
+              }
 #pragma unroll
               for (int g8 = 0; g8 < 2; ++g8) {
                 float h[8];
                 unpack8<FMT>(hu[g8], h);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int col = c + g8 * 8 + j;
-                  v[g8 * 8 + j] = (col < nv && rvalid) ? v[g8 * 8 + j] * tc_dact_from_out<ACT>(h[j]) : 0.f;
-                }
-                const uint4 u = pack8<FMT>(v + 8 * g8);
+                for (int j = 0; j < 8; ++j) v[g8 * 8 + j] *= tc_dact_from_out<ACT>(h[j]);
+                uint4 u = pack8<FMT>(v + 8 * g8);
+                u.x &= rmask; u.y &= rmask; u.z &= rmask; u.w &= rmask;
                 *reinterpret_cast<uint4*>(Gt + ((c >> 3) + g8) * kLboA + rowoff) = u;
-                if (a.want_images)
+                if (a.want_images && tile_ok && !dbg_nost)
                   *reinterpret_cast<uint4*>(img + (size_t)((c >> 3) + g8) * kTileRows * 8 + row * 8) = u;
               }
             }
@@ -321,7 +362,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             const int st2 = a.k2 | 1;
             float* stage1 = reinterpret_cast<float*>(smem + a.sm.off_tile[0]);
             float* stage2 = stage1 + (size_t)kTileRows * st1;
-            const bool staged = (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);
+            const bool staged = !a.pair && (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);   // (paired tiles: the other tile is live)
             const bool v4 = ((a.k1 & 3) == 0);
             for (int c = part * 16; c < ph.Np; c += kBwdParts * 16) {
               float v[16];
