@@ -1148,10 +1148,11 @@ static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const
   for (int a = 0; a < A; ++a) {
     const float mean = cfg.mean_scale * tanhf(raw[r * 2 * A + a] / cfg.mean_scale);
     const float sd = softplusf_(raw[r * 2 * A + A + a] + cfg.raw_init_std) + cfg.min_std;
-    const float var2 = 2.f * sd * sd, log_sd = logf(sd), inv_var = 1.f / (sd * sd), inv_sd = 1.f / sd;
+    const float log_sd = logf(sd), inv_var = 1.f / (sd * sd), inv_sd = 1.f / sd;
+    const float neg_half_inv_var = -0.5f * inv_var, lp_const = -log_sd - kLogSqrt2Pi;
     const float* ee = eps_e + ((long long)t * J * N + n) * A + a;
     float lp_sum = 0.f, dm_sum = 0.f, ds_sum = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = q; j < J; j += SPLIT) {
       const float e = ee[(long long)j * N * A];
       const float y = tanhf(mean + e * sd);
@@ -1162,7 +1163,7 @@ static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const
       const float la = __logf(1.f + yc), lb = __logf(1.f - yc);
       const float xh = 0.5f * (la - lb);
       const float d = xh - mean;
-      lp_sum += -(d * d) / var2 - log_sd - kLogSqrt2Pi - (la + lb);
+      lp_sum += fmaf(d * d, neg_half_inv_var, lp_const) - (la + lb);     // log N(x; mean, sd) - log|d tanh / dx|
       const float dlp = -d * inv_var + 2.f * yc;
       dm_sum += d * inv_var + gate * dlp;
       ds_sum += d * d * inv_var * inv_sd - inv_sd + gate * e * dlp;

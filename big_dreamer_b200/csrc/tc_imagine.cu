@@ -36,10 +36,11 @@ size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N) { return saved_
 // the actor's saved hidden images inside tc_saved (layout of mlp_backward's `saved`: layer after layer), or null
 // when the actor has more hidden layers than the buffer holds / the debug switch BD_NO_ACTOR_SAVE is set
 const void* imagine_saved_actor(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved) {
-  // (small row counts run latency-bound in column-split clusters: there the extra stores cost the rollout what
-  // the backward saves -- measured at 2 500 rows: rollout +0.03 ms, actor backward -0.02 ms)
+  // (small row counts run latency-bound in column-split clusters, where the extra stores cost the rollout part of
+  // what the backward saves -- measured at 2 500 rows with the layer-0 images also coming from the rollout:
+  // rollout +0.03 ms, actor backward -0.05 ms)
   const char* e = getenv("BD_ACTOR_SAVE_MIN_ROWS");      // (read per call: the tests switch it)
-  const long long min_rows = e ? atoll(e) : 8192;
+  const long long min_rows = e ? atoll(e) : 2048;
   if (!tc_saved || actor.n_layers - 1 > kSavedActorLayers || N < min_rows || getenv("BD_NO_ACTOR_SAVE")) return nullptr;
   return static_cast<const char*>(tc_saved) + saved_layout(r, T, N).off_act;
 }
