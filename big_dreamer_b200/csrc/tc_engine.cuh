@@ -1130,6 +1130,46 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
 // per row left c2 (35 000 row-steps) with 35 000 threads walking 100 dependent-latency MUFU chains: 58 us,
 // 35 us with SPLIT = 8.  At large row counts the machine is full anyway and the strided noise reads of a
 // split cost more than they give (2^17 rows: 0.66 ms unsplit, 1.15 ms with 8), so the host picks SPLIT.
+// Per-(row, action) constants of the sample loop and one Monte-Carlo sample.
+struct EntRow { float mean, sd, inv_var, inv_sd, nhiv, lp_const; };
+__device__ __forceinline__ EntRow ent_row(const bd_actor_cfg& cfg, float raw_mean, float raw_std) {
+  EntRow p;
+  p.mean = cfg.mean_scale * tanhf(raw_mean / cfg.mean_scale);
+  p.sd = softplusf_(raw_std + cfg.raw_init_std) + cfg.min_std;
+  p.inv_var = 1.f / (p.sd * p.sd); p.inv_sd = 1.f / p.sd;
+  p.nhiv = -0.5f * p.inv_var; p.lp_const = -logf(p.sd) - 0.9189385332046727f;    // - log sd - log sqrt(2 pi)
+  return p;
+}
+// Branch-free, three MUFU operations per sample (tanhf's two code paths diverged per lane and, with the two
+// logarithms of 1 +- y, cost ~110 instructions per sample): with u = e^{-2x},
+//   y = tanh x = 2 / (1 + u) - 1,   atanh(y) = x,   log|d tanh / dx| = 2 (ln 2 - x - ln(1 + u))
+// (src/models.py:668-673 evaluates exactly this expression at x' = atanh(y)); no cancellation in 1 - y.
+// Clamped samples (|tanh x| > kClamp, |x| > ~8.7): the reference inverts the CLAMPED y (src/models.py:656-666), so
+// x' = +-atanh(kClamp) (kXc) and the log-det is the constant at that point (kLadjC).
+__device__ __forceinline__ void ent_sample(const EntRow& p, float e, float kXc, float kLadjC, float& lp_sum,
+                                           float& dm_sum, float& ds_sum) {
+  const float kClamp = 0.99999997f, kLog2 = 0.6931471805599453f;
+  const float x = fmaf(e, p.sd, p.mean);
+  float u, r, l2w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(x * -2.8853900817779268f));     // -2 log2(e)
+  const float w = 1.f + u;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2w) : "f"(w));
+  const float y = fmaf(2.f, r, -1.f);
+  const bool clamped = fabsf(y) > kClamp;
+  const float gate = clamped ? 0.f : 1.f;
+  const float yc = clamped ? copysignf(kClamp, y) : y;
+  // (explicit roundings: both entropy kernels inline this function and must agree bit for bit -- rows are
+  // independent of how a batch is split, tests/test_gpu_properties.py)
+  const float d = clamped ? __fsub_rn(copysignf(kXc, y), p.mean) : __fmul_rn(e, p.sd);
+  const float ladj = clamped ? kLadjC : fmaf(-2.f, fmaf(l2w, kLog2, x), 2.f * kLog2);
+  const float dd = __fmul_rn(d, d), div = __fmul_rn(d, p.inv_var);
+  lp_sum = __fadd_rn(lp_sum, __fsub_rn(fmaf(dd, p.nhiv, p.lp_const), ladj));     // log N(x'; mean, sd) - log|d tanh / dx|
+  const float dlp = fmaf(2.f, yc, -div);
+  dm_sum = __fadd_rn(dm_sum, fmaf(gate, dlp, div));
+  ds_sum = __fadd_rn(ds_sum, fmaf(__fmul_rn(gate, e), dlp, fmaf(__fmul_rn(dd, p.inv_var), p.inv_sd, -p.inv_sd)));
+}
+
 template <int SPLIT>
 static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const float* __restrict__ eps_e,
                                      bd_actor_cfg cfg, long long N, int A,
@@ -1141,33 +1181,17 @@ static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const
   const long long n = valid ? n_ : N - 1;          // no early exit: the shuffles below are warp-wide
   const int t = blockIdx.y;
   const long long r = (long long)t * N + n;
-  const float kClamp = 0.99999997f, kLogSqrt2Pi = 0.9189385332046727f, kLog2 = 0.6931471805599453f;
-  (void)kLog2;
+  const float kClamp = 0.99999997f;
+  const float kXc = 0.5f * (logf(1.f + kClamp) - logf(1.f - kClamp));
+  const float kLadjC = logf(1.f + kClamp) + logf(1.f - kClamp);        // = log(1 - kClamp^2)
   const int J = cfg.entropy_samples;
   float ent_acc = 0.f;
   for (int a = 0; a < A; ++a) {
-    const float mean = cfg.mean_scale * tanhf(raw[r * 2 * A + a] / cfg.mean_scale);
-    const float sd = softplusf_(raw[r * 2 * A + A + a] + cfg.raw_init_std) + cfg.min_std;
-    const float log_sd = logf(sd), inv_var = 1.f / (sd * sd), inv_sd = 1.f / sd;
-    const float neg_half_inv_var = -0.5f * inv_var, lp_const = -log_sd - kLogSqrt2Pi;
+    const EntRow p = ent_row(cfg, raw[r * 2 * A + a], raw[r * 2 * A + A + a]);
     const float* ee = eps_e + ((long long)t * J * N + n) * A + a;
     float lp_sum = 0.f, dm_sum = 0.f, ds_sum = 0.f;
-#pragma unroll 8
-    for (int j = q; j < J; j += SPLIT) {
-      const float e = ee[(long long)j * N * A];
-      const float y = tanhf(mean + e * sd);
-      const float yc = fminf(fmaxf(y, -kClamp), kClamp);
-      const float gate = (yc == y) ? 1.f : 0.f;
-      // atanh(yc) = (la - lb) / 2 and the tanh log-det 2 (ln2 - x - softplus(-2x)) = ln(1 - yc^2)
-      // = la + lb share the two logarithms; tanh(atanh(yc)) = yc
-      const float la = __logf(1.f + yc), lb = __logf(1.f - yc);
-      const float xh = 0.5f * (la - lb);
-      const float d = xh - mean;
-      lp_sum += fmaf(d * d, neg_half_inv_var, lp_const) - (la + lb);     // log N(x; mean, sd) - log|d tanh / dx|
-      const float dlp = -d * inv_var + 2.f * yc;
-      dm_sum += d * inv_var + gate * dlp;
-      ds_sum += d * d * inv_var * inv_sd - inv_sd + gate * e * dlp;
-    }
+#pragma unroll 4
+    for (int j = q; j < J; j += SPLIT) ent_sample(p, ee[(long long)j * N * A], kXc, kLadjC, lp_sum, dm_sum, ds_sum);
 #pragma unroll
     for (int o = 1; o < SPLIT; o <<= 1) {
       lp_sum += __shfl_xor_sync(0xffffffffu, lp_sum, o);
@@ -1181,6 +1205,41 @@ static __global__ void actor_entropy_kernel(const float* __restrict__ raw, const
     }
   }
   if (valid && q == 0) entropy[r] = -ent_acc / (float)J;
+}
+
+// Large row counts, one action dimension, N a multiple of 4: a thread owns FOUR consecutive rows and reads their
+// samples as one 16-byte load per j -- a block then reads 2 KB runs of the (T, J, N) noise tensor instead of 512-byte
+// runs at a 4 N-byte stride (the scalar kernel streamed it at 1.1 TB/s: 0.66 ms at 2^17 start states).
+static __global__ void __launch_bounds__(128) actor_entropy_vec4_kernel(const float* __restrict__ raw,
+                                                                        const float* __restrict__ eps_e,
+                                                                        bd_actor_cfg cfg, long long N,
+                                                                        float* __restrict__ entropy,
+                                                                        float* __restrict__ dent) {
+  const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (n >= N) return;
+  const int t = blockIdx.y;
+  const long long r = (long long)t * N + n;
+  const float kClamp = 0.99999997f;
+  const float kXc = 0.5f * (logf(1.f + kClamp) - logf(1.f - kClamp));
+  const float kLadjC = logf(1.f + kClamp) + logf(1.f - kClamp);
+  const int J = cfg.entropy_samples;
+  const float4 ra = *reinterpret_cast<const float4*>(raw + r * 2), rb = *reinterpret_cast<const float4*>(raw + r * 2 + 4);
+  const EntRow p0 = ent_row(cfg, ra.x, ra.y), p1 = ent_row(cfg, ra.z, ra.w);
+  const EntRow p2 = ent_row(cfg, rb.x, rb.y), p3 = ent_row(cfg, rb.z, rb.w);
+  float lp[4] = {0.f, 0.f, 0.f, 0.f}, dm[4] = {0.f, 0.f, 0.f, 0.f}, ds[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* ee = eps_e + (long long)t * J * N + n;
+#pragma unroll 2
+  for (int j = 0; j < J; ++j) {
+    const float4 e = *reinterpret_cast<const float4*>(ee + (long long)j * N);
+    ent_sample(p0, e.x, kXc, kLadjC, lp[0], dm[0], ds[0]);
+    ent_sample(p1, e.y, kXc, kLadjC, lp[1], dm[1], ds[1]);
+    ent_sample(p2, e.z, kXc, kLadjC, lp[2], dm[2], ds[2]);
+    ent_sample(p3, e.w, kXc, kLadjC, lp[3], dm[3], ds[3]);
+  }
+  const float fj = (float)J;      // (divisions, like the one-row kernel: the two must round alike)
+  *reinterpret_cast<float4*>(entropy + r) = make_float4(-lp[0] / fj, -lp[1] / fj, -lp[2] / fj, -lp[3] / fj);
+  *reinterpret_cast<float4*>(dent + r * 2) = make_float4(-dm[0] / fj, -ds[0] / fj, -dm[1] / fj, -ds[1] / fj);
+  *reinterpret_cast<float4*>(dent + r * 2 + 4) = make_float4(-dm[2] / fj, -ds[2] / fj, -dm[3] / fj, -ds[3] / fj);
 }
 
 }  // namespace tc

@@ -463,6 +463,11 @@ static int imagine_forward_impl(const bd_imagine_args* a, const HeadsFwd* hd, vo
   if ((long long)a->T * a->N <= (1 << 16)) {        // few row-steps: 8 lanes per row
     dim3 egrid((unsigned)((a->N * 8 + 127) / 128), (unsigned)a->T);
     actor_entropy_kernel<8><<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy, a->dent);
+  } else if (A == 1 && (a->N & 3) == 0 && !getenv("BD_ENT_SCALAR") &&
+             ((reinterpret_cast<uintptr_t>(a->actor_raw) | reinterpret_cast<uintptr_t>(a->eps_e) |
+               reinterpret_cast<uintptr_t>(a->entropy) | reinterpret_cast<uintptr_t>(a->dent)) & 15) == 0) {
+    dim3 egrid((unsigned)((a->N / 4 + 127) / 128), (unsigned)a->T);     // four consecutive rows per thread
+    actor_entropy_vec4_kernel<<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, a->entropy, a->dent);
   } else {
     dim3 egrid((unsigned)((a->N + 127) / 128), (unsigned)a->T);
     actor_entropy_kernel<1><<<egrid, 128, 0, s>>>(a->actor_raw, a->eps_e, a->actor_cfg, a->N, A, a->entropy, a->dent);

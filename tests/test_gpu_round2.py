@@ -242,6 +242,21 @@ def test_actor_backward_from_saved_hidden_images(d, prec, tol, cluster, save_row
         assert e < tol, (k, res["errors"])
 
 
+def test_entropy_four_rows_per_thread_vs_oracle_and_scalar_kernel(monkeypatch):
+    """The 100-sample policy entropy (src/models.py:725-733) at a row count that takes the four-rows-per-thread
+    kernel (T * N > 2^16, N a multiple of 4): against the fp64 oracle in the well-conditioned regime and against the
+    one-row-per-thread kernel (BD_ENT_SCALAR) on the same inputs, entropy values and actor gradients."""
+    d = dict(Be=32, Hi=32, S=30, A=1, E=8, N=5000, H=15, act="ELU")
+    res = pu.run_imagine_case(d, seed=3, precision="fp16", oracle_dtype=torch.float64, small_std=True)
+    print({k: f"{v:.2e}" for k, v in res["errors"].items()})
+    assert res["errors"]["entropy"] < 1e-3, res["errors"]
+    for k, e in res["errors"].items():
+        assert e < 1e-2, (k, res["errors"])
+    monkeypatch.setenv("BD_ENT_SCALAR", "1")
+    res1 = pu.run_imagine_case(d, seed=3, precision="fp16", oracle_dtype=torch.float64, small_std=True)
+    assert abs(res1["errors"]["entropy"] - res["errors"]["entropy"]) < 1e-5, (res1["errors"], res["errors"])
+
+
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("fp16", 1e-2)])
 def test_value_update_vs_reference_fixture(prec, tol):
     """bd.value_update against the reference's own critic regression block (src/dreamer.py:369-391;
