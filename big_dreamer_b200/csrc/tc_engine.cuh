@@ -647,6 +647,42 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
         // one 8-column group (16 B of the operand tile) per item; consecutive threads take
         // consecutive rows of the same group -> conflict-free 16 B shared stores
         const int gb = a.Kp_b >> 3;
+        if (be4 && (reinterpret_cast<uintptr_t>(a.prev_belief) & 15) == 0) {
+          // 16-byte loads, four items (8 columns of one row each) requested per thread before the first is used:
+          // one item at a time with scalar loads left ~9 dependent memory round trips in this prologue (~17 K
+          // cycles per tile -- a third of a whole MLP-forward tile)
+          for (int i0 = etid; i0 < kTileRows * gb; i0 += 4 * kEpiThreads2) {
+            float4 lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * kEpiThreads2;
+              const int kg = i / kTileRows, r = i - kg * kTileRows;
+              const long long gr = tile * kTileRows + r;
+              const long long sr = a.cem_cl ? gr / a.cem_cl : gr;     // CEM: latents are per batch row
+              lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (i < kTileRows * gb && gr < a.N) {
+                const float* src = a.prev_belief + sr * Be + kg * 8;
+                if (kg * 8 + 4 <= Be) lo[u] = *reinterpret_cast<const float4*>(src);
+                if (kg * 8 + 8 <= Be) hi[u] = *reinterpret_cast<const float4*>(src + 4);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * kEpiThreads2;
+              if (i >= kTileRows * gb) break;
+              const int kg = i / kTileRows, r = i - kg * kTileRows;
+              float v[8] = {lo[u].x, lo[u].y, lo[u].z, lo[u].w, hi[u].x, hi[u].y, hi[u].z, hi[u].w}, z[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {           // (Be is a multiple of 4: the ones column starts a 4-group)
+                const int k = kg * 8 + j;
+                if (k == Be) v[j] = 1.f;
+                z[j] = (k == Be) ? 1.f : 0.f;
+              }
+              store8<FMT>(B0 + kg * kLboA + r * 16, v);
+              if (a.has_b1) store8<FMT>(B1 + kg * kLboA + r * 16, z);
+            }
+          }
+        } else {
         for (int i = etid; i < kTileRows * gb; i += kEpiThreads2) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = tile * kTileRows + r;
@@ -660,6 +696,7 @@ __global__ void __launch_bounds__(kThreads2, 1) rollout_fwd_kernel(const __grid_
           }
           store8<FMT>(B0 + kg * kLboA + r * 16, v);
           if (a.has_b1) store8<FMT>(B1 + kg * kLboA + r * 16, z);
+        }
         }
         const int gs = a.Kp_sa >> 3;
         for (int i = etid; i < kTileRows * gs; i += kEpiThreads2) {

@@ -196,6 +196,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
         const long long tile = tl[sb], trow0 = tr0[sb];
         const int tvalid = tv[sb];
         const int gb = a.Kp_b >> 3;
+        if ((a.k1 & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.x1) | reinterpret_cast<uintptr_t>(a.x1b)) & 15) == 0) {
+          // 16-byte loads, four items (8 columns of one row) requested per thread before the first is used (one
+          // item at a time with scalar loads: ~9 dependent memory round trips per tile in this prologue)
+          for (int i0 = etid; i0 < kTileRows * gb; i0 += 4 * kBwdEpiThreads) {
+            float4 lo[4], hi[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const int i = i0 + u4 * kBwdEpiThreads;
+              const int kg = i / kTileRows, r = i - kg * kTileRows;
+              const long long gr = trow0 + r;
+              lo[u4] = hi[u4] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (i < kTileRows * gb && r < tvalid) {
+                const float* src = (gr < a.split ? a.x1 + gr * a.k1 : a.x1b + (gr - a.split) * a.k1) + kg * 8;
+                if (kg * 8 + 4 <= a.k1) lo[u4] = *reinterpret_cast<const float4*>(src);
+                if (kg * 8 + 8 <= a.k1) hi[u4] = *reinterpret_cast<const float4*>(src + 4);
+              }
+            }
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const int i = i0 + u4 * kBwdEpiThreads;
+              if (i >= kTileRows * gb) break;
+              const int kg = i / kTileRows, r = i - kg * kTileRows;
+              float v[8] = {lo[u4].x, lo[u4].y, lo[u4].z, lo[u4].w, hi[u4].x, hi[u4].y, hi[u4].z, hi[u4].w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (kg * 8 + j == a.k1 && r < tvalid) v[j] = 1.f;       // (k1 is a multiple of 4: starts a 4-group)
+              const uint4 u = pack8<FMT>(v);
+              if (!a.pair) *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
+              if (a.want_images)
+                *reinterpret_cast<uint4*>(a.x0b + (size_t)tile * kTileRows * a.Kp_b + (size_t)kg * kTileRows * 8 + r * 8) = u;
+            }
+          }
+        } else {
         for (int i = etid; i < kTileRows * gb; i += kBwdEpiThreads) {
           const int kg = i / kTileRows, r = i - kg * kTileRows;
           const long long gr = trow0 + r;
@@ -211,6 +244,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
           if (!a.pair) *reinterpret_cast<uint4*>(B0 + kg * kLboA + r * 16) = u;
           if (a.want_images)
             *reinterpret_cast<uint4*>(a.x0b + (size_t)tile * kTileRows * a.Kp_b + (size_t)kg * kTileRows * 8 + r * 8) = u;
+        }
         }
         const int gs = a.Ks >> 3;
         for (int i = etid; i < kTileRows * gs; i += kBwdEpiThreads) {
