@@ -231,7 +231,7 @@ def test_imagine_and_returns_fused_vs_oracle(d, prec, tol, cluster, monkeypatch)
                                dict(Be=48, Hi=40, S=10, A=3, E=8, N=129, H=7, act="Tanh")])
 def test_actor_backward_from_saved_hidden_images(d, prec, tol, cluster, save_rows, monkeypatch):
     """The batched actor backward of imagine_ahead reads the hidden activations the rollout saved per (step, row
-    tile) (row counts >= BD_ACTOR_SAVE_MIN_ROWS, default 8192) or recomputes the actor's forward pass: both against
+    tile) (row counts >= BD_ACTOR_SAVE_MIN_ROWS, default 2048) or recomputes the actor's forward pass: both against
     the oracle's actor gradients (src/dreamer.py:363), with and without column-split clusters, on row counts that
     are not a multiple of the 128-row tile."""
     monkeypatch.setenv("BD_ACTOR_SAVE_MIN_ROWS", save_rows)
