@@ -215,6 +215,21 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {        // same war
                : "memory");
 }
 
+// CTA pair (cta_group::2): the allocating warp of EACH CTA of the pair runs these
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_holder) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_holder)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(kCols)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4   [16,30) LBO>>4   [32,46) SBO>>4   [46,48) version=1   [61,64) layout=0
@@ -303,6 +318,27 @@ __device__ __forceinline__ void umma_f16_u(uint32_t d_tmem, uint64_t a_desc, uin
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// CTA pair: D[256 x N] (+)= A[256 x K] B[N x K]^T, A's rows 128 per CTA (each CTA's own tile at the same shared-memory
+// offset), B's rows N/2 per CTA, D's rows 128 per CTA at the same TMEM address; issued by the leader CTA only
+__device__ __forceinline__ void umma_f16_pair_u(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.u32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of the pair's MMAs so far -> the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair_mc_elect(uint32_t bar_addr, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar_addr), "h"(mask)
       : "memory");
 }
 // bulk copy + its expect_tx, both predicated on the elected lane (producer warp, converged)

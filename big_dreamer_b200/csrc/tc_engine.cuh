@@ -211,6 +211,7 @@ __device__ __forceinline__ void store1(uint8_t* tile, int row, int col, float v)
 // MMA-issuer warp.  Kernels differ only in their tile initialisation and epilogues.
 struct EngineShared {
   uint64_t w_full[8], w_empty[8], acc_full[4], epi_done[8];
+  uint64_t w_peer[8];       // CTA-pair mode, leader only: the peer's half of ring stage i has landed (relay_role)
   uint32_t tmem_holder;
 };
 
@@ -227,22 +228,39 @@ __device__ __forceinline__ void stage_program(Program& dst, const Program& src) 
 
 // ws > 1 (weight-share cluster, see producer_role): a ring stage is refilled by all ws producers of the
 // cluster, so it is free only when the issuers of all ws CTAs have consumed it.
+//
+// CTA-pair mode (pair2, clusters of 2; see issuer_role<.., PAIR2>): every CTA owns its OWN row tile, the leader (cluster
+// rank 0) issues tcgen05.mma.cta_group::2 for both, and every weight-ring stage holds HALF of the weight rows in
+// each CTA -- the weight bytes a CTA pulls from L2 per row tile are halved.  Barriers: w_full (local copy landed),
+// w_peer (leader: the peer's half landed), w_empty / acc_full (the leader's commits, multicast to both CTAs),
+// epi_done (leader: one arrival per epilogue warp of BOTH CTAs).
+// (PAIR2 is a template parameter: a kernel that merely CONTAINS cta_group::2 instructions can no longer be launched
+// without a cluster -- "cluster misconfiguration" -- so the pair variants are separate instantiations)
+template <bool PAIR2 = false>
 __device__ __forceinline__ uint32_t engine_setup(EngineShared& sh, uint32_t nstage, uint32_t R = 1,
                                                  uint32_t epi_threads = kEpiThreads, uint32_t ws = 1) {
+  constexpr bool pair2 = PAIR2;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (uint32_t i = 0; i < nstage; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], ws); }
-    for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], R);
+    for (uint32_t i = 0; i < nstage; ++i) {
+      mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], ws);
+      if (pair2) mbar_init(&sh.w_peer[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&sh.acc_full[i], pair2 ? 1 : R);
     // epi_threads == kEpiThreads2: the 16-warp kernels arrive once per warp; the 8-warp kernels once per thread
     for (int i = 0; i < 8; ++i)
-      mbar_init(&sh.epi_done[i], (R == 1 && epi_threads == kEpiThreads) ? epi_threads : (epi_threads / 32) * R);
+      mbar_init(&sh.epi_done[i], pair2 ? (epi_threads / 32) * 2
+                                       : ((R == 1 && epi_threads == kEpiThreads) ? epi_threads : (epi_threads / 32) * R));
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(&sh.tmem_holder);
+  if (warp == 1) {
+    if constexpr (PAIR2) tmem_alloc_pair<512>(&sh.tmem_holder);
+    else tmem_alloc<512>(&sh.tmem_holder);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (R > 1 || ws > 1) cluster_sync_all();   // peers' barriers are initialised before anyone arrives remotely
+  if (R > 1 || ws > 1 || pair2) cluster_sync_all();   // peers' barriers are initialised before anyone arrives remotely
   return sh.tmem_holder;
 }
 
@@ -260,7 +278,7 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
                                               const uint16_t* wpack, long long ntiles, int T,
                                               uint8_t* smem, EngineShared& sh,
                                               const PrefetchPlan* pf = nullptr, uint32_t R = 1, uint32_t ws = 1,
-                                              bool dbg_no_copy = false) {
+                                              bool dbg_no_copy = false, int pair_rank = -1) {
   const uint32_t wrank = ws > 1 ? (uint32_t)blockIdx.x % ws : 0u;
   const uint16_t wmask = (uint16_t)((1u << ws) - 1u);
   const uint32_t ring = smem_u32(smem) + sm.off_ring;
@@ -269,6 +287,31 @@ __device__ __forceinline__ void producer_role(const Program& P, const SmemPlan& 
   asm volatile("" : "+r"(nstage), "+r"(stage_bytes));     // (kept in registers, see issuer_role)
   uint32_t st = 0, ph = 0;
   const long long tile0 = blockIdx.x / R, tstride = gridDim.x / R;
+  if (pair_rank >= 0) {
+    // CTA-pair mode (R = 2; ntiles = tile pairs): this CTA's half of every stage -- rows [Np/2 rank, +Np/2) of the
+    // weight image, packed as two half images (PackJob::split2) so a K range of a half is one contiguous copy
+    for (long long tile = tile0; tile < ntiles; tile += tstride)
+      for (int t = 0; t < T; ++t) {
+        if (pf && pf->n) {
+          const long long mine = tile * 2 + pair_rank;       // (prefetch plans are per row tile)
+          if (t == 0 && tile == tile0) prefetch_step(*pf, mine, pf->reverse ? T - 1 : 0);
+          if (t + 1 < T) prefetch_step(*pf, mine, pf->reverse ? T - 2 - t : t + 1);
+          else if (tile + tstride < ntiles) prefetch_step(*pf, mine + 2 * tstride, pf->reverse ? T - 1 : 0);
+        }
+        for (int gi = 0; gi < P.n_gemms; ++gi) {
+          const Gemm g = P.g[gi];
+          const uint32_t nh = g.Np / 2u;
+          const uint16_t* src = wpack + g.w_off + (size_t)pair_rank * nh * g.Kp;
+          for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+            const int kc = min((int)g.kc, g.Kp - k0);
+            mbar_wait_u(bar_empty + st * 8, ph ^ 1);
+            tma_bulk_g2s_elect(ring + st * stage_bytes, src + (size_t)k0 * nh, nh * kc * 2u, bar_full + st * 8);
+            if (++st == nstage) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    return;
+  }
   for (long long tile = tile0; tile < ntiles; tile += tstride)
     for (int t = 0; t < T; ++t) {
       if (pf && pf->n) {      // inputs of the NEXT step (and of step 0 when a tile starts)
@@ -431,6 +474,101 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
   }
   if (x0_on && lane == 0) bulk_wait_all();     // the images are in global memory before the CTA retires
   __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair mode (clusters of 2, engine_setup(pair2 = true)).  Both CTAs walk the same program over their OWN row
+// tiles (pair p: tiles 2p and 2p + 1); `npairs` is the loop bound.
+//   leader (cluster rank 0), warp 1: issuer_pair_role -- the ONE issuer of the pair: M = 256 MMAs
+//       (tcgen05.mma.cta_group::2) whose A operand is each CTA's own tile at the same shared-memory offset, whose B
+//       operand is the two half stages, and whose accumulators land at the same TMEM address in both CTAs; commits
+//       are multicast, so both producers see w_empty and both epilogues see acc_full.
+//   peer (rank 1), warp 1: relay_role -- forwards "my half of stage s has landed" to the leader's w_peer[s].
+// The epilogue warps of both CTAs arrive on the LEADER's epi_done (release at cluster scope after a proxy fence: the
+// pair's MMAs read both CTAs' operand tiles through the async proxy).
+template <int FMT>
+__device__ __forceinline__ void issuer_pair_role(const Program& P, const SmemPlan& sm, long long npairs, int T,
+                                                 uint8_t* smem, EngineShared& sh, uint32_t tmem_base) {
+  uint32_t nstage = sm.nstage, stage_bytes = sm.stage_bytes;
+  asm volatile("" : "+r"(nstage), "+r"(stage_bytes));
+  uint32_t st = 0, wph = 0, Ge = 0, Gm = 0;
+  uint32_t waited = 0xFFFFFFFFu;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t ring_addr = smem_base + sm.off_ring;
+  const uint32_t bar_w_full = smem_u32(&sh.w_full[0]), bar_w_empty = smem_u32(&sh.w_empty[0]);
+  const uint32_t bar_w_peer = smem_u32(&sh.w_peer[0]);
+  const uint32_t bar_acc_full = smem_u32(&sh.acc_full[0]), bar_epi_done = smem_u32(&sh.epi_done[0]);
+  const uint64_t desc_hi = make_smem_desc(0, 0, 128);
+  for (long long pr = blockIdx.x / 2; pr < npairs; pr += gridDim.x / 2) {
+    ++Ge;  // the tile-initialisation pseudo-phase
+    for (int t = 0; t < T; ++t) {
+      const uint32_t par = (uint32_t)t & 1u;
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        const Phase ph = P.p[pi];
+        for (int gi = ph.g0; gi < ph.g0 + ph.ng; ++gi) {
+          const Gemm g = P.g[gi];
+          {
+            const uint32_t D = Ge - g.dep_back;
+            if ((int)(D - waited) > 0) {
+              mbar_wait_cluster_u(bar_epi_done + (D & 7) * 8, (D >> 3) & 1);
+              fence_proxy_async_all();
+              tc_fence_after_sync();
+              waited = D;
+            }
+          }
+          uint32_t tile_id = g.a_tile;
+          if (tile_id < 2) tile_id ^= par;
+          uint64_t a_desc = desc_hi | ((uint64_t)(kLboA >> 4) << 16) |
+                            (uint64_t)((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) +
+                                       (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4));
+          const uint32_t idesc = make_idesc_f16(FMT, 2 * kTileRows, g.Np);
+          const uint32_t lbo_b = (uint32_t)(g.Np / 2) * 16;       // a half stage holds Np / 2 weight rows
+          const uint32_t d_tmem = tmem_base + g.d_col;
+          uint32_t acc = g.accumulate == 2 ? (t > 0 ? 1u : 0u) : g.accumulate;
+          for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+            const int kc = min((int)g.kc, g.Kp - k0);
+            mbar_wait_u(bar_w_full + st * 8, wph);
+            mbar_wait_cluster_u(bar_w_peer + st * 8, wph);
+            uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
+                              (uint64_t)(((ring_addr + st * stage_bytes) >> 4) & 0x3FFFu);
+            for (int ks = 0; ks < kc; ks += 16) {
+              umma_f16_pair_u(d_tmem, a_desc, b_desc, idesc, acc);
+              acc = 1;
+              a_desc += 2 * (kLboA >> 4);
+              b_desc += 2 * (lbo_b >> 4);
+            }
+            umma_commit_pair_mc_elect(bar_w_empty + st * 8, (uint16_t)3);    // the stage is free in both CTAs
+            if (++st == nstage) { st = 0; wph ^= 1; }
+          }
+        }
+        umma_commit_pair_mc_elect(bar_acc_full + (Gm & 3) * 8, (uint16_t)3);
+        ++Gm;
+        Ge += ph.n_sub;
+      }
+    }
+  }
+  __syncwarp();
+}
+// peer CTA, warp 1: the same walk over the ring stages, forwarding each local completion to the leader
+__device__ __forceinline__ void relay_role(const Program& P, const SmemPlan& sm, long long npairs, int T,
+                                           EngineShared& sh) {
+  uint32_t nstage = sm.nstage;
+  asm volatile("" : "+r"(nstage));
+  uint32_t st = 0, wph = 0;
+  const uint32_t bar_w_full = smem_u32(&sh.w_full[0]);
+  const uint32_t peer0 = mapa_u32(smem_u32(&sh.w_peer[0]), 0);      // the leader's w_peer[0]
+  const int lane = threadIdx.x & 31;
+  for (long long pr = blockIdx.x / 2; pr < npairs; pr += gridDim.x / 2)
+    for (int t = 0; t < T; ++t)
+      for (int gi = 0; gi < P.n_gemms; ++gi) {
+        const Gemm g = P.g[gi];
+        for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
+          mbar_wait_u(bar_w_full + st * 8, wph);
+          if (lane == 0) mbar_arrive_cluster(peer0 + st * 8);
+          __syncwarp();
+          if (++st == nstage) { st = 0; wph ^= 1; }
+        }
+      }
 }
 
 // ---------------------------------------------------------------------------------------------

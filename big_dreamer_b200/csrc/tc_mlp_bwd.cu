@@ -57,12 +57,29 @@ size_t mlp_backward_workspace_bytes(const bd_mlp& m, int k1, int k2, int64_t row
   return al256(p.pack_elems * 2) + 256 + p.dwp_bytes + tiles * p.per_tile_bytes + 65536;
 }
 
+template <typename K>
+static cudaError_t launch_bwd_pair(K kernel, unsigned grid, const MlpBwdArgs& ba, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBwdThreads);
+  cfg.dynamicSmemBytes = ba.sm.total; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, ba);
+}
 template <int FMT>
 static int launch_bwd_act(int act, unsigned grid, const MlpBwdArgs& ba, cudaStream_t s) {
 #define BD_LAUNCH_BWD(ACTV)                                                                          \
   do {                                                                                               \
-    set_smem_attr(mlp_bwd_kernel<FMT, ACTV>, ba.sm.total);                                           \
-    mlp_bwd_kernel<FMT, ACTV><<<grid, kBwdThreads, ba.sm.total, s>>>(ba);                               \
+    if (ba.c2pair) {                                                                                 \
+      set_smem_attr(mlp_bwd_kernel<FMT, ACTV, true>, ba.sm.total);                                   \
+      cudaError_t e_ = launch_bwd_pair(mlp_bwd_kernel<FMT, ACTV, true>, grid, ba, s);                \
+      if (e_ != cudaSuccess) BD_FAIL(BD_ERR_CUDA, "mlp_backward pair launch: %s", cudaGetErrorString(e_)); \
+    } else {                                                                                         \
+      set_smem_attr(mlp_bwd_kernel<FMT, ACTV, false>, ba.sm.total);                                  \
+      mlp_bwd_kernel<FMT, ACTV, false><<<grid, kBwdThreads, ba.sm.total, s>>>(ba);                   \
+    }                                                                                                \
   } while (0)
   switch (act) {
     case BD_ACT_ELU: BD_LAUNCH_BWD(BD_ACT_ELU); break;
@@ -134,6 +151,9 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   bool pair = false;
   if (const char* e = getenv("BD_BWD_PAIR")) pair = have_saved && atoi(e) != 0;
   (void)total_tiles_; (void)sms_;
+  // CTA-pair mode (cta_group::2, see issuer_pair_role): opt-in, BD_TC_PAIR2=1; needs an even tile count per launch
+  const bool c2 = getenv("BD_TC_PAIR2") && atoi(getenv("BD_TC_PAIR2")) != 0 && !pair && total_tiles_ % 2 == 0 &&
+                  total_tiles_ >= 2;
   const int nsub = pair ? 2 : 1;
   const int sub_tile[2] = {TILE_H2, TILE_H};
   const int dep = pair ? 2 : 1;
@@ -200,10 +220,13 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   const long long seg_tiles = seg ? (seg_rows + 127) / 128 : 0;
   const long long total_tiles = seg ? (a->rows / seg_rows) * seg_tiles : (a->rows + 127) / 128;
   if (chunk_tiles > total_tiles) chunk_tiles = total_tiles;
+  if (c2) chunk_tiles &= ~1LL;       // (CTA pairs: every launch takes an even number of tiles)
   if (chunk_tiles < 1) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core mlp_backward: workspace too small");
   char* scratch = base + off;
 
   // ---- pack weights once
+  if (c2)
+    for (int i = 0; i < b.pack.njobs; ++i) b.pack.job[i].split2 = 1;
   {
     long long max_img = 0;
     for (int i = 0; i < b.pack.njobs; ++i)
@@ -241,7 +264,8 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     sm.nstage = min(8u, (budget - o) / sm.stage_bytes);
     sm.total = o + sm.nstage * sm.stage_bytes + 1024;
   }
-  b.finalize_blocks(ba.sm.stage_bytes);
+  // (CTA pair: a stage holds HALF of the weight rows, so it takes twice the K columns)
+  b.finalize_blocks(c2 ? 2 * ba.sm.stage_bytes : ba.sm.stage_bytes);
   ba.prog = b.prog;
   ba.wpack = wpack; ba.T = 1; ba.prof = nullptr; ba.amax_bits = amax;
   ba.k1 = k1; ba.k2 = k2; ba.out = m->layer[L - 1].out_features; ba.n_layers = L; ba.act = m->activation;
@@ -284,6 +308,9 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     }
     ba.N = nrows; ba.ntiles = nt;
     ba.pair = pair ? 1 : 0; ba.nloop = pair ? (nt + 1) / 2 : nt;
+    ba.c2pair = (c2 && nt % 2 == 0) ? 1 : 0;
+    if (c2 && !ba.c2pair) BD_FAIL(BD_ERR_UNSUPPORTED, "mlp_backward: CTA-pair mode needs an even tile count per launch");
+    if (ba.c2pair) ba.nloop = nt / 2;
 #ifdef BD_BWD_DBG
     ba.dbg = getenv("BD_BWD_DBGV") ? atoi(getenv("BD_BWD_DBGV")) : 0;
 #endif
@@ -310,7 +337,8 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
     ba.dx1 = a->dx1 ? a->dx1 + r0 * k1 : nullptr;
     ba.dx2 = a->dx2 ? a->dx2 + r0 * k2 : nullptr;
     }
-    const unsigned grid = (unsigned)(ba.nloop < sms ? ba.nloop : sms);
+    unsigned grid = (unsigned)(ba.nloop < sms ? ba.nloop : sms);
+    if (ba.c2pair) grid = 2u * (unsigned)(ba.nloop < sms / 2 ? ba.nloop : sms / 2);
     {
       // the producer warp pulls the NEXT tile's inputs (rows of x1 / x2 / dy, saved hidden images) into L2
       PrefetchPlan& pf = ba.pf;

@@ -46,6 +46,8 @@ struct MlpBwdArgs {
   // the MMAs that read it are complete when its epilogue runs) and one 256-column TMEM half.  nloop = tile pairs.
   int pair;
   long long nloop;
+  int c2pair;                     // 1: CTA-pair launch (clusters of 2, cta_group::2 MMAs, half weight stages per CTA; see
+                                  // tc_engine.cuh issuer_pair_role); ntiles is even, nloop = tile pairs
   int dbg;                        // BD_BWD_DBG builds only (BD_BWD_DBGV): 1 no hidden-image loads, 2 no image stores, 4 no epilogue math
   float *dx1, *dx2;
   uint16_t* xs[BD_MAX_LAYERS];  // xs[l]: images of hidden h_l (cols kp_xs[l]), l = 0..L-2
@@ -129,7 +131,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 constexpr int kBwdParts = 3;
 constexpr int kBwdEpiThreads = kBwdParts * 128;
 constexpr int kBwdThreads = 64 + kBwdEpiThreads;
-template <int FMT, int ACT>
+template <int FMT, int ACT, bool C2 = false>
 __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_constant__ MlpBwdArgs A_) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const MlpBwdArgs& a = A_;
@@ -139,21 +141,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role code stays on the uniform datapath
   __shared__ Program sprog;
   stage_program(sprog, a.prog);
-  const uint32_t tmem_base = engine_setup(sh, a.sm.nstage, 1, kBwdEpiThreads);
+  constexpr bool c2 = C2;                                   // CTA-pair variant (launched in clusters of 2)
+  const uint32_t crank = c2 ? (blockIdx.x & 1u) : 0u;       // = %cluster_ctarank for (2,1,1) clusters
+  const uint32_t tmem_base = engine_setup<C2>(sh, a.sm.nstage, 1, kBwdEpiThreads, 1);
   const long long ntiles = a.ntiles;
-  const long long nloop = a.pair ? a.nloop : a.ntiles;     // loop items per CTA walk: tiles, or tile pairs
+  const long long nloop = (a.pair || c2) ? a.nloop : a.ntiles;     // loop items per CTA walk: tiles, or tile pairs
   const Program& P = sprog;
 
   if (warp == 0) {
-    producer_role(P, a.sm, a.wpack, nloop, 1, smem, sh, &a.pf);
+    producer_role(P, a.sm, a.wpack, nloop, 1, smem, sh, &a.pf, c2 ? 2u : 1u, 1, false, c2 ? (int)crank : -1);
   } else if (warp == 1) {
-    issuer_role<FMT, false>(P, a.sm, nloop, 1, smem, sh, tmem_base, nullptr);
+    if constexpr (!C2) {
+      issuer_role<FMT, false>(P, a.sm, nloop, 1, smem, sh, tmem_base, nullptr);
+    } else {
+      if (crank == 0) issuer_pair_role<FMT>(P, a.sm, nloop, 1, smem, sh, tmem_base);
+      else relay_role(P, a.sm, nloop, 1, sh);
+    }
   } else {
     const int q = warp & 3, part = (warp - 2) >> 2;
-    auto epi_arrive = [&](uint32_t ge) {     // one arrival per warp
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.epi_done[ge & 7]);
+    const uint32_t lead_epi_done = c2 ? mapa_u32(smem_u32(&sh.epi_done[0]), 0) : 0u;
+    auto epi_arrive = [&](uint32_t ge) {     // one arrival per warp (CTA pair: on the leader's barrier)
+      if (!c2) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.epi_done[ge & 7]);
+      } else {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_epi_done + (ge & 7) * 8);
+      }
     };
     const int row = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -166,7 +182,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
     float inv_scale;
     const float scale = grad_scale(a.amax_bits, &inv_scale);
     const int nsub = a.pair ? 2 : 1;
-    for (long long it = blockIdx.x; it < nloop; it += gridDim.x) {
+    const long long it0 = c2 ? blockIdx.x / 2 : blockIdx.x, itstep = c2 ? gridDim.x / 2 : gridDim.x;
+    for (long long it = it0; it < nloop; it += itstep) {
       // the one or two row tiles of this walk: index, first row, valid rows (0 for the missing half of an odd pair,
       // which runs through the phases on zeros and touches no global memory)
       long long tl[2] = {0, 0}, tr0[2] = {0, 0};
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
       bool tok[2] = {false, false};
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
-        const long long tile_s = a.pair ? it * 2 + sb : it;
+        const long long tile_s = c2 ? it * 2 + crank : (a.pair ? it * 2 + sb : it);
         if (sb >= nsub || tile_s >= ntiles) continue;
         tok[sb] = true; tl[sb] = tile_s;
         if (a.seg_tiles > 0) {
@@ -470,7 +487,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (C2) {
+    cluster_sync_all();        // neither CTA retires while the pair's MMAs / commits may still touch it
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+  } else {
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,6 +22,8 @@ struct PackJob {
   int transpose;        // 1: packed(n, k) = w[(src row = k-mapped), (src col = row0 + n)]  (dgrad)
   int nrseg;            // > 0: image rows are stacked from several source row ranges (GRU gates)
   PackSeg rseg[3];      // dst rows [dst_k0, +len) <- src rows [src_c0, +len)   (fields reused)
+  int split2;           // 1: CTA-pair layout -- two half images (rows [0, Np/2) and [Np/2, Np)) one after the other,
+                        //    each a KM8 image of Np/2 rows: a K range of one half is one contiguous byte range
 };
 constexpr int kMaxPackJobs = 64;
 struct PackTable { int njobs; PackJob job[kMaxPackJobs]; };
@@ -34,10 +36,14 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable tab, uint1
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     // iterate in DESTINATION order (coalesced writes): decode KM8 offset -> (n, k)
-    const long long per_kgroup = (long long)j.Np * 8;        // elements per 8-col group
-    int kg = (int)(i / per_kgroup);
-    int rem = (int)(i - (long long)kg * per_kgroup);
-    int n = rem >> 3, k = kg * 8 + (rem & 7);
+    const int rows_img = j.split2 ? j.Np / 2 : j.Np;         // rows per KM8 image
+    const long long img_elems = (long long)rows_img * j.Kp;
+    const int half = j.split2 ? (int)(i / img_elems) : 0;
+    const long long ii = i - (long long)half * img_elems;
+    const long long per_kgroup = (long long)rows_img * 8;    // elements per 8-col group
+    int kg = (int)(ii / per_kgroup);
+    int rem = (int)(ii - (long long)kg * per_kgroup);
+    int n = half * rows_img + (rem >> 3), k = kg * 8 + (rem & 7);
     float v = 0.f;
     int srow = -1;                       // source row of image row n
     if (j.nrseg > 0) {

@@ -242,6 +242,21 @@ def test_actor_backward_from_saved_hidden_images(d, prec, tol, cluster, save_row
         assert e < tol, (k, res["errors"])
 
 
+@pytest.mark.parametrize("prec,tol", [("fp16", 1e-2), ("bf16", 5e-2)])
+def test_mlp_backward_cta_pair_mode(prec, tol, monkeypatch):
+    """BD_TC_PAIR2=1: the MLP backward launched in clusters of two CTAs -- tcgen05.mma.cta_group::2 (M = 256: each CTA's
+    own 128-row tile, each CTA holding half of every weight stage), multicast commits, the peer's stage completions
+    relayed to the leader.  Same oracle comparison as the default launch (actor gradients of the whole actor-loss
+    step, src/dreamer.py:363; the heads' and the actor's backward all take even tile counts here)."""
+    monkeypatch.setenv("BD_TC_PAIR2", "1")
+    monkeypatch.setenv("BD_ACTOR_SAVE_MIN_ROWS", "0")
+    d = dict(Be=200, Hi=200, S=30, A=1, E=8, N=512, H=15, act="ELU")
+    res = pu.run_imagine_case(d, seed=7, precision=prec, oracle_dtype=torch.float64)
+    print(prec, {k: f"{v:.2e}" for k, v in res["errors"].items()})
+    for k, e in res["errors"].items():
+        assert e < tol, (k, res["errors"])
+
+
 def test_entropy_four_rows_per_thread_vs_oracle_and_scalar_kernel(monkeypatch):
     """The 100-sample policy entropy (src/models.py:725-733) at a row count that takes the four-rows-per-thread
     kernel (T * N > 2^16, N a multiple of 4): against the fp64 oracle in the well-conditioned regime and against the
