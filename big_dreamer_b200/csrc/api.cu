@@ -168,6 +168,32 @@ int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t 
   return f32::mlp_backward(m, a, ws, ws_bytes, stream);
 }
 
+int bd_heads_forward_supported(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int precision) {
+  if (!(reward && value) || k1 <= 0 || k2 <= 0) return 0;
+  if (f32::check_mlp(*reward, k1 + k2) != BD_OK || f32::check_mlp(*value, k1 + k2) != BD_OK) return 0;
+  return (tc::heads_pair_supported(*reward, *value, k1, k2, precision) &&
+          tc::mlp_backward_supported(*reward, k1, k2, precision) &&
+          tc::mlp_backward_supported(*value, k1, k2, precision)) ? 1 : 0;
+}
+size_t bd_heads_forward_workspace_bytes(const bd_mlp* reward, const bd_mlp* value) {
+  return (reward && value) ? tc::heads_pair_pack_bytes(*reward, *value) + 65536 : 0;
+}
+int bd_heads_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2,
+                     int k2, int64_t rows, float* y_reward, float* y_value, void* saved_reward,
+                     void* saved_value, void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
+  BD_NEED(reward, "reward"); BD_NEED(value, "value");
+  if (rows == 0) return BD_OK;
+  BD_NEED(x1, "x1"); BD_NEED(x2, "x2"); BD_NEED(y_reward, "y_reward"); BD_NEED(y_value, "y_value");
+  BD_NEED(ws, "workspace");
+  BD_CHECK_ARG(k1 > 0 && k2 > 0, "bd_heads_forward: bad k1/k2");
+  BD_TRY(f32::check_mlp(*reward, k1 + k2));
+  BD_TRY(f32::check_mlp(*value, k1 + k2));
+  if (!bd_heads_forward_supported(reward, value, k1, k2, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "bd_heads_forward: configuration not supported (see bd_heads_forward_supported)");
+  return tc::heads_pair_forward(reward, value, x1, k1, x2, k2, rows, y_reward, y_value, saved_reward, saved_value,
+                                ws, ws_bytes, precision, stream);
+}
+
 int bd_lambda_return_forward(const float* reward, const float* value, const float* bootstrap, int T,
                              int64_t N, double discount, double lambda_, float* returns,
                              bd_stream_t stream) {

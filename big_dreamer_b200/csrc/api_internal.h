@@ -61,6 +61,11 @@ int imagine_forward(const bd_imagine_args* a, void* ws, size_t ws_bytes, int pre
                     bd_stream_t stream);
 size_t imagine_saved_bytes(const bd_rssm& r, int T, long long N);
 const void* imagine_saved_actor(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved);
+bool heads_pair_supported(const bd_mlp& reward, const bd_mlp& value, int k1, int k2, int precision);
+size_t heads_pair_pack_bytes(const bd_mlp& reward, const bd_mlp& value);
+int heads_pair_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2, int k2,
+                       int64_t rows, float* y_reward, float* y_value, void* saved_reward, void* saved_value,
+                       void* ws, size_t ws_bytes, int precision, bd_stream_t stream);
 const void* imagine_saved_actor_x0(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved,
                                    const void** x0s);
 // fused imagine + reward/value heads + lambda_return (SURVEY 8b level L2)

@@ -303,20 +303,25 @@ static HeadsSaved heads_saved_layout(const bd_mlp& reward, int T, long long N) {
 }
 size_t heads_saved_bytes(const bd_mlp& reward, int T, long long N) { return heads_saved_layout(reward, T, N).total + 256; }
 
-static void add_head_phases(Builder& b, const bd_rssm& r, const HeadsFwd& hd, int rank, int R, int Kp_b, int Ks) {
+// in_tile / hid1_tile: where the (belief | 1) input sits and which tile the second head's chain lives in -- the rollout
+// reads the NEW belief (TILE_BNXT) and parks the value chain in the old one; the stand-alone pair forward
+// (heads_pair_forward) reads TILE_BCUR and uses TILE_BNXT.  hidden_images: the hidden layers leave their activations
+// as sv_mlp images (aux0 = 3 + k (L - 1) + l, the layout bd_mlp_backward reads) instead of act' images (sv_hd).
+static void add_head_phases(Builder& b, const bd_rssm& r, const HeadsFwd& hd, int rank, int R, int Kp_b, int Ks,
+                            int in_tile = TILE_BNXT, int hid1_tile = TILE_BCUR, bool hidden_images = false) {
   const int Be = r.belief_size, S = r.state_size;
   const int L = hd.head[0]->n_layers;
   for (int l = 0; l < L; ++l)
     for (int k = 0; k < 2; ++k) {
       const bd_mlp& m = *hd.head[k];
       const bd_linear& Lr = m.layer[l];
-      const int tile = k == 0 ? TILE_H : TILE_BCUR;        // this head's hidden tile
+      const int tile = k == 0 ? TILE_H : hid1_tile;        // this head's hidden tile
       const int dep = (l == 0 && k == 0) ? 1 : 2;           // the same head's previous layer is two phases back
       const int n = Lr.out_features;
       if (l + 1 < L) {
-        const int aux = hd.saved ? 16 + k * BD_MAX_LAYERS + l : 0;
+        const int aux = !hd.saved ? 0 : (hidden_images ? 3 + k * (L - 1) + l : 16 + k * BD_MAX_LAYERS + l);
         if (l == 0) {
-          ActSrc s0[2] = {{Lr.w, Be + S, 0, Be, Kp_b, TILE_BNXT, Lr.b, Be},
+          ActSrc s0[2] = {{Lr.w, Be + S, 0, Be, Kp_b, in_tile, Lr.b, Be},
                           {Lr.w, Be + S, Be, S, Ks, TILE_SA, nullptr, -1}};
           add_act_phase(b, rank, R, s0, 2, n, r16(n + 1), aux, tile, 0, dep, false);
         } else {
@@ -1066,6 +1071,102 @@ int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k
   BD_CUDA_LAUNCH_CHECK();
   ProfScope ps(BD_PROF_MLP_FWD, s);
   return launch_rollout(fmt, m->activation, false, false, grid, ra, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two heads on the same rows in ONE launch (the reward and value models of Dreamer's behaviour step on the T*N
+// imagined latents, src/dreamer.py:321-322, when the step runs piecewise): one tile prologue for both, and the two
+// chains interleaved phase by phase exactly as in the fused rollout (every phase depends on the epilogue two phases
+// back), so the MMAs of one head run under the epilogue of the other.  Hidden activations are left as the images
+// bd_mlp_backward reads (one buffer per head, bd_mlp_saved_bytes each).
+// ---------------------------------------------------------------------------------------------
+bool heads_pair_supported(const bd_mlp& reward, const bd_mlp& value, int k1, int k2, int precision) {
+  const bd_mlp* hs[2] = {&reward, &value};
+  if (k2 <= 0 || reward.n_layers != value.n_layers || reward.activation != value.activation) return false;
+  if (reward.n_layers < 2 || 2 * (reward.n_layers - 1) > BD_MAX_LAYERS) return false;
+  for (const bd_mlp* m : hs) {
+    if (!mlp_supported(*m, k1, k2, precision)) return false;
+    if (m->layer[0].in_features != k1 + k2 || m->layer[m->n_layers - 1].out_features != 1) return false;
+    const int hh = head_hidden(*m);
+    for (int l = 0; l + 1 < m->n_layers; ++l)
+      if (m->layer[l].out_features != hh || (l > 0 && m->layer[l].in_features != hh)) return false;
+    if (r16(hh + 1) > r16(k1 + 1)) return false;            // the second chain's hidden tile is a belief tile
+  }
+  if (4 * reward.n_layers + 2 > kMaxGemms || 2 * reward.n_layers > kMaxPhases) return false;
+  bd_rssm r{};
+  r.belief_size = k1; r.state_size = k2; r.action_size = 0; r.hidden_size = max(head_hidden(reward), head_hidden(value));
+  return rollout_tiles_fit(r, r.hidden_size);
+}
+size_t heads_pair_pack_bytes(const bd_mlp& reward, const bd_mlp& value) {
+  return mlp_pack_bytes(reward) + mlp_pack_bytes(value) + 2 * 16 * 272 * 2 + 4096;
+}
+int heads_pair_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2, int k2,
+                       int64_t rows, float* y_reward, float* y_value, void* saved_reward, void* saved_value,
+                       void* ws, size_t ws_bytes, int precision, bd_stream_t stream) {
+  if (!heads_pair_supported(*reward, *value, k1, k2, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_forward: configuration not supported");
+  bd_rssm r{};
+  r.belief_size = k1; r.state_size = k2;
+  HeadsFwd hd{};
+  hd.head[0] = reward; hd.head[1] = value;
+  hd.saved = (saved_reward && saved_value) ? saved_reward : nullptr;      // (only tested for null below)
+  const int Kp_b = r16(k1 + 1), Ks = r16(k2);
+  const int Kp_h = max(r16(head_hidden(*reward) + 1), r16(head_hidden(*value) + 1));
+  const int L = reward->n_layers;
+  Builder b;
+  add_head_phases(b, r, hd, 0, 1, Kp_b, Ks, TILE_BCUR, TILE_BNXT, true);
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_forward: program too large");
+  const size_t pack_bytes = (size_t)b.w_elems * 2;
+  if (pack_bytes > ws_bytes)
+    BD_FAIL(BD_ERR_WORKSPACE, "tensor-core heads_pair_forward: workspace %zu < %zu", ws_bytes, pack_bytes);
+  RolloutArgs ra{};
+  if (!plan_smem(Kp_b, max(Ks, 16), Kp_h, b.max_stage, ra.sm, true))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_forward: tiles do not fit shared memory");
+  set_programs(ra, b, 1);
+  ra.wpack = static_cast<const uint16_t*>(ws);
+  ra.N = rows; ra.T = 1; ra.Be = k1; ra.S = k2; ra.A = 0; ra.Hi = 0; ra.J = 0;
+  ra.Kp_b = Kp_b; ra.Kp_sa = max(Ks, 16); ra.Kp_h = Kp_h; ra.act = reward->activation;
+  ra.prev_belief = x1; ra.prev_state = x2; ra.has_b1 = 1;
+  ra.head_out[0] = y_reward; ra.head_out[1] = y_value;
+  {
+    PrefetchPlan& pf = ra.pf;
+    pf.reverse = 0;
+    pf.base[0] = reinterpret_cast<const char*>(x1); pf.step_stride[0] = 0;
+    pf.tile_stride[0] = (long long)kTileRows * k1 * 4; pf.bytes[0] = (unsigned)(kTileRows * k1 * 4);
+    pf.base[1] = reinterpret_cast<const char*>(x2); pf.step_stride[1] = 0;
+    pf.tile_stride[1] = (long long)kTileRows * k2 * 4; pf.bytes[1] = (unsigned)(kTileRows * k2 * 4);
+    pf.n = 2;
+  }
+  if (hd.saved) {   // per head: hidden images layer after layer, [tiles][128 x Kp_l] (what mlp_backward reads)
+    const size_t tiles = (size_t)((rows + kTileRows - 1) / kTileRows);
+    void* sv[2] = {saved_reward, saved_value};
+    for (int k = 0; k < 2; ++k) {
+      char* sb = static_cast<char*>(sv[k]);
+      const bd_mlp& m = *hd.head[k];
+      for (int l = 0; l + 1 < L; ++l) {
+        ra.sv_mlp[k * (L - 1) + l] = reinterpret_cast<uint16_t*>(sb);
+        sb += tiles * kTileRows * r16(m.layer[l].out_features + 1) * 2;
+      }
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long max_img = 0;
+  for (int i = 0; i < b.pack.njobs; ++i)
+    max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+  long long pgx = (max_img + 255) / 256;
+  if (pgx > 64) pgx = 64;
+  dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+  const long long ntiles = (rows + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+  if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, static_cast<uint16_t*>(ws));
+  BD_CUDA_LAUNCH_CHECK();
+  ProfScope ps(BD_PROF_MLP_FWD, s);
+  return launch_rollout(fmt, reward->activation, false, false, grid, ra, s);
 }
 
 }  // namespace tc

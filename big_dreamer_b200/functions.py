@@ -141,6 +141,101 @@ class MlpFunction(torch.autograd.Function):
         return tuple(grads)
 
 
+def _mlp_backward_call(act_id, prec, a1, a2, ws_, bs_, dy2, mlp_saved, need_x1, need_x2, need_w, need_b):
+    """One bd_mlp_backward call -> (dx1, dx2, dws, dbs); shared by MlpFunction and HeadsPairFunction."""
+    lib = _lib.load()
+    n = len(ws_)
+    mlp = _lib.make_mlp(ws_, bs_, act_id)
+    rows = a1.shape[0]
+    dx1 = torch.empty_like(a1) if need_x1 else None
+    dx2 = torch.empty_like(a2) if (a2 is not None and need_x2) else None
+    g = _zero_grads(list(need_w) + list(need_b), list(ws_) + list(bs_))
+    dws, dbs = g[:n], g[n:]
+    args = _lib.MlpBwdArgs()
+    args.x1, args.k1 = _lib.ptr(a1), a1.shape[1]
+    args.x2, args.k2 = _lib.ptr(a2), (a2.shape[1] if a2 is not None else 0)
+    args.rows, args.dy = rows, _lib.ptr(dy2)
+    args.dx1, args.dx2 = _lib.ptr(dx1), _lib.ptr(dx2)
+    for i in range(n):
+        args.dw[i], args.db[i] = _lib.ptr(dws[i]), _lib.ptr(dbs[i])
+    if mlp_saved is not None:
+        args.saved = mlp_saved.data_ptr()
+    nbytes = lib.bd_mlp_workspace_bytes(C.byref(mlp), rows, 1)
+    ws = _lib.workspace(nbytes, a1.device)
+    _lib.check(lib.bd_mlp_backward(C.byref(mlp), C.byref(args), ws.data_ptr(), ws.numel(), prec,
+                                   _lib.stream_ptr()), "bd_mlp_backward")
+    return dx1, dx2, dws, dbs
+
+
+class HeadsPairFunction(torch.autograd.Function):
+    """reward_model(beliefs, states) and value_model(beliefs, states) (src/dreamer.py:321-322) as ONE forward
+    launch (bd_heads_forward: one tile prologue, the two chains interleaved); the backward is one
+    bd_mlp_backward per head on the hidden images the forward left.  Tensor-core modes only."""
+
+    @staticmethod
+    def forward(ctx, act_id: int, n_layers: int, x1: torch.Tensor, x2: torch.Tensor, *params):
+        lib = _lib.load()
+        pr, pv = params[:2 * n_layers], params[2 * n_layers:]
+        wr, br = [_f32c(p) for p in pr[0::2]], [_f32c(p) for p in pr[1::2]]
+        wv, bv = [_f32c(p) for p in pv[0::2]], [_f32c(p) for p in pv[1::2]]
+        lead = x1.shape[:-1]
+        a1 = _f32c(x1).reshape(-1, x1.shape[-1])
+        a2 = _f32c(x2).reshape(-1, x2.shape[-1])
+        rows, k1, k2 = a1.shape[0], a1.shape[1], a2.shape[1]
+        mr, mv = _lib.make_mlp(wr, br, act_id), _lib.make_mlp(wv, bv, act_id)
+        yr = torch.empty(rows, 1, device=a1.device, dtype=torch.float32)
+        yv = torch.empty(rows, 1, device=a1.device, dtype=torch.float32)
+        ws = _lib.workspace(lib.bd_heads_forward_workspace_bytes(C.byref(mr), C.byref(mv)), a1.device)
+        prec = _prec()
+        want = rows and any(ctx.needs_input_grad)
+        sr = torch.empty(lib.bd_mlp_saved_bytes(C.byref(mr), k1, k2, rows, prec), dtype=torch.uint8,
+                         device=a1.device) if want else None
+        sv = torch.empty(lib.bd_mlp_saved_bytes(C.byref(mv), k1, k2, rows, prec), dtype=torch.uint8,
+                         device=a1.device) if want else None
+        _lib.check(lib.bd_heads_forward(C.byref(mr), C.byref(mv), _lib.ptr(a1), k1, _lib.ptr(a2), k2, rows,
+                                        _lib.ptr(yr), _lib.ptr(yv), sr.data_ptr() if want else None,
+                                        sv.data_ptr() if want else None, ws.data_ptr(), ws.numel(), prec,
+                                        _lib.stream_ptr()), "bd_heads_forward")
+        ctx.saved_r, ctx.saved_v, ctx.prec, ctx.act_id, ctx.n_layers = sr, sv, prec, act_id, n_layers
+        ctx.x1_shape, ctx.x2_shape = x1.shape, x2.shape
+        ctx.save_for_backward(a1, a2, *wr, *br, *wv, *bv)
+        return yr.reshape(*lead, 1), yv.reshape(*lead, 1)
+
+    @staticmethod
+    def backward(ctx, d_reward, d_value):
+        saved = list(ctx.saved_tensors)
+        a1, a2 = saved[0], saved[1]
+        n = ctx.n_layers
+        wr, br, wv, bv = saved[2:2 + n], saved[2 + n:2 + 2 * n], saved[2 + 2 * n:2 + 3 * n], saved[2 + 3 * n:]
+        need = ctx.needs_input_grad     # (act_id, n_layers, x1, x2, reward w0, b0, ..., value w0, b0, ...)
+        rows = a1.shape[0]
+        outs = []
+        for k, (ws_, bs_, dy, sv) in enumerate(((wr, br, d_reward, ctx.saved_r), (wv, bv, d_value, ctx.saved_v))):
+            base = 4 + 2 * n * k
+            if dy is None:
+                dy = torch.zeros(rows, 1, device=a1.device, dtype=torch.float32)
+            outs.append(_mlp_backward_call(ctx.act_id, ctx.prec, a1, a2, ws_, bs_, _f32c(dy).reshape(rows, 1), sv,
+                                           need[2], need[3], [need[base + 2 * i] for i in range(n)],
+                                           [need[base + 2 * i + 1] for i in range(n)]))
+        (dx1r, dx2r, dwr, dbr), (dx1v, dx2v, dwv, dbv) = outs
+        dx1 = (dx1r + dx1v).reshape(ctx.x1_shape) if need[2] else None
+        dx2 = (dx2r + dx2v).reshape(ctx.x2_shape) if need[3] else None
+        grads: List[Optional[torch.Tensor]] = [None, None, dx1, dx2]
+        for dws, dbs in ((dwr, dbr), (dwv, dbv)):
+            for i in range(n):
+                grads += [dws[i], dbs[i]]
+        return tuple(grads)
+
+
+def heads_pair_supported(act_id: int, x1, x2, wr, br, wv, bv) -> bool:
+    if _precision == "fp32" or not (x1.is_cuda and x2 is not None) or len(wr) != len(wv):
+        return False
+    lib = _lib.load()
+    det = lambda ps: [_f32c(p.detach()) for p in ps]
+    mr, mv = _lib.make_mlp(det(wr), det(br), act_id), _lib.make_mlp(det(wv), det(bv), act_id)
+    return bool(lib.bd_heads_forward_supported(C.byref(mr), C.byref(mv), x1.shape[-1], x2.shape[-1], _prec()))
+
+
 def mlp_apply(act_id: int, x1, x2, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]):
     params = []
     for w, b in zip(weights, biases):

@@ -452,10 +452,26 @@ def imagine_and_returns(self, prev_state: Tensor, prev_belief: Tensor, reward_mo
             *flat(la), *rp, *[t.detach() for t in flat(lr)], *[t.detach() for t in flat(lv)])
         return beliefs, states, (means, stds), entropy, reward, value, returns
     beliefs, states, (means, stds), entropy = imagine_ahead(self, prev_state, prev_belief, noise)
-    reward = reward_model(beliefs, states)
-    value = value_model(beliefs, states)
+    reward, value = heads_pair(reward_model, value_model, beliefs, states)
     returns = lambda_return(reward, value, value[-1], discount, lambda_)
     return beliefs, states, (means, stds), entropy, reward, value, returns
+
+
+def heads_pair(reward_model, value_model, beliefs: Tensor, states: Tensor):
+    """``reward_model(beliefs, states), value_model(beliefs, states)`` (src/dreamer.py:321-322).  Two DenseModels of
+    the same shape run as ONE launch in the tensor-core modes (bd_heads_forward: one tile prologue, the two layer
+    chains interleaved so the MMAs of one head run under the epilogue of the other); anything else is the two calls."""
+    if (isinstance(reward_model, DenseModel) and isinstance(value_model, DenseModel) and beliefs.is_cuda
+            and os.environ.get("BD_HEADS_PAIR", "1") != "0"
+            and _mlp_act_id(reward_model.model) == _mlp_act_id(value_model.model)):
+        lr, lv = _linears(reward_model.model), _linears(value_model.model)
+        wr, br = [l.weight for l in lr], [l.bias for l in lr]
+        wv, bv = [l.weight for l in lv], [l.bias for l in lv]
+        act = _mlp_act_id(reward_model.model)
+        if len(lr) == len(lv) and F_.heads_pair_supported(act, beliefs, states, wr, br, wv, bv):
+            flat = lambda ws, bs: [t for w, b in zip(ws, bs) for t in (w, b)]
+            return F_.HeadsPairFunction.apply(act, len(lr), beliefs, states, *flat(wr, br), *flat(wv, bv))
+    return reward_model(beliefs, states), value_model(beliefs, states)
 
 
 # =============================================================================

@@ -151,6 +151,18 @@ int bd_mlp_forward_save(const bd_mlp* m, const float* x1, int k1, const float* x
                         int precision, bd_stream_t stream);
 int bd_mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_bytes,
                     int precision, bd_stream_t stream);
+/* Two scalar heads on the same rows in one call: reward_model(beliefs, states) and value_model(beliefs, states)
+ * of Dreamer's behaviour step (src/dreamer.py:321-322; DenseModel.forward, src/models.py:393-408).  Tensor-core
+ * modes only (bd_heads_forward_supported: same depth / activation / hidden width, one output each): one launch,
+ * one tile prologue, the two chains interleaved so the MMAs of one head run under the epilogue of the other.
+ * y_reward, y_value: (rows); saved_reward / saved_value: optional buffers of bd_mlp_saved_bytes() each, in the
+ * layout bd_mlp_backward reads -- the backward of each head is a plain bd_mlp_backward call.
+ * ws: bd_heads_forward_workspace_bytes(). */
+int bd_heads_forward_supported(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int precision);
+size_t bd_heads_forward_workspace_bytes(const bd_mlp* reward, const bd_mlp* value);
+int bd_heads_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2,
+                     int k2, int64_t rows, float* y_reward, float* y_value, void* saved_reward,
+                     void* saved_value, void* ws, size_t ws_bytes, int precision, bd_stream_t stream);
 
 /* -------------------------------------------------------- lambda_return ---- */
 /* reward, value, returns: (T, N); bootstrap: (N).  src/dreamer.py:447-471.

@@ -257,6 +257,39 @@ def test_mlp_backward_cta_pair_mode(prec, tol, monkeypatch):
         assert e < tol, (k, res["errors"])
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("rows_shape", [(14, 2500), (3, 77)])
+def test_heads_pair_matches_separate_calls(prec, rows_shape, monkeypatch):
+    """bd_heads_forward (reward and value models on the same latents as ONE launch, src/dreamer.py:321-322) against the
+    two separate DenseModel calls: outputs, input gradients and head weight gradients (the backward of the pair is
+    one bd_mlp_backward per head on the hidden images the paired forward left)."""
+    from big_dreamer_b200 import modules as M
+    bd.set_precision(prec)
+    d = dict(Be=200, Hi=200, S=30, A=1, E=8, act="ELU")
+    trans, actor, reward, value = orc.make_models(2, d["Be"], d["S"], d["A"], d["Hi"], d["E"])
+    mods = pu.build_gpu_models(d, trans, actor, reward, value)
+    g = torch.Generator().manual_seed(5)
+    T, N = rows_shape
+    b = torch.randn(T, N, d["Be"], generator=g).cuda().requires_grad_(True)
+    s = torch.randn(T, N, d["S"], generator=g).cuda().requires_grad_(True)
+    wr = torch.randn(T, N, 1, generator=g).cuda()
+    wv = torch.randn(T, N, 1, generator=g).cuda()
+    params = list(mods.reward.parameters()) + list(mods.critic.parameters())
+
+    def run(pair):
+        monkeypatch.setenv("BD_HEADS_PAIR", "1" if pair else "0")
+        for t in [b, s] + params:
+            t.grad = None
+        r, v = M.heads_pair(mods.reward, mods.critic, b, s)
+        ((r * wr).sum() + (v * wv).sum()).backward()
+        return [r.detach().clone(), v.detach().clone(), b.grad.clone(), s.grad.clone()] + [p.grad.clone() for p in params]
+
+    one, two = run(True), run(False)
+    assert one[0].shape == (T, N, 1) and one[1].shape == (T, N, 1)
+    for x, y in zip(one, two):
+        assert pu.relerr(x, y) < 2e-3, pu.relerr(x, y)
+
+
 def test_entropy_four_rows_per_thread_vs_oracle_and_scalar_kernel(monkeypatch):
     """The 100-sample policy entropy (src/models.py:725-733) at a row count that takes the four-rows-per-thread
     kernel (T * N > 2^16, N a multiple of 4): against the fp64 oracle in the well-conditioned regime and against the
