@@ -143,6 +143,10 @@ SIGNATURES = {
                                   C.c_int, C.c_void_p]),
     "bd_heads_forward_supported": (C.c_int, [C.POINTER(Mlp), C.POINTER(Mlp), C.c_int, C.c_int, C.c_int]),
     "bd_heads_forward_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.POINTER(Mlp)]),
+    "bd_heads_backward_workspace_bytes": (C.c_size_t, [C.POINTER(Mlp), C.POINTER(Mlp), C.c_int, C.c_int]),
+    "bd_heads_backward": (C.c_int, [C.POINTER(Mlp), C.POINTER(Mlp), C.c_int, C.c_int, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_size_t, C.c_int, C.c_void_p]),
     "bd_heads_forward": (C.c_int, [C.POINTER(Mlp), C.POINTER(Mlp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_size_t, C.c_int, C.c_void_p]),

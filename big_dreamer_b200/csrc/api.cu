@@ -194,6 +194,25 @@ int bd_heads_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1,
                                 ws, ws_bytes, precision, stream);
 }
 
+size_t bd_heads_backward_workspace_bytes(const bd_mlp* reward, const bd_mlp* value, int k1, int k2) {
+  return (reward && value) ? tc::heads_pair_backward_workspace_bytes(*reward, *value, k1, k2) : 0;
+}
+int bd_heads_backward(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int64_t rows,
+                      const float* dy_reward, const float* dy_value, const void* saved_reward,
+                      const void* saved_value, float* dx1, float* dx2, void* ws, size_t ws_bytes,
+                      int precision, bd_stream_t stream) {
+  BD_NEED(reward, "reward"); BD_NEED(value, "value");
+  if (rows == 0) return BD_OK;
+  BD_NEED(dy_reward, "dy_reward"); BD_NEED(dy_value, "dy_value"); BD_NEED(ws, "workspace");
+  BD_NEED(saved_reward, "saved_reward"); BD_NEED(saved_value, "saved_value");
+  BD_CHECK_ARG(dx1 || dx2, "bd_heads_backward: no output requested");
+  BD_CHECK_ARG(k1 > 0 && k2 > 0, "bd_heads_backward: bad k1/k2");
+  if (!bd_heads_forward_supported(reward, value, k1, k2, precision))
+    BD_FAIL(BD_ERR_UNSUPPORTED, "bd_heads_backward: configuration not supported (see bd_heads_forward_supported)");
+  return tc::heads_pair_backward(reward, value, k1, k2, rows, dy_reward, dy_value, saved_reward, saved_value, dx1,
+                                 dx2, ws, ws_bytes, precision, stream);
+}
+
 int bd_lambda_return_forward(const float* reward, const float* value, const float* bootstrap, int T,
                              int64_t N, double discount, double lambda_, float* returns,
                              bd_stream_t stream) {

@@ -66,6 +66,11 @@ size_t heads_pair_pack_bytes(const bd_mlp& reward, const bd_mlp& value);
 int heads_pair_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2, int k2,
                        int64_t rows, float* y_reward, float* y_value, void* saved_reward, void* saved_value,
                        void* ws, size_t ws_bytes, int precision, bd_stream_t stream);
+size_t heads_pair_backward_workspace_bytes(const bd_mlp& reward, const bd_mlp& value, int k1, int k2);
+int heads_pair_backward(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int64_t rows,
+                        const float* dy_reward, const float* dy_value, const void* saved_reward,
+                        const void* saved_value, float* dx1, float* dx2, void* ws, size_t ws_bytes, int precision,
+                        bd_stream_t stream);
 const void* imagine_saved_actor_x0(const bd_rssm& r, const bd_mlp& actor, int T, long long N, const void* tc_saved,
                                    const void** x0s);
 // fused imagine + reward/value heads + lambda_return (SURVEY 8b level L2)

@@ -435,5 +435,163 @@ int mlp_backward(const bd_mlp* m, const bd_mlp_bwd_args* a, void* ws, size_t ws_
   return BD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward of two scalar heads on the same rows (the pair of bd_heads_forward; frozen heads: only d x1 / d x2) as
+// ONE launch: the two dgrad chains are interleaved phase by phase (each depending on the epilogue two phases back:
+// the MMAs of one head run under the epilogue of the other), each in its own G tile and TMEM half, and their last
+// GEMMs accumulate into ONE dX accumulator -- the sum of the two heads' input gradients, which is what flows into
+// the beliefs / states (src/dreamer.py:321-335).
+// ---------------------------------------------------------------------------------------------
+size_t heads_pair_backward_workspace_bytes(const bd_mlp& reward, const bd_mlp& value, int k1, int k2) {
+  BwdPlan pr, pv;
+  make_plan(reward, k1, k2, false, pr);
+  make_plan(value, k1, k2, false, pv);
+  return al256((pr.pack_elems + pv.pack_elems) * 2) + 256 + 65536;
+}
+int heads_pair_backward(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int64_t rows,
+                        const float* dy_reward, const float* dy_value, const void* saved_reward,
+                        const void* saved_value, float* dx1, float* dx2, void* ws, size_t ws_bytes, int precision,
+                        bd_stream_t stream) {
+  const bd_mlp* hs[2] = {reward, value};
+  const int L = reward->n_layers;
+  if (!mlp_backward_supported(*reward, k1, k2, precision) || !mlp_backward_supported(*value, k1, k2, precision) ||
+      value->n_layers != L || L < 2 || reward->activation != value->activation)
+    BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_backward: configuration not supported");
+  for (int l = 0; l < L; ++l)
+    if (reward->layer[l].out_features != value->layer[l].out_features ||
+        reward->layer[l].in_features != value->layer[l].in_features)
+      BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_backward: the two heads differ in shape");
+  BwdPlan p;
+  make_plan(*reward, k1, k2, false, p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int fmt = precision == BD_PREC_FP16 ? 0 : 1;
+
+  Builder b;
+  const int sub_tile[2] = {TILE_H2, TILE_H};
+  for (int sb = 0; sb < 2; ++sb) {
+    b.end_phase(EPI_B_LOAD_DY, 1, 1, 0, 0, 0, L - 1, sub_tile[sb]);
+    b.prog.p[b.prog.n_phases - 1].pad = (uint8_t)sb;
+  }
+  auto pack_T = [&](const bd_linear& Lr) -> uint32_t {     // W^T image: packed(n_in, k_out) = W[k_out, n_in]
+    const int kin = Lr.in_features, n = Lr.out_features;
+    PackJob& j = b.pack.job[b.pack.njobs++];
+    j = PackJob{};
+    j.w = Lr.w; j.bias = nullptr; j.dst_off = b.w_elems; j.ld = kin; j.row0 = 0; j.N = kin; j.Np = r16(kin);
+    j.Kp = r16(n); j.bias_k = -1; j.nseg = 1; j.seg[0] = {0, 0, n}; j.transpose = 1;
+    const uint32_t woff = (uint32_t)b.w_elems;
+    b.w_elems += (long long)r16(kin) * r16(n);
+    return woff;
+  };
+  if (2 * L + 2 > kMaxPackJobs) BD_FAIL(BD_ERR_UNSUPPORTED, "heads_pair_backward: too many layers");
+  for (int l = L - 1; l >= 1; --l)
+    for (int sb = 0; sb < 2; ++sb) {
+      const bd_linear& Lr = hs[sb]->layer[l];
+      const int kin = Lr.in_features, n = Lr.out_features;
+      const uint32_t woff = pack_T(Lr);
+      const int d = b.dcol();
+      b.add_gemm(woff, r16(kin), r16(n), sub_tile[sb], 0, d, 0);
+      b.end_phase(EPI_B_DACT, 2, kin, r16(kin), p.kp_ds[l - 1], d, l - 1, sub_tile[sb]);
+      b.prog.p[b.prog.n_phases - 1].pad = (uint8_t)sb;
+    }
+  {   // dX = dY_0(reward) W_0(reward) + dY_0(value) W_0(value): two GEMMs into one accumulator, one epilogue
+    const int kin = k1 + k2, n = reward->layer[0].out_features;
+    const int d = b.dcol();
+    const uint32_t w0 = pack_T(reward->layer[0]), w1 = pack_T(value->layer[0]);
+    b.add_gemm(w0, r16(kin), r16(n), sub_tile[0], 0, d, 0);
+    b.add_gemm(w1, r16(kin), r16(n), sub_tile[1], 0, d, 1);
+    b.end_phase(EPI_B_DX, 1, kin, r16(kin), 0, d, 0, sub_tile[0]);
+    b.prog.g[b.prog.n_gemms - 2].dep_back = 2;      // the first head's last epilogue is two phases back
+  }
+  if (!b.ok) BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_backward: program too large");
+
+  char* base = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = base + off; off += al256(bytes); return r; };
+  uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
+  unsigned int* amax = reinterpret_cast<unsigned int*>(take(256));
+  if (off + 4096 > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core heads_pair_backward: workspace %zu too small", ws_bytes);
+  cudaMemsetAsync(amax, 0, 256, s);
+  {   // one power-of-two scale for both heads' upstream gradients
+    AbsmaxJobs jobs{};
+    jobs.x[0] = dy_reward; jobs.n[0] = rows; jobs.x[1] = dy_value; jobs.n[1] = rows;
+    long long g = (rows + 255) / 256;
+    if (g > 592) g = 592;
+    absmax_multi_kernel<<<dim3((unsigned)(g < 1 ? 1 : g), 2), 256, 0, s>>>(jobs, amax);
+    BD_CUDA_LAUNCH_CHECK();
+  }
+  {
+    long long max_img = 0;
+    for (int i = 0; i < b.pack.njobs; ++i)
+      max_img = max(max_img, (long long)b.pack.job[i].Np * b.pack.job[i].Kp);
+    long long pgx = (max_img + 255) / 256;
+    if (pgx > 64) pgx = 64;
+    dim3 pgrid((unsigned)pgx, (unsigned)b.pack.njobs);
+    if (fmt == 0) pack_weights_kernel<0><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
+    BD_CUDA_LAUNCH_CHECK();
+  }
+  MlpBwdArgs ba{};
+  {
+    SmemPlan& sm = ba.sm;
+    uint32_t o = 0;
+    auto tk = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 1023) & ~1023u; return r; };
+    sm.off_tile[4] = tk(kTileRows * p.Kp_g * 2);          // G tile of the first head (TILE_H2)
+    sm.off_tile[3] = tk(kTileRows * p.Kp_g * 2);          // G tile of the second head (TILE_H)
+    sm.off_tile[0] = sm.off_tile[1] = sm.off_tile[2] = sm.off_tile[4];
+    // (room for the dX tile staged row-major over both dead G tiles by the EPI_B_DX epilogue)
+    const int st1 = k1 + ((12 - k1 % 8) % 8), st2 = k2 | 1;
+    const uint32_t stage_dx = (uint32_t)kTileRows * (st1 + st2) * 4;
+    if (o < stage_dx) o = (stage_dx + 1023) & ~1023u;
+    sm.stage_bytes = align_stage(b.max_stage);
+    sm.off_ring = o;
+    const uint32_t budget = 227 * 1024 - 4096;
+    if (o + 2 * sm.stage_bytes > budget)
+      BD_FAIL(BD_ERR_UNSUPPORTED, "tensor-core heads_pair_backward: tiles do not fit shared memory");
+    sm.nstage = min(8u, (budget - o) / sm.stage_bytes);
+    sm.total = o + sm.nstage * sm.stage_bytes + 1024;
+  }
+  b.finalize_blocks(ba.sm.stage_bytes);
+  ba.prog = b.prog;
+  ba.wpack = wpack; ba.T = 1; ba.prof = nullptr; ba.amax_bits = amax;
+  ba.k1 = k1; ba.k2 = k2; ba.out = 1; ba.n_layers = L; ba.act = reward->activation;
+  ba.Kp_b = p.Kp_b; ba.Ks = p.Ks; ba.Kp_h = p.Kp_h; ba.Kp_g = p.Kp_g; ba.want_images = 0; ba.need_x = 0;
+  for (int l = 0; l < L; ++l) { ba.kp_xs[l] = p.kp_xs[l]; ba.kp_ds[l] = p.kp_ds[l]; }
+  const long long nt = (rows + 127) / 128;
+  ba.N = rows; ba.ntiles = nt; ba.pair = 2; ba.nloop = nt; ba.c2pair = 0;
+  ba.seg_tiles = 0; ba.seg_rows = 0; ba.tile_base = 0; ba.split = rows;
+  ba.dy = dy_reward; ba.dy_b = dy_value; ba.dx1 = dx1; ba.dx2 = dx2;
+  {
+    const char* sr = static_cast<const char*>(saved_reward);
+    const char* sv = static_cast<const char*>(saved_value);
+    for (int l = 0; l + 1 < L; ++l) {
+      ba.xs[l] = reinterpret_cast<uint16_t*>(const_cast<char*>(sr));
+      ba.xs_b[l] = reinterpret_cast<uint16_t*>(const_cast<char*>(sv));
+      sr += (size_t)nt * 128 * p.kp_xs[l] * 2;
+      sv += (size_t)nt * 128 * p.kp_xs[l] * 2;
+    }
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(nt < sms ? nt : sms);
+  {
+    PrefetchPlan& pf = ba.pf;
+    pf.n = 0; pf.reverse = 0;
+    auto add = [&](const void* ptr, size_t tile_bytes) {
+      if (!ptr || pf.n >= 6) return;
+      pf.base[pf.n] = static_cast<const char*>(ptr); pf.step_stride[pf.n] = 0;
+      pf.tile_stride[pf.n] = (long long)tile_bytes; pf.bytes[pf.n] = (unsigned int)tile_bytes; ++pf.n;
+    };
+    for (int l = 0; l + 1 < L && pf.n < 6; ++l) {
+      add(ba.xs[l], (size_t)128 * p.kp_xs[l] * 2);
+      add(ba.xs_b[l], (size_t)128 * p.kp_xs[l] * 2);
+    }
+  }
+  ProfScope ps(BD_PROF_MLP_BWD, s);
+  if (fmt == 0) BD_TRY(launch_bwd_act<0>(reward->activation, grid, ba, s));
+  else BD_TRY(launch_bwd_act<1>(reward->activation, grid, ba, s));
+  return BD_OK;
+}
+
 }  // namespace tc
 }  // namespace bd

@@ -44,7 +44,11 @@ struct MlpBwdArgs {
   // interleaves their dgrad chains (phase.pad = sub-tile, each phase depending on the epilogue two phases back), so
   // the MMAs of one tile run under the epilogue of the other.  Each sub-tile owns one G tile (rewritten in place:
   // the MMAs that read it are complete when its epilogue runs) and one 256-column TMEM half.  nloop = tile pairs.
-  int pair;
+  int pair;                       // 1: two row tiles (above); 2: two HEADS on the same row tile (heads_pair_backward): the
+                                  // sub-chains differ in weights, upstream gradient (dy / dy_b) and hidden images
+                                  // (xs / xs_b); their last GEMMs accumulate into ONE dX accumulator
+  const float* dy_b;              // pair == 2: upstream gradient of the second head
+  uint16_t* xs_b[BD_MAX_LAYERS];  // pair == 2: hidden images of the second head
   long long nloop;
   int c2pair;                     // 1: CTA-pair launch (clusters of 2, cta_group::2 MMAs, half weight stages per CTA; see
                                   // tc_engine.cuh issuer_pair_role); ntiles is even, nloop = tile pairs
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
   const uint32_t crank = c2 ? (blockIdx.x & 1u) : 0u;       // = %cluster_ctarank for (2,1,1) clusters
   const uint32_t tmem_base = engine_setup<C2>(sh, a.sm.nstage, 1, kBwdEpiThreads, 1);
   const long long ntiles = a.ntiles;
-  const long long nloop = (a.pair || c2) ? a.nloop : a.ntiles;     // loop items per CTA walk: tiles, or tile pairs
+  const long long nloop = (a.pair == 1 || c2) ? a.nloop : a.ntiles;     // loop items per CTA walk: tiles, or tile pairs
   const Program& P = sprog;
 
   if (warp == 0) {
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
       bool tok[2] = {false, false};
 #pragma unroll
       for (int sb = 0; sb < 2; ++sb) {
-        const long long tile_s = c2 ? it * 2 + crank : (a.pair ? it * 2 + sb : it);
+        const long long tile_s = c2 ? it * 2 + crank : (a.pair == 1 ? it * 2 + sb : it);
         if (sb >= nsub || tile_s >= ntiles) continue;
         tok[sb] = true; tl[sb] = tile_s;
         if (a.seg_tiles > 0) {
@@ -341,9 +345,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
             for (int c = part * 8; c < kp; c += kBwdParts * 8) {
               float v[8];
+              const float* dyp = (a.pair == 2 && sb) ? a.dy_b : a.dy;
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                v[j] = (rvalid && c + j < a.out) ? a.dy[grow * a.out + c + j] * scale : 0.f;
+                v[j] = (rvalid && c + j < a.out) ? dyp[grow * a.out + c + j] * scale : 0.f;
               const uint4 u = pack8<FMT>(v);
               *reinterpret_cast<uint4*>(Gt + (c >> 3) * kLboA + rowoff) = u;
               if (a.want_images && tile_ok) *reinterpret_cast<uint4*>(img + (size_t)(c >> 3) * kTileRows * 8 + row * 8) = u;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
           case EPI_B_DACT: {
             const int l = ph.aux0;          // produces dY_l from D and h_l
             const int nv = ph.n_valid, kp = a.kp_ds[l];
-            const uint16_t* himg = a.xs[l] + (size_t)tile * kTileRows * a.kp_xs[l];
+            const uint16_t* himg = ((a.pair == 2 && sb) ? a.xs_b[l] : a.xs[l]) + (size_t)tile * kTileRows * a.kp_xs[l];
             uint16_t* img = a.ds[l] + (size_t)tile * kTileRows * kp;
             // 16-column chunks c = 16 (part + kBwdParts k); the hidden-image pieces of three chunks are in flight
             // (rotating registers), the first ones requested before the accumulator wait
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) mlp_bwd_kernel(const __grid_co
             const int st2 = a.k2 | 1;
             float* stage1 = reinterpret_cast<float*>(smem + a.sm.off_tile[0]);
             float* stage2 = stage1 + (size_t)kTileRows * st1;
-            const bool staged = !a.pair && (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);   // (paired tiles: the other tile is live)
+            const bool staged = a.pair != 1 && (size_t)kTileRows * (st1 + st2) * 4 <= (size_t)(a.sm.off_ring - a.sm.off_tile[0]);   // (paired tiles: the other tile is live)
             const bool v4 = ((a.k1 & 3) == 0);
             for (int c = part * 16; c < ph.Np; c += kBwdParts * 16) {
               float v[16];

@@ -7,6 +7,8 @@ own loss code, ``.detach()`` calls and logging keep working on the outputs
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -209,6 +211,23 @@ class HeadsPairFunction(torch.autograd.Function):
         wr, br, wv, bv = saved[2:2 + n], saved[2 + n:2 + 2 * n], saved[2 + 2 * n:2 + 3 * n], saved[2 + 3 * n:]
         need = ctx.needs_input_grad     # (act_id, n_layers, x1, x2, reward w0, b0, ..., value w0, b0, ...)
         rows = a1.shape[0]
+        if (not any(need[4:]) and (need[2] or need[3]) and d_reward is not None and d_value is not None
+                and ctx.saved_r is not None and os.environ.get("BD_HEADS_PAIR_BWD", "1") != "0"):
+            # frozen heads (the behaviour step, src/dreamer.py:320): both chains and the sum of their input
+            # gradients in ONE launch
+            lib = _lib.load()
+            mr, mv = _lib.make_mlp(wr, br, ctx.act_id), _lib.make_mlp(wv, bv, ctx.act_id)
+            k1, k2 = a1.shape[1], a2.shape[1]
+            dx1 = torch.empty_like(a1) if need[2] else None
+            dx2 = torch.empty_like(a2) if need[3] else None
+            ws = _lib.workspace(lib.bd_heads_backward_workspace_bytes(C.byref(mr), C.byref(mv), k1, k2), a1.device)
+            dr, dv = _f32c(d_reward).reshape(rows), _f32c(d_value).reshape(rows)
+            _lib.check(lib.bd_heads_backward(C.byref(mr), C.byref(mv), k1, k2, rows, _lib.ptr(dr), _lib.ptr(dv),
+                                             ctx.saved_r.data_ptr(), ctx.saved_v.data_ptr(), _lib.ptr(dx1),
+                                             _lib.ptr(dx2), ws.data_ptr(), ws.numel(), ctx.prec,
+                                             _lib.stream_ptr()), "bd_heads_backward")
+            return (None, None, dx1.reshape(ctx.x1_shape) if dx1 is not None else None,
+                    dx2.reshape(ctx.x2_shape) if dx2 is not None else None) + (None,) * (4 * n)
         outs = []
         for k, (ws_, bs_, dy, sv) in enumerate(((wr, br, d_reward, ctx.saved_r), (wv, bv, d_value, ctx.saved_v))):
             base = 4 + 2 * n * k

@@ -163,6 +163,16 @@ size_t bd_heads_forward_workspace_bytes(const bd_mlp* reward, const bd_mlp* valu
 int bd_heads_forward(const bd_mlp* reward, const bd_mlp* value, const float* x1, int k1, const float* x2,
                      int k2, int64_t rows, float* y_reward, float* y_value, void* saved_reward,
                      void* saved_value, void* ws, size_t ws_bytes, int precision, bd_stream_t stream);
+/* Input gradients of that pair, heads frozen (FreezeParameters(value_model / reward_model), src/dreamer.py:320):
+ *   dx1 (rows,k1), dx2 (rows,k2) = d(reward)/dx . dy_reward + d(value)/dx . dy_value   (overwritten)
+ * from the buffers bd_heads_forward saved; dy_reward, dy_value: (rows).  One launch: the two dgrad chains are
+ * interleaved and their last GEMMs accumulate into one dX accumulator.  Weight gradients: bd_mlp_backward per head.
+ * ws: bd_heads_backward_workspace_bytes(). */
+size_t bd_heads_backward_workspace_bytes(const bd_mlp* reward, const bd_mlp* value, int k1, int k2);
+int bd_heads_backward(const bd_mlp* reward, const bd_mlp* value, int k1, int k2, int64_t rows,
+                      const float* dy_reward, const float* dy_value, const void* saved_reward,
+                      const void* saved_value, float* dx1, float* dx2, void* ws, size_t ws_bytes,
+                      int precision, bd_stream_t stream);
 
 /* -------------------------------------------------------- lambda_return ---- */
 /* reward, value, returns: (T, N); bootstrap: (N).  src/dreamer.py:447-471.

@@ -257,12 +257,14 @@ def test_mlp_backward_cta_pair_mode(prec, tol, monkeypatch):
         assert e < tol, (k, res["errors"])
 
 
+@pytest.mark.parametrize("frozen", [False, True])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("rows_shape", [(14, 2500), (3, 77)])
-def test_heads_pair_matches_separate_calls(prec, rows_shape, monkeypatch):
+def test_heads_pair_matches_separate_calls(prec, rows_shape, frozen, monkeypatch):
     """bd_heads_forward (reward and value models on the same latents as ONE launch, src/dreamer.py:321-322) against the
-    two separate DenseModel calls: outputs, input gradients and head weight gradients (the backward of the pair is
-    one bd_mlp_backward per head on the hidden images the paired forward left)."""
+    two separate DenseModel calls: outputs, input gradients and head weight gradients (heads trainable: the backward
+    of the pair is one bd_mlp_backward per head on the hidden images the paired forward left; heads frozen as in the
+    behaviour step, :320: bd_heads_backward, both dgrad chains and the sum of their input gradients in one launch)."""
     from big_dreamer_b200 import modules as M
     bd.set_precision(prec)
     d = dict(Be=200, Hi=200, S=30, A=1, E=8, act="ELU")
@@ -275,6 +277,9 @@ def test_heads_pair_matches_separate_calls(prec, rows_shape, monkeypatch):
     wr = torch.randn(T, N, 1, generator=g).cuda()
     wv = torch.randn(T, N, 1, generator=g).cuda()
     params = list(mods.reward.parameters()) + list(mods.critic.parameters())
+    if frozen:
+        pu.freeze(mods.reward, mods.critic)
+        params = []
 
     def run(pair):
         monkeypatch.setenv("BD_HEADS_PAIR", "1" if pair else "0")
