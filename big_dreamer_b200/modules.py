@@ -221,8 +221,12 @@ def draw_imagine_noise(T: int, N: int, S: int, A: int, device, generator=None):
     """ε_a (T,N,A), ε_e (T,100,N,A), ε_s (T,N,S).  (The reference draws them per step in
     the order action, entropy, prior state: src/dreamer.py:443-444, src/models.py:72.)"""
     kw = dict(device=device, dtype=torch.float32, generator=generator)
-    return dict(eps_a=torch.randn(T, N, A, **kw), eps_e=torch.randn(T, ENTROPY_SAMPLES, N, A, **kw),
-                eps_s=torch.randn(T, N, S, **kw))
+    # ONE generator launch for the three tensors (views of one buffer; the entropy noise first: it is read with
+    # 16-byte loads and stays 16-byte aligned there)
+    ne, ns, na = T * ENTROPY_SAMPLES * N * A, T * N * S, T * N * A
+    buf = torch.randn(ne + ns + na, **kw)
+    return dict(eps_a=buf[ne + ns:].view(T, N, A), eps_e=buf[:ne].view(T, ENTROPY_SAMPLES, N, A),
+                eps_s=buf[ne:ne + ns].view(T, N, S))
 
 
 def imagine_ahead(self, prev_state: Tensor, prev_belief: Tensor,
