@@ -341,6 +341,21 @@ __device__ __forceinline__ void umma_commit_pair_mc_elect(uint32_t bar_addr, uin
       ::"r"(bar_addr), "h"(mask)
       : "memory");
 }
+// Same MMA with the descriptors given as (low, high) 32-bit halves: only the low word of a shared-memory descriptor
+// (start address >> 4 | LBO >> 4 << 16) changes between the MMAs of a GEMM, and a 14-bit address field never carries
+// out -- the issuer then advances descriptors with one 32-bit add instead of a 64-bit add-with-carry pair.
+__device__ __forceinline__ void umma_f16_u32(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // bulk copy + its expect_tx, both predicated on the elected lane (producer warp, converged)
 __device__ __forceinline__ void tma_bulk_g2s_elect(uint32_t smem_dst, const void* gmem_src, uint32_t bytes,
                                                    uint32_t bar_addr) {

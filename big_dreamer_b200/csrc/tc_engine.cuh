@@ -369,9 +369,13 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t ring_addr = smem_base + sm.off_ring;
   const uint32_t bar_w_full = smem_u32(&sh.w_full[0]), bar_w_empty = smem_u32(&sh.w_empty[0]);
+  // the ring slot of the next stage as running values (no multiply, no constant-bank reload per stage): its
+  // descriptor address field, and the byte offset of its barrier pair
+  const uint32_t ring16 = (ring_addr >> 4) & 0x3FFFu, stage16 = stage_bytes >> 4;
+  uint32_t slot16 = ring16, bar_off = 0;
   const uint32_t bar_acc_full = smem_u32(&sh.acc_full[0]), bar_epi_done = smem_u32(&sh.epi_done[0]);
   // descriptor high word: SBO = 128 B, version 1, no swizzle; low word: start >> 4 | LBO >> 4 << 16
-  const uint64_t desc_hi = make_smem_desc(0, 0, 128);
+  const uint32_t desc_hi32 = (uint32_t)(make_smem_desc(0, 0, 128) >> 32);
   // per-stage clock reads cost ~70 cycles each on this warp's critical path: only on request
   // (BD_TC_PROF=2); the default debug build times whole phases and dependency waits only
   const bool fine = PROF && prof != nullptr && prof[39 * 8 + 7] != 0;
@@ -405,11 +409,11 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
           if (tile_id < 2) tile_id ^= par;
           // (in a cluster launch the shared-window address carries the CTA rank in its upper bits:
           // the descriptor takes only the 18-bit offset)
-          uint64_t a_desc = desc_hi | ((uint64_t)(kLboA >> 4) << 16) |
-                            (uint64_t)((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) +
-                                       (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4));
+          uint32_t a_lo = ((uint32_t)(kLboA >> 4) << 16) |
+                          ((((smem_base + sm.off_tile[tile_id]) >> 4) & 0x3FFFu) + (uint32_t)(g.a_k0 >> 3) * (kLboA >> 4));
           const uint32_t idesc = make_idesc_f16(FMT, kTileRows, g.Np);
-          const uint32_t lbo_b = (uint32_t)g.Np * 16;
+          const uint32_t lbo_b16 = (uint32_t)g.Np;                // (Np * 16 bytes) >> 4
+          const uint32_t b_lbo = lbo_b16 << 16;
           const uint32_t d_tmem = tmem_base + g.d_col;
           uint32_t acc = g.accumulate == 2 ? (t > 0 ? 1u : 0u) : g.accumulate;
           for (int k0 = 0; k0 < g.Kp; k0 += g.kc) {
@@ -419,25 +423,26 @@ __device__ __forceinline__ void issuer_role(const Program& P, const SmemPlan& sm
             // (no tcgen05.fence here: the weights arrive through the async proxy and their mbarrier
             // completion orders them before the MMAs; a fence::after_thread_sync per ring stage measured
             // ~220 cycles of issue stall each -- it is only needed after the epilogue hand-offs above)
-            if (!(PROF && dbg_no_ring)) mbar_wait_u(bar_w_full + st * 8, wph);
+            if (!(PROF && dbg_no_ring)) mbar_wait_u(bar_w_full + bar_off, wph);
             if (PROF && fine) wsum += clock64() - w0;
-            uint64_t b_desc = desc_hi | ((uint64_t)(lbo_b >> 4) << 16) |
-                              (uint64_t)(((ring_addr + st * stage_bytes) >> 4) & 0x3FFFu);
+            uint32_t b_lo = b_lbo | slot16;
             long long m0 = 0;
             if (PROF && fine) m0 = clock64();
+#pragma unroll 1
             for (int ks = 0; ks < kc; ks += 16) {
-              // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes
-              umma_f16_u(d_tmem, a_desc, b_desc, idesc, acc);
+              // one K=16 step = two 8-column groups: A advances 2*kLboA bytes, B 2*lbo_b bytes (both >> 4)
+              umma_f16_u32(d_tmem, a_lo, b_lo, desc_hi32, idesc, acc);
               acc = 1;
-              a_desc += 2 * (kLboA >> 4);
-              b_desc += 2 * (lbo_b >> 4);
+              a_lo += 2 * (kLboA >> 4);
+              b_lo += 2 * lbo_b16;
             }
             if (PROF && fine) msum += clock64() - m0;
             if (PROF && dbg_no_ring) {}
-            else if (ws == 1) umma_commit_elect(bar_w_empty + st * 8);
-            else umma_commit_mc_elect(bar_w_empty + st * 8, wmask);     // the stage is free in every CTA of the cluster
+            else if (ws == 1) umma_commit_elect(bar_w_empty + bar_off);
+            else umma_commit_mc_elect(bar_w_empty + bar_off, wmask);     // the stage is free in every CTA of the cluster
             if (PROF && fine) csum += clock64() - m0;
-            if (++st == nstage) { st = 0; wph ^= 1; }
+            slot16 += stage16; bar_off += 8;
+            if (++st == nstage) { st = 0; wph ^= 1; slot16 = ring16; bar_off = 0; }
           }
         }
         if (x0_on && pi <= 1) {
