@@ -514,13 +514,23 @@ bool cem_supported(const bd_rssm& r, const bd_mlp& reward, int precision) {
   return (r.belief_size + 63) / 64 * 6 + 2 * reward.n_layers + 6 <= kMaxPackJobs;
 }
 size_t cem_tc_workspace_bytes(const bd_rssm& r, const bd_mlp& reward, long long rows, int H) {
-  return imagine_pack_bytes(r, reward) + mlp_pack_bytes(reward) +
-         ((size_t)H * rows * r.belief_size + (size_t)H * rows) * sizeof(float) + 8192;
+  // packed transition (+ head) images | the deferred head's own pack | beliefs | means, stds, states | rewards
+  return imagine_pack_bytes(r, reward) + 2 * mlp_pack_bytes(reward) +
+         ((size_t)H * rows * (r.belief_size + 3 * r.state_size) + (size_t)H * rows) * sizeof(float) + 16384;
 }
 
-// Candidate evaluation of one CEM iteration on the rollout engine: actions are given, the reward
-// head is fused into every step, only the per-step rewards leave the SM (plus the fp32 belief).
-// a->actions must already hold the sampled local actions (H, B, Cl, A).
+int mlp_forward(const bd_mlp* m, const float* x1, int k1, const float* x2, int k2, int64_t rows,
+                float* y, void* ws, size_t ws_bytes, int precision, bd_stream_t stream, void* saved);
+
+// Candidate evaluation of one CEM iteration on the rollout engine: actions are given; a->actions must already hold
+// the sampled local actions (H, B, Cl, A).
+// The reward head does not feed the recurrence, so it does not have to sit on the per-step serial chain of a plan
+// that is 120 strictly dependent steps long: by default the rollout only leaves (beliefs, states) of every step
+// (fp32, (H, rows, .)) and ONE batched MLP forward over all H * rows latents computes the rewards afterwards
+// (src/planner.py:68-72 evaluates the reward model on the stacked latents in the same way).  The rollout's step
+// shrinks from 8 to 4 dependent phases (column-split clusters of 4: embed, GRU, prior hidden, prior output).
+// Used while the row tiles leave SMs idle (<= 70 tiles); BD_CEM_FUSED_HEAD=1 / 0 forces the head inside the rollout
+// (every step: + one phase per head layer) / the batched pass.
 int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precision, float* rew_out,
                 bd_stream_t stream, bool weights_packed) {
   const bd_rssm& r = a->rssm;
@@ -531,8 +541,13 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   const int Cl = a->c_end - a->c_begin;
   const long long rows = (long long)a->B * Cl;
   const long long ntiles = (rows + kTileRows - 1) / kTileRows;
+  // (measured: 1 000 candidates = 8 row tiles: 4.22 -> 2.77 ms per plan; 10 000 candidates = 79 tiles: 4.38 -> 4.61 ms --
+  // once the row tiles fill the GPU the step is no longer pure latency and the batched pass costs more than it saves)
+  bool defer_head = ntiles <= 70;
+  if (const char* e = getenv("BD_CEM_FUSED_HEAD")) defer_head = atoi(e) == 0;
+  defer_head = defer_head && mlp_supported(hd, Be, S, precision);
   int act_n[2 + BD_MAX_LAYERS] = {Hi, Be}, act_kp[2 + BD_MAX_LAYERS] = {Kp_hid, Kp_x}, nact = 2;
-  for (int l = 0; l + 1 < hd.n_layers; ++l) {
+  for (int l = 0; l + 1 < hd.n_layers && !defer_head; ++l) {
     act_n[nact] = hd.layer[l].out_features; act_kp[nact] = r16(hd.layer[l].out_features + 1); ++nact;
     Kp_h = max(Kp_h, r16(hd.layer[l].out_features + 1));
   }
@@ -543,7 +558,7 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
     add_transition_phases(b, r, rank, R, Kp_b, Kp_sa, Kp_hid, Kp_x, false);
     // reward head on (b', s'): DenseModel (src/planner.py:68-72)
     int sp_hd = 0;
-    for (int l = 0; l < hd.n_layers; ++l) {
+    for (int l = 0; l < hd.n_layers && !defer_head; ++l) {
       const bd_linear& L = hd.layer[l];
       const bool last = (l == hd.n_layers - 1);
       const int n = L.out_features;
@@ -575,6 +590,15 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   auto take = [&](size_t bytes) { char* p_ = base + off; off += (bytes + 255) & ~size_t(255); return p_; };
   uint16_t* wpack = reinterpret_cast<uint16_t*>(take((size_t)b.w_elems * 2));
   float* beliefs = reinterpret_cast<float*>(take((size_t)a->H * rows * Be * sizeof(float)));
+  float *means = nullptr, *stds = nullptr, *states = nullptr;
+  char* head_ws = nullptr;
+  const size_t head_ws_bytes = mlp_pack_bytes(hd) + 4096;
+  if (defer_head) {
+    means = reinterpret_cast<float*>(take((size_t)a->H * rows * S * sizeof(float)));
+    stds = reinterpret_cast<float*>(take((size_t)a->H * rows * S * sizeof(float)));
+    states = reinterpret_cast<float*>(take((size_t)a->H * rows * S * sizeof(float)));
+    head_ws = take(head_ws_bytes);
+  }
   if (off > ws_bytes) BD_FAIL(BD_ERR_WORKSPACE, "tensor-core CEM: workspace %zu < %zu", ws_bytes, off);
 
   RolloutArgs ra{};
@@ -585,8 +609,8 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
   ra.N = rows; ra.T = a->H; ra.Be = Be; ra.S = S; ra.A = A; ra.Hi = Hi; ra.J = 0;
   ra.Kp_b = Kp_b; ra.Kp_sa = Kp_sa; ra.Kp_h = Kp_h; ra.act = r.activation; ra.min_std = r.min_std_dev;
   ra.prev_state = a->state; ra.prev_belief = a->belief; ra.eps_s = a->eps_s;
-  ra.beliefs = beliefs; ra.states = nullptr; ra.means = nullptr; ra.stds = nullptr;
-  ra.head_out[0] = rew_out; ra.ext_actions = a->actions; ra.has_b1 = 1;
+  ra.beliefs = beliefs; ra.states = states; ra.means = means; ra.stds = stds;
+  ra.head_out[0] = defer_head ? nullptr : rew_out; ra.ext_actions = a->actions; ra.has_b1 = 1;
   ra.cem_cl = Cl; ra.cem_c = a->C; ra.cem_c0 = a->c_begin;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long max_img = 0;
@@ -605,8 +629,14 @@ int cem_rollout(const bd_cem_eval_args* a, void* ws, size_t ws_bytes, int precis
     else pack_weights_kernel<1><<<pgrid, 256, 0, s>>>(b.pack, wpack);
     BD_CUDA_LAUNCH_CHECK();
   }
-  ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
-  return launch_rollout(fmt, r.activation, false, false, grid, ra, s);
+  {
+    ProfScope ps(BD_PROF_ROLLOUT_FWD, s);
+    BD_TRY(launch_rollout(fmt, r.activation, false, false, grid, ra, s));
+  }
+  if (!defer_head) return BD_OK;
+  // rewards of all (step, candidate) latents in one batched pass: rew_out[t * rows + n]
+  return mlp_forward(&hd, beliefs, Be, states, S, (int64_t)a->H * rows, rew_out, head_ws, head_ws_bytes, precision,
+                     stream, nullptr);
 }
 
 // TransitionModel.forward, prior-only mode without a nonterminal mask (src/models.py:239-260), on the

@@ -257,6 +257,22 @@ def test_mlp_backward_cta_pair_mode(prec, tol, monkeypatch):
         assert e < tol, (k, res["errors"])
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_cem_deferred_reward_head_matches_fused(prec, monkeypatch):
+    """The CEM rollout with the reward head as ONE batched MLP pass over all (step, candidate) latents (the default
+    while the row tiles leave SMs idle) against the head fused into every rollout step (BD_CEM_FUSED_HEAD=1): the same
+    16-bit operands and accumulation order, so returns, elite sets and the planned action agree (src/planner.py:53-90)."""
+    d = dict(Be=200, Hi=200, S=30, A=1, E=8, B=1, C=1000, K=100, H=12, iters=4, act="ELU")
+    monkeypatch.setenv("BD_CEM_FUSED_HEAD", "1")
+    fused = pu.run_cem_case(d, seed=4, precision=prec)
+    monkeypatch.setenv("BD_CEM_FUSED_HEAD", "0")
+    deferred = pu.run_cem_case(d, seed=4, precision=prec)
+    print(prec, fused["action_err"], deferred["action_err"], fused["returns_err"], deferred["returns_err"])
+    assert abs(fused["returns_err"] - deferred["returns_err"]) < 1e-4
+    assert abs(fused["action_err"] - deferred["action_err"]) < 1e-3
+    assert deferred["returns_err"] < (1e-2 if prec == "fp16" else 5e-2)
+
+
 @pytest.mark.parametrize("frozen", [False, True])
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 @pytest.mark.parametrize("rows_shape", [(14, 2500), (3, 77)])
