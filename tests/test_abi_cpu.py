@@ -130,3 +130,39 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src, f"{fn} references the oracle"
+
+
+def test_imagine_noise_is_one_buffer_with_aligned_entropy_noise():
+    """bd.draw_imagine_noise: the reference's three draws (src/dreamer.py:443-444, src/models.py:72) as ONE generator
+    launch -- views of one buffer with the reference's shapes, contiguous, the entropy noise first (the large-batch
+    entropy kernel reads it with 16-byte loads)."""
+    import torch
+    import big_dreamer_b200 as bd
+    T, N, S, A = 14, 2500, 30, 1
+    nz = bd.draw_imagine_noise(T, N, S, A, "cpu", generator=torch.Generator().manual_seed(0))
+    assert nz["eps_a"].shape == (T, N, A) and nz["eps_s"].shape == (T, N, S) and nz["eps_e"].shape == (T, 100, N, A)
+    assert all(v.is_contiguous() and v.dtype == torch.float32 for v in nz.values())
+    base = nz["eps_e"].untyped_storage().data_ptr()
+    assert all(v.untyped_storage().data_ptr() == base for v in nz.values())
+    assert nz["eps_e"].storage_offset() == 0 and nz["eps_e"].data_ptr() % 16 == 0
+    flat = torch.cat([nz["eps_e"].reshape(-1), nz["eps_s"].reshape(-1), nz["eps_a"].reshape(-1)])
+    assert abs(float(flat.mean())) < 5e-3 and abs(float(flat.std()) - 1.0) < 5e-3
+
+
+def test_heads_pair_falls_back_to_the_two_calls_for_foreign_modules():
+    """bd.heads_pair only pairs two bd.DenseModel heads on CUDA tensors; anything else is exactly
+    reward_model(b, s), value_model(b, s) (src/dreamer.py:321-322)."""
+    import torch
+    import big_dreamer_b200 as bd
+
+    class Head(torch.nn.Module):
+        def __init__(self, scale):
+            super().__init__()
+            self.scale = scale
+
+        def forward(self, b, s):
+            return (b.sum(-1, keepdim=True) + s.sum(-1, keepdim=True)) * self.scale
+
+    b, s = torch.randn(3, 5, 8), torch.randn(3, 5, 2)
+    r, v = bd.heads_pair(Head(2.0), Head(-1.0), b, s)
+    assert torch.equal(r, Head(2.0)(b, s)) and torch.equal(v, Head(-1.0)(b, s))
