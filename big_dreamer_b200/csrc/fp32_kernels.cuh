@@ -282,9 +282,64 @@ __global__ void __launch_bounds__(256) sgemm_skinny_kernel(GemmArgs g) {
   }
 }
 
+// Row-vector variant for M <= 4 rows and a (N, K) row-major weight (the acting path: one environment step is ONE
+// row through every layer, src/planet.py:370-403).  One warp per output column: the lanes read the weight row with
+// all their loads in flight (one L2 round trip for the whole K) and meet by shuffle; the skinny kernel above walks K
+// in 128-column chunks, one round trip each (19 us per layer at K = 1024 against ~3 us here).
+constexpr int GV_MAXM = 4;
+template <int EPI>
+__global__ void __launch_bounds__(256) sgemm_gemv_kernel(GemmArgs g) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= g.N) return;
+  const int K = g.K1 + g.K2;
+  const float* __restrict__ w = g.B + (long long)n * g.ldb;
+  float acc[GV_MAXM];
+#pragma unroll
+  for (int m = 0; m < GV_MAXM; ++m) acc[m] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = w[k];
+    const bool seg1 = k < g.K1;
+#pragma unroll
+    for (int m = 0; m < GV_MAXM; ++m) {
+      if (m < g.M) {
+        float a = seg1 ? g.A1[(long long)m * g.lda1 + k] : g.A2[(long long)m * g.lda2 + (k - g.K1)];
+        if (seg1 && g.rowscale1) a *= g.rowscale1[m];
+        acc[m] = fmaf(a, wv, acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < GV_MAXM; ++m)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  if (lane < g.M) {
+    float v = 0.f;
+#pragma unroll
+    for (int m = 0; m < GV_MAXM; ++m)
+      if (lane == m) v = acc[m];
+    float* c = g.C + (long long)lane * g.ldc + n;
+    if (EPI == EPI_BIAS_ACT) {
+      if (g.bias) v += g.bias[n];
+      v = act_fwd(g.act, v);
+    } else {
+      if (g.aux) v *= act_bwd_from_out(g.act, g.aux[(long long)lane * g.ldaux + n]);
+    }
+    if (g.beta) v += *c;
+    *c = v;
+  }
+}
+
 template <bool A_TRANS, bool B_TRANS, int EPI>
 inline int launch_gemm(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return BD_OK;
+  if constexpr (!A_TRANS && B_TRANS && EPI != EPI_ATOMIC) {
+    if (g.M <= GV_MAXM) {
+      sgemm_gemv_kernel<EPI><<<(g.N + 7) / 8, 256, 0, s>>>(g);
+      BD_CUDA_LAUNCH_CHECK();
+      return BD_OK;
+    }
+  }
   if constexpr (!A_TRANS && EPI != EPI_ATOMIC) {
     if (g.M <= 64) {
       sgemm_skinny_kernel<B_TRANS, EPI><<<(g.N + SK_BN - 1) / SK_BN, 256, 0, s>>>(g);
