@@ -464,7 +464,9 @@ static int time_batched_param_grads(const bd_rssm& r, const bd_transition_args& 
 constexpr int64_t kPersistMaxRows = 8 * obs::kR;      // up to 8 clusters of 16 CTAs
 static bool persist_shape_ok(const bd_rssm& r, int L, int64_t B) {
   const int Be = r.belief_size, Hi = r.hidden_size, S = r.state_size, A = r.action_size;
-  return L >= 1 && B >= 1 && B <= kPersistMaxRows && Be <= 256 && Hi <= 256 && S <= 128 && S + A <= obs::kMaxSmallK &&
+  // (L = 1, the acting path's posterior step: the cluster kernels' per-call set-up -- per-CTA weight packing, a
+  // 16-CTA cluster launch -- costs more than the handful of per-step launches: 133 vs 119 us per acting step)
+  return L >= 2 && B >= 1 && B <= kPersistMaxRows && Be <= 256 && Hi <= 256 && S <= 128 && S + A <= obs::kMaxSmallK &&
          2 * S <= obs::kMaxSmallK;
 }
 static int obs_prof_flag() {
